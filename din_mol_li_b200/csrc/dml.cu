@@ -1,0 +1,659 @@
+// dml.cu — C-ABI entry points of libdml.so (declared in include/dml.h) and the host orchestration of
+// the kernels in dml_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/dml.h"
+#include "dml_kernels.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+using namespace dml;
+
+namespace {
+
+struct ProfEv { cudaEvent_t a, b; int cls; };
+
+template <typename T>
+struct DBuf {
+  T *p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t n, cudaStream_t st, bool keep = false) {
+    if (n <= cap) return cudaSuccess;
+    size_t nc = std::max(n, cap + cap / 2);
+    T *np_ = nullptr;
+    cudaError_t e = cudaMalloc(&np_, nc * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (keep && p && cap) cudaMemcpyAsync(np_, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+    p = np_; cap = nc;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct dml_ctx {
+  dml_config cfg;
+  std::string err;
+  cudaStream_t st = nullptr;
+  int cap = 0, n = 0;
+  Geo geo; Phys ph;
+  bool tessellated = false, listed = false, cells_sorted = false, binned = false;
+  int nct = 0;
+  int64_t nupd = 0, step = 0, choques2 = 0, overlap_passes = 0;
+  double t = 0.0;
+  int64_t launches = 0;
+  bool profiling = false; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
+  double prof_ms[8] = {0}; int64_t prof_n[8] = {0};
+  // particle state
+  DBuf<double4> posm, sorted_posm;
+  DBuf<double> vel, acel, force, epot, pos_old, old_cg, ranv;
+  DBuf<int> uid, slot_b;
+  // cells
+  DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, chain_pos;
+  // rows
+  DBuf<int> row_start, row_len, row_cap, cols;
+  DBuf<int> scan_sums;
+  DBuf<double> part;
+  // overlap
+  DBuf<int> parent, ovst, comp_cnt, comp_off, members, roots;
+  // replay
+  DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
+  // staging
+  DBuf<double> stage_d; DBuf<int> stage_i;
+  DevScal *sc = nullptr; DevScal *hsc = nullptr;    // device / pinned host mirror
+  // chunk template (reservoir 2)
+  std::vector<double> ch_pos, ch_pos_old; double ch_dist = 0, ch_rhomedia = 0; bool have_chunk = false;
+  int row_slack = 0;
+};
+
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
+#define FAIL(msg) do { ctx->err = (msg); return -1; } while (0)
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+static int gcmc_run_impl(dml_ctx *ctx);
+
+enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
+
+static void prof_begin(dml_ctx *ctx, int cls) {
+  ctx->launches++;
+  if (!ctx->profiling) return;
+  ProfEv ev;
+  if (!ctx->pool.empty()) { ev = ctx->pool.back(); ctx->pool.pop_back(); }
+  else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
+  ev.cls = cls;
+  cudaEventRecord(ev.a, ctx->st);
+  ctx->evs.push_back(ev);
+}
+static void prof_end(dml_ctx *ctx) { if (ctx->profiling) cudaEventRecord(ctx->evs.back().b, ctx->st); }
+static void prof_collect(dml_ctx *ctx) {
+  if (ctx->evs.empty()) return;
+  cudaStreamSynchronize(ctx->st);
+  for (auto &ev : ctx->evs) {
+    float ms = 0; cudaEventElapsedTime(&ms, ev.a, ev.b);
+    ctx->prof_ms[ev.cls] += ms; ctx->prof_n[ev.cls]++;
+    ctx->pool.push_back(ev);
+  }
+  ctx->evs.clear();
+}
+#define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx); } while (0)
+
+static inline int nblk(int n, int b = TPB) { return std::max(1, (n + b - 1) / b); }
+
+static const char *dev_err_msg(int e) {
+  switch (e) {
+    case DML_E_OUT_OF_TESS: return "Particle out of tessellation";
+    case DML_E_SUPERO_Z0: return "supero z0";
+    case DML_E_ROW_OVERFLOW: return "neighbour row overflow";
+    case DML_E_CAPACITY: return "slot capacity exhausted";
+    case DML_E_NO_PARTICLES: return "No more particles";
+    case DML_E_COLS_OVERFLOW: return "neighbour storage exhausted";
+    case DML_E_GCMC_CHOSEN: return "Chosen particle does not exists";
+    case DML_E_REPLAY_EXHAUSTED: return "replay stream exhausted";
+  }
+  return "unknown device error";
+}
+
+static int pull_scal(dml_ctx *ctx) {
+  CKC(cudaMemcpyAsync(ctx->hsc, ctx->sc, sizeof(DevScal), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  if (ctx->hsc->err) { ctx->err = dev_err_msg(ctx->hsc->err); return -ctx->hsc->err - 100; }
+  return 0;
+}
+static int push_scal(dml_ctx *ctx) {
+  CKC(cudaMemcpyAsync(ctx->sc, ctx->hsc, sizeof(DevScal), cudaMemcpyHostToDevice, ctx->st));
+  return 0;
+}
+
+static void set_box(dml_ctx *ctx, const double box[3]) {
+  for (int k = 0; k < 3; ++k) { ctx->geo.box[k] = box[k]; ctx->geo.one_box[k] = 1.0 / box[k]; ctx->geo.half_box[k] = box[k] * .5; }
+}
+
+// cgroup_tessellate — Cells.F90:180-265 (host side: it depends only on the box and rcut+nb_dcut)
+static void tessellate(dml_ctx *ctx) {
+  Geo &g = ctx->geo;
+  double rc = ctx->cfg.rcut + ctx->cfg.nb_dcut;
+  if (ctx->tessellated) {
+    bool ok1 = true, ok2 = true;
+    for (int k = 0; k < 3; ++k) if (!((double)(g.nc[k] + 1) >= g.box[k] / rc)) ok1 = false;
+    if (ok1) {
+      for (int k = 0; k < 3; ++k) if (!(rc < g.box[k] / (double)g.nc[k])) ok2 = false;
+      if (ok2) { for (int k = 0; k < 3; ++k) g.cell[k] = g.box[k] / (double)g.nc[k]; return; }
+    }
+  }
+  int nc[3];
+  for (int k = 0; k < 3; ++k) nc[k] = (int)(g.box[k] / rc);
+  for (int k = 0; k < 3; ++k) g.nc[k] = nc[k];
+  if (nc[0] < 4 && nc[1] < 4 && nc[2] < 4) return;       // reference falls back to the O(N^2) list
+  for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
+  ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
+  ctx->tessellated = true;
+}
+
+static int scan_excl(dml_ctx *ctx, const int *in, int *out, int n, int *total_out, int *total_out2, int cls) {
+  int nb = nblk(n, 1024);
+  CKC(ctx->scan_sums.ensure(nb + 1, ctx->st));
+  LAUNCH(cls, k_scan_local, nb, TPB, in, out, ctx->scan_sums.p, n);
+  LAUNCH(cls, k_scan_sums, 1, 1024, ctx->scan_sums.p, nb, total_out, total_out2);
+  if (nb > 1) LAUNCH(cls, k_scan_add, nb, TPB, out, ctx->scan_sums.p, n);
+  return 0;
+}
+
+static int ensure_particles(dml_ctx *ctx, int n) {
+  if (n > ctx->cap) FAIL("slot capacity exhausted (dml_config.capacity)");
+  return 0;
+}
+
+static int sort_cells(dml_ctx *ctx, bool snapshot) {
+  int n = ctx->n, nct = ctx->nct;
+  TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, nullptr, CLS_LIST));
+  CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, (size_t)nct * sizeof(int), ctx->st));
+  LAUNCH(CLS_LIST, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
+         ctx->sorted_slot.p, n, snapshot ? 1 : 0);
+  LAUNCH(CLS_LIST, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->sorted_slot.p,
+         ctx->sorted_posm.p, nct);
+  ctx->cells_sorted = true;
+  return 0;
+}
+
+// update() + ngroup_cells — Neighbor.F90:608-633, 465-548
+static int rebuild(dml_ctx *ctx) {
+  int n = ctx->n;
+  ctx->nupd++;
+  TRY(sort_cells(ctx, true));
+  CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
+  LAUNCH(CLS_LIST, (k_rows<false>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
+  LAUNCH(CLS_LIST, k_row_caps, nblk(n), TPB, ctx->row_len.p, ctx->row_cap.p, n, ctx->row_slack);
+  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, nullptr, CLS_LIST));
+  TRY(pull_scal(ctx));
+  size_t need = (size_t)ctx->hsc->cols_used + (size_t)ctx->row_slack * 64 + 1024;
+  if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st));
+  LAUNCH(CLS_LIST, (k_rows<true>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
+  ctx->hsc->nlimbo = 0;
+  ctx->listed = true;
+  return 0;
+}
+
+static int do_test_update(dml_ctx *ctx) {
+  tessellate(ctx);
+  if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction: the reference's O(N^2) ngroup_verlet path is not implemented on the device");
+  int n = ctx->n, nct = ctx->nct;
+  CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
+  CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, (size_t)nct * sizeof(int), ctx->st));
+  int nb = nblk(n);
+  CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
+  LAUNCH(CLS_BIN, k_pbc_bin, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->part.p, ctx->sc, ctx->geo, n, 1);
+  LAUNCH(CLS_BIN, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->listed ? 1 : 0, ctx->cfg.nb_dcut);
+  ctx->cells_sorted = false; ctx->binned = true;
+  TRY(pull_scal(ctx));
+  if (ctx->hsc->need_rebuild) TRY(rebuild(ctx));
+  return 0;
+}
+
+static int do_integrate(dml_ctx *ctx, bool ermak) {
+  int n = ctx->n;
+  ctx->step++;
+  if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
+  if (ermak)
+    LAUNCH(CLS_INTEG, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+  else
+    LAUNCH(CLS_INTEG, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+  ctx->have_rp = false;
+  return 0;
+}
+
+static int do_fuerza(dml_ctx *ctx) {
+  if (!ctx->listed) FAIL("fuerza called without a neighbour list");
+  int n = ctx->n;
+  if (ctx->cfg.strict_order)
+    LAUNCH(CLS_FORCE, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->uid.p, ctx->force.p,
+           ctx->epot.p, ctx->geo, ctx->ph, n);
+  else
+    LAUNCH(CLS_FORCE, (k_fuerza<false>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->uid.p, ctx->force.p,
+           ctx->epot.p, ctx->geo, ctx->ph, n);
+  return 0;
+}
+
+static int do_overlap(dml_ctx *ctx) {
+  if (!ctx->listed) FAIL("overlap_moveback called without a neighbour list");
+  int n = ctx->n;
+  ctx->hsc->again = 0; ctx->hsc->n_roots = 0; ctx->hsc->member_cursor = 0;
+  // only the three control words are reset on the device (the rest of the struct lives there)
+  CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(&ctx->sc->n_roots, 0, sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(&ctx->sc->member_cursor, 0, sizeof(int), ctx->st));
+  LAUNCH(CLS_OVERLAP, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+  LAUNCH(CLS_OVERLAP, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
+         ctx->ovst.p, ctx->sc, ctx->geo, n);
+  LAUNCH(CLS_OVERLAP, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+  LAUNCH(CLS_OVERLAP, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
+  LAUNCH(CLS_OVERLAP, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
+  TRY(pull_scal(ctx));
+  int nroots = ctx->hsc->n_roots;
+  int64_t ch_prev = ctx->hsc->choques;
+  std::vector<int64_t> marks;
+  if (nroots > 0) {
+    LAUNCH(CLS_OVERLAP, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
+    for (int pass = 0;; ++pass) {
+      CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
+      LAUNCH(CLS_OVERLAP, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
+             ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p,
+             ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, pass);
+      ctx->overlap_passes++;
+      TRY(pull_scal(ctx));
+      marks.push_back(ctx->hsc->choques);
+      if (!ctx->hsc->again) break;
+      if (pass > 100000) FAIL("overlap_moveback does not converge");
+    }
+  } else { ctx->overlap_passes++; marks.push_back(ch_prev); }
+  for (size_t lv = 0; lv < marks.size(); ++lv) ctx->choques2 = std::max<int64_t>(ctx->choques2, (int64_t)ctx->hsc->choques - marks[lv]);
+  LAUNCH(CLS_OVERLAP, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, n);
+  ctx->have_rp_ovl = false;
+  return 0;
+}
+
+static int do_promote(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
+static int do_calc_rho(dml_ctx *ctx) {
+  LAUNCH(CLS_OTHER, k_calc_rho, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, ctx->n);
+  return 0;
+}
+static int do_maxz(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_maxz, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->cfg.h / ctx->cfg.tau, ctx->n); return 0; }
+
+static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
+  if (!src) return 0;
+  CKC(cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  return 0;
+}
+
+// bloques — dana.F90:716-773
+static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double *cpos_old, double dist, double rhomedia, int *fired) {
+  TRY(pull_scal(ctx));
+  double drho = ctx->hsc->rho - rhomedia;
+  if (fired) *fired = 0;
+  if (std::fabs(drho) < (rhomedia * (double)0.186f)) return 0;
+  if (fired) *fired = 1;
+  int n0 = ctx->n;
+  TRY(ensure_particles(ctx, n0 + nchunk));
+  ctx->hsc->z0 += dist; ctx->hsc->z1 += dist; ctx->hsc->zmax += dist;
+  std::vector<double> zero3((size_t)nchunk * 3, 0.0), og((size_t)nchunk * 3, 1e8);
+  std::vector<int> z(nchunk, 1), fl(nchunk, DML_F_REF), uid(nchunk), sb(nchunk);
+  for (int i = 0; i < nchunk; ++i) { uid[i] = ctx->hsc->next_uid + i; sb[i] = n0 + i; }
+  ctx->hsc->next_uid += nchunk; ctx->hsc->n_slots = n0 + nchunk; ctx->hsc->nat_sys += nchunk; ctx->hsc->nat_ref += nchunk;
+  TRY(push_scal(ctx));
+  CKC(ctx->stage_d.ensure((size_t)nchunk * 3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)nchunk * 2, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_d.p, cpos, (size_t)nchunk * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_i.p, z.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_i.p + nchunk, fl.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  LAUNCH(CLS_OTHER, k_pack, nblk(nchunk), TPB, ctx->posm.p + n0, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + nchunk, nchunk);
+  TRY(upload_d(ctx, ctx->pos_old.p + (size_t)3 * n0, cpos_old, (size_t)nchunk * 3));
+  TRY(upload_d(ctx, ctx->vel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
+  TRY(upload_d(ctx, ctx->acel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
+  TRY(upload_d(ctx, ctx->force.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
+  TRY(upload_d(ctx, ctx->epot.p + n0, zero3.data(), (size_t)nchunk));
+  TRY(upload_d(ctx, ctx->old_cg.p + (size_t)3 * n0, og.data(), (size_t)nchunk * 3));
+  CKC(cudaMemcpyAsync(ctx->uid.p + n0, uid.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->slot_b.p + n0, sb.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));                     // host vectors go out of scope
+  ctx->n = n0 + nchunk;
+  ctx->listed = false;
+  double box[3] = {ctx->geo.box[0], ctx->geo.box[1], ctx->hsc->zmax};
+  set_box(ctx, box);
+  return do_test_update(ctx);
+}
+
+static int do_step(dml_ctx *ctx) {
+  if (ctx->cfg.integrador) { TRY(do_integrate(ctx, true)); TRY(do_fuerza(ctx)); LAUNCH(CLS_INTEG, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n); }
+  else TRY(do_integrate(ctx, false));
+  TRY(do_test_update(ctx));
+  TRY(do_overlap(ctx));
+  TRY(do_test_update(ctx));
+  LAUNCH(CLS_OTHER, k_msd_book, 1, 1, ctx->sc);
+  TRY(do_promote(ctx));
+  if (ctx->cfg.reservoir == 3) TRY(gcmc_run_impl(ctx));
+  TRY(do_calc_rho(ctx));
+  if (ctx->cfg.reservoir == 2) {
+    if (!ctx->have_chunk) FAIL("reservoir 2: call dml_set_chunk_template before dml_step");
+    int fired = 0;
+    int nch = (int)(ctx->ch_pos.size() / 3);
+    TRY(do_bloques(ctx, nch, ctx->ch_pos.data(), ctx->ch_pos_old.data(), ctx->ch_dist, ctx->ch_rhomedia, &fired));
+    if (fired) for (int i = 0; i < nch; ++i) { ctx->ch_pos[3 * i + 2] += ctx->ch_dist; ctx->ch_pos_old[3 * i + 2] += ctx->ch_dist; }
+  }
+  if (ctx->cfg.reservoir == 1) TRY(do_maxz(ctx));
+  ctx->t = ctx->t + ctx->cfg.h;
+  return 0;
+}
+
+#include "dml_gcmc.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *dml_version(void) { return "dml-b200 0.1 (sm_100a)"; }
+const char *dml_last_error(dml_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int dml_create(dml_ctx **out, const dml_config *cfg) {
+  if (!out || !cfg) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -2;      // no CPU fallback
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return -3;
+  dml_ctx *ctx = new dml_ctx;
+  ctx->cfg = *cfg;
+  *out = ctx;
+  CKC(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+  int cap = ctx->cap = std::max(cfg->capacity, 256);
+  memset(&ctx->geo, 0, sizeof ctx->geo);
+  set_box(ctx, cfg->box);
+  for (int k = 0; k < 3; ++k) { ctx->geo.pbc[k] = cfg->pbc[k]; ctx->geo.nc[k] = 1; }
+  double rl = cfg->rcut + cfg->nb_dcut;
+  ctx->geo.rc_list2 = rl * rl; ctx->geo.rcut2 = cfg->rcut * cfg->rcut;
+  Phys &ph = ctx->ph; memset(&ph, 0, sizeof ph);
+  for (int i = 0; i < 9; ++i) {
+    ph.eps[i] = cfg->eps[i]; ph.r0[i] = cfg->r0[i]; ph.r0sq[i] = cfg->r0[i] * cfg->r0[i];
+    double x = cfg->r0[i], x2 = x * x, x4 = x2 * x2; ph.r0p6[i] = x2 * x4;
+  }
+  for (int i = 0; i < 3; ++i) { ph.mass[i] = cfg->mass[i]; ph.sqrt_mass[i] = std::sqrt(cfg->mass[i]); }
+  ph.h = cfg->h; ph.prob = cfg->prob; ph.tau = cfg->tau;
+  {                                                       // set_ermak — dana.F90:947-971
+    double h = cfg->h, gama = cfg->gama;
+    ph.cc0 = std::exp(-h * gama);
+    ph.cc1 = (1.0 - ph.cc0) / gama;
+    ph.cc2 = (1.0 - ph.cc1 / h) / gama;
+    ph.sdr = std::sqrt(h / gama * (2.0 - (3.0 - 4.0 * ph.cc0 + ph.cc0 * ph.cc0) / (h * gama)));
+    ph.sdv = std::sqrt(1.0 - ph.cc0 * ph.cc0);
+    ph.crv1 = (1.0 - ph.cc0) * (1.0 - ph.cc0) / (gama * ph.sdr * ph.sdv);
+    ph.crv2 = std::sqrt(1.0 - (ph.crv1 * ph.crv1));
+    ph.skt = std::sqrt(cfg->kB_ui * cfg->Tsist);
+    ph.cc1mcc2 = ph.cc1 - ph.cc2; ph.cc2h = ph.cc2 * h;
+  }
+  ph.dif_sc = cfg->dif_sc; ph.dif_sei = cfg->dif_sei; ph.z_sei = cfg->z_sei;
+  ph.fac_sc = std::sqrt(2.0 * cfg->dif_sc * cfg->h); ph.fac_sei = std::sqrt(2.0 * cfg->dif_sei * cfg->h);
+  ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
+  ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
+  ctx->row_slack = cfg->reservoir == 3 ? 6 : 0;
+  size_t c3 = (size_t)cap * 3;
+  CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st));
+  CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->force.ensure(c3, ctx->st));
+  CKC(ctx->epot.ensure(cap, ctx->st)); CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
+  CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
+  CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
+  CKC(ctx->row_start.ensure(cap + 1, ctx->st)); CKC(ctx->row_len.ensure(cap, ctx->st)); CKC(ctx->row_cap.ensure(cap, ctx->st));
+  CKC(ctx->cols.ensure((size_t)cap * 16 + 4096, ctx->st));
+  CKC(ctx->parent.ensure(cap, ctx->st)); CKC(ctx->ovst.ensure(cap, ctx->st)); CKC(ctx->comp_cnt.ensure(cap, ctx->st));
+  CKC(ctx->comp_off.ensure(cap, ctx->st)); CKC(ctx->members.ensure(cap, ctx->st)); CKC(ctx->roots.ensure(cap, ctx->st));
+  CKC(ctx->rp_gauss.ensure((size_t)cap * 6, ctx->st)); CKC(ctx->rp_upbc.ensure(cap, ctx->st)); CKC(ctx->rp_uovl.ensure(cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)cap * sizeof(double4), ctx->st));
+  CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)cap * sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(ctx->force.p, 0, c3 * sizeof(double), ctx->st));
+  CKC(cudaMemsetAsync(ctx->epot.p, 0, (size_t)cap * sizeof(double), ctx->st));
+  CKC(cudaMalloc(&ctx->sc, sizeof(DevScal)));
+  CKC(cudaMallocHost(&ctx->hsc, sizeof(DevScal)));
+  memset(ctx->hsc, 0, sizeof(DevScal));
+  ctx->hsc->z0 = cfg->z0; ctx->hsc->z1 = cfg->z1; ctx->hsc->zmax = cfg->zmax;
+  TRY(push_scal(ctx));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+void dml_destroy(dml_ctx *ctx) {
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->st);
+  prof_collect(ctx);
+  for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  ctx->posm.release(); ctx->sorted_posm.release(); ctx->vel.release(); ctx->acel.release(); ctx->force.release(); ctx->epot.release();
+  ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
+  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
+  ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
+  ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
+  ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
+  ctx->stage_d.release(); ctx->stage_i.release();
+  if (ctx->sc) cudaFree(ctx->sc);
+  if (ctx->hsc) cudaFreeHost(ctx->hsc);
+  if (ctx->st) cudaStreamDestroy(ctx->st);
+  delete ctx;
+}
+
+int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, const double *acel, const double *pos_old,
+               const double *old_cg, const int32_t *z, const int32_t *flags, const int32_t *uid, const int32_t *slot_b) {
+  TRY(ensure_particles(ctx, n));
+  if (!pos || !z || !flags) FAIL("dml_upload: pos, z and flags are required");
+  size_t n3 = (size_t)n * 3;
+  CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_d.p, pos, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_i.p, z, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_i.p + n, flags, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)ctx->cap * sizeof(double4), ctx->st));
+  LAUNCH(CLS_OTHER, k_pack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
+  TRY(upload_d(ctx, ctx->vel.p, vel, n3)); TRY(upload_d(ctx, ctx->acel.p, acel, n3));
+  TRY(upload_d(ctx, ctx->pos_old.p, pos_old ? pos_old : pos, n3));
+  if (old_cg) TRY(upload_d(ctx, ctx->old_cg.p, old_cg, n3));
+  if (!vel) CKC(cudaMemsetAsync(ctx->vel.p, 0, n3 * sizeof(double), ctx->st));
+  if (!acel) CKC(cudaMemsetAsync(ctx->acel.p, 0, n3 * sizeof(double), ctx->st));
+  std::vector<int> tmp;
+  int mx = -1;
+  if (uid) { CKC(cudaMemcpyAsync(ctx->uid.p, uid, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); for (int i = 0; i < n; ++i) mx = std::max(mx, uid[i]); }
+  else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; mx = n - 1; CKC(cudaMemcpyAsync(ctx->uid.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
+  if (slot_b) CKC(cudaMemcpyAsync(ctx->slot_b.p, slot_b, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; CKC(cudaMemcpyAsync(ctx->slot_b.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
+  ctx->n = n; ctx->listed = false; ctx->cells_sorted = false; ctx->binned = false;
+  TRY(pull_scal(ctx));
+  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+  TRY(push_scal(ctx));
+  LAUNCH(CLS_OTHER, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel, double *force, double *epot, double *pos_old,
+                 double *old_cg, int32_t *z, int32_t *flags, int32_t *uid, int32_t *slot_b) {
+  if (n > ctx->n) FAIL("dml_download: n exceeds the number of slots");
+  size_t n3 = (size_t)n * 3;
+  CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
+  LAUNCH(CLS_OTHER, k_unpack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
+  if (pos) CKC(cudaMemcpyAsync(pos, ctx->stage_d.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (z) CKC(cudaMemcpyAsync(z, ctx->stage_i.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  if (flags) CKC(cudaMemcpyAsync(flags, ctx->stage_i.p + n, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  if (vel) CKC(cudaMemcpyAsync(vel, ctx->vel.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (acel) CKC(cudaMemcpyAsync(acel, ctx->acel.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (force) CKC(cudaMemcpyAsync(force, ctx->force.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (epot) CKC(cudaMemcpyAsync(epot, ctx->epot.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (pos_old) CKC(cudaMemcpyAsync(pos_old, ctx->pos_old.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (old_cg) CKC(cudaMemcpyAsync(old_cg, ctx->old_cg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (uid) CKC(cudaMemcpyAsync(uid, ctx->uid.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  if (slot_b) CKC(cudaMemcpyAsync(slot_b, ctx->slot_b.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+
+int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s) {
+  TRY(pull_scal(ctx));
+  ctx->hsc->z0 = s->z0; ctx->hsc->z1 = s->z1; ctx->hsc->zmax = s->zmax; ctx->hsc->rho = s->rho; ctx->hsc->rho0 = s->rho0;
+  TRY(push_scal(ctx));
+  set_box(ctx, s->box);
+  ctx->t = s->t; ctx->step = s->step;
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+int dml_get_scalars(dml_ctx *ctx, dml_scalars *s) {
+  TRY(pull_scal(ctx));
+  for (int k = 0; k < 3; ++k) s->box[k] = ctx->geo.box[k];
+  s->z0 = ctx->hsc->z0; s->z1 = ctx->hsc->z1; s->zmax = ctx->hsc->zmax; s->rho = ctx->hsc->rho; s->rho0 = ctx->hsc->rho0;
+  s->t = ctx->t; s->step = ctx->step;
+  return 0;
+}
+int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
+  TRY(pull_scal(ctx));
+  memset(c, 0, sizeof *c);
+  if (ctx->listed) {
+    CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
+    LAUNCH(CLS_OTHER, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
+    TRY(pull_scal(ctx));
+  }
+  DevScal *h = ctx->hsc;
+  c->nupd_vlist = ctx->nupd; c->try_ = h->try_; c->depo = h->depo; c->choques = h->choques; c->choques2 = ctx->choques2; c->choques3 = h->choques3;
+  c->list_entries = ctx->listed ? h->list_entries : 0; c->overlap_passes = ctx->overlap_passes;
+  c->gcmc_created = h->gcmc_created; c->gcmc_destroyed = h->gcmc_destroyed; c->row_overflow = h->row_overflow;
+  c->max_vel = h->max_vel; c->msd_t = h->msd_t; c->msd_max = h->msd_max;
+  c->n_slots = ctx->n; c->nat_sys = h->nat_sys; c->nat_ref = h->nat_ref; c->nat_gcmc = h->nat_gcmc;
+  for (int k = 0; k < 3; ++k) { c->ncells[k] = ctx->geo.nc[k]; c->cell[k] = ctx->geo.cell[k]; }
+  c->tessellated = ctx->tessellated; c->listed = ctx->listed;
+  return 0;
+}
+int dml_reset_try_depo(dml_ctx *ctx) {
+  CKC(cudaMemsetAsync(&ctx->sc->try_, 0, sizeof(long long), ctx->st));
+  CKC(cudaMemsetAsync(&ctx->sc->depo, 0, sizeof(long long), ctx->st));
+  return 0;
+}
+
+int dml_test_update(dml_ctx *ctx) { return do_test_update(ctx); }
+int dml_fuerza(dml_ctx *ctx) { return do_fuerza(ctx); }
+int dml_ermak_a(dml_ctx *ctx) { return do_integrate(ctx, true); }
+int dml_ermak_b(dml_ctx *ctx) {
+  LAUNCH(CLS_INTEG, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n);
+  return 0;
+}
+int dml_cbrownian_hs(dml_ctx *ctx) { return do_integrate(ctx, false); }
+int dml_overlap_moveback(dml_ctx *ctx) { return do_overlap(ctx); }
+int dml_msd_book(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_msd_book, 1, 1, ctx->sc); return 0; }
+int dml_promote(dml_ctx *ctx) { return do_promote(ctx); }
+int dml_gcmc_run(dml_ctx *ctx) { return gcmc_run_impl(ctx); }
+int dml_calc_rho(dml_ctx *ctx, double *rho) {
+  TRY(do_calc_rho(ctx));
+  if (rho) { TRY(pull_scal(ctx)); *rho = ctx->hsc->rho; }
+  return 0;
+}
+int dml_maxz(dml_ctx *ctx, double *zmax) {
+  TRY(do_maxz(ctx));
+  if (zmax) { TRY(pull_scal(ctx)); *zmax = ctx->hsc->zmax; }
+  return 0;
+}
+int dml_bloques(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia, int32_t *fired) {
+  return do_bloques(ctx, nchunk, chunk_pos, chunk_pos_old, dist, rhomedia, fired);
+}
+int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia) {
+  ctx->ch_pos.assign(chunk_pos, chunk_pos + (size_t)nchunk * 3);
+  ctx->ch_pos_old.assign(chunk_pos_old, chunk_pos_old + (size_t)nchunk * 3);
+  ctx->ch_dist = dist; ctx->ch_rhomedia = rhomedia; ctx->have_chunk = true;
+  return 0;
+}
+int dml_step(dml_ctx *ctx, int32_t nsteps) {
+  for (int i = 0; i < nsteps; ++i) TRY(do_step(ctx));
+  return 0;
+}
+
+int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) {
+  if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
+  if (!ctx->cells_sorted) TRY(sort_cells(ctx, false));
+  CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
+  LAUNCH(CLS_OTHER, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
+  std::vector<int> lin(n);
+  CKC(cudaMemcpyAsync(lin.data(), ctx->cell_of.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaMemcpyAsync(chain_pos, ctx->chain_pos.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  for (int i = 0; i < n; ++i) {
+    if (lin[i] < 0) { cell_xyz[3 * i] = cell_xyz[3 * i + 1] = cell_xyz[3 * i + 2] = -1; continue; }
+    int r = lin[i] / ctx->geo.hd[0];
+    cell_xyz[3 * i] = lin[i] % ctx->geo.hd[0]; cell_xyz[3 * i + 1] = r % ctx->geo.hd[1]; cell_xyz[3 * i + 2] = r / ctx->geo.hd[1];
+  }
+  return 0;
+}
+
+int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) {
+  if (!ctx->listed) FAIL("no neighbour list");
+  TRY(pull_scal(ctx));
+  std::vector<int> rs(n), rl(n), cols((size_t)std::max(ctx->hsc->cols_used, 1));
+  CKC(cudaMemcpyAsync(rs.data(), ctx->row_start.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaMemcpyAsync(rl.data(), ctx->row_len.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaMemcpyAsync(cols.data(), ctx->cols.p, cols.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  int rc = 0;
+  for (int i = 0; i < n; ++i) {
+    nn[i] = rl[i];
+    for (int m = 0; m < rl[i]; ++m) { if (m >= width) { rc = 1; break; } rows[(size_t)i * width + m] = cols[rs[i] + m]; }
+  }
+  return rc;
+}
+int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn, const int32_t *rows) {
+  if (n > ctx->n) FAIL("dml_set_neighbors: n exceeds the number of slots");
+  std::vector<int> rs(n + 1), rl(ctx->n, 0), rc(ctx->n, 0), cols;
+  int off = 0;
+  for (int i = 0; i < n; ++i) {
+    rs[i] = off; rl[i] = nn[i]; rc[i] = nn[i] + ctx->row_slack;
+    for (int m = 0; m < nn[i]; ++m) cols.push_back(rows[(size_t)i * width + m]);
+    for (int m = 0; m < ctx->row_slack; ++m) cols.push_back(-1);
+    off += rc[i];
+  }
+  rs[n] = off;
+  CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->row_start.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->row_len.p, rl.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->row_cap.p, rc.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  if (off) CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), (size_t)off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  TRY(pull_scal(ctx));
+  ctx->hsc->cols_used = off;
+  TRY(push_scal(ctx));
+  CKC(cudaStreamSynchronize(ctx->st));
+  ctx->listed = true;
+  return 0;
+}
+
+int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, const double *unif_pbc, const double *unif_ovl) {
+  if (n > ctx->cap) FAIL("replay arrays exceed capacity");
+  if (gauss) CKC(cudaMemcpyAsync(ctx->rp_gauss.p, gauss, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  if (unif_pbc) CKC(cudaMemcpyAsync(ctx->rp_upbc.p, unif_pbc, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  else CKC(cudaMemsetAsync(ctx->rp_upbc.p, 0, (size_t)n * sizeof(double), ctx->st));
+  if (unif_ovl) { CKC(cudaMemcpyAsync(ctx->rp_uovl.p, unif_ovl, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->st)); ctx->have_rp_ovl = true; }
+  CKC(cudaStreamSynchronize(ctx->st));
+  ctx->have_rp = gauss != nullptr;
+  return 0;
+}
+int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss) {
+  CKC(ctx->rp_gu.ensure((size_t)std::max(nu, 1), ctx->st)); CKC(ctx->rp_gg.ensure((size_t)std::max(ng, 1), ctx->st));
+  if (nu) CKC(cudaMemcpyAsync(ctx->rp_gu.p, unif, (size_t)nu * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  if (ng) CKC(cudaMemcpyAsync(ctx->rp_gg.p, gauss, (size_t)ng * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  ctx->rp_nu = nu; ctx->rp_ng = ng;
+  return 0;
+}
+
+int dml_profile(dml_ctx *ctx, int32_t enable) { prof_collect(ctx); ctx->profiling = enable != 0; return 0; }
+int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset) {
+  prof_collect(ctx);
+  double m = 0; int64_t l = 0;
+  if (cls == CLS_ALL) { for (int i = 0; i < 8; ++i) { m += ctx->prof_ms[i]; l += ctx->prof_n[i]; } }
+  else if (cls >= 0 && cls < 8) { m = ctx->prof_ms[cls]; l = ctx->prof_n[cls]; }
+  if (ms) *ms = m;
+  if (launches) *launches = l;
+  if (reset) for (int i = 0; i < 8; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+  return 0;
+}
+int64_t dml_launch_count(dml_ctx *ctx) { return ctx->launches; }
+void *dml_stream(dml_ctx *ctx) { return (void *)ctx->st; }
+
+} // extern "C"

@@ -1,0 +1,150 @@
+// dml_device.cuh — device-side building blocks shared by the kernels of libdml.so.
+//
+// Bit-exactness notes (SURVEY.md §7 "Hard parts"): the whole library is compiled with -fmad=false so no
+// multiply-add is contracted; fp64 division and sqrt are IEEE round-to-nearest on the device; idnint is
+// round() (half away from zero); int(x) is a C cast (truncation).  With those four rules the distance tests
+// and the force arithmetic below round exactly like the reference's -O0 x86-64 build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dml {
+
+// ---- particle record: double4 {x, y, z, meta}; meta is an int64 bit-cast into the 4th lane -------------
+constexpr long long MF_TYPE = 3;    // bits 0-1: element id (0 empty, 1 Li, 2 CG, 3 F)  dana.F90:82-84
+constexpr long long MF_REF = 4;     // member of hs%ref
+constexpr long long MF_GCMC = 8;    // member of gcmc
+constexpr long long MF_SKIP = 16;   // atom%skip
+constexpr long long MF_LIMBO = 32;  // slot parked on hs%limbo until the next full build
+
+__device__ __forceinline__ long long meta_of(const double4 &p) { return __double_as_longlong(p.w); }
+__device__ __forceinline__ double meta_as_double(long long m) { return __longlong_as_double(m); }
+
+// One 256-bit load of a particle record (sm_100: ld.global.v4.f64 needs 32-byte alignment; cudaMalloc gives 256).
+__device__ __forceinline__ double4 ld_rec(const double4 *p) {
+  double4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double4 ld_rec_nc(const double4 *p) {   // read-only path (record not written in this kernel)
+  double4 r;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_rec(double4 *p, const double4 &r) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w) : "memory");
+}
+
+// ---- device-resident scalars (one struct in global memory; the host mirrors it on demand) --------------
+struct DevScal {
+  double z0, z1, zmax, rho, rho0;
+  double d1, d2;                 // two largest squared displacements (inq_dispmax, Neighbor.F90:635-666)
+  double max_vel, msd_t, msd_max;
+  long long try_, depo, choques, choques3;
+  long long list_entries;
+  long long gcmc_created, gcmc_destroyed, row_overflow;
+  int rho_count;
+  int need_rebuild;
+  int again;                     // overlap_moveback: another pass needed
+  int any_active;
+  int err;                       // first device-side error (DML_E_*)
+  int n_involved, n_roots, member_cursor;
+  int n_slots;                   // hs%amax (device copy; gcmc may grow it)
+  int nat_sys, nat_ref, nat_gcmc, nlimbo;
+  int cols_used;                 // bump pointer into cols[]
+  int next_uid;
+  unsigned int ticket;
+  int pad_;
+};
+
+enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,
+       DML_E_COLS_OVERFLOW = 6, DML_E_GCMC_CHOSEN = 7, DML_E_REPLAY_EXHAUSTED = 8 };
+
+// ---- geometry parameters passed by value ----------------------------------------------------------------
+struct Geo {
+  double box[3], one_box[3], half_box[3];
+  double cell[3];
+  int nc[3];      // ncells
+  int hd[3];      // nc+2 (halo-inclusive extents, Cells.F90:248)
+  int pbc[3];
+  double rc_list2;   // (rcut+nb_dcut)^2
+  double rcut2;      // rcut^2
+};
+
+// vdistance (Groups.F90:995-1016): a minus b, idnint minimum image on periodic axes, |.|^2 = (x²+y²)+z²
+__device__ __forceinline__ double dist2_idnint(const Geo &g, double ax, double ay, double az, double bx, double by, double bz) {
+  double vx = ax - bx, vy = ay - by, vz = az - bz;
+  if (g.pbc[0]) vx = vx - g.box[0] * round(vx * g.one_box[0]);
+  if (g.pbc[1]) vy = vy - g.box[1] * round(vy * g.one_box[1]);
+  if (g.pbc[2]) vz = vz - g.box[2] * round(vz * g.one_box[2]);
+  return (vx * vx + vy * vy) + vz * vz;
+}
+
+// cell index triple int(pos/cell)+1 (Cells.F90:289); returns false when outside 0..nc+1
+__device__ __forceinline__ bool cell_index(const Geo &g, double x, double y, double z, int &cx, int &cy, int &cz) {
+  cx = (int)(x / g.cell[0]) + 1; cy = (int)(y / g.cell[1]) + 1; cz = (int)(z / g.cell[2]) + 1;
+  return !(cx < 0 || cy < 0 || cz < 0 || cx > g.nc[0] + 1 || cy > g.nc[1] + 1 || cz > g.nc[2] + 1);
+}
+__device__ __forceinline__ int cell_lin(const Geo &g, int cx, int cy, int cz) { return cx + g.hd[0] * (cy + g.hd[1] * cz); }
+
+// ---- libgcc __powidf2 order for x**6, x**7 (gfortran -O0) ---------------------------------
+__device__ __forceinline__ double pow6(double x) { double x2 = x * x; double x4 = x2 * x2; return x2 * x4; }
+__device__ __forceinline__ double pow7(double x) { double x2 = x * x; double y = x * x2; double x4 = x2 * x2; return y * x4; }
+
+// ---- Philox4x32-10 counter-based RNG ----------------------------------------------------------------------
+struct Philox {
+  uint32_t c[4], k[2];
+  __device__ __forceinline__ void round_() {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ __forceinline__ void run(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3; k[0] = (uint32_t)seed; k[1] = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) { round_(); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+  }
+  // two uniforms in (0,1) with 53-bit resolution
+  __device__ __forceinline__ double u01(int i) const {
+    uint64_t b = ((uint64_t)c[2 * i] << 32) | c[2 * i + 1];
+    return ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  // two independent standard normals (Box–Muller, fp64)
+  __device__ __forceinline__ void gauss2(double &g0, double &g1) const {
+    double u = u01(0), v = u01(1);
+    double r = sqrt(-2.0 * log(u));
+    double s, c_; sincospi(2.0 * v, &s, &c_);
+    g0 = r * c_; g1 = r * s;
+  }
+};
+
+// streams of the counter's third word
+enum { RS_INTEG0 = 0, RS_INTEG1 = 1, RS_INTEG2 = 2, RS_PBC = 3, RS_OVERLAP = 4, RS_GCMC = 5 };
+
+// ---- top-2 merge (order independent) -----------------------------------------------------------------------
+__device__ __forceinline__ void top2_merge(double &a1, double &a2, double b1, double b2) {
+  double m1 = fmax(a1, b1);
+  double m2 = fmax(fmin(a1, b1), fmax(a2, b2));
+  a1 = m1; a2 = m2;
+}
+
+__constant__ int c_map[27][3] = {   // Cells.F90:28-36, stencil order fixes the order of every row
+  {0,0,0},{1,0,0},{1,1,0},{0,1,0},{-1,1,0},{1,0,-1},{1,1,-1},{0,1,-1},{-1,1,-1},
+  {1,0,1},{1,1,1},{0,1,1},{-1,1,1},{0,0,1},{-1,0,0},{-1,-1,0},{0,-1,0},{1,-1,0},
+  {-1,0,1},{-1,-1,1},{0,-1,1},{1,-1,1},{-1,0,-1},{-1,-1,-1},{0,-1,-1},{1,-1,-1},{0,0,-1}};
+
+// pair tables (dana.F90:87-100) and integrator constants, set per ctx before launches
+struct Phys {
+  double eps[9], r0[9], r0sq[9], r0p6[9];
+  double mass[3], sqrt_mass[3];
+  double h, prob, tau;
+  double cc0, cc1, cc2, sdr, sdv, crv1, crv2, skt;    // set_ermak, dana.F90:947-971
+  double cc1mcc2, cc2h;
+  double dif_sc, dif_sei, z_sei, fac_sc, fac_sei;     // cbrownian_hs, dana.F90:817-823
+  int integrador, piston, chunks, rng_mode;
+  unsigned long long seed;
+};
+
+} // namespace dml

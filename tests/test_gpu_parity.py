@@ -1,0 +1,92 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libdml.so) against the CPU oracle on the same
+inputs.  Bit-exact for cells, neighbour rows, integrator/overlap/reservoir state; forces bit-exact in strict
+order and within 1e-12 relative in row order (BASELINE.json north_star)."""
+import os
+import numpy as np
+import pytest
+from oracle import oracle as O
+from din_mol_li_b200 import dml
+import parity as P
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def case(name, **over):
+    d = O.read_case(os.path.join(GOLD, name))
+    d.update(over)
+    return d, O.Oracle(**d)
+
+
+@pytest.mark.parametrize("name", ["ermak", "brown", "gcmc"])
+def test_cells_and_rows_bit_exact_t0(name):
+    d, o = case(name)
+    ctx = P.ctx_from_oracle(o)
+    ctx.test_update()
+    a = P.oracle_slot_arrays(o)
+    n = len(a["z"])
+    # cell triples and in-cell chain order (Cells.F90:267-302)
+    ocell, ochain = o.cells()
+    gcell, gchain = ctx.cells(n)
+    sb = a["slot_b"]
+    assert np.array_equal(gcell[a["alive"]], ocell[sb[a["alive"]]])
+    assert np.array_equal(gchain[a["alive"]], ochain[sb[a["alive"]]])
+    # rows: same entries in the same order (Neighbor.F90:465-548)
+    nn, rows, _ = o.rows(width=64)
+    gnn, grows = ctx.neighbors(n, width=64)
+    assert np.array_equal(gnn, nn[:n])
+    assert P.rows_as_lists(gnn, grows, 0) == P.rows_as_lists(nn, rows, 1)
+    assert ctx.counters().list_entries == int(nn.sum())
+
+
+@pytest.mark.parametrize("strict", [1, 0])
+def test_fuerza_matches_oracle(strict):
+    d, o = case("ermak")
+    o.step(150)                       # deposits exist, some pairs are inside the cut-off after ermak_a
+    o.call(O.ERMAK_A)
+    ctx = P.ctx_from_oracle(o, strict=strict)
+    P.push_rows(o, ctx)
+    o.call(O.FUERZA)
+    ctx.fuerza()
+    dd, a = P.compare_state(o, ctx, fields=("pos",), force=True, rtol=0.0 if strict else 1e-12, what="fuerza")
+    ref = a["alive"] & ((a["flags"] & 1) > 0)
+    assert (np.abs(a["force"][ref]).sum(axis=1) > 0).sum() > 5      # the comparison is not vacuous
+
+
+@pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40)])
+def test_lockstep_replay_bit_exact(name, nsteps):
+    d, o = case(name)
+    ls = P.Lockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s step %d" % (name, i + 1))
+
+
+def test_brown_fixture_on_device():
+    """The whole tests/brown case on the device in replay mode must end on the reference's ref.xyz."""
+    d, o = case("brown")
+    ls = P.Lockstep(o, strict=1, chunk_xyz=d["chunk_xyz"])
+    for i in range(d["nst"]):
+        ls.step(check=(i % 50 == 49), tag="brown step %d" % (i + 1))
+    rzmax, rz, rpos = O.read_xyz_frame(os.path.join(GOLD, "brown", "ref.xyz"))
+    a = P.oracle_slot_arrays(o)
+    g = ls.ctx.download(len(a["z"]))
+    st = o.state()
+    s = st["slot_hs"] - 1
+    assert np.array_equal(g["pos"][s], rpos) and np.array_equal(g["z"][s], rz)
+    assert ls.ctx.scalars().zmax == rzmax
+
+
+def test_ermak_fixture_on_device():
+    """tests/ermak (10000 steps, forces + piston) replayed on the device: bit-identical to ref.xyz."""
+    d, o = case("ermak")
+    ls = P.Lockstep(o, strict=1)
+    zmax_pre = None
+    for i in range(d["nst"]):
+        if i == d["nst"] - 1:
+            pass
+        ls.step(check=(i % 1000 == 999), tag="ermak step %d" % (i + 1))
+    # ref.xyz holds the frame written by salida() BEFORE the last maxz: compare the oracle's
+    # frame with ref.xyz (CPU test) and the device with the oracle's final state here.
+    P.compare_state(o, ls.ctx, what="ermak final")
+    c = ls.ctx.counters()
+    assert c.choques == o.scalars().choques == 49905
