@@ -46,7 +46,7 @@ struct dml_ctx {
   double t = 0.0;
   int64_t launches = 0;
   bool profiling = false; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
-  double prof_ms[8] = {0}; int64_t prof_n[8] = {0};
+  double prof_ms[32] = {0}; int64_t prof_n[32] = {0};
   // particle state
   DBuf<double4> posm, sorted_posm;
   DBuf<double> vel, acel, force, epot, pos_old, old_cg, ranv;
@@ -55,6 +55,8 @@ struct dml_ctx {
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, chain_pos;
   // rows
   DBuf<int> row_start, row_len, row_cap, cols;
+  DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
+  int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums;
   DBuf<double> part;
   // overlap
@@ -76,6 +78,16 @@ struct dml_ctx {
 static int gcmc_run_impl(dml_ctx *ctx);
 
 enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
+// one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
+enum { K_SCAN = 0, K_PBC_BIN, K_TOP2, K_SCATTER, K_CELL_ORDER, K_ROWS_COUNT, K_ROWS_FILL, K_ROW_CAPS, K_FUERZA, K_INTEGRATE,
+       K_ERMAK_B, K_OV_INIT, K_OV_DETECT, K_OV_COUNT, K_OV_ALLOC, K_OV_FILL, K_OV_SORT, K_OV_PASS, K_OV_APPLY, K_PROMOTE,
+       K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_NKERN };
+static const char *const kern_name[K_NKERN] = {"scan", "pbc_bin", "top2_final", "scatter", "cell_order", "rows_count", "rows_fill",
+  "row_caps", "fuerza", "integrate", "ermak_b", "ov_init", "ov_detect", "ov_count", "ov_alloc", "ov_fill", "ov_sort", "ov_pass",
+  "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows"};
+static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_FORCE, CLS_INTEG,
+  CLS_INTEG, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OTHER,
+  CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST};
 
 static void prof_begin(dml_ctx *ctx, int cls) {
   ctx->launches++;
@@ -152,7 +164,8 @@ static void tessellate(dml_ctx *ctx) {
   ctx->tessellated = true;
 }
 
-static int scan_excl(dml_ctx *ctx, const int *in, int *out, int n, int *total_out, int *total_out2, int cls) {
+static int scan_excl(dml_ctx *ctx, const int *in, int *out, int n, int *total_out, int *total_out2) {
+  const int cls = K_SCAN;
   int nb = nblk(n, 1024);
   CKC(ctx->scan_sums.ensure(nb + 1, ctx->st));
   LAUNCH(cls, k_scan_local, nb, TPB, in, out, ctx->scan_sums.p, n);
@@ -168,11 +181,11 @@ static int ensure_particles(dml_ctx *ctx, int n) {
 
 static int sort_cells(dml_ctx *ctx, bool snapshot) {
   int n = ctx->n, nct = ctx->nct;
-  TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, nullptr, CLS_LIST));
+  TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, nullptr));
   CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, (size_t)nct * sizeof(int), ctx->st));
-  LAUNCH(CLS_LIST, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
+  LAUNCH(K_SCATTER, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
          ctx->sorted_slot.p, n, snapshot ? 1 : 0);
-  LAUNCH(CLS_LIST, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->sorted_slot.p,
+  LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->sorted_slot.p,
          ctx->sorted_posm.p, nct);
   ctx->cells_sorted = true;
   return 0;
@@ -184,17 +197,18 @@ static int rebuild(dml_ctx *ctx) {
   ctx->nupd++;
   TRY(sort_cells(ctx, true));
   CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
-  LAUNCH(CLS_LIST, (k_rows<false>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
          ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
-  LAUNCH(CLS_LIST, k_row_caps, nblk(n), TPB, ctx->row_len.p, ctx->row_cap.p, n, ctx->row_slack);
-  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, nullptr, CLS_LIST));
+  LAUNCH(K_ROW_CAPS, k_row_caps, nblk(n), TPB, ctx->row_len.p, ctx->row_cap.p, n, ctx->row_slack);
+  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, nullptr));
   TRY(pull_scal(ctx));
   size_t need = (size_t)ctx->hsc->cols_used + (size_t)ctx->row_slack * 64 + 1024;
   if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st));
-  LAUNCH(CLS_LIST, (k_rows<true>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+  LAUNCH(K_ROWS_FILL, (k_rows<true>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
          ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
   ctx->hsc->nlimbo = 0;
   ctx->listed = true;
+  ctx->rows_asym = ctx->hsc->halo_flag != 0; ctx->rev_valid = false;
   return 0;
 }
 
@@ -204,10 +218,11 @@ static int do_test_update(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
   CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
   CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, (size_t)nct * sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(&ctx->sc->halo_flag, 0, sizeof(int), ctx->st));
   int nb = nblk(n);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(CLS_BIN, k_pbc_bin, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->part.p, ctx->sc, ctx->geo, n, 1);
-  LAUNCH(CLS_BIN, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->listed ? 1 : 0, ctx->cfg.nb_dcut);
+  LAUNCH(K_PBC_BIN, k_pbc_bin, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->part.p, ctx->sc, ctx->geo, n, 1);
+  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->listed ? 1 : 0, ctx->cfg.nb_dcut);
   ctx->cells_sorted = false; ctx->binned = true;
   TRY(pull_scal(ctx));
   if (ctx->hsc->need_rebuild) TRY(rebuild(ctx));
@@ -219,24 +234,40 @@ static int do_integrate(dml_ctx *ctx, bool ermak) {
   ctx->step++;
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
   if (ermak)
-    LAUNCH(CLS_INTEG, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+    LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
            ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
   else
-    LAUNCH(CLS_INTEG, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+    LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
            ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
   ctx->have_rp = false;
+  return 0;
+}
+
+static int build_rev(dml_ctx *ctx) {
+  int n = ctx->n;
+  CKC(ctx->rev_start.ensure(ctx->cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(ctx->cap, ctx->st)); CKC(ctx->rev_cur.ensure(ctx->cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->rev_len.p, 0, (size_t)n * sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(ctx->rev_cur.p, 0, (size_t)n * sizeof(int), ctx->st));
+  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_len.p, n);
+  TRY(scan_excl(ctx, ctx->rev_len.p, ctx->rev_start.p, n, &ctx->sc->rev_used, nullptr));
+  TRY(pull_scal(ctx));
+  CKC(ctx->rev_cols.ensure((size_t)ctx->hsc->rev_used + 1024, ctx->st));
+  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, ctx->rev_cur.p, ctx->rev_cols.p, n);
+  ctx->rev_valid = true;
   return 0;
 }
 
 static int do_fuerza(dml_ctx *ctx) {
   if (!ctx->listed) FAIL("fuerza called without a neighbour list");
   int n = ctx->n;
+  if (ctx->rows_asym && !ctx->rev_valid) TRY(build_rev(ctx));
+  int asym = ctx->rows_asym ? 1 : 0;
   if (ctx->cfg.strict_order)
-    LAUNCH(CLS_FORCE, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->uid.p, ctx->force.p,
-           ctx->epot.p, ctx->geo, ctx->ph, n);
+    LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
+           ctx->rev_len.p, ctx->rev_cols.p, asym, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
   else
-    LAUNCH(CLS_FORCE, (k_fuerza<false>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->uid.p, ctx->force.p,
-           ctx->epot.p, ctx->geo, ctx->ph, n);
+    LAUNCH(K_FUERZA, (k_fuerza<false>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
+           ctx->rev_len.p, ctx->rev_cols.p, asym, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
   return 0;
 }
 
@@ -248,23 +279,24 @@ static int do_overlap(dml_ctx *ctx) {
   CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
   CKC(cudaMemsetAsync(&ctx->sc->n_roots, 0, sizeof(int), ctx->st));
   CKC(cudaMemsetAsync(&ctx->sc->member_cursor, 0, sizeof(int), ctx->st));
-  LAUNCH(CLS_OVERLAP, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
-  LAUNCH(CLS_OVERLAP, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
+  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
          ctx->ovst.p, ctx->sc, ctx->geo, n);
-  LAUNCH(CLS_OVERLAP, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
-  LAUNCH(CLS_OVERLAP, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
-  LAUNCH(CLS_OVERLAP, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
+  LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+  LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
+  LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
   TRY(pull_scal(ctx));
   int nroots = ctx->hsc->n_roots;
   int64_t ch_prev = ctx->hsc->choques;
   std::vector<int64_t> marks;
   if (nroots > 0) {
-    LAUNCH(CLS_OVERLAP, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
+    LAUNCH(K_OV_SORT, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
     for (int pass = 0;; ++pass) {
       CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
-      LAUNCH(CLS_OVERLAP, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
+      LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
              ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p,
-             ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, pass);
+             ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, pass,
+             (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
       ctx->overlap_passes++;
       TRY(pull_scal(ctx));
       marks.push_back(ctx->hsc->choques);
@@ -273,17 +305,17 @@ static int do_overlap(dml_ctx *ctx) {
     }
   } else { ctx->overlap_passes++; marks.push_back(ch_prev); }
   for (size_t lv = 0; lv < marks.size(); ++lv) ctx->choques2 = std::max<int64_t>(ctx->choques2, (int64_t)ctx->hsc->choques - marks[lv]);
-  LAUNCH(CLS_OVERLAP, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, n);
+  LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, n);
   ctx->have_rp_ovl = false;
   return 0;
 }
 
-static int do_promote(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
+static int do_promote(dml_ctx *ctx) { LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
 static int do_calc_rho(dml_ctx *ctx) {
-  LAUNCH(CLS_OTHER, k_calc_rho, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, ctx->n);
+  LAUNCH(K_CALC_RHO, k_calc_rho, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, ctx->n);
   return 0;
 }
-static int do_maxz(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_maxz, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->cfg.h / ctx->cfg.tau, ctx->n); return 0; }
+static int do_maxz(dml_ctx *ctx) { LAUNCH(K_MAXZ, k_maxz, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->cfg.h / ctx->cfg.tau, ctx->n); return 0; }
 
 static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
   if (!src) return 0;
@@ -310,7 +342,7 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   CKC(cudaMemcpyAsync(ctx->stage_d.p, cpos, (size_t)nchunk * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_i.p, z.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_i.p + nchunk, fl.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
-  LAUNCH(CLS_OTHER, k_pack, nblk(nchunk), TPB, ctx->posm.p + n0, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + nchunk, nchunk);
+  LAUNCH(K_PACK, k_pack, nblk(nchunk), TPB, ctx->posm.p + n0, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + nchunk, nchunk);
   TRY(upload_d(ctx, ctx->pos_old.p + (size_t)3 * n0, cpos_old, (size_t)nchunk * 3));
   TRY(upload_d(ctx, ctx->vel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
   TRY(upload_d(ctx, ctx->acel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
@@ -328,12 +360,12 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
 }
 
 static int do_step(dml_ctx *ctx) {
-  if (ctx->cfg.integrador) { TRY(do_integrate(ctx, true)); TRY(do_fuerza(ctx)); LAUNCH(CLS_INTEG, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n); }
+  if (ctx->cfg.integrador) { TRY(do_integrate(ctx, true)); TRY(do_fuerza(ctx)); LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n); }
   else TRY(do_integrate(ctx, false));
   TRY(do_test_update(ctx));
   TRY(do_overlap(ctx));
   TRY(do_test_update(ctx));
-  LAUNCH(CLS_OTHER, k_msd_book, 1, 1, ctx->sc);
+  LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
   TRY(do_promote(ctx));
   if (ctx->cfg.reservoir == 3) TRY(gcmc_run_impl(ctx));
   TRY(do_calc_rho(ctx));
@@ -431,6 +463,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
+  ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
@@ -449,7 +482,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   CKC(cudaMemcpyAsync(ctx->stage_i.p, z, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_i.p + n, flags, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)ctx->cap * sizeof(double4), ctx->st));
-  LAUNCH(CLS_OTHER, k_pack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
+  LAUNCH(K_PACK, k_pack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
   TRY(upload_d(ctx, ctx->vel.p, vel, n3)); TRY(upload_d(ctx, ctx->acel.p, acel, n3));
   TRY(upload_d(ctx, ctx->pos_old.p, pos_old ? pos_old : pos, n3));
   if (old_cg) TRY(upload_d(ctx, ctx->old_cg.p, old_cg, n3));
@@ -465,7 +498,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   TRY(pull_scal(ctx));
   ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
   TRY(push_scal(ctx));
-  LAUNCH(CLS_OTHER, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
+  LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
   CKC(cudaStreamSynchronize(ctx->st));
   return 0;
 }
@@ -475,7 +508,7 @@ int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel
   if (n > ctx->n) FAIL("dml_download: n exceeds the number of slots");
   size_t n3 = (size_t)n * 3;
   CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
-  LAUNCH(CLS_OTHER, k_unpack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
+  LAUNCH(K_PACK, k_unpack, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, ctx->stage_i.p, ctx->stage_i.p + n, n);
   if (pos) CKC(cudaMemcpyAsync(pos, ctx->stage_d.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   if (z) CKC(cudaMemcpyAsync(z, ctx->stage_i.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
   if (flags) CKC(cudaMemcpyAsync(flags, ctx->stage_i.p + n, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -512,7 +545,7 @@ int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
   memset(c, 0, sizeof *c);
   if (ctx->listed) {
     CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
-    LAUNCH(CLS_OTHER, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
+    LAUNCH(K_MISC, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
     TRY(pull_scal(ctx));
   }
   DevScal *h = ctx->hsc;
@@ -535,12 +568,12 @@ int dml_test_update(dml_ctx *ctx) { return do_test_update(ctx); }
 int dml_fuerza(dml_ctx *ctx) { return do_fuerza(ctx); }
 int dml_ermak_a(dml_ctx *ctx) { return do_integrate(ctx, true); }
 int dml_ermak_b(dml_ctx *ctx) {
-  LAUNCH(CLS_INTEG, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n);
+  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n);
   return 0;
 }
 int dml_cbrownian_hs(dml_ctx *ctx) { return do_integrate(ctx, false); }
 int dml_overlap_moveback(dml_ctx *ctx) { return do_overlap(ctx); }
-int dml_msd_book(dml_ctx *ctx) { LAUNCH(CLS_OTHER, k_msd_book, 1, 1, ctx->sc); return 0; }
+int dml_msd_book(dml_ctx *ctx) { LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc); return 0; }
 int dml_promote(dml_ctx *ctx) { return do_promote(ctx); }
 int dml_gcmc_run(dml_ctx *ctx) { return gcmc_run_impl(ctx); }
 int dml_calc_rho(dml_ctx *ctx, double *rho) {
@@ -571,7 +604,7 @@ int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
   if (!ctx->cells_sorted) TRY(sort_cells(ctx, false));
   CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
-  LAUNCH(CLS_OTHER, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
+  LAUNCH(K_MISC, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
   std::vector<int> lin(n);
   CKC(cudaMemcpyAsync(lin.data(), ctx->cell_of.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaMemcpyAsync(chain_pos, ctx->chain_pos.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -620,6 +653,7 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
   ctx->listed = true;
+  ctx->rows_asym = true; ctx->rev_valid = false;      // rows supplied by the caller: make no symmetry assumption
   return 0;
 }
 
@@ -646,13 +680,21 @@ int dml_profile(dml_ctx *ctx, int32_t enable) { prof_collect(ctx); ctx->profilin
 int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset) {
   prof_collect(ctx);
   double m = 0; int64_t l = 0;
-  if (cls == CLS_ALL) { for (int i = 0; i < 8; ++i) { m += ctx->prof_ms[i]; l += ctx->prof_n[i]; } }
-  else if (cls >= 0 && cls < 8) { m = ctx->prof_ms[cls]; l = ctx->prof_n[cls]; }
+  for (int i = 0; i < K_NKERN; ++i) if (cls == CLS_ALL || kern_cls[i] == cls) { m += ctx->prof_ms[i]; l += ctx->prof_n[i]; }
   if (ms) *ms = m;
   if (launches) *launches = l;
-  if (reset) for (int i = 0; i < 8; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
+  if (reset) for (int i = 0; i < 32; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
   return 0;
 }
+int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches) {
+  prof_collect(ctx);
+  if (kid < 0 || kid >= K_NKERN) return 1;
+  if (name) *name = kern_name[kid];
+  if (ms) *ms = ctx->prof_ms[kid];
+  if (launches) *launches = ctx->prof_n[kid];
+  return 0;
+}
+int32_t dml_n_slots(dml_ctx *ctx) { return ctx->n; }
 int64_t dml_launch_count(dml_ctx *ctx) { return ctx->launches; }
 void *dml_stream(dml_ctx *ctx) { return (void *)ctx->st; }
 

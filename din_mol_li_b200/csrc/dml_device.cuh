@@ -54,7 +54,8 @@ struct DevScal {
   int cols_used;                 // bump pointer into cols[]
   int next_uid;
   unsigned int ticket;
-  int pad_;
+  int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
+  int rev_used, pad_;
 };
 
 enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,

@@ -101,6 +101,7 @@ __global__ void k_pbc_bin(double4 *__restrict__ posm, double *__restrict__ pos_o
           int lin = cell_lin(g, cx, cy, cz);
           cell_of[s] = lin;
           atomicAdd(&cell_cnt[lin], 1);
+          if (cx == 0 || cy == 0 || cz == 0 || cx == g.nc[0] + 1 || cy == g.nc[1] + 1 || cz == g.nc[2] + 1) sc->halo_flag = 1;
         } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
       }
       double vx = q[0] - po[0], vy = q[1] - po[1], vz = q[2] - po[2];
@@ -261,9 +262,29 @@ __device__ __forceinline__ bool pair_terms(const Geo &g, const Phys &ph, const d
   return true;
 }
 
+// Transposed rows: rev(i) = { j : i in row(j) }.  Needed when rows can be asymmetric (a particle in a halo cell is
+// never found as a candidate, Cells.F90:248 + cell_pbc wrap; incremental gcmc appends use <= instead of <).
+__global__ void k_rev_count(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
+                            int *__restrict__ rev_len, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int b = row_start[s], len = row_len[s];
+  for (int jj = 0; jj < len; ++jj) atomicAdd(&rev_len[cols[b + jj]], 1);
+}
+__global__ void k_rev_fill(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
+                           const int *__restrict__ rev_start, int *__restrict__ rev_cur, int *__restrict__ rev_cols, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int b = row_start[s], len = row_len[s];
+  for (int jj = 0; jj < len; ++jj) { int j = cols[b + jj]; rev_cols[rev_start[j] + atomicAdd(&rev_cur[j], 1)] = s; }
+}
+
+// Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
 template <bool STRICT>
 __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm, const int *__restrict__ row_start,
                                                 const int *__restrict__ row_len, const int *__restrict__ cols,
+                                                const int *__restrict__ rev_start, const int *__restrict__ rev_len,
+                                                const int *__restrict__ rev_cols, int asym,
                                                 const int *__restrict__ uid, double *__restrict__ force, double *__restrict__ epot,
                                                 Geo g, Phys ph, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,6 +294,8 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
   if (!(m1 & MF_REF)) return;
   int k = (int)(m1 & MF_TYPE);
   int b = row_start[s], len = row_len[s];
+  const int *rv = asym ? rev_cols + rev_start[s] : cols + b;
+  int rvlen = asym ? rev_len[s] : len;
   double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
   if (!STRICT) {
     for (int jj = 0; jj < len; ++jj) {
@@ -284,81 +307,84 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
       double f[3], u;
       if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
       fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
-      if (m2 & MF_REF) { fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u; }
+      if (!asym && (m2 & MF_REF)) { fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u; }
+    }
+    if (asym) {
+      for (int jj = 0; jj < rvlen; ++jj) {
+        int j = rv[jj];
+        double4 p2 = ld_rec_nc(&posm[j]);
+        long long m2 = meta_of(p2);
+        int m = (int)(m2 & MF_TYPE);
+        if (m == 0 || !(m2 & MF_REF)) continue;
+        double f[3], u;
+        if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
+        fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
+      }
     }
   } else {
-    // Visiting order of the reference for atom i: (j in ref, rank_j < rank_i, ascending rank) as o2 of j's row,
-    // then i's own row in row order, then (j in ref, rank_j > rank_i, ascending) again as o2.  Only entries
-    // inside the cut-off contribute, so they are collected first (a handful at most) and then ordered.
-    constexpr int KMAX = 16;
+    // Visiting order of the reference for atom i: reverse visits by row owners j with rank_j < rank_i (ascending
+    // rank; the term -f_ji equals +f_ij bit for bit), then i's own row in row order, then reverse visits with
+    // rank_j > rank_i.  Only entries inside the cut-off contribute, so they are collected first and then ordered.
+    constexpr int KMAX = 12;
     int myuid = uid[s];
-    int cu[KMAX]; double cf[KMAX][4]; int nc_ = 0; bool overflow = false;
-    for (int jj = 0; jj < len; ++jj) {
-      int j = cols[b + jj];
+    int cu[KMAX]; double cf[KMAX][4]; int nrev = 0; bool overflow = false;
+    for (int jj = 0; jj < rvlen; ++jj) {
+      int j = rv[jj];
       double4 p2 = ld_rec_nc(&posm[j]);
       long long m2 = meta_of(p2);
       int m = (int)(m2 & MF_TYPE);
-      if (m == 0) continue;
+      if (m == 0 || !(m2 & MF_REF)) continue;
       double f[3], u;
       if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
-      if (nc_ == KMAX) { overflow = true; break; }
-      cu[nc_] = (m2 & MF_REF) ? uid[j] : -1;
-      cf[nc_][0] = f[0]; cf[nc_][1] = f[1]; cf[nc_][2] = f[2]; cf[nc_][3] = u; ++nc_;
+      if (nrev == KMAX) { overflow = true; break; }
+      cu[nrev] = uid[j]; cf[nrev][0] = f[0]; cf[nrev][1] = f[1]; cf[nrev][2] = f[2]; cf[nrev][3] = u; ++nrev;
     }
-    if (!overflow) {
-      for (int phase = 0; phase < 3; ++phase) {
-        if (phase == 1) {
-          for (int i = 0; i < nc_; ++i) { fx = fx + cf[i][0]; fy = fy + cf[i][1]; fz = fz + cf[i][2]; ep = ep + cf[i][3]; }
-        } else {
-          int last = phase == 0 ? -1 : myuid;
-          for (;;) {
-            int best = 0x7fffffff, bi = -1;
-            for (int i = 0; i < nc_; ++i) {
-              int uj = cu[i];
-              if (uj < 0 || uj <= last || uj >= best) continue;
-              if (phase == 0 && uj >= myuid) continue;
-              bi = i; best = uj;
-            }
-            if (bi < 0) break;
-            last = best;
-            fx = fx + cf[bi][0]; fy = fy + cf[bi][1]; fz = fz + cf[bi][2]; ep = ep + cf[bi][3];
-          }
+    for (int phase = 0; phase < 3; ++phase) {
+      if (phase == 1) {
+        for (int jj = 0; jj < len; ++jj) {
+          int j = cols[b + jj];
+          double4 p2 = ld_rec_nc(&posm[j]);
+          int m = (int)(meta_of(p2) & MF_TYPE);
+          if (m == 0) continue;
+          double f[3], u;
+          if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
+          fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
         }
-      }
-    } else {
-      // dense neighbourhood: same ordering by repeated selection over the whole row
-      for (int phase = 0; phase < 3; ++phase) {
-        if (phase == 1) {
-          for (int jj = 0; jj < len; ++jj) {
-            int j = cols[b + jj];
-            double4 p2 = ld_rec_nc(&posm[j]);
-            int m = (int)(meta_of(p2) & MF_TYPE);
-            if (m == 0) continue;
-            double f[3], u;
-            if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
-            fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
+      } else if (!overflow) {
+        int last = phase == 0 ? -1 : myuid;
+        for (;;) {
+          int best = 0x7fffffff, bi = -1;
+          for (int i = 0; i < nrev; ++i) {
+            int uj = cu[i];
+            if (uj <= last || uj >= best) continue;
+            if (phase == 0 && uj >= myuid) continue;
+            bi = i; best = uj;
           }
-        } else {
-          int last = phase == 0 ? -1 : myuid;
-          for (;;) {
-            int best = 0x7fffffff, bj = -1;
-            for (int jj = 0; jj < len; ++jj) {
-              int j = cols[b + jj];
-              int uj = uid[j];
-              if (uj <= last || uj >= best) continue;
-              if (phase == 0 && uj >= myuid) continue;
-              bj = j; best = uj;
-            }
-            if (bj < 0) break;
-            last = best;
-            double4 p2 = ld_rec_nc(&posm[bj]);
-            long long m2 = meta_of(p2);
-            int m = (int)(m2 & MF_TYPE);
-            if (m == 0 || !(m2 & MF_REF)) continue;
-            double f[3], u;
-            if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
-            fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
+          if (bi < 0) break;
+          last = best;
+          fx = fx + cf[bi][0]; fy = fy + cf[bi][1]; fz = fz + cf[bi][2]; ep = ep + cf[bi][3];
+        }
+      } else {
+        // dense neighbourhood: same ordering by repeated selection over the candidate list
+        int last = phase == 0 ? -1 : myuid;
+        for (;;) {
+          int best = 0x7fffffff, bj = -1;
+          for (int jj = 0; jj < rvlen; ++jj) {
+            int j = rv[jj];
+            int uj = uid[j];
+            if (uj <= last || uj >= best) continue;
+            if (phase == 0 && uj >= myuid) continue;
+            bj = j; best = uj;
           }
+          if (bj < 0) break;
+          last = best;
+          double4 p2 = ld_rec_nc(&posm[bj]);
+          long long m2 = meta_of(p2);
+          int m = (int)(m2 & MF_TYPE);
+          if (m == 0 || !(m2 & MF_REF)) continue;
+          double f[3], u;
+          if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
+          fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
         }
       }
     }
@@ -603,7 +629,7 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
                           const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
                           const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
-                          DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass) {
+                          DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sc->n_roots) return;
   int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
@@ -639,7 +665,7 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
         }
         break;
       }
-      if (ph.piston) {                                         // unsolvable pair guard (dana.F90:920-927)
+      if (ph.piston || guard) {                                // unsolvable pair guard (dana.F90:920-927)
         double og2[3] = {old_cg[3 * a2], old_cg[3 * a2 + 1], old_cg[3 * a2 + 2]};
         if (q2[0] == og2[0] && q2[1] == og2[1] && q2[2] == og2[2]) {
           double og1[3] = {old_cg[3 * a1], old_cg[3 * a1 + 1], old_cg[3 * a1 + 2]};

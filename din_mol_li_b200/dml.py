@@ -49,7 +49,7 @@ SYMBOLS = [
     "dml_ermak_b", "dml_cbrownian_hs", "dml_overlap_moveback", "dml_msd_book", "dml_promote", "dml_gcmc_run",
     "dml_calc_rho", "dml_maxz", "dml_bloques", "dml_set_chunk_template", "dml_step", "dml_get_cells",
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
-    "dml_profile_get", "dml_launch_count", "dml_stream",
+    "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_launch_count", "dml_stream",
 ]
 
 _lib = None
@@ -89,6 +89,8 @@ def lib():
         L.dml_set_replay_gcmc.argtypes = [vp, i32, vp, i32, vp]
         L.dml_profile.argtypes = [vp, i32]
         L.dml_profile_get.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(C.c_int64), i32]
+        L.dml_profile_kernel.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(dbl), C.POINTER(C.c_int64)]
+        L.dml_n_slots.argtypes = [vp]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -112,6 +114,26 @@ def _i32(a):
     if a is None:
         return None
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class HostRng(C.Structure):
+    """dana's RNG state (include/dml_host.h)."""
+    _fields_ = [("idum", C.c_int32), ("ix", C.c_int32), ("iy", C.c_int32), ("stored", C.c_int32), ("g", C.c_double), ("calls", C.c_uint64)]
+
+
+def host_pos_inic(idum, xi, yi, alto):
+    """pos_inic (src/dana.F90:330-396) on the host side of libdml: returns (xyz[n,3], rng state)."""
+    L = lib()
+    L.dmlh_rng_init.argtypes = [C.POINTER(HostRng), C.c_int32]
+    L.dmlh_pos_inic.argtypes = [C.POINTER(HostRng), C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int32]
+    r = HostRng()
+    L.dmlh_rng_init(C.byref(r), idum)
+    cap = int(xi * yi * alto * 6.1e-4) + 16
+    xyz = np.empty((cap, 3))
+    n = L.dmlh_pos_inic(C.byref(r), xi, yi, alto, _p(xyz), cap)
+    if n < 0:
+        raise DmlError("pos_inic failed (%d)" % n)
+    return xyz[:n].copy(), r
 
 
 # dana's pair tables (src/dana.F90:87-100), stored [(k-1)*3+(m-1)]
@@ -325,6 +347,20 @@ class Ctx:
         nl = C.c_int64()
         self._chk(lib().dml_profile_get(self.h, cls, C.byref(ms), C.byref(nl), 1 if reset else 0))
         return ms.value, nl.value
+
+    def profile_kernels(self):
+        """{kernel name: (total ms, launches)} accumulated while profiling was on."""
+        out = {}
+        kid = 0
+        while True:
+            name, ms, nl = C.c_char_p(), C.c_double(), C.c_int64()
+            if lib().dml_profile_kernel(self.h, kid, C.byref(name), C.byref(ms), C.byref(nl)) != 0:
+                return out
+            out[name.value.decode()] = (ms.value, nl.value)
+            kid += 1
+
+    def n_slots(self):
+        return lib().dml_n_slots(self.h)
 
     def launch_count(self):
         return lib().dml_launch_count(self.h)

@@ -128,6 +128,9 @@ int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng
  * the last call with reset!=0.  cls: 0 pair force, 1 list build, 2 integrator, 3 overlap, 4 all. */
 int dml_profile(dml_ctx *ctx, int32_t enable);
 int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset);
+/* per-kernel timing: kid = 0,1,2,... until the call returns 1; name points to a static string */
+int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches);
+int32_t dml_n_slots(dml_ctx *ctx);         /* hs%amax as known to the host side (no synchronisation) */
 int64_t dml_launch_count(dml_ctx *ctx);   /* kernels launched by this ctx so far */
 void *dml_stream(dml_ctx *ctx);           /* cudaStream_t used by every kernel of this ctx */
 

@@ -23,6 +23,9 @@
 #include <vector>
 #include <stdexcept>
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 
@@ -484,12 +487,17 @@ void NGroup::cells_atom(int i) {            // ngroup_cells_atom — Neighbor.F9
 void NGroup::build_cells() {                // ngroup_cells — Neighbor.F90:465-548
   std::fill(nn.begin(), nn.end(), 0);
   clean();
+  // The reference spawns one OpenMP task per ref atom (Neighbor.F90:492-544); each task owns row i, so a
+  // parallel-for over the same atoms is the same computation.  Threads: OMP_NUM_THREADS (1 if built without OpenMP).
+  std::vector<int> idx; idx.reserve(ref.nat);
   Node *la = ref.alist;
-  for (int ii = 1; ii <= ref.nat; ++ii) {
-    la = la->next; Atom *ai = la->o;
-    int i = ai->gid(id);
-    cells_atom(i);
+  for (int ii = 1; ii <= ref.nat; ++ii) { la = la->next; idx.push_back(la->o->gid(id)); }
+  int failed = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int q = 0; q < (int)idx.size(); ++q) {
+    try { cells_atom(idx[q]); } catch (...) { failed = 1; }
   }
+  if (failed) throw Halt("oracle: neighbour row overflow (mnb)");
   listed = true;
 }
 void NGroup::verlet_atom(int i) {           // ngroup_verlet_atom — Neighbor.F90:426-463
@@ -835,8 +843,12 @@ void Dana::cbrownian_hs() {                  // dana.F90:798-846
 
 void Dana::overlap_moveback() {              // dana.F90:849-943 (tail recursion written as a loop)
   std::vector<int64_t> marks;                // choques at entry of each recursion level
-  for (;;) {
+  for (int pass = 0;; ++pass) {
     bool again = false;
+    // Optional (ov_guard_pass>0, NOT reference behaviour, default off): from that recursion depth on apply the
+    // piston-mode guard in every mode, so pairs that overlap at their previous positions — on which the reference
+    // recurses forever — are skipped and counted in choques3.  Used only by bench.py on large synthetic boxes.
+    bool guard = s_piston || (P.ov_guard_pass > 0 && pass >= P.ov_guard_pass);
     Node *la = hs.ref.alist;
     for (int ii = 1; ii <= hs.ref.nat; ++ii) {
       la = la->next; Atom *o1 = la->o;
@@ -862,7 +874,7 @@ void Dana::overlap_moveback() {              // dana.F90:849-943 (tail recursion
           }
           break;
         }
-        if (s_piston) {
+        if (guard) {
           bool same2 = o2->pos[0] == o2->old_cg[0] && o2->pos[1] == o2->old_cg[1] && o2->pos[2] == o2->old_cg[2];
           if (same2) {
             bool same1 = o1->pos[0] == o1->old_cg[0] && o1->pos[1] == o1->old_cg[1] && o1->pos[2] == o1->old_cg[2];
@@ -1149,6 +1161,13 @@ void orc_trace_get(void *h, int32_t *kind, int64_t *uid, double *val) {
   for (size_t i = 0; i < D->trace.size(); ++i) { kind[i] = D->trace[i].kind; uid[i] = D->trace[i].uid; val[i] = D->trace[i].val; }
 }
 
+int orc_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 void orc_rng_kat(int32_t idum, int n_ran, double *ran_out, int n_gas, double *gas_out) {
   Rng a; a.idum = idum; for (int i = 0; i < n_ran; ++i) ran_out[i] = a.ran();
   Rng b; b.idum = idum; for (int i = 0; i < n_gas; ++i) gas_out[i] = b.gasdev();

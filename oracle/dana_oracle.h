@@ -38,7 +38,7 @@ typedef struct orc_params {
   int32_t n_init;      /* >0: skip pos_inic, take n_init explicit atoms below   */
   const double  *init_xyz; /* n_init*3 */
   const int32_t *init_z;   /* n_init element ids (1 Li, 2 CG, 3 F) */
-  int32_t box_z_override;  /* unused, keep 0 */
+  int32_t ov_guard_pass;   /* 0 = faithful (default); >0: see overlap_moveback in dana_oracle.cpp */
 } orc_params;
 
 enum orc_op {
@@ -99,6 +99,8 @@ void  orc_trace_enable(void *h, int on);
 void  orc_trace_clear(void *h);
 int64_t orc_trace_size(void *h);
 void  orc_trace_get(void *h, int32_t *kind, int64_t *uid, double *val);
+
+int   orc_threads(void);                      /* threads the list build uses (OpenMP, like the reference) */
 
 /* Stand-alone pieces (known-answer tests / generators) */
 void  orc_rng_kat(int32_t idum, int n_ran, double *ran_out, int n_gas, double *gas_out);

@@ -23,7 +23,7 @@ class Params(C.Structure):
         ("integrador", C.c_int32), ("reservoir", C.c_int32), ("act", C.c_double), ("nadj", C.c_int32),
         ("nchunk", C.c_int32), ("chunk_xyz", C.POINTER(C.c_double)), ("mnb", C.c_int32), ("fast_init", C.c_int32),
         ("n_init", C.c_int32), ("init_xyz", C.POINTER(C.c_double)), ("init_z", C.POINTER(C.c_int32)),
-        ("box_z_override", C.c_int32),
+        ("ov_guard_pass", C.c_int32),
     ]
 
 
@@ -77,6 +77,7 @@ def lib():
         L.orc_trace_size.restype = C.c_int64
         L.orc_trace_size.argtypes = [C.c_void_p]
         L.orc_trace_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_threads.restype = C.c_int
         L.orc_rng_kat.argtypes = [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_pos_inic.argtypes = [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -137,14 +138,14 @@ class Oracle:
 
     def __init__(self, idum=-104012, prob=1.0, h=1e-2, nst=1, nwr=1, xi=100.0, yi=100.0, dist=50.0, z0=100.0,
                  zmax=200.0, dif_sc=250.0, dif_sei=250.0, nb_dcut=10.0, integrador=1, reservoir=1, act=0.0, nadj=0,
-                 chunk_xyz=None, mnb=10000, fast_init=0, init_xyz=None, init_z=None):
+                 chunk_xyz=None, mnb=10000, fast_init=0, init_xyz=None, init_z=None, ov_guard_pass=0):
         L = lib()
         p = Params()
         p.idum, p.prob, p.h, p.nst, p.nwr = idum, prob, h, nst, nwr
         p.xi, p.yi, p.dist, p.z0, p.zmax = xi, yi, dist, z0, zmax
         p.dif_sc, p.dif_sei, p.nb_dcut = dif_sc, dif_sei, nb_dcut
         p.integrador, p.reservoir, p.act, p.nadj = integrador, reservoir, act, nadj
-        p.mnb, p.fast_init = mnb, fast_init
+        p.mnb, p.fast_init, p.ov_guard_pass = mnb, fast_init, ov_guard_pass
         self._keep = []
         if chunk_xyz is not None:
             ch = np.ascontiguousarray(chunk_xyz, dtype=np.float64)
@@ -252,6 +253,10 @@ def from_case(case_dir, **over):
     d = read_case(case_dir)
     d.update(over)
     return Oracle(**d)
+
+
+def threads():
+    return lib().orc_threads()
 
 
 def rng_kat(idum, n_ran, n_gas):
