@@ -2,6 +2,7 @@
 // the kernels in dml_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/dml.h"
 #include "dml_kernels.cuh"
+namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos, DevScal *__restrict__ sc, int n); }
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -61,6 +62,8 @@ struct dml_ctx {
   DBuf<double> part;
   // overlap
   DBuf<int> parent, ovst, comp_cnt, comp_off, members, roots;
+  // gcmc
+  DBuf<int> gorder, gpos, gcc, gpend, b_occ; int gorder_cap = 0;
   // replay
   DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
   // staging
@@ -76,6 +79,8 @@ struct dml_ctx {
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 static int gcmc_run_impl(dml_ctx *ctx);
+static int sort_cells(dml_ctx *ctx, bool snapshot);
+static int pull_scal(dml_ctx *ctx);
 
 enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
 // one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
@@ -206,7 +211,7 @@ static int rebuild(dml_ctx *ctx) {
   if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st));
   LAUNCH(K_ROWS_FILL, (k_rows<true>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
          ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
-  ctx->hsc->nlimbo = 0;
+  CKC(cudaMemsetAsync(&ctx->sc->nlimbo, 0, sizeof(int), ctx->st));
   ctx->listed = true;
   ctx->rows_asym = ctx->hsc->halo_flag != 0; ctx->rev_valid = false;
   return 0;
@@ -310,7 +315,9 @@ static int do_overlap(dml_ctx *ctx) {
   return 0;
 }
 
-static int do_promote(dml_ctx *ctx) { LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
+static int do_promote(dml_ctx *ctx) {
+  if (ctx->cfg.reservoir == 3) LAUNCH(K_PROMOTE, k_gcmc_tomb, nblk(ctx->n), TPB, ctx->posm.p, ctx->gorder.p, ctx->gpos.p, ctx->sc, ctx->n);
+  LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
 static int do_calc_rho(dml_ctx *ctx) {
   LAUNCH(K_CALC_RHO, k_calc_rho, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, ctx->n);
   return 0;
@@ -336,7 +343,7 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   std::vector<double> zero3((size_t)nchunk * 3, 0.0), og((size_t)nchunk * 3, 1e8);
   std::vector<int> z(nchunk, 1), fl(nchunk, DML_F_REF), uid(nchunk), sb(nchunk);
   for (int i = 0; i < nchunk; ++i) { uid[i] = ctx->hsc->next_uid + i; sb[i] = n0 + i; }
-  ctx->hsc->next_uid += nchunk; ctx->hsc->n_slots = n0 + nchunk; ctx->hsc->nat_sys += nchunk; ctx->hsc->nat_ref += nchunk;
+  ctx->hsc->next_uid += nchunk; ctx->hsc->n_slots = n0 + nchunk; ctx->hsc->b_amax = n0 + nchunk; ctx->hsc->nat_sys += nchunk; ctx->hsc->nat_ref += nchunk;
   TRY(push_scal(ctx));
   CKC(ctx->stage_d.ensure((size_t)nchunk * 3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)nchunk * 2, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_d.p, cpos, (size_t)nchunk * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
@@ -428,7 +435,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.fac_sc = std::sqrt(2.0 * cfg->dif_sc * cfg->h); ph.fac_sei = std::sqrt(2.0 * cfg->dif_sei * cfg->h);
   ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
-  ctx->row_slack = cfg->reservoir == 3 ? 6 : 0;
+  ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->force.ensure(c3, ctx->st));
@@ -439,6 +446,9 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->cols.ensure((size_t)cap * 16 + 4096, ctx->st));
   CKC(ctx->parent.ensure(cap, ctx->st)); CKC(ctx->ovst.ensure(cap, ctx->st)); CKC(ctx->comp_cnt.ensure(cap, ctx->st));
   CKC(ctx->comp_off.ensure(cap, ctx->st)); CKC(ctx->members.ensure(cap, ctx->st)); CKC(ctx->roots.ensure(cap, ctx->st));
+  ctx->gorder_cap = 2 * cap + 2048;
+  CKC(ctx->gorder.ensure((size_t)2 * ctx->gorder_cap, ctx->st)); CKC(ctx->gpos.ensure(cap, ctx->st));
+  CKC(ctx->gcc.ensure((size_t)ctx->gorder_cap / 1024 + 8, ctx->st)); CKC(ctx->b_occ.ensure(cap, ctx->st));
   CKC(ctx->rp_gauss.ensure((size_t)cap * 6, ctx->st)); CKC(ctx->rp_upbc.ensure(cap, ctx->st)); CKC(ctx->rp_uovl.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)cap * sizeof(double4), ctx->st));
   CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)cap * sizeof(int), ctx->st));
@@ -464,6 +474,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release();
+  ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
@@ -495,7 +506,26 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   if (slot_b) CKC(cudaMemcpyAsync(ctx->slot_b.p, slot_b, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; CKC(cudaMemcpyAsync(ctx->slot_b.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
   ctx->n = n; ctx->listed = false; ctx->cells_sorted = false; ctx->binned = false;
+  // gcmc membership in list order (= creation order) and occupancy of the b index (Groups.F90:1083-1093)
+  std::vector<std::pair<int, int>> gm;
+  std::vector<int> bocc(ctx->cap, 0), gpos(ctx->cap, 0), gord;
+  int b_amax = 0;
+  for (int i = 0; i < n; ++i) {
+    bool alive = z[i] >= 1 && z[i] <= 3 && !(flags[i] & DML_F_LIMBO);
+    if (!alive) continue;
+    int sb = slot_b ? slot_b[i] : i;
+    if (sb < 0 || sb >= ctx->cap) FAIL("dml_upload: slot_b out of range");
+    bocc[sb] = 1; b_amax = std::max(b_amax, sb + 1);
+    if (flags[i] & DML_F_GCMC) gm.push_back({uid ? uid[i] : i, i});
+  }
+  std::sort(gm.begin(), gm.end());
+  for (size_t q = 0; q < gm.size(); ++q) { gord.push_back(gm[q].second); gpos[gm[q].second] = (int)q; }
+  if ((int)gord.size() + 8 > ctx->gorder_cap) FAIL("gcmc membership exceeds capacity");
+  if (!gord.empty()) CKC(cudaMemcpyAsync(ctx->gorder.p, gord.data(), gord.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->gpos.p, gpos.data(), (size_t)ctx->cap * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->b_occ.p, bocc.data(), (size_t)ctx->cap * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
+  ctx->hsc->glen = (int)gord.size(); ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = b_amax;
   ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
   TRY(push_scal(ctx));
   LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);

@@ -55,7 +55,9 @@ struct DevScal {
   int next_uid;
   unsigned int ticket;
   int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
-  int rev_used, pad_;
+  int rev_used;
+  int glen, ghead, gtomb, b_amax;   // gcmc membership array (list order) and hs%b%amax
+  int pad_;
 };
 
 enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,

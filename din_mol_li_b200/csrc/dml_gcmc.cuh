@@ -1,7 +1,352 @@
-// dml_gcmc.cuh — grand-canonical insertion/deletion trials on the device (gcmc_run, dana.F90:590-713).
-// Included by dml.cu after dml_ctx is defined.
+// dml_gcmc.cuh — grand-canonical insertion/deletion trials on the device (gcmc_run, dana.F90:590-713) with
+// the incremental neighbour-list maintenance they trigger (ngroup_attach_atom/ngroup_sort_atom/ngroup_cells_atom
+// Neighbor.F90:173-318,550-603; ngroup_detach_atom 226-269; cgroup_attach/unsort Cells.F90:105-144,304-352;
+// igroup index reuse Groups.F90:1083-1093).  Included by dml.cu after dml_ctx is defined.
+//
+// The nadj attempts of one call are sequentially dependent (n, the inserted atoms and the deletions feed the next
+// attempt), so one thread block runs them in order; inside an attempt the O(N) scans of the reference become
+// block-parallel searches: the overlap test visits the 27 cells around the trial point plus the atoms inserted
+// earlier in this call, the "m-th atom inside the control volume in list order" is a two-level prefix count over
+// the gcmc membership array kept in list order, and the lowest-free-slot searches are block-wide minima.
 #pragma once
 
+namespace dml {
+
+struct GcmcArgs {
+  double4 *posm; double *vel, *acel, *force, *epot, *pos_old, *old_cg;
+  int *uid, *slot_b, *b_occ;
+  const int *cell_of_unused; const int *cell_start; const int *sorted_slot; const double4 *sorted_posm;
+  int *row_start, *row_len, *row_cap, *cols; int cols_cap;
+  int *gorder, *gpos, *gcc; int gorder_cap;
+  int *pend;                       // slots inserted during this call, in insertion order
+  const double *rp_u, *rp_g; int rp_nu, rp_ng;
+  DevScal *sc; Geo g; Phys ph;
+  double act, beta_kT;             // beta = sqrt(kB_ui*Tsist/mass) uses beta_kT = kB_ui(gems_constants)*Tsist
+  int nadj, cap, listed, row_slack; unsigned int step;
+};
+
+constexpr int GB = 1024;           // threads of the gcmc block
+
+__device__ __forceinline__ int block_excl_scan(int v, int *total, int *sh /*33 ints*/) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  __syncthreads();
+  if (lane == 31) sh[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    int s = sh[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+    sh[lane] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sh[32] = sh[31];
+  int excl = x - v + (w ? sh[w - 1] : 0);
+  __syncthreads();
+  *total = sh[32];
+  return excl;
+}
+
+// one entry of the replay stream or a Philox draw; thread 0 only
+struct GcmcRng {
+  const GcmcArgs *A; int iu, ig, ctr;
+  __device__ double unif() {
+    if (A->ph.rng_mode == 1) { if (iu >= A->rp_nu) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.5; } return A->rp_u[iu++]; }
+    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step, RS_GCMC, 0u); return r.u01(0);
+  }
+  __device__ double gauss() {
+    if (A->ph.rng_mode == 1) { if (ig >= A->rp_ng) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.0; } return A->rp_g[ig++]; }
+    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step, RS_GCMC, 1u); double a, b; r.gauss2(a, b); return a;
+  }
+};
+
+__device__ __forceinline__ bool in_volume(const double4 &p, double z0, double zmax) { return !(p.z < z0 || p.z > zmax); }
+
+__global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
+  __shared__ int sh_scan[33];
+  __shared__ int s_i[16];
+  __shared__ double s_d[8];
+  DevScal *sc = A.sc;
+  const Geo &g = A.g;
+  const int tid = threadIdx.x;
+  GcmcRng rng = {&A, 0, 0, 0};
+  const double z0 = sc->z0, zmax = sc->zmax;
+  const double v = g.box[0] * g.box[1] * (zmax - z0);
+  const double rc2 = g.rcut2;
+
+  // ---- compaction of the membership array when it carries many tombstones or is nearly full ----
+  int glen = sc->glen;
+  if (sc->gtomb * 4 > glen || glen + A.nadj + 8 > A.gorder_cap) {
+    int *tmp = A.gorder + A.gorder_cap;                  // second half of the allocation is scratch
+    int outn = 0;
+    for (int base = 0; base < glen; base += GB) {
+      int i = base + tid;
+      int s = i < glen ? A.gorder[i] : -1;
+      int tot; int ex = block_excl_scan(s >= 0 ? 1 : 0, &tot, sh_scan);
+      if (s >= 0) tmp[outn + ex] = s;
+      outn += tot;
+    }
+    __syncthreads();
+    for (int i = tid; i < outn; i += GB) { int s = tmp[i]; A.gorder[i] = s; A.gpos[s] = i; }
+    __syncthreads();
+    glen = outn;
+    if (tid == 0) { sc->glen = glen; sc->gtomb = 0; sc->ghead = 0; }
+    __syncthreads();
+  }
+  // ---- control-volume census: n and the per-1024 chunk counts (dana.F90:608-615) ----
+  int n = 0;
+  for (int base = 0, c = 0; base < glen; base += GB, ++c) {
+    int i = base + tid, in = 0;
+    if (i < glen) { int s = A.gorder[i]; if (s >= 0) in = in_volume(ld_rec(&A.posm[s]), z0, zmax) ? 1 : 0; }
+    int cnt = __syncthreads_count(in);
+    if (tid == 0) A.gcc[c] = cnt;
+    n += cnt;
+  }
+  if (tid == 0) A.gcc[(glen + GB - 1) / GB] = 0;
+  int npend = 0;
+  __syncthreads();
+
+  for (int att = 0; att < A.nadj; ++att) {
+    // -- template atom = first member of the list (dana.F90:622-624) --
+    if (tid == 0) {
+      int h = sc->ghead;
+      while (h < glen && A.gorder[h] < 0) ++h;
+      sc->ghead = h;
+      s_i[0] = h < glen ? A.gorder[h] : -1;
+      if (h >= glen) atomicCAS(&sc->err, 0, DML_E_NO_PARTICLES);
+      s_i[1] = (s_i[0] >= 0 && rng.unif() < 0.5) ? 1 : 0;          // creation or destruction
+    }
+    __syncthreads();
+    const int tmpl = s_i[0];
+    if (tmpl < 0) break;
+    const int create = s_i[1];
+    __syncthreads();
+    if (create) {
+      if (tid == 0) {
+        int acc = !(A.act * v / (n + 1) < rng.unif());
+        s_i[2] = acc;
+        if (acc) {
+          s_d[0] = rng.unif() * g.box[0];
+          s_d[1] = rng.unif() * g.box[1];
+          s_d[2] = rng.unif() * (zmax - z0) + z0;
+        }
+      }
+      __syncthreads();
+      if (!s_i[2]) { __syncthreads(); continue; }
+      const double rx = s_d[0], ry = s_d[1], rz = s_d[2];
+      int rcx, rcy, rcz;
+      bool okc = cell_index(g, rx, ry, rz, rcx, rcy, rcz);
+      // -- overlap with any member of the gcmc group (dana.F90:638-653): 27 cells + atoms inserted in this call --
+      int found = 0;
+      if (okc && tid < 27) {
+        int nx = (c_map[tid][0] + rcx - 1 + g.nc[0]) % g.nc[0] + 1;
+        int ny = (c_map[tid][1] + rcy - 1 + g.nc[1]) % g.nc[1] + 1;
+        int nz = (c_map[tid][2] + rcz - 1 + g.nc[2]) % g.nc[2] + 1;
+        int nl = cell_lin(g, nx, ny, nz);
+        for (int u = A.cell_start[nl]; u < A.cell_start[nl + 1]; ++u) {
+          int s = A.sorted_slot[u];
+          double4 p = ld_rec(&A.posm[s]);
+          if (!(meta_of(p) & MF_GCMC)) continue;
+          // distance(o%pos, r, o%pbc): r minus pos
+          if (dist2_idnint(g, rx, ry, rz, p.x, p.y, p.z) < rc2) { found = 1; break; }
+        }
+      }
+      for (int q = tid; q < npend; q += GB) {
+        int s = A.pend[q];
+        double4 p = ld_rec(&A.posm[s]);
+        if (!(meta_of(p) & MF_GCMC)) continue;
+        if (dist2_idnint(g, rx, ry, rz, p.x, p.y, p.z) < rc2) found = 1;
+      }
+      if (__syncthreads_or(found)) continue;
+      // -- accepted: index assignment (lowest hole or append, Groups.F90:1083-1093) --
+      if (tid == 0) { s_i[3] = 0x7fffffff; s_i[4] = 0x7fffffff; }
+      __syncthreads();
+      const int amax = sc->n_slots, nat_new = sc->nat_sys + 1, nlimbo = sc->nlimbo, b_amax = sc->b_amax;
+      const bool hs_hole = amax >= nat_new + nlimbo, b_hole = b_amax >= nat_new;
+      if (hs_hole) {
+        int best = 0x7fffffff;
+        for (int i = tid; i < amax && best == 0x7fffffff; i += GB) if (meta_of(ld_rec(&A.posm[i])) == 0) best = i;
+        if (best != 0x7fffffff) atomicMin(&s_i[3], best);
+      }
+      if (b_hole) {
+        int best = 0x7fffffff;
+        for (int i = tid; i < b_amax && best == 0x7fffffff; i += GB) if (A.b_occ[i] == 0) best = i;
+        if (best != 0x7fffffff) atomicMin(&s_i[4], best);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int ns = hs_hole ? s_i[3] : amax;
+        int nb = b_hole ? s_i[4] : b_amax;
+        if (ns >= A.cap || nb >= A.cap || ns == 0x7fffffff || nb == 0x7fffffff) { atomicCAS(&sc->err, 0, DML_E_CAPACITY); s_i[5] = -1; }
+        else {
+          s_i[5] = ns;
+          if (!hs_hole) sc->n_slots = amax + 1;
+          if (!b_hole) sc->b_amax = b_amax + 1;
+          n = n + 1;
+          // velocity from the Maxwell-Boltzmann distribution lands on the LAST atom of the list (dana.F90:665-668, Q6)
+          int l = glen - 1;
+          while (l >= 0 && A.gorder[l] < 0) --l;
+          int last = A.gorder[l];
+          double4 pt = ld_rec(&A.posm[tmpl]);
+          int zt = (int)(meta_of(pt) & MF_TYPE);
+          double beta = sqrt(A.beta_kT / A.ph.mass[zt - 1]);
+          // new atom copies the template (atom_asign, Groups.F90:484-502) BEFORE the draw touches anybody's velocity
+          for (int k = 0; k < 3; ++k) {
+            A.vel[3 * ns + k] = A.vel[3 * tmpl + k]; A.force[3 * ns + k] = A.force[3 * tmpl + k]; A.acel[3 * ns + k] = A.acel[3 * tmpl + k];
+            A.old_cg[3 * ns + k] = 1e8;
+          }
+          A.epot[ns] = A.epot[tmpl];
+          A.pos_old[3 * ns] = rx; A.pos_old[3 * ns + 1] = ry; A.pos_old[3 * ns + 2] = rz;
+          for (int k = 0; k < 3; ++k) A.vel[3 * last + k] = beta * rng.gauss();
+          double4 pn = {rx, ry, rz, meta_as_double((long long)zt | MF_REF | MF_GCMC)};
+          st_rec(&A.posm[ns], pn);
+          A.uid[ns] = sc->next_uid++;
+          A.slot_b[ns] = nb; A.b_occ[nb] = 1;
+          sc->nat_sys++; sc->nat_ref++; sc->nat_gcmc++; sc->gcmc_created++;
+          // membership array (list order = creation order)
+          A.gorder[glen] = ns; A.gpos[ns] = glen; A.gcc[glen / GB] += 1;
+          if ((glen + 1) % GB == 0) A.gcc[(glen + 1) / GB] = 0;
+          A.pend[npend] = ns;
+          // -- ngroup_sort_atom (Neighbor.F90:271-318): own row (strict <, stencil x chain order) and append to the rows
+          //    of every ref atom within the list radius (<=) --
+          if (A.listed) {
+            int base = sc->cols_used, cnt = 0;
+            bool ovf = false;
+            for (int nab = 0; nab < 27 && okc; ++nab) {
+              int nx = (c_map[nab][0] + rcx - 1 + g.nc[0]) % g.nc[0] + 1;
+              int ny = (c_map[nab][1] + rcy - 1 + g.nc[1]) % g.nc[1] + 1;
+              int nz = (c_map[nab][2] + rcz - 1 + g.nc[2]) % g.nc[2] + 1;
+              int nl = cell_lin(g, nx, ny, nz);
+              int cb = A.cell_start[nl], ce = A.cell_start[nl + 1];
+              // chain = atoms inserted in this call that fell into this cell (most recent first), then the sorted segment
+              for (int q = npend + (ce - cb) - 1; q >= 0; --q) {
+                int s;
+                if (q >= ce - cb) {
+                  s = A.pend[q - (ce - cb)];
+                  if (s == ns) continue;
+                  double4 pp = ld_rec(&A.posm[s]);
+                  if (!(meta_of(pp) & MF_TYPE)) continue;
+                  int cx, cy, cz;
+                  if (!cell_index(g, pp.x, pp.y, pp.z, cx, cy, cz) || cell_lin(g, cx, cy, cz) != nl) continue;
+                } else s = A.sorted_slot[cb + (ce - cb - 1 - q)];
+                double4 p = ld_rec(&A.posm[s]);
+                long long m = meta_of(p);
+                if (!(m & MF_TYPE)) continue;                       // removed from its chain (cgroup_unsort_atom)
+                double rd = dist2_idnint(g, p.x, p.y, p.z, rx, ry, rz);
+                if (rd < g.rc_list2) {
+                  if (base + cnt < A.cols_cap) A.cols[base + cnt] = s; else ovf = true;
+                  ++cnt;
+                }
+                if ((m & MF_REF) && !(rd > g.rc_list2)) {
+                  int len = A.row_len[s];
+                  if (len < A.row_cap[s]) { A.cols[A.row_start[s] + len] = ns; A.row_len[s] = len + 1; }
+                  else { sc->row_overflow++; atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
+                }
+              }
+            }
+            if (ovf) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW);
+            A.row_start[ns] = base; A.row_len[ns] = cnt; A.row_cap[ns] = cnt + A.row_slack;
+            sc->cols_used = base + cnt + A.row_slack;
+          } else A.row_len[ns] = 0;
+        }
+      }
+      __syncthreads();
+      if (s_i[5] >= 0) { glen += 1; npend += 1; if (tid != 0) n = n + 1; }
+      __syncthreads();
+    } else {
+      // ---- destruction attempt (dana.F90:680-708) ----
+      if (tid == 0) {
+        int acc = !((double)n / (v * A.act) < rng.unif());
+        s_i[2] = acc;
+        if (acc) { int m = (int)floor(rng.unif() * n) + 1; if (m > n) m = n; s_i[6] = m; }
+      }
+      __syncthreads();
+      if (!s_i[2]) { __syncthreads(); continue; }
+      int m = s_i[6];
+      if (tid == 0) s_i[9] = -1;
+      if (m <= 0) { if (tid == 0) atomicCAS(&sc->err, 0, DML_E_GCMC_CHOSEN); __syncthreads(); continue; }
+      // chunk holding the m-th in-volume member
+      int nchunk = (glen + GB - 1) / GB, before = 0, chunk = -1;
+      for (int base = 0; base < nchunk && chunk < 0; base += GB) {
+        int c = base + tid;
+        int cnt = c < nchunk ? A.gcc[c] : 0;
+        int tot; int ex = block_excl_scan(cnt, &tot, sh_scan);
+        if (tid == 0) s_i[7] = -1;
+        __syncthreads();
+        if (c < nchunk && before + ex < m && m <= before + ex + cnt) { s_i[7] = c; s_i[8] = before + ex; }
+        __syncthreads();
+        if (s_i[7] >= 0) { chunk = s_i[7]; before = s_i[8]; } else before += tot;
+        __syncthreads();
+      }
+      if (chunk < 0) { if (tid == 0) atomicCAS(&sc->err, 0, DML_E_GCMC_CHOSEN); __syncthreads(); continue; }
+      {
+        int i = chunk * GB + tid, in = 0, s = -1;
+        if (i < glen) { s = A.gorder[i]; if (s >= 0) in = in_volume(ld_rec(&A.posm[s]), z0, zmax) ? 1 : 0; }
+        int tot; int ex = block_excl_scan(in, &tot, sh_scan);
+        if (in && before + ex + 1 == m) s_i[9] = s;
+        __syncthreads();
+        (void)tot;
+      }
+      if (tid == 0 && s_i[9] < 0) atomicCAS(&sc->err, 0, DML_E_GCMC_CHOSEN);
+      if (tid == 0 && s_i[9] >= 0) {
+        int s = s_i[9];
+        // atom%dest(): detach from gcmc, hs (row dropped, slot to limbo), ref, b (chain), sys — Groups.F90:433-467
+        n = n - 1;
+        A.gcc[A.gpos[s] / GB] -= 1;
+        A.gorder[A.gpos[s]] = -1; sc->gtomb++;
+        A.row_len[s] = 0;
+        A.b_occ[A.slot_b[s]] = 0;
+        double4 p = ld_rec(&A.posm[s]);
+        p.w = meta_as_double(A.listed ? MF_LIMBO : 0);
+        st_rec(&A.posm[s], p);
+        if (A.listed) sc->nlimbo++;
+        sc->nat_sys--; sc->nat_ref--; sc->nat_gcmc--; sc->gcmc_destroyed++;
+      }
+      __syncthreads();
+      if (tid != 0 && s_i[9] >= 0) n = n - 1;
+      __syncthreads();
+    }
+  }
+  if (tid == 0) sc->glen = glen;
+}
+
+// k_promote variant that also drops promoted atoms from the gcmc membership array (dana.F90:235)
+__global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos,
+                            DevScal *__restrict__ sc, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  long long m = meta_of(ld_rec_nc(&posm[s]));
+  if ((m & MF_REF) && (m & MF_TYPE) == 3 && (m & MF_GCMC)) { gorder[gpos[s]] = -1; atomicAdd(&sc->gtomb, 1); }
+}
+
+} // namespace dml
+
 static int gcmc_run_impl(dml_ctx *ctx) {
-  FAIL("gcmc_run: not implemented yet");
+  using namespace dml;
+  if (ctx->cfg.reservoir != 3) return 0;
+  if (!ctx->binned || !ctx->tessellated) FAIL("gcmc_run: call test_update first");
+  if (!ctx->cells_sorted) TRY(sort_cells(ctx, false));
+  TRY(pull_scal(ctx));
+  int nadj = ctx->cfg.nadj;
+  if (ctx->hsc->n_slots + nadj > ctx->cap) FAIL("slot capacity exhausted (dml_config.capacity)");
+  size_t need = (size_t)ctx->hsc->cols_used + (size_t)nadj * (1024 + ctx->row_slack) + 1024;
+  if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st, true));
+  CKC(ctx->gpend.ensure((size_t)nadj + 8, ctx->st));
+  if (ctx->ph.rng_mode == DML_RNG_REPLAY && ctx->rp_nu == 0 && nadj > 0) FAIL("replay mode: call dml_set_replay_gcmc before gcmc_run");
+  GcmcArgs A;
+  A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.force = ctx->force.p; A.epot = ctx->epot.p;
+  A.pos_old = ctx->pos_old.p; A.old_cg = ctx->old_cg.p; A.uid = ctx->uid.p; A.slot_b = ctx->slot_b.p; A.b_occ = ctx->b_occ.p;
+  A.cell_of_unused = nullptr; A.cell_start = ctx->cell_start.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
+  A.row_start = ctx->row_start.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.cols = ctx->cols.p; A.cols_cap = (int)ctx->cols.cap;
+  A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
+  A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
+  A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;
+  A.nadj = nadj; A.cap = ctx->cap; A.listed = ctx->listed ? 1 : 0; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
+  LAUNCH(K_GCMC, k_gcmc, 1, GB, A);
+  TRY(pull_scal(ctx));
+  ctx->n = ctx->hsc->n_slots;
+  ctx->rows_asym = true; ctx->rev_valid = false;       // appended entries use <= (Neighbor.F90:307), rows may be asymmetric
+  ctx->rp_nu = ctx->rp_ng = 0;
+  return 0;
 }

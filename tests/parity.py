@@ -81,6 +81,19 @@ def compare_state(o, ctx, fields=("pos", "vel", "acel", "pos_old", "old_cg", "z"
     return d, a
 
 
+def compare_rows(o, ctx, what=""):
+    """Neighbour rows of every ref atom: same entries in the same order."""
+    a = oracle_slot_arrays(o)
+    n = len(a["z"])
+    nn, rows, _ = o.rows(width=64)
+    gnn, grows = ctx.neighbors(n, width=64)
+    ref = a["alive"] & ((a["flags"] & 1) > 0)
+    assert np.array_equal(gnn[ref], nn[:n][ref]), what + ": row lengths differ"
+    lo, lg = rows_as_lists(nn[:n], rows, 1), rows_as_lists(gnn, grows, 0)
+    for i in np.flatnonzero(ref):
+        assert lo[i] == lg[i], "%s: row of slot %d differs: oracle %s device %s" % (what, i, lo[i], lg[i])
+
+
 def replay_from_trace(o, slot_of_uid, amax, ng):
     """Split the oracle's RNG trace of one call into per-slot injection arrays."""
     kind, uid, val = o.trace()
@@ -190,6 +203,9 @@ class Lockstep:
             _, _, _, gu, gg = replay_from_trace(o, u2s, amax, 3)
             ctx.set_replay_gcmc(gu, gg)
             ctx.gcmc_run()
+            if check:
+                compare_state(o, ctx, fields=("pos", "vel", "acel", "pos_old", "z", "flags", "uid", "slot_b"), what=tag + " gcmc_run")
+                compare_rows(o, ctx, what=tag + " gcmc_run")
         o.call(O.CALC_RHO)
         rho = ctx.calc_rho()
         assert rho == o.scalars().rho, tag + " rho"

@@ -53,7 +53,7 @@ def test_fuerza_matches_oracle(strict):
     assert (np.abs(a["force"][ref]).sum(axis=1) > 0).sum() > 5      # the comparison is not vacuous
 
 
-@pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40)])
+@pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40), ("gcmc", 400)])
 def test_lockstep_replay_bit_exact(name, nsteps):
     d, o = case(name)
     ls = P.Lockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
@@ -90,3 +90,20 @@ def test_ermak_fixture_on_device():
     P.compare_state(o, ls.ctx, what="ermak final")
     c = ls.ctx.counters()
     assert c.choques == o.scalars().choques == 49905
+
+
+def test_gcmc_fixture_on_device():
+    """tests/gcmc (5000 steps: insertions, deletions, index reuse, limbo, incremental rows) replayed on the device."""
+    d, o = case("gcmc")
+    ls = P.Lockstep(o, strict=1)
+    for i in range(d["nst"]):
+        ls.step(check=(i % 250 == 249), tag="gcmc step %d" % (i + 1))
+    rzmax, rz, rpos = O.read_xyz_frame(os.path.join(GOLD, "gcmc", "ref.xyz"))
+    a = P.oracle_slot_arrays(o)
+    g = ls.ctx.download(len(a["z"]))
+    st = o.state()
+    s = st["slot_hs"] - 1
+    assert np.array_equal(g["pos"][s], rpos) and np.array_equal(g["z"][s], rz)
+    c = ls.ctx.counters()
+    assert c.gcmc_created > 0 and c.gcmc_destroyed > 0
+    assert c.nat_sys == 594
