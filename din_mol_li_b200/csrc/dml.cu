@@ -5,6 +5,7 @@
 namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos, DevScal *__restrict__ sc, int n); }
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -57,8 +58,10 @@ struct dml_ctx {
   // rows
   DBuf<int> row_start, row_len, row_cap, cols;
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
+  int force_lanes = 2;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
-  DBuf<int> scan_sums;
+  DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
+  DBuf<int> rev_cnt;
   DBuf<double> part;
   // overlap
   DBuf<int> parent, ovst, comp_cnt, comp_off, members, roots;
@@ -79,20 +82,21 @@ struct dml_ctx {
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 static int gcmc_run_impl(dml_ctx *ctx);
-static int sort_cells(dml_ctx *ctx, bool snapshot);
+static int enq_sort_cells(dml_ctx *ctx, int force);
+static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
 
 enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
 // one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
 enum { K_SCAN = 0, K_PBC_BIN, K_TOP2, K_SCATTER, K_CELL_ORDER, K_ROWS_COUNT, K_ROWS_FILL, K_ROW_CAPS, K_FUERZA, K_INTEGRATE,
        K_ERMAK_B, K_OV_INIT, K_OV_DETECT, K_OV_COUNT, K_OV_ALLOC, K_OV_FILL, K_OV_SORT, K_OV_PASS, K_OV_APPLY, K_PROMOTE,
-       K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_NKERN };
-static const char *const kern_name[K_NKERN] = {"scan", "pbc_bin", "top2_final", "scatter", "cell_order", "rows_count", "rows_fill",
+       K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_BIN, K_NKERN };
+static const char *const kern_name[K_NKERN] = {"scan", "pbc_disp", "top2_final", "scatter", "cell_order", "rows_count", "rows_fill",
   "row_caps", "fuerza", "integrate", "ermak_b", "ov_init", "ov_detect", "ov_count", "ov_alloc", "ov_fill", "ov_sort", "ov_pass",
-  "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows"};
+  "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows", "bin"};
 static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_FORCE, CLS_INTEG,
   CLS_INTEG, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OTHER,
-  CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST};
+  CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST, CLS_LIST};
 
 static void prof_begin(dml_ctx *ctx, int cls) {
   ctx->launches++;
@@ -169,13 +173,15 @@ static void tessellate(dml_ctx *ctx) {
   ctx->tessellated = true;
 }
 
-static int scan_excl(dml_ctx *ctx, const int *in, int *out, int n, int *total_out, int *total_out2) {
-  const int cls = K_SCAN;
+// single-pass scan (decoupled look-back).  guard_mode: 0 rebuild guard (| force), 1 transposed-rows guard, 2 always
+static int scan_excl(dml_ctx *ctx, int *in, int *out, int n, int *total_out, bool zero_in, int guard_mode, int force) {
   int nb = nblk(n, 1024);
-  CKC(ctx->scan_sums.ensure(nb + 1, ctx->st));
-  LAUNCH(cls, k_scan_local, nb, TPB, in, out, ctx->scan_sums.p, n);
-  LAUNCH(cls, k_scan_sums, 1, 1024, ctx->scan_sums.p, nb, total_out, total_out2);
-  if (nb > 1) LAUNCH(cls, k_scan_add, nb, TPB, out, ctx->scan_sums.p, n);
+  CKC(ctx->scan_state.ensure((size_t)nb + 8, ctx->st));
+  if (!ctx->scan_tickets) { CKC(cudaMalloc(&ctx->scan_tickets, 2 * sizeof(unsigned int))); CKC(cudaMemsetAsync(ctx->scan_tickets, 0, 2 * sizeof(unsigned int), ctx->st)); }
+  unsigned int ep = ++ctx->scan_epoch;
+  if ((ep & 0x3fffffffu) == 0) ep = ++ctx->scan_epoch;
+  if (zero_in) LAUNCH(K_SCAN, (k_scan<true>), nb, TPB, in, out, n, ctx->scan_state.p, ctx->scan_tickets, ep, total_out, ctx->sc, force, guard_mode);
+  else LAUNCH(K_SCAN, (k_scan<false>), nb, TPB, in, out, n, ctx->scan_state.p, ctx->scan_tickets, ep, total_out, ctx->sc, force, guard_mode);
   return 0;
 }
 
@@ -184,57 +190,47 @@ static int ensure_particles(dml_ctx *ctx, int n) {
   return 0;
 }
 
-static int sort_cells(dml_ctx *ctx, bool snapshot) {
+// cell binning + counting sort; guarded on the device by need_rebuild | force
+static int enq_sort_cells(dml_ctx *ctx, int force) {
   int n = ctx->n, nct = ctx->nct;
-  TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, nullptr));
-  CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, (size_t)nct * sizeof(int), ctx->st));
+  LAUNCH(K_BIN, k_bin, nblk(n), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->row_len.p, ctx->row_cap.p, ctx->sc, ctx->geo, n, force);
+  TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, true, 0, force));
   LAUNCH(K_SCATTER, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
-         ctx->sorted_slot.p, n, snapshot ? 1 : 0);
-  LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->sorted_slot.p,
-         ctx->sorted_posm.p, nct);
-  ctx->cells_sorted = true;
+         ctx->sorted_slot.p, ctx->sc, n, force);
+  LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
+         ctx->sorted_posm.p, ctx->sc, nct, force);
   return 0;
 }
 
-// update() + ngroup_cells — Neighbor.F90:608-633, 465-548
-static int rebuild(dml_ctx *ctx) {
-  int n = ctx->n;
-  ctx->nupd++;
-  TRY(sort_cells(ctx, true));
-  CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
-  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
-  LAUNCH(K_ROW_CAPS, k_row_caps, nblk(n), TPB, ctx->row_len.p, ctx->row_cap.p, n, ctx->row_slack);
-  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, nullptr));
-  TRY(pull_scal(ctx));
-  size_t need = (size_t)ctx->hsc->cols_used + (size_t)ctx->row_slack * 64 + 1024;
-  if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st));
-  LAUNCH(K_ROWS_FILL, (k_rows<true>), nblk(n, 128), 128, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_start.p, ctx->cols.p, ctx->geo, ctx->nct);
-  CKC(cudaMemsetAsync(&ctx->sc->nlimbo, 0, sizeof(int), ctx->st));
-  ctx->listed = true;
-  ctx->rows_asym = ctx->hsc->halo_flag != 0; ctx->rev_valid = false;
-  return 0;
-}
-
-static int do_test_update(dml_ctx *ctx) {
+// test_update (Neighbor.F90:668-713) enqueued without any host round trip: the rebuild decision is taken by
+// k_top2_final on the device and the rebuild kernels (update + ngroup_cells, Neighbor.F90:608-633,465-548) are
+// always launched but return immediately when no rebuild is due.
+static int enq_test_update(dml_ctx *ctx) {
   tessellate(ctx);
   if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction: the reference's O(N^2) ngroup_verlet path is not implemented on the device");
   int n = ctx->n, nct = ctx->nct;
-  CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
-  CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, (size_t)nct * sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(&ctx->sc->halo_flag, 0, sizeof(int), ctx->st));
+  if ((size_t)nct + 2 > ctx->cell_start.cap) {
+    CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
+    CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, ctx->cell_cnt.cap * sizeof(int), ctx->st));
+    CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
+  }
   int nb = nblk(n);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_bin, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->part.p, ctx->sc, ctx->geo, n, 1);
-  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->listed ? 1 : 0, ctx->cfg.nb_dcut);
-  ctx->cells_sorted = false; ctx->binned = true;
-  TRY(pull_scal(ctx));
-  if (ctx->hsc->need_rebuild) TRY(rebuild(ctx));
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->geo, n);
+  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->cfg.nb_dcut);
+  int force = ctx->cfg.reservoir == 3 ? 1 : 0;       // gcmc_run needs the cells of the current positions every step
+  TRY(enq_sort_cells(ctx, force));
+  int nw = std::min(nblk(n * 32), 148 * 32);          // grid-stride over warps: an idle (guarded) launch stays cheap
+  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 0, 0));
+  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  ctx->binned = true;
   return 0;
 }
 
-static int do_integrate(dml_ctx *ctx, bool ermak) {
+static int enq_integrate(dml_ctx *ctx, bool ermak) {
   int n = ctx->n;
   ctx->step++;
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
@@ -248,81 +244,74 @@ static int do_integrate(dml_ctx *ctx, bool ermak) {
   return 0;
 }
 
-static int build_rev(dml_ctx *ctx) {
+static int enq_fuerza(dml_ctx *ctx) {
   int n = ctx->n;
-  CKC(ctx->rev_start.ensure(ctx->cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(ctx->cap, ctx->st)); CKC(ctx->rev_cur.ensure(ctx->cap, ctx->st));
-  CKC(cudaMemsetAsync(ctx->rev_len.p, 0, (size_t)n * sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(ctx->rev_cur.p, 0, (size_t)n * sizeof(int), ctx->st));
-  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_len.p, n);
-  TRY(scan_excl(ctx, ctx->rev_len.p, ctx->rev_start.p, n, &ctx->sc->rev_used, nullptr));
-  TRY(pull_scal(ctx));
-  CKC(ctx->rev_cols.ensure((size_t)ctx->hsc->rev_used + 1024, ctx->st));
-  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, ctx->rev_cur.p, ctx->rev_cols.p, n);
-  ctx->rev_valid = true;
-  return 0;
-}
-
-static int do_fuerza(dml_ctx *ctx) {
-  if (!ctx->listed) FAIL("fuerza called without a neighbour list");
-  int n = ctx->n;
-  if (ctx->rows_asym && !ctx->rev_valid) TRY(build_rev(ctx));
-  int asym = ctx->rows_asym ? 1 : 0;
+  // transposed rows, built on the device only when rows can be asymmetric (guarded launches)
+  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p, ctx->sc, n);
+  TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
+  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
+         ctx->rev_cols.p, ctx->sc, n);
+  LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
-           ctx->rev_len.p, ctx->rev_cols.p, asym, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
+           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
   else
-    LAUNCH(K_FUERZA, (k_fuerza<false>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
-           ctx->rev_len.p, ctx->rev_cols.p, asym, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
+  {
+#define FSUB(L) LAUNCH(K_FUERZA, (k_fuerza_sub<L>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n)
+    switch (ctx->force_lanes) { case 1: FSUB(1); break; case 2: FSUB(2); break; case 4: FSUB(4); break; default: FSUB(8); break; }
+#undef FSUB
+  }
   return 0;
 }
 
-static int do_overlap(dml_ctx *ctx) {
-  if (!ctx->listed) FAIL("overlap_moveback called without a neighbour list");
+// overlap_moveback (dana.F90:849-943)
+static int enq_overlap(dml_ctx *ctx) {
   int n = ctx->n;
-  ctx->hsc->again = 0; ctx->hsc->n_roots = 0; ctx->hsc->member_cursor = 0;
-  // only the three control words are reset on the device (the rest of the struct lives there)
-  CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(&ctx->sc->n_roots, 0, sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(&ctx->sc->member_cursor, 0, sizeof(int), ctx->st));
-  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
          ctx->ovst.p, ctx->sc, ctx->geo, n);
   LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
   LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
   LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
-  TRY(pull_scal(ctx));
-  int nroots = ctx->hsc->n_roots;
-  int64_t ch_prev = ctx->hsc->choques;
-  std::vector<int64_t> marks;
-  if (nroots > 0) {
-    LAUNCH(K_OV_SORT, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
-    for (int pass = 0;; ++pass) {
-      CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
-      LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
-             ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p,
-             ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, pass,
-             (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
-      ctx->overlap_passes++;
-      TRY(pull_scal(ctx));
-      marks.push_back(ctx->hsc->choques);
-      if (!ctx->hsc->again) break;
-      if (pass > 100000) FAIL("overlap_moveback does not converge");
+  const double *uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr;
+  if (ctx->cfg.prob >= 1.0) {
+    LAUNCH(K_OV_PASS, k_ov_resolve, nblk(n, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->ovst.p,
+           ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+           (unsigned int)ctx->step, ctx->ov_guard_pass);
+  } else {
+    // prob<1: a failed deposition leaves skip=.false. without asking for another pass, so whether that atom is looked at
+    // again depends on the other components: keep the reference's global recursion levels (one launch + one flag read each)
+    TRY(pull_scal(ctx));
+    int nroots = ctx->hsc->n_roots;
+    if (nroots > 0) {
+      LAUNCH(K_OV_SORT, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
+      for (int pass = 0;; ++pass) {
+        CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
+        LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
+               ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+               (unsigned int)ctx->step, pass, (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
+        TRY(pull_scal(ctx));
+        if (!ctx->hsc->again) { CKC(cudaMemsetAsync(&ctx->sc->any_active, 0, sizeof(int), ctx->st)); ctx->hsc->any_active = pass + 1;
+                                CKC(cudaMemcpyAsync(&ctx->sc->any_active, &ctx->hsc->any_active, sizeof(int), cudaMemcpyHostToDevice, ctx->st)); break; }
+      }
     }
-  } else { ctx->overlap_passes++; marks.push_back(ch_prev); }
-  for (size_t lv = 0; lv < marks.size(); ++lv) ctx->choques2 = std::max<int64_t>(ctx->choques2, (int64_t)ctx->hsc->choques - marks[lv]);
-  LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, n);
+  }
+  LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, ctx->sc, n);
   ctx->have_rp_ovl = false;
   return 0;
 }
 
-static int do_promote(dml_ctx *ctx) {
+static int enq_promote(dml_ctx *ctx) {
   if (ctx->cfg.reservoir == 3) LAUNCH(K_PROMOTE, k_gcmc_tomb, nblk(ctx->n), TPB, ctx->posm.p, ctx->gorder.p, ctx->gpos.p, ctx->sc, ctx->n);
-  LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n); return 0; }
-static int do_calc_rho(dml_ctx *ctx) {
+  LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n);
+  return 0;
+}
+static int enq_calc_rho(dml_ctx *ctx) {
   LAUNCH(K_CALC_RHO, k_calc_rho, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, ctx->n);
   return 0;
 }
-static int do_maxz(dml_ctx *ctx) { LAUNCH(K_MAXZ, k_maxz, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->cfg.h / ctx->cfg.tau, ctx->n); return 0; }
+static int enq_maxz(dml_ctx *ctx) { LAUNCH(K_MAXZ, k_maxz, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->cfg.h / ctx->cfg.tau, ctx->n); return 0; }
 
 static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
   if (!src) return 0;
@@ -330,7 +319,24 @@ static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
   return 0;
 }
 
-// bloques — dana.F90:716-773
+// End of a public call: one device->host read of the scalar block; refresh the host mirrors, surface device-side
+// errors, and grow the neighbour storage while there is still head-room.
+static int finish(dml_ctx *ctx) {
+  TRY(pull_scal(ctx));
+  ctx->n = ctx->hsc->n_slots;
+  size_t used = (size_t)std::max(ctx->hsc->cols_used, ctx->hsc->rev_used);
+  if (used * 2 > ctx->cols.cap) {
+    size_t want = used * 3 + 4096;
+    CKC(ctx->cols.ensure(want, ctx->st, true)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st, false));
+    ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
+    ctx->hsc->rev_valid = 0;
+    TRY(push_scal(ctx));
+    CKC(cudaStreamSynchronize(ctx->st));
+  }
+  return 0;
+}
+
+// bloques — dana.F90:716-773 (host side: needs rho, appends the template block, changes the box)
 static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double *cpos_old, double dist, double rhomedia, int *fired) {
   TRY(pull_scal(ctx));
   double drho = ctx->hsc->rho - rhomedia;
@@ -341,9 +347,11 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   TRY(ensure_particles(ctx, n0 + nchunk));
   ctx->hsc->z0 += dist; ctx->hsc->z1 += dist; ctx->hsc->zmax += dist;
   std::vector<double> zero3((size_t)nchunk * 3, 0.0), og((size_t)nchunk * 3, 1e8);
-  std::vector<int> z(nchunk, 1), fl(nchunk, DML_F_REF), uid(nchunk), sb(nchunk);
+  std::vector<int> z(nchunk, 1), fl(nchunk, DML_F_REF), uid(nchunk), sb(nchunk), one(nchunk, 1);
   for (int i = 0; i < nchunk; ++i) { uid[i] = ctx->hsc->next_uid + i; sb[i] = n0 + i; }
-  ctx->hsc->next_uid += nchunk; ctx->hsc->n_slots = n0 + nchunk; ctx->hsc->b_amax = n0 + nchunk; ctx->hsc->nat_sys += nchunk; ctx->hsc->nat_ref += nchunk;
+  ctx->hsc->next_uid += nchunk; ctx->hsc->n_slots = n0 + nchunk; ctx->hsc->b_amax = n0 + nchunk;
+  ctx->hsc->nat_sys += nchunk; ctx->hsc->nat_ref += nchunk;
+  ctx->hsc->listed = 0;                                   // hs%listed=.false. (dana.F90:737)
   TRY(push_scal(ctx));
   CKC(ctx->stage_d.ensure((size_t)nchunk * 3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)nchunk * 2, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_d.p, cpos, (size_t)nchunk * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
@@ -358,24 +366,32 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   TRY(upload_d(ctx, ctx->old_cg.p + (size_t)3 * n0, og.data(), (size_t)nchunk * 3));
   CKC(cudaMemcpyAsync(ctx->uid.p + n0, uid.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->slot_b.p + n0, sb.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->b_occ.p + n0, one.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaStreamSynchronize(ctx->st));                     // host vectors go out of scope
   ctx->n = n0 + nchunk;
-  ctx->listed = false;
   double box[3] = {ctx->geo.box[0], ctx->geo.box[1], ctx->hsc->zmax};
   set_box(ctx, box);
-  return do_test_update(ctx);
+  return enq_test_update(ctx);
 }
 
-static int do_step(dml_ctx *ctx) {
-  if (ctx->cfg.integrador) { TRY(do_integrate(ctx, true)); TRY(do_fuerza(ctx)); LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n); }
-  else TRY(do_integrate(ctx, false));
-  TRY(do_test_update(ctx));
-  TRY(do_overlap(ctx));
-  TRY(do_test_update(ctx));
-  LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
-  TRY(do_promote(ctx));
-  if (ctx->cfg.reservoir == 3) TRY(gcmc_run_impl(ctx));
-  TRY(do_calc_rho(ctx));
+// one iteration of dana's loop body (dana.F90:173-265), enqueue only (reservoir 2 reads rho once per step)
+static int enq_step(dml_ctx *ctx) {
+  int n = ctx->n;
+  if (ctx->cfg.integrador) {
+    TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx));
+    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, n);
+  } else TRY(enq_integrate(ctx, false));
+  TRY(enq_test_update(ctx));
+  TRY(enq_overlap(ctx));
+  TRY(enq_test_update(ctx));
+  if (ctx->cfg.reservoir == 3) {
+    LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
+    TRY(enq_promote(ctx));
+    TRY(gcmc_run_impl(ctx));
+    TRY(enq_calc_rho(ctx));
+  } else {
+    LAUNCH(K_PROMOTE, k_promote_rho, nblk(n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, n);
+  }
   if (ctx->cfg.reservoir == 2) {
     if (!ctx->have_chunk) FAIL("reservoir 2: call dml_set_chunk_template before dml_step");
     int fired = 0;
@@ -383,7 +399,7 @@ static int do_step(dml_ctx *ctx) {
     TRY(do_bloques(ctx, nch, ctx->ch_pos.data(), ctx->ch_pos_old.data(), ctx->ch_dist, ctx->ch_rhomedia, &fired));
     if (fired) for (int i = 0; i < nch; ++i) { ctx->ch_pos[3 * i + 2] += ctx->ch_dist; ctx->ch_pos_old[3 * i + 2] += ctx->ch_dist; }
   }
-  if (ctx->cfg.reservoir == 1) TRY(do_maxz(ctx));
+  if (ctx->cfg.reservoir == 1) TRY(enq_maxz(ctx));
   ctx->t = ctx->t + ctx->cfg.h;
   return 0;
 }
@@ -416,6 +432,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   for (int i = 0; i < 9; ++i) {
     ph.eps[i] = cfg->eps[i]; ph.r0[i] = cfg->r0[i]; ph.r0sq[i] = cfg->r0[i] * cfg->r0[i];
     double x = cfg->r0[i], x2 = x * x, x4 = x2 * x2; ph.r0p6[i] = x2 * x4;
+    ph.r0sq_max = std::max(ph.r0sq_max, ph.r0sq[i]);
   }
   for (int i = 0; i < 3; ++i) { ph.mass[i] = cfg->mass[i]; ph.sqrt_mass[i] = std::sqrt(cfg->mass[i]); }
   ph.h = cfg->h; ph.prob = cfg->prob; ph.tau = cfg->tau;
@@ -436,6 +453,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
+  if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->force.ensure(c3, ctx->st));
@@ -443,7 +461,10 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
   CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
   CKC(ctx->row_start.ensure(cap + 1, ctx->st)); CKC(ctx->row_len.ensure(cap, ctx->st)); CKC(ctx->row_cap.ensure(cap, ctx->st));
-  CKC(ctx->cols.ensure((size_t)cap * 16 + 4096, ctx->st));
+  CKC(ctx->cols.ensure((size_t)cap * 48 + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
+  CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->rev_cnt.p, 0, (size_t)cap * sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(ctx->row_cap.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(ctx->parent.ensure(cap, ctx->st)); CKC(ctx->ovst.ensure(cap, ctx->st)); CKC(ctx->comp_cnt.ensure(cap, ctx->st));
   CKC(ctx->comp_off.ensure(cap, ctx->st)); CKC(ctx->members.ensure(cap, ctx->st)); CKC(ctx->roots.ensure(cap, ctx->st));
   ctx->gorder_cap = 2 * cap + 2048;
@@ -454,10 +475,28 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(cudaMemsetAsync(ctx->force.p, 0, c3 * sizeof(double), ctx->st));
   CKC(cudaMemsetAsync(ctx->epot.p, 0, (size_t)cap * sizeof(double), ctx->st));
+  {
+    // Keep the 32-byte particle records resident in the 126 MB L2 across the kernels of a step: every gather of the
+    // pair-force / overlap / list kernels then hits L2 and HBM only sees the streaming arrays.
+    cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("DML_NO_L2_PERSIST")) {
+      size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)cap * sizeof(double4));
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+      attr.accessPolicyWindow.base_ptr = ctx->posm.p;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)cap * sizeof(double4), (size_t)prop.accessPolicyMaxWindowSize);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(ctx->st, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
   CKC(cudaMalloc(&ctx->sc, sizeof(DevScal)));
   CKC(cudaMallocHost(&ctx->hsc, sizeof(DevScal)));
   memset(ctx->hsc, 0, sizeof(DevScal));
   ctx->hsc->z0 = cfg->z0; ctx->hsc->z1 = cfg->z1; ctx->hsc->zmax = cfg->zmax;
+  ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
   return 0;
@@ -473,7 +512,8 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
-  ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release();
+  ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
+  ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_i.release();
@@ -505,7 +545,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; mx = n - 1; CKC(cudaMemcpyAsync(ctx->uid.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
   if (slot_b) CKC(cudaMemcpyAsync(ctx->slot_b.p, slot_b, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; CKC(cudaMemcpyAsync(ctx->slot_b.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
-  ctx->n = n; ctx->listed = false; ctx->cells_sorted = false; ctx->binned = false;
+  ctx->n = n; ctx->binned = false;
   // gcmc membership in list order (= creation order) and occupancy of the b index (Groups.F90:1083-1093)
   std::vector<std::pair<int, int>> gm;
   std::vector<int> bocc(ctx->cap, 0), gpos(ctx->cap, 0), gord;
@@ -526,7 +566,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   CKC(cudaMemcpyAsync(ctx->b_occ.p, bocc.data(), (size_t)ctx->cap * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->glen = (int)gord.size(); ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = b_amax;
-  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
   TRY(push_scal(ctx));
   LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
   CKC(cudaStreamSynchronize(ctx->st));
@@ -573,19 +613,19 @@ int dml_get_scalars(dml_ctx *ctx, dml_scalars *s) {
 int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
   TRY(pull_scal(ctx));
   memset(c, 0, sizeof *c);
-  if (ctx->listed) {
+  if (ctx->hsc->listed) {
     CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
     LAUNCH(K_MISC, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
     TRY(pull_scal(ctx));
   }
   DevScal *h = ctx->hsc;
-  c->nupd_vlist = ctx->nupd; c->try_ = h->try_; c->depo = h->depo; c->choques = h->choques; c->choques2 = ctx->choques2; c->choques3 = h->choques3;
-  c->list_entries = ctx->listed ? h->list_entries : 0; c->overlap_passes = ctx->overlap_passes;
+  c->nupd_vlist = h->nupd; c->try_ = h->try_; c->depo = h->depo; c->choques = h->choques; c->choques2 = h->choques2; c->choques3 = h->choques3;
+  c->list_entries = h->listed ? h->list_entries : 0; c->overlap_passes = h->overlap_passes;
   c->gcmc_created = h->gcmc_created; c->gcmc_destroyed = h->gcmc_destroyed; c->row_overflow = h->row_overflow;
   c->max_vel = h->max_vel; c->msd_t = h->msd_t; c->msd_max = h->msd_max;
   c->n_slots = ctx->n; c->nat_sys = h->nat_sys; c->nat_ref = h->nat_ref; c->nat_gcmc = h->nat_gcmc;
   for (int k = 0; k < 3; ++k) { c->ncells[k] = ctx->geo.nc[k]; c->cell[k] = ctx->geo.cell[k]; }
-  c->tessellated = ctx->tessellated; c->listed = ctx->listed;
+  c->tessellated = ctx->tessellated; c->listed = h->listed; c->rows_asym = h->rows_asym;
   return 0;
 }
 int dml_reset_try_depo(dml_ctx *ctx) {
@@ -594,30 +634,41 @@ int dml_reset_try_depo(dml_ctx *ctx) {
   return 0;
 }
 
-int dml_test_update(dml_ctx *ctx) { return do_test_update(ctx); }
-int dml_fuerza(dml_ctx *ctx) { return do_fuerza(ctx); }
-int dml_ermak_a(dml_ctx *ctx) { return do_integrate(ctx, true); }
+int dml_test_update(dml_ctx *ctx) { TRY(enq_test_update(ctx)); return finish(ctx); }
+int dml_fuerza(dml_ctx *ctx) {
+  TRY(pull_scal(ctx));
+  if (!ctx->hsc->listed) FAIL("fuerza called without a neighbour list");
+  TRY(enq_fuerza(ctx)); return finish(ctx);
+}
+int dml_ermak_a(dml_ctx *ctx) { TRY(enq_integrate(ctx, true)); return finish(ctx); }
 int dml_ermak_b(dml_ctx *ctx) {
   LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n);
-  return 0;
+  return finish(ctx);
 }
-int dml_cbrownian_hs(dml_ctx *ctx) { return do_integrate(ctx, false); }
-int dml_overlap_moveback(dml_ctx *ctx) { return do_overlap(ctx); }
+int dml_cbrownian_hs(dml_ctx *ctx) { TRY(enq_integrate(ctx, false)); return finish(ctx); }
+int dml_overlap_moveback(dml_ctx *ctx) {
+  TRY(pull_scal(ctx));
+  if (!ctx->hsc->listed) FAIL("overlap_moveback called without a neighbour list");
+  TRY(enq_overlap(ctx)); return finish(ctx);
+}
 int dml_msd_book(dml_ctx *ctx) { LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc); return 0; }
-int dml_promote(dml_ctx *ctx) { return do_promote(ctx); }
-int dml_gcmc_run(dml_ctx *ctx) { return gcmc_run_impl(ctx); }
+int dml_promote(dml_ctx *ctx) { TRY(enq_promote(ctx)); return finish(ctx); }
+int dml_gcmc_run(dml_ctx *ctx) { TRY(gcmc_run_impl(ctx)); return finish(ctx); }
 int dml_calc_rho(dml_ctx *ctx, double *rho) {
-  TRY(do_calc_rho(ctx));
-  if (rho) { TRY(pull_scal(ctx)); *rho = ctx->hsc->rho; }
+  TRY(enq_calc_rho(ctx));
+  TRY(finish(ctx));
+  if (rho) *rho = ctx->hsc->rho;
   return 0;
 }
 int dml_maxz(dml_ctx *ctx, double *zmax) {
-  TRY(do_maxz(ctx));
-  if (zmax) { TRY(pull_scal(ctx)); *zmax = ctx->hsc->zmax; }
+  TRY(enq_maxz(ctx));
+  TRY(finish(ctx));
+  if (zmax) *zmax = ctx->hsc->zmax;
   return 0;
 }
 int dml_bloques(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia, int32_t *fired) {
-  return do_bloques(ctx, nchunk, chunk_pos, chunk_pos_old, dist, rhomedia, fired);
+  TRY(do_bloques(ctx, nchunk, chunk_pos, chunk_pos_old, dist, rhomedia, fired));
+  return finish(ctx);
 }
 int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia) {
   ctx->ch_pos.assign(chunk_pos, chunk_pos + (size_t)nchunk * 3);
@@ -626,13 +677,16 @@ int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos
   return 0;
 }
 int dml_step(dml_ctx *ctx, int32_t nsteps) {
-  for (int i = 0; i < nsteps; ++i) TRY(do_step(ctx));
-  return 0;
+  for (int i = 0; i < nsteps; ++i) {
+    TRY(enq_step(ctx));
+    if ((i & 15) == 15) TRY(finish(ctx));              // periodic error check / storage growth; no other host round trip
+  }
+  return finish(ctx);
 }
 
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) {
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
-  if (!ctx->cells_sorted) TRY(sort_cells(ctx, false));
+  TRY(enq_sort_cells(ctx, 1));
   CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
   LAUNCH(K_MISC, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
   std::vector<int> lin(n);
@@ -648,8 +702,8 @@ int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos
 }
 
 int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) {
-  if (!ctx->listed) FAIL("no neighbour list");
   TRY(pull_scal(ctx));
+  if (!ctx->hsc->listed) FAIL("no neighbour list");
   std::vector<int> rs(n), rl(n), cols((size_t)std::max(ctx->hsc->cols_used, 1));
   CKC(cudaMemcpyAsync(rs.data(), ctx->row_start.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaMemcpyAsync(rl.data(), ctx->row_len.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -673,17 +727,17 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
     off += rc[i];
   }
   rs[n] = off;
-  CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st));
+  CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_start.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_len.p, rl.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_cap.p, rc.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   if (off) CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), (size_t)off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->cols_used = off;
+  ctx->hsc->listed = 1; ctx->hsc->rows_asym = 1; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption
+  ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
-  ctx->listed = true;
-  ctx->rows_asym = true; ctx->rev_valid = false;      // rows supplied by the caller: make no symmetry assumption
   return 0;
 }
 
@@ -706,7 +760,12 @@ int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng
   return 0;
 }
 
-int dml_profile(dml_ctx *ctx, int32_t enable) { prof_collect(ctx); ctx->profiling = enable != 0; return 0; }
+int dml_profile(dml_ctx *ctx, int32_t enable) {
+  prof_collect(ctx);
+  ctx->profiling = enable != 0;
+  if (enable) while (ctx->pool.size() < 8192) { ProfEv ev; cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.cls = 0; ctx->pool.push_back(ev); }
+  return 0;
+}
 int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset) {
   prof_collect(ctx);
   double m = 0; int64_t l = 0;

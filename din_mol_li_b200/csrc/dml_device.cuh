@@ -17,7 +17,12 @@ constexpr long long MF_GCMC = 8;    // member of gcmc
 constexpr long long MF_SKIP = 16;   // atom%skip
 constexpr long long MF_LIMBO = 32;  // slot parked on hs%limbo until the next full build
 
+// bits 32-63: float32 upper bound of |pos - old_cg| (minimum image) since the last integrator call, +inf when unknown.
+// It only feeds the exact-safe prefilter of k_ov_detect; all flag tests mask the low bits.
+constexpr unsigned int DISP_INF = 0x7f800000u;
 __device__ __forceinline__ long long meta_of(const double4 &p) { return __double_as_longlong(p.w); }
+__device__ __forceinline__ float disp_of(long long m) { return __int_as_float((int)((unsigned long long)m >> 32)); }
+__device__ __forceinline__ long long with_disp(long long m, unsigned int bits) { return (m & 0xffffffffll) | ((long long)bits << 32); }
 __device__ __forceinline__ double meta_as_double(long long m) { return __longlong_as_double(m); }
 
 // One 256-bit load of a particle record (sm_100: ld.global.v4.f64 needs 32-byte alignment; cudaMalloc gives 256).
@@ -57,6 +62,12 @@ struct DevScal {
   int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
   int rev_used;
   int glen, ghead, gtomb, b_amax;   // gcmc membership array (list order) and hs%b%amax
+  int rows_asym, rev_valid;         // rows may be asymmetric (halo cells / gcmc appends); transposed rows are current
+  int listed;                       // hs%listed (Neighbor.F90:53)
+  int cols_cap;                     // capacity of cols[] / rev_cols[]
+  long long nupd;                   // nupd_vlist (Neighbor.F90:110)
+  long long choques2, ch_later;     // dana.F90:941 bookkeeping
+  long long overlap_passes;
   int pad_;
 };
 
@@ -141,6 +152,7 @@ __constant__ int c_map[27][3] = {   // Cells.F90:28-36, stencil order fixes the 
 // pair tables (dana.F90:87-100) and integrator constants, set per ctx before launches
 struct Phys {
   double eps[9], r0[9], r0sq[9], r0p6[9];
+  double r0sq_max;                                    // largest cut-off squared of the table (cheap first test)
   double mass[3], sqrt_mass[3];
   double h, prob, tau;
   double cc0, cc1, cc2, sdr, sdv, crv1, crv2, skt;    // set_ermak, dana.F90:947-971

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           A.epot[ns] = A.epot[tmpl];
           A.pos_old[3 * ns] = rx; A.pos_old[3 * ns + 1] = ry; A.pos_old[3 * ns + 2] = rz;
           for (int k = 0; k < 3; ++k) A.vel[3 * last + k] = beta * rng.gauss();
-          double4 pn = {rx, ry, rz, meta_as_double((long long)zt | MF_REF | MF_GCMC)};
+          double4 pn = {rx, ry, rz, meta_as_double(with_disp((long long)zt | MF_REF | MF_GCMC, DISP_INF))};
           st_rec(&A.posm[ns], pn);
           A.uid[ns] = sc->next_uid++;
           A.slot_b[ns] = nb; A.b_occ[nb] = 1;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           A.pend[npend] = ns;
           // -- ngroup_sort_atom (Neighbor.F90:271-318): own row (strict <, stencil x chain order) and append to the rows
           //    of every ref atom within the list radius (<=) --
-          if (A.listed) {
+          if (sc->listed) {
             int base = sc->cols_used, cnt = 0;
             bool ovf = false;
             for (int nab = 0; nab < 27 && okc; ++nab) {
@@ -298,9 +298,9 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
         A.row_len[s] = 0;
         A.b_occ[A.slot_b[s]] = 0;
         double4 p = ld_rec(&A.posm[s]);
-        p.w = meta_as_double(A.listed ? MF_LIMBO : 0);
+        p.w = meta_as_double(sc->listed ? MF_LIMBO : 0);
         st_rec(&A.posm[s], p);
-        if (A.listed) sc->nlimbo++;
+        if (sc->listed) sc->nlimbo++;
         sc->nat_sys--; sc->nat_ref--; sc->nat_gcmc--; sc->gcmc_destroyed++;
       }
       __syncthreads();
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
       __syncthreads();
     }
   }
-  if (tid == 0) sc->glen = glen;
+  if (tid == 0) { sc->glen = glen; if (npend > 0) { sc->rows_asym = 1; sc->rev_valid = 0; } }   // appended entries use <= (Neighbor.F90:307)
 }
 
 // k_promote variant that also drops promoted atoms from the gcmc membership array (dana.F90:235)
@@ -326,12 +326,8 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   using namespace dml;
   if (ctx->cfg.reservoir != 3) return 0;
   if (!ctx->binned || !ctx->tessellated) FAIL("gcmc_run: call test_update first");
-  if (!ctx->cells_sorted) TRY(sort_cells(ctx, false));
-  TRY(pull_scal(ctx));
   int nadj = ctx->cfg.nadj;
-  if (ctx->hsc->n_slots + nadj > ctx->cap) FAIL("slot capacity exhausted (dml_config.capacity)");
-  size_t need = (size_t)ctx->hsc->cols_used + (size_t)nadj * (1024 + ctx->row_slack) + 1024;
-  if (need > ctx->cols.cap) CKC(ctx->cols.ensure(need + need / 4, ctx->st, true));
+  if (ctx->n + nadj > ctx->cap) { TRY(finish(ctx)); if (ctx->n + nadj > ctx->cap) FAIL("slot capacity exhausted (dml_config.capacity)"); }
   CKC(ctx->gpend.ensure((size_t)nadj + 8, ctx->st));
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && ctx->rp_nu == 0 && nadj > 0) FAIL("replay mode: call dml_set_replay_gcmc before gcmc_run");
   GcmcArgs A;
@@ -342,11 +338,9 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;
-  A.nadj = nadj; A.cap = ctx->cap; A.listed = ctx->listed ? 1 : 0; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
+  A.nadj = nadj; A.cap = ctx->cap; A.listed = 1; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
   LAUNCH(K_GCMC, k_gcmc, 1, GB, A);
-  TRY(pull_scal(ctx));
-  ctx->n = ctx->hsc->n_slots;
-  ctx->rows_asym = true; ctx->rev_valid = false;       // appended entries use <= (Neighbor.F90:307), rows may be asymmetric
+  ctx->n = std::min(ctx->cap, ctx->n + nadj);          // upper bound of hs%amax until the next read-back (empty slots are skipped)
   ctx->rp_nu = ctx->rp_ng = 0;
   return 0;
 }

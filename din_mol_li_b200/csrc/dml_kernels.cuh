@@ -7,15 +7,31 @@ namespace dml {
 
 constexpr int TPB = 256;
 
+// Guard used by every kernel of the rebuild sequence: they are always launched (no host round trip) and return
+// immediately unless test_update decided to rebuild (or the caller forces the cell sort, e.g. for gcmc).
+#define REBUILD_GUARD(sc, force) if (!(((volatile const DevScal *)(sc))->need_rebuild | (force))) return
+
 // ================================================================================================
-// Generic exclusive scan of int32 (3 small kernels; 1024 items per block)
+// Exclusive scan of int32, single pass with decoupled look-back (1024 items per tile).
+// state[tile] = epoch:30 | flag:2 | value:32; tiles are handed out by a ticket so a tile only ever waits for
+// tiles whose blocks are already running.  The epoch makes re-zeroing of state[] unnecessary.
+// ZERO_IN=true clears the input after reading it (cell histogram invariant: all zero between rebuilds).
 // ================================================================================================
-__global__ void k_scan_local(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ sums, int n) {
+template <bool ZERO_IN>
+__global__ void __launch_bounds__(TPB) k_scan(int *__restrict__ in, int *__restrict__ out, int n, unsigned long long *state,
+                                              unsigned int *tickets, unsigned int epoch, int *total_out,
+                                              const DevScal *sc, int force, int guard_mode) {
+  if (guard_mode == 0) { REBUILD_GUARD(sc, force); }
+  else if (guard_mode == 1) { if (!(((volatile const DevScal *)sc)->rows_asym && !((volatile const DevScal *)sc)->rev_valid)) return; }
   __shared__ int wsum[8];
-  int base = blockIdx.x * 1024 + threadIdx.x * 4;
+  __shared__ int s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&tickets[0], 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  int base = tile * 1024 + threadIdx.x * 4;
   int v[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+  for (int i = 0; i < 4; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; if (ZERO_IN && base + i < n) in[base + i] = 0; }
   int t = v[0] + v[1] + v[2] + v[3];
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int x = t;
@@ -24,59 +40,51 @@ __global__ void k_scan_local(const int *__restrict__ in, int *__restrict__ out, 
   if (lane == 31) wsum[w] = x;
   __syncthreads();
   if (w == 0) {
-    int s = lane < 8 ? wsum[lane] : 0;
+    int q = lane < 8 ? wsum[lane] : 0;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-    if (lane < 8) wsum[lane] = s;
+    for (int o = 1; o < 8; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += y; }
+    if (lane < 8) wsum[lane] = q;
   }
   __syncthreads();
-  int excl = x - t + (w ? wsum[w - 1] : 0);
-  int run = excl;
+  const int T = wsum[7];
+  if (threadIdx.x == 0) {
+    const unsigned long long ep = (unsigned long long)(epoch & 0x3fffffffu) << 34;
+    int prefix = 0;
+    if (tile == 0) {
+      ((volatile unsigned long long *)state)[0] = ep | (2ull << 32) | (unsigned int)T;
+    } else {
+      ((volatile unsigned long long *)state)[tile] = ep | (1ull << 32) | (unsigned int)T;
+      __threadfence();
+      for (int j = tile - 1; j >= 0; --j) {
+        unsigned long long sv;
+        do { sv = ((volatile unsigned long long *)state)[j]; } while ((sv >> 34) != (ep >> 34) || ((sv >> 32) & 3ull) == 0);
+        prefix += (int)(unsigned int)sv;
+        if (((sv >> 32) & 3ull) == 2) break;
+      }
+      ((volatile unsigned long long *)state)[tile] = ep | (2ull << 32) | (unsigned int)(prefix + T);
+    }
+    __threadfence();
+    s_prefix = prefix;
+    if (tile == (int)gridDim.x - 1 && total_out) *total_out = prefix + T;
+  }
+  __syncthreads();
+  int run = x - t + (w ? wsum[w - 1] : 0) + s_prefix;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { if (base + i < n) out[base + i] = run; run += v[i]; }
-  if (threadIdx.x == TPB - 1) sums[blockIdx.x] = run;
-}
-__global__ void k_scan_sums(int *__restrict__ sums, int nb, int *__restrict__ total_out, int *__restrict__ total_out2) {
-  __shared__ int wsum[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  if (tile == (int)gridDim.x - 1 && threadIdx.x == TPB - 1 && base + 4 >= n) { /* out[n] is written through total_out by the caller's choice */ }
   __syncthreads();
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int base = 0; base < nb; base += 1024) {
-    int i = base + threadIdx.x;
-    int t = i < nb ? sums[i] : 0, x = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-    if (lane == 31) wsum[w] = x;
-    __syncthreads();
-    if (w == 0) {
-      int s = wsum[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-      wsum[lane] = s;
-    }
-    __syncthreads();
-    int excl = x - t + (w ? wsum[w - 1] : 0) + carry;
-    if (i < nb) sums[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + t;
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int d = atomicAdd(&tickets[1], 1u);
+    if (d == gridDim.x - 1) { tickets[0] = 0; tickets[1] = 0; __threadfence(); }
   }
-  if (threadIdx.x == 0) { if (total_out) *total_out = carry; if (total_out2) *total_out2 = carry; }
-}
-__global__ void k_scan_add(int *__restrict__ out, const int *__restrict__ sums, int n) {
-  int i = blockIdx.x * 1024 + threadIdx.x * 4;
-  int add = sums[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) if (i + k < n) out[i + k] += add;
 }
 
 // ================================================================================================
-// K1  do_pbc + cell binning + displacement top-2        (test_update, Neighbor.F90:668-713;
-//     do_pbc Groups.F90:1440-1467; cgroup_sort_atom index math Cells.F90:281-302; inq_dispmax 635-666)
+// K1  test_update (Neighbor.F90:668-713): do_pbc (Groups.F90:1440-1467) + the two largest squared displacements
+//     (inq_dispmax, Neighbor.F90:635-666) in one streaming pass; k_top2_final takes the rebuild decision on the device.
 // ================================================================================================
-__global__ void k_pbc_bin(double4 *__restrict__ posm, double *__restrict__ pos_old, int *__restrict__ cell_of,
-                          int *__restrict__ cell_cnt, double *__restrict__ part, DevScal *__restrict__ sc, Geo g, int n, int do_bin) {
+__global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ part,
+                                                  Geo g, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   double a1 = -1.0, a2 = -1.0;
   if (s < n) {
@@ -95,20 +103,10 @@ __global__ void k_pbc_bin(double4 *__restrict__ posm, double *__restrict__ pos_o
         p.x = q[0]; p.y = q[1]; p.z = q[2]; st_rec(&posm[s], p);
         pos_old[3 * s] = po[0]; pos_old[3 * s + 1] = po[1]; pos_old[3 * s + 2] = po[2];
       }
-      if (do_bin) {
-        int cx, cy, cz;
-        if (cell_index(g, q[0], q[1], q[2], cx, cy, cz)) {
-          int lin = cell_lin(g, cx, cy, cz);
-          cell_of[s] = lin;
-          atomicAdd(&cell_cnt[lin], 1);
-          if (cx == 0 || cy == 0 || cz == 0 || cx == g.nc[0] + 1 || cy == g.nc[1] + 1 || cz == g.nc[2] + 1) sc->halo_flag = 1;
-        } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
-      }
       double vx = q[0] - po[0], vy = q[1] - po[1], vz = q[2] - po[2];
       a1 = (vx * vx + vy * vy) + vz * vz;
-    } else if (do_bin) cell_of[s] = -1;
+    }
   }
-  // block top-2
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
@@ -128,7 +126,7 @@ __global__ void k_pbc_bin(double4 *__restrict__ posm, double *__restrict__ pos_o
     if (lane == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
   }
 }
-__global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, int listed, double nb_dcut) {
+__global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, double nb_dcut) {
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
   for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, part[2 * i], part[2 * i + 1]);
 #pragma unroll
@@ -143,21 +141,47 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
   if (threadIdx.x == 0) {
     for (int i = 1; i < (int)(blockDim.x >> 5); ++i) top2_merge(a1, a2, s1[i], s2[i]);
     sc->d1 = a1; sc->d2 = a2;
-    sc->need_rebuild = (!listed) || (sqrt(a1) + sqrt(a2) > nb_dcut);   // Neighbor.F90:697-710
+    int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > nb_dcut);     // Neighbor.F90:697-710
+    sc->need_rebuild = need;
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; }
   }
 }
 
 // ================================================================================================
-// K2  counting sort into cells.  In-cell order must be DESCENDING b-slot (head insertion of ascending
-//     slots, Cells.F90:267-302): scatter with an atomic cursor, then order every cell segment.
-//     k_scatter also performs update()'s pos_old=pos (Neighbor.F90:620-624) and igroup_clean
-//     (Groups.F90:1036-1053) because both happen exactly when the list is rebuilt.
+// K2  cell binning + counting sort (cgroup_sort, Cells.F90:267-302).  In-cell order must be DESCENDING b-slot
+//     (head insertion of ascending slots): scatter with an atomic cursor, then order every cell segment.
+//     k_scatter also performs update()'s pos_old=pos (Neighbor.F90:620-624) and igroup_clean (Groups.F90:1036-1053)
+//     because both happen exactly when the list is rebuilt.  Invariant: cell_cnt and cell_cur are all zero
+//     between rebuilds (the scan clears cell_cnt, k_cell_order clears cell_cur).
 // ================================================================================================
-__global__ void k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
-                          const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
-                          int n, int snapshot) {
+__global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                             int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, Geo g,
+                                             int n, int force) {
+  REBUILD_GUARD(sc, force);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  double4 p = ld_rec_nc(&posm[s]);
+  const bool rebuild = ((volatile const DevScal *)sc)->need_rebuild != 0;
+  if (meta_of(p) & MF_TYPE) {
+    int cx, cy, cz;
+    if (cell_index(g, p.x, p.y, p.z, cx, cy, cz)) {
+      int lin = cell_lin(g, cx, cy, cz);
+      cell_of[s] = lin;
+      atomicAdd(&cell_cnt[lin], 1);
+      if (rebuild && (cx == 0 || cy == 0 || cz == 0 || cx == g.nc[0] + 1 || cy == g.nc[1] + 1 || cz == g.nc[2] + 1)) sc->halo_flag = 1;
+    } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
+  } else {
+    cell_of[s] = -1;
+    if (rebuild) { row_len[s] = 0; row_cap[s] = 0; }
+  }
+}
+__global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
+                                                 const int *__restrict__ cell_start, int *__restrict__ cell_cur,
+                                                 int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force) {
+  REBUILD_GUARD(sc, force);
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const bool snapshot = ((volatile const DevScal *)sc)->need_rebuild != 0;
   double4 p = ld_rec(&posm[s]);
   long long m = meta_of(p);
   if (m & MF_TYPE) {
@@ -168,9 +192,13 @@ __global__ void k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_o
 }
 // one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
 __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
-                             int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm, int ncell) {
+                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
+                             DevScal *__restrict__ sc, int ncell, int force) {
+  REBUILD_GUARD(sc, force);
   int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag;
   if (c >= ncell) return;
+  cell_cur[c] = 0;
   int b = cell_start[c], e = cell_start[c + 1];
   for (int i = b + 1; i < e; ++i) {
     int s = sorted_slot[i], key = slot_b[s], j = i - 1;
@@ -182,44 +210,60 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 
 // ================================================================================================
 // K3  Verlet rows over linked cells      (ngroup_cells, Neighbor.F90:465-548; cell_pbc Cells.F90:378-404;
-//     vdistance Groups.F90:995-1016).  One thread per cell-sorted particle; rows are written in the
-//     reference's order (stencil order x chain order) because one thread walks them sequentially.
-//     FILL=false counts, FILL=true writes cols[row_start[slot] ...].
+//     vdistance Groups.F90:995-1016).  One warp per cell-sorted ref particle, one lane per stencil cell: lane l walks
+//     the chain of cell map(:,l) and an exclusive prefix over the lanes (= stencil order) places its hits, so rows
+//     come out in the reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
 // ================================================================================================
 template <bool FILL>
-__global__ void k_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot, const int *__restrict__ cell_of,
-                       const int *__restrict__ cell_start, int *__restrict__ row_len, const int *__restrict__ row_start,
-                       int *__restrict__ cols, Geo g, int ncell) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= cell_start[ncell]) return;                 // number of binned particles
-  double4 p = ld_rec_nc(&sorted_posm[t]);
-  if (!(meta_of(p) & MF_REF)) return;                 // rows exist only for ref atoms
-  int s = sorted_slot[t];
-  int lin = cell_of[s];
-  if (lin < 0) return;
-  int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-  int cnt = 0;
-  int base = FILL ? row_start[s] : 0;
-#pragma unroll 1
-  for (int nab = 0; nab < 27; ++nab) {
-    int nx = (c_map[nab][0] + cx - 1 + g.nc[0]) % g.nc[0] + 1;       // wraps every axis, z included
-    int ny = (c_map[nab][1] + cy - 1 + g.nc[1]) % g.nc[1] + 1;
-    int nz = (c_map[nab][2] + cz - 1 + g.nc[2]) % g.nc[2] + 1;
-    int nl = cell_lin(g, nx, ny, nz);
-    int b = cell_start[nl], e = cell_start[nl + 1];
+__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
+                                              const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                                              int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
+                                              int *__restrict__ cols, DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
+  REBUILD_GUARD(sc, 0);
+  const int lane = threadIdx.x & 31;
+  const int nsorted = cell_start[ncell];              // number of binned particles
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  if (FILL && sc->cols_used > sc->cols_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); return; }
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nsorted; t += nwarps) {
+    double4 p = ld_rec_nc(&sorted_posm[t]);
+    const int s = sorted_slot[t];
+    if (!(meta_of(p) & MF_REF)) {                     // rows exist only for ref atoms
+      if (!FILL && lane == 0) { row_len[s] = 0; row_cap[s] = 0; }
+      continue;
+    }
+    int lin = cell_of[s];
+    if (lin < 0) continue;
+    int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
+    int b = 0, e = 0;
+    if (lane < 27) {
+      int nx = (c_map[lane][0] + cx - 1 + g.nc[0]) % g.nc[0] + 1;       // wraps every axis, z included
+      int ny = (c_map[lane][1] + cy - 1 + g.nc[1]) % g.nc[1] + 1;
+      int nz = (c_map[lane][2] + cz - 1 + g.nc[2]) % g.nc[2] + 1;
+      int nl = cell_lin(g, nx, ny, nz);
+      b = cell_start[nl]; e = cell_start[nl + 1];
+    }
+    int cnt = 0;
     for (int u = b; u < e; ++u) {
       if (u == t) continue;
       double4 q = ld_rec_nc(&sorted_posm[u]);
       double rd = dist2_idnint(g, q.x, q.y, q.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
-      if (rd < g.rc_list2) { if (FILL) cols[base + cnt] = sorted_slot[u]; ++cnt; }
+      if (rd < g.rc_list2) ++cnt;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (!FILL) {
+      if (lane == 31) { row_len[s] = incl; row_cap[s] = incl + slack; }
+    } else {
+      int w = row_start[s] + incl - cnt;
+      for (int u = b; u < e; ++u) {
+        if (u == t) continue;
+        double4 q = ld_rec_nc(&sorted_posm[u]);
+        double rd = dist2_idnint(g, q.x, q.y, q.z, p.x, p.y, p.z);
+        if (rd < g.rc_list2) cols[w++] = sorted_slot[u];
+      }
     }
   }
-  if (!FILL) row_len[s] = cnt;
-}
-// row capacity = length + slack (room for incremental gcmc appends, Neighbor.F90:309-312)
-__global__ void k_row_caps(const int *__restrict__ row_len, int *__restrict__ row_cap, int n, int slack) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n) row_cap[s] = row_len[s] + slack;
 }
 __global__ void k_sum_int(const int *__restrict__ v, int n, long long *__restrict__ out) {
   long long a = 0;
@@ -264,27 +308,36 @@ __device__ __forceinline__ bool pair_terms(const Geo &g, const Phys &ph, const d
 
 // Transposed rows: rev(i) = { j : i in row(j) }.  Needed when rows can be asymmetric (a particle in a halo cell is
 // never found as a candidate, Cells.F90:248 + cell_pbc wrap; incremental gcmc appends use <= instead of <).
+#define REV_GUARD(sc) if (!(((volatile const DevScal *)(sc))->rows_asym && !((volatile const DevScal *)(sc))->rev_valid)) return
 __global__ void k_rev_count(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
-                            int *__restrict__ rev_len, int n) {
+                            const double4 *__restrict__ posm, int *__restrict__ rev_len, int *__restrict__ rev_cnt,
+                            const DevScal *__restrict__ sc, int n) {
+  REV_GUARD(sc);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
+  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
   int b = row_start[s], len = row_len[s];
-  for (int jj = 0; jj < len; ++jj) atomicAdd(&rev_len[cols[b + jj]], 1);
+  for (int jj = 0; jj < len; ++jj) atomicAdd(&rev_cnt[cols[b + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
 }
 __global__ void k_rev_fill(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
-                           const int *__restrict__ rev_start, int *__restrict__ rev_cur, int *__restrict__ rev_cols, int n) {
+                           const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
+                           int *__restrict__ rev_cols, const DevScal *__restrict__ sc, int n) {
+  REV_GUARD(sc);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
   int b = row_start[s], len = row_len[s];
-  for (int jj = 0; jj < len; ++jj) { int j = cols[b + jj]; rev_cols[rev_start[j] + atomicAdd(&rev_cur[j], 1)] = s; }
+  // the scan cleared rev_len; it is rebuilt here as the fill cursor and ends as the row length
+  for (int jj = 0; jj < len; ++jj) { int j = cols[b + jj]; rev_cols[rev_start[j] + atomicAdd(&rev_len[j], 1)] = s; }
 }
-
+__global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
 template <bool STRICT>
 __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm, const int *__restrict__ row_start,
                                                 const int *__restrict__ row_len, const int *__restrict__ cols,
                                                 const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-                                                const int *__restrict__ rev_cols, int asym,
+                                                const int *__restrict__ rev_cols, const DevScal *__restrict__ sc,
                                                 const int *__restrict__ uid, double *__restrict__ force, double *__restrict__ epot,
                                                 Geo g, Phys ph, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -293,6 +346,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
   long long m1 = meta_of(p1);
   if (!(m1 & MF_REF)) return;
   int k = (int)(m1 & MF_TYPE);
+  const int asym = sc->rows_asym;
   int b = row_start[s], len = row_len[s];
   const int *rv = asym ? rev_cols + rev_start[s] : cols + b;
   int rvlen = asym ? rev_len[s] : len;
@@ -390,6 +444,78 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
     }
   }
   force[3 * s] = fx; force[3 * s + 1] = fy; force[3 * s + 2] = fz; epot[s] = ep;
+}
+
+// Production variant of the pair force: LANES lanes per ref particle share its row (n̄n ≈ 6 in solution), so the
+// index loads and record gathers of one particle are in flight together; partial sums are combined with shuffles
+// (no atomics).  Same terms as k_fuerza<false>; only the summation order differs (1e-12 budget of the north star).
+// the rarely taken heavy part (pair inside the cut-off) lives out of line so the gather loop stays lean in registers
+__device__ __noinline__ double4 lj_terms(double vx, double vy, double vz, double dr2, double eps, double r0p6) {
+  double dr = sqrt(dr2);
+  double b = r0p6;
+  double c = eps * 12.0 * b;
+  c = c / pow7(dr);
+  b = b / pow6(dr);
+  double aux = c * (b - 1.0);
+  double4 r;
+  r.x = aux * vx / dr; r.y = aux * vy / dr; r.z = aux * vz / dr;
+  aux = eps * b * (b - 2.0);
+  aux = aux + eps;
+  r.w = aux * .5;
+  return r;
+}
+template <int LANES>
+__global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
+    const double4 *__restrict__ posm, const int *__restrict__ row_start, const int *__restrict__ row_len,
+    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
+    const int *__restrict__ rev_cols, const DevScal *__restrict__ sc, double *__restrict__ force, double *__restrict__ epot,
+    Geo g, Phys ph, int n) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = gt / LANES, sub = gt % LANES;
+  bool act = s < n;
+  double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+  const long long m1 = meta_of(p1);
+  act = act && (m1 & MF_REF);
+  double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
+  bool hit = false;
+  if (act) {
+    const int asym = __ldg(&sc->rows_asym);
+    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+    const int npass = asym ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+      const int *lst = pass == 0 ? cols + row_start[s] : rev_cols + rev_start[s];
+      const int len = pass == 0 ? row_len[s] : rev_len[s];
+#pragma unroll 2
+      for (int jj = sub; jj < len; jj += LANES) {
+        const int j = __ldg(&lst[jj]);
+        const double4 p2 = ld_rec_nc(&posm[j]);
+        double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
+        if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
+        if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
+        const double dr2 = (vx * vx + vy * vy) + vz * vz;
+        if (dr2 > ph.r0sq_max) continue;
+        const long long m2 = meta_of(p2);
+        const int m = (int)(m2 & MF_TYPE);
+        if (m == 0) continue;                                        // limbo / removed
+        if (pass == 1 && !(m2 & MF_REF)) continue;                   // reverse visits come from row owners only
+        const int km = k3 + m - 1;
+        if (dr2 > ph.r0sq[km]) continue;
+        const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
+        const double w = (!asym && (m2 & MF_REF)) ? 2.0 : 1.0;       // exact doubling, then one rounding per add
+        fx += w * t.x; fy += w * t.y; fz += w * t.z; ep += w * t.w; hit = true;
+      }
+    }
+  }
+  if (LANES > 1) {
+    if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o); ep += __shfl_xor_sync(0xffffffffu, ep, o);
+      }
+    }
+  }
+  if (act && sub == 0) { force[3 * s] = fx; force[3 * s + 1] = fy; force[3 * s + 2] = fz; epot[s] = ep; }
 }
 
 // ================================================================================================
@@ -490,6 +616,12 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
         if (!ERMAK) acc.mv = fmax(acc.mv, (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
         m &= ~MF_SKIP;
       }
+      {
+        double dx = q[0] - og[0], dy = q[1] - og[1], dz = q[2] - og[2];
+        dx = dx - g.box[0] * round(dx * g.one_box[0]); dy = dy - g.box[1] * round(dy * g.one_box[1]);
+        float df = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * 1.000001f;
+        m = with_disp(m, (unsigned int)__float_as_int(df));
+      }
       p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
       st_rec(&posm[s], p);
       vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2];
@@ -528,8 +660,9 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
 constexpr int OV_MOVED = 1, OV_SKIP = 2, OV_TSHIFT = 2, OV_INVOLVED = 16, OV_ZERO = 32;
 
 __global__ void k_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
-                          int *__restrict__ comp_cnt, int n) {
+                          int *__restrict__ comp_cnt, DevScal *__restrict__ sc, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
   if (s >= n) return;
   long long m = meta_of(ld_rec_nc(&posm[s]));
   parent[s] = s; comp_cnt[s] = 0;
@@ -563,6 +696,8 @@ __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ p
   long long m1 = meta_of(p1);
   if (!(m1 & MF_REF)) return;
   double o1[3] = {old_cg[3 * s], old_cg[3 * s + 1], old_cg[3 * s + 2]};
+  const float d1 = disp_of(m1);
+  const double rcut = sqrt(g.rcut2);
   int b = row_start[s], len = row_len[s];
   bool inv = false;
   for (int jj = 0; jj < len; ++jj) {
@@ -570,8 +705,14 @@ __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ p
     double4 p2 = ld_rec_nc(&posm[j]);
     long long m2 = meta_of(p2);
     if (!(m2 & MF_TYPE)) continue;
-    bool hit = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z) <= g.rcut2 ||
-               dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
+    // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
+    // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
+    double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
+    {
+      double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
+      if (rd_nn > thr * thr) continue;
+    }
+    bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
     if (m2 & MF_REF) {
       double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
       hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
@@ -624,17 +765,15 @@ __device__ __forceinline__ void ov_pos(const double4 *posm, const double *old_cg
   if (st & OV_MOVED) { q[0] = old_cg[3 * a]; q[1] = old_cg[3 * a + 1]; q[2] = old_cg[3 * a + 2]; }
   else { double4 p = ld_rec_nc(&posm[a]); q[0] = p.x; q[1] = p.y; q[2] = p.z; }
 }
-// one reference pass (one recursion level) for every component
-__global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                          const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
-                          const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
-                          const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
-                          DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= sc->n_roots) return;
-  int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
-  long long tr = 0, de = 0, ch = 0, ch3 = 0; bool again = false;
-  double z0 = sc->z0;
+// one reference pass (one recursion level) over the members [b,e) of one component; returns "again"
+struct OvAcc { long long tr, de, ch, ch3; };
+__device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
+                                            const int *__restrict__ row_start, const int *__restrict__ row_len,
+                                            const int *__restrict__ cols, int *__restrict__ ovst, const int *__restrict__ members,
+                                            const int *__restrict__ uid, const double *__restrict__ rp_uovl, DevScal *__restrict__ sc,
+                                            const Geo &g, const Phys &ph, unsigned int step, int pass, int guard, double z0,
+                                            int b, int e, OvAcc &acc) {
+  bool again = false;
   for (int i = b; i < e; ++i) {
     int a1 = members[i];
     int st1 = ((volatile int *)ovst)[a1];
@@ -652,12 +791,12 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
       double dr = dist2_idnint(g, q1[0], q1[1], q1[2], q2[0], q2[1], q2[2]);
       if (dr > g.rcut2) continue;
       if (t2 == 2) {                                           // contact with metal: deposition attempt
-        tr++;
+        acc.tr++;
         double ne;
         if (ph.rng_mode == 1) ne = rp_uovl ? rp_uovl[a1] : 0.0;
         else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
         if (ne < ph.prob) {
-          de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
+          acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
           if (q1[2] > z0) atomicCAS(&sc->err, 0, DML_E_SUPERO_Z0);
         } else {
           st1 |= OV_MOVED; st1 &= ~OV_SKIP;
@@ -669,26 +808,78 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
         double og2[3] = {old_cg[3 * a2], old_cg[3 * a2 + 1], old_cg[3 * a2 + 2]};
         if (q2[0] == og2[0] && q2[1] == og2[1] && q2[2] == og2[2]) {
           double og1[3] = {old_cg[3 * a1], old_cg[3 * a1 + 1], old_cg[3 * a1 + 2]};
-          if (q1[0] == og1[0] && q1[1] == og1[1] && q1[2] == og1[2]) { ch3++; continue; }
+          if (q1[0] == og1[0] && q1[1] == og1[1] && q1[2] == og1[2]) { acc.ch3++; continue; }
         }
       }
       // o2 goes back to its previous position; velocities are zeroed when the state is applied
       st2 = (st2 | OV_MOVED | OV_ZERO) & ~OV_SKIP;
       ovst[a2] = st2;
-      ch++; again = true;
+      acc.ch++; again = true;
     }
     ovst[a1] = st1;
   }
-  if (tr) atomicAdd((unsigned long long *)&sc->try_, (unsigned long long)tr);
-  if (de) atomicAdd((unsigned long long *)&sc->depo, (unsigned long long)de);
-  if (ch) atomicAdd((unsigned long long *)&sc->choques, (unsigned long long)ch);
-  if (ch3) atomicAdd((unsigned long long *)&sc->choques3, (unsigned long long)ch3);
+  return again;
+}
+__device__ __forceinline__ void ov_flush(const OvAcc &acc, DevScal *sc) {
+  if (acc.tr) atomicAdd((unsigned long long *)&sc->try_, (unsigned long long)acc.tr);
+  if (acc.de) atomicAdd((unsigned long long *)&sc->depo, (unsigned long long)acc.de);
+  if (acc.ch) atomicAdd((unsigned long long *)&sc->choques, (unsigned long long)acc.ch);
+  if (acc.ch3) atomicAdd((unsigned long long *)&sc->choques3, (unsigned long long)acc.ch3);
+}
+// Global-synchronous variant: one launch = one recursion level for every component (needed when prob<1, where a
+// failed deposition leaves skip=.false. without requesting another pass, so the pass count couples components).
+__global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
+                          const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                          const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
+                          const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                          DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= sc->n_roots) return;
+  int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
+  OvAcc acc = {0, 0, 0, 0};
+  bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass, guard, sc->z0, b, e, acc);
+  ov_flush(acc, sc);
+  if (pass >= 1 && acc.ch) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)acc.ch);
   if (again) sc->again = 1;
+}
+// Fused variant (prob>=1: every metal contact deposits, nothing couples components): each component thread orders its
+// members and replays all recursion levels locally.  No host round trip, one launch.
+__global__ void k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
+                             const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                             const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
+                             int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= sc->n_roots) return;
+  int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
+  for (int i = b + 1; i < e; ++i) {                            // order by creation rank (= order of hs%ref%alist)
+    int s = members[i], key = uid[s], j = i - 1;
+    while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
+    members[j + 1] = s;
+  }
+  OvAcc acc = {0, 0, 0, 0};
+  long long later = 0;
+  double z0 = sc->z0;
+  int pass = 0;
+  for (;; ++pass) {
+    long long ch0 = acc.ch;
+    bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
+                             (guard_pass > 0 && pass >= guard_pass) ? 1 : 0, z0, b, e, acc);
+    if (pass >= 1) later += acc.ch - ch0;
+    if (!again) break;
+  }
+  ov_flush(acc, sc);
+  if (later) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)later);
+  atomicMax(&sc->any_active, pass + 1);                        // deepest recursion level of this call
 }
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
 __global__ void k_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
-                           const double *__restrict__ old_cg, const int *__restrict__ ovst, int n) {
+                           const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) {                                                // choques2=max(choques2,choques-i), dana.F90:939-941
+    if (sc->ch_later > sc->choques2) sc->choques2 = sc->ch_later;
+    sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
+  }
   if (s >= n) return;
   double4 p = ld_rec(&posm[s]);
   long long m = meta_of(p);
@@ -723,6 +914,39 @@ __global__ void k_promote(double4 *__restrict__ posm, DevScal *__restrict__ sc, 
   }
   dref = __reduce_add_sync(0xffffffffu, dref); dg = __reduce_add_sync(0xffffffffu, dg);
   if ((threadIdx.x & 31) == 0) { if (dref) atomicSub(&sc->nat_ref, dref); if (dg) atomicSub(&sc->nat_gcmc, dg); }
+}
+// promotion + msd bookkeeping + calc_rho in one pass (reservoirs 1 and 2, where nothing runs between them)
+__global__ void __launch_bounds__(TPB) k_promote_rho(double4 *__restrict__ posm, DevScal *__restrict__ sc, double area, int use_z1, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double z0 = sc->z0, zl = use_z1 ? sc->z1 : sc->zmax;
+  int c = 0, dref = 0;
+  if (s < n) {
+    double4 p = ld_rec(&posm[s]);
+    long long m = meta_of(p);
+    if ((m & MF_REF) && (m & MF_TYPE) == 3) {
+      dref = 1;
+      m = (m & ~(MF_TYPE | MF_REF | MF_GCMC)) | 2;
+      p.w = meta_as_double(m); st_rec(&posm[s], p);
+    }
+    if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c = 1;
+  }
+  c = __reduce_add_sync(0xffffffffu, c); dref = __reduce_add_sync(0xffffffffu, dref);
+  __shared__ int last;
+  if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(&sc->rho_count, c); if (dref) atomicAdd(&sc->n_involved, dref); }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    int gct = *((volatile int *)&sc->rho_count), dr = *((volatile int *)&sc->n_involved);
+    sc->msd_t = sc->msd_t / sc->nat_ref;                 // dana.F90:201-202 (before the promotion loop)
+    sc->msd_max = fmax(sc->msd_max, sc->msd_t);
+    sc->nat_ref -= dr;
+    double vol = area * (zl - z0);
+    sc->rho = gct / vol;
+    sc->rho_count = 0; sc->n_involved = 0; sc->ticket = 0;
+  }
 }
 __global__ void k_calc_rho(const double4 *__restrict__ posm, DevScal *__restrict__ sc, double area, int use_z1, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -765,7 +989,7 @@ __global__ void k_pack(double4 *__restrict__ posm, const double *__restrict__ po
   long long m = 0;
   int zz = z[s], f = flags[s];
   if (f & 8) m = MF_LIMBO;
-  else if (zz >= 1 && zz <= 3) m = zz | ((f & 1) ? MF_REF : 0) | ((f & 2) ? MF_GCMC : 0) | ((f & 4) ? MF_SKIP : 0);
+  else if (zz >= 1 && zz <= 3) m = with_disp(zz | ((f & 1) ? MF_REF : 0) | ((f & 2) ? MF_GCMC : 0) | ((f & 4) ? MF_SKIP : 0), DISP_INF);
   double4 p = {pos[3 * s], pos[3 * s + 1], pos[3 * s + 2], meta_as_double(m)};
   st_rec(&posm[s], p);
 }

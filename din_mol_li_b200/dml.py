@@ -34,6 +34,7 @@ class Counters(C.Structure):
         ("max_vel", C.c_double), ("msd_t", C.c_double), ("msd_max", C.c_double),
         ("n_slots", C.c_int32), ("nat_sys", C.c_int32), ("nat_ref", C.c_int32), ("nat_gcmc", C.c_int32),
         ("ncells", C.c_int32 * 3), ("cell", C.c_double * 3), ("tessellated", C.c_int32), ("listed", C.c_int32),
+        ("rows_asym", C.c_int32),
     ]
 
 

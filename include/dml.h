@@ -66,6 +66,7 @@ typedef struct dml_counters {
   int32_t n_slots;       /* hs%amax */
   int32_t nat_sys, nat_ref, nat_gcmc;
   int32_t ncells[3]; double cell[3]; int32_t tessellated, listed;
+  int32_t rows_asym;     /* rows may be asymmetric (halo cells, gcmc appends): the pair force uses the transposed rows */
 } dml_counters;
 
 typedef struct dml_scalars { double box[3]; double z0, z1, zmax, rho, rho0, t; int64_t step; } dml_scalars;
