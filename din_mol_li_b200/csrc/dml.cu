@@ -2,6 +2,7 @@
 // the kernels in dml_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/dml.h"
 #include "dml_kernels.cuh"
+#include "dml_coop.cuh"
 namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos, DevScal *__restrict__ sc, int n); }
 #include <cmath>
 #include <cstdio>
@@ -50,14 +51,17 @@ struct dml_ctx {
   bool profiling = false; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
   double prof_ms[32] = {0}; int64_t prof_n[32] = {0};
   // particle state
-  DBuf<double4> posm, sorted_posm;
-  DBuf<double> vel, acel, force, epot, pos_old, old_cg, ranv;
+  DBuf<double4> posm, sorted_posm, fe;                 // fe = {force(3), epot}
+  DBuf<double> vel, acel, pos_old, old_cg, ranv;
   DBuf<int> uid, slot_b;
   // cells
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, chain_pos;
   // rows
   DBuf<int> row_start, row_len, row_cap, cols;
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
+  bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
+  int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates
+  bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_lanes = 2;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
@@ -70,7 +74,7 @@ struct dml_ctx {
   // replay
   DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
   // staging
-  DBuf<double> stage_d; DBuf<int> stage_i;
+  DBuf<double> stage_d, stage_f; DBuf<int> stage_i;
   DevScal *sc = nullptr; DevScal *hsc = nullptr;    // device / pinned host mirror
   // chunk template (reservoir 2)
   std::vector<double> ch_pos, ch_pos_old; double ch_dist = 0, ch_rhomedia = 0; bool have_chunk = false;
@@ -90,13 +94,13 @@ enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4,
 // one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
 enum { K_SCAN = 0, K_PBC_BIN, K_TOP2, K_SCATTER, K_CELL_ORDER, K_ROWS_COUNT, K_ROWS_FILL, K_ROW_CAPS, K_FUERZA, K_INTEGRATE,
        K_ERMAK_B, K_OV_INIT, K_OV_DETECT, K_OV_COUNT, K_OV_ALLOC, K_OV_FILL, K_OV_SORT, K_OV_PASS, K_OV_APPLY, K_PROMOTE,
-       K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_BIN, K_NKERN };
+       K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_BIN, K_TU_COOP, K_OV_COOP, K_NKERN };
 static const char *const kern_name[K_NKERN] = {"scan", "pbc_disp", "top2_final", "scatter", "cell_order", "rows_count", "rows_fill",
   "row_caps", "fuerza", "integrate", "ermak_b", "ov_init", "ov_detect", "ov_count", "ov_alloc", "ov_fill", "ov_sort", "ov_pass",
-  "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows", "bin"};
+  "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows", "bin", "test_update_coop", "overlap_coop"};
 static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_FORCE, CLS_INTEG,
   CLS_INTEG, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OTHER,
-  CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST, CLS_LIST};
+  CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST, CLS_LIST, CLS_LIST, CLS_OVERLAP};
 
 static void prof_begin(dml_ctx *ctx, int cls) {
   ctx->launches++;
@@ -120,6 +124,10 @@ static void prof_collect(dml_ctx *ctx) {
   ctx->evs.clear();
 }
 #define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx); } while (0)
+
+#define LAUNCH_COOP(kid, kern, grid, argstruct) do { prof_begin(ctx, kid); void *a_[] = {(void *)&(argstruct)}; \
+  cudaError_t e_ = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TPB), a_, 0, ctx->st); prof_end(ctx); \
+  if (e_ != cudaSuccess) { ctx->err = std::string("cooperative launch of " #kern ": ") + cudaGetErrorString(e_); return -1; } } while (0)
 
 static inline int nblk(int n, int b = TPB) { return std::max(1, (n + b - 1) / b); }
 
@@ -202,6 +210,18 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
   return 0;
 }
 
+// ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending
+static int enq_materialize_rows(dml_ctx *ctx) {
+  int n = ctx->n, nct = ctx->nct;
+  int nw = std::min(nblk(n * 32), 148 * 32);          // grid-stride over warps: an idle (guarded) launch stays cheap
+  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 3, 0));
+  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  return 0;
+}
+
 // test_update (Neighbor.F90:668-713) enqueued without any host round trip: the rebuild decision is taken by
 // k_top2_final on the device and the rebuild kernels (update + ngroup_cells, Neighbor.F90:608-633,465-548) are
 // always launched but return immediately when no rebuild is due.
@@ -214,18 +234,24 @@ static int enq_test_update(dml_ctx *ctx) {
     CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, ctx->cell_cnt.cap * sizeof(int), ctx->st));
     CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
   }
+  int force = ctx->cfg.reservoir == 3 ? 1 : 0;       // gcmc_run needs the cells of the current positions every step
+  if (ctx->use_coop && n <= ctx->coop_max_n) {
+    TUArgs A;
+    A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
+    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
+    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p;
+    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
+    A.nb_dcut = ctx->cfg.nb_dcut;
+    LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
+    ctx->binned = true;
+    return 0;
+  }
   int nb = nblk(n);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
   LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->geo, n);
   LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->cfg.nb_dcut);
-  int force = ctx->cfg.reservoir == 3 ? 1 : 0;       // gcmc_run needs the cells of the current positions every step
   TRY(enq_sort_cells(ctx, force));
-  int nw = std::min(nblk(n * 32), 148 * 32);          // grid-stride over warps: an idle (guarded) launch stays cheap
-  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
-  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 0, 0));
-  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   ctx->binned = true;
   return 0;
 }
@@ -246,6 +272,7 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
 
 static int enq_fuerza(dml_ctx *ctx) {
   int n = ctx->n;
+  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   // transposed rows, built on the device only when rows can be asymmetric (guarded launches)
   LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p, ctx->sc, n);
   TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
@@ -254,11 +281,11 @@ static int enq_fuerza(dml_ctx *ctx) {
   LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
-           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n);
+           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
   else
   {
 #define FSUB(L) LAUNCH(K_FUERZA, (k_fuerza_sub<L>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->force.p, ctx->epot.p, ctx->geo, ctx->ph, n)
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
     switch (ctx->force_lanes) { case 1: FSUB(1); break; case 2: FSUB(2); break; case 4: FSUB(4); break; default: FSUB(8); break; }
 #undef FSUB
   }
@@ -268,6 +295,18 @@ static int enq_fuerza(dml_ctx *ctx) {
 // overlap_moveback (dana.F90:849-943)
 static int enq_overlap(dml_ctx *ctx) {
   int n = ctx->n;
+  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
+    OVArgs A;
+    A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.row_start = ctx->row_start.p;
+    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.uid = ctx->uid.p;
+    A.rp_uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
+    A.n = n; A.guard_pass = ctx->ov_guard_pass; A.stop_after_fill = 0;
+    LAUNCH_COOP(K_OV_COOP, k_overlap_coop, ctx->coop_grid_ov, A);
+    ctx->have_rp_ovl = false;
+    return 0;
+  }
   LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
          ctx->ovst.p, ctx->sc, ctx->geo, n);
@@ -361,8 +400,7 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   TRY(upload_d(ctx, ctx->pos_old.p + (size_t)3 * n0, cpos_old, (size_t)nchunk * 3));
   TRY(upload_d(ctx, ctx->vel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
   TRY(upload_d(ctx, ctx->acel.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
-  TRY(upload_d(ctx, ctx->force.p + (size_t)3 * n0, zero3.data(), (size_t)nchunk * 3));
-  TRY(upload_d(ctx, ctx->epot.p + n0, zero3.data(), (size_t)nchunk));
+  CKC(cudaMemsetAsync(ctx->fe.p + n0, 0, (size_t)nchunk * sizeof(double4), ctx->st));
   TRY(upload_d(ctx, ctx->old_cg.p + (size_t)3 * n0, og.data(), (size_t)nchunk * 3));
   CKC(cudaMemcpyAsync(ctx->uid.p + n0, uid.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->slot_b.p + n0, sb.data(), nchunk * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
@@ -379,7 +417,7 @@ static int enq_step(dml_ctx *ctx) {
   int n = ctx->n;
   if (ctx->cfg.integrador) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx));
-    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, n);
+    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
   } else TRY(enq_integrate(ctx, false));
   TRY(enq_test_update(ctx));
   TRY(enq_overlap(ctx));
@@ -453,11 +491,13 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
+  ctx->lazy_rows = !cfg->integrador && cfg->reservoir != 3 && !getenv("DML_EAGER_ROWS");
+  if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = atoi(e);
   if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st));
-  CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->force.ensure(c3, ctx->st));
-  CKC(ctx->epot.ensure(cap, ctx->st)); CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
+  CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
+  CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
   CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
   CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
   CKC(ctx->row_start.ensure(cap + 1, ctx->st)); CKC(ctx->row_len.ensure(cap, ctx->st)); CKC(ctx->row_cap.ensure(cap, ctx->st));
@@ -473,8 +513,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->rp_gauss.ensure((size_t)cap * 6, ctx->st)); CKC(ctx->rp_upbc.ensure(cap, ctx->st)); CKC(ctx->rp_uovl.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)cap * sizeof(double4), ctx->st));
   CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)cap * sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(ctx->force.p, 0, c3 * sizeof(double), ctx->st));
-  CKC(cudaMemsetAsync(ctx->epot.p, 0, (size_t)cap * sizeof(double), ctx->st));
+  CKC(cudaMemsetAsync(ctx->fe.p, 0, (size_t)cap * sizeof(double4), ctx->st));
   {
     // Keep the 32-byte particle records resident in the 126 MB L2 across the kernels of a step: every gather of the
     // pair-force / overlap / list kernels then hits L2 and HBM only sees the streaming arrays.
@@ -492,6 +531,19 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
       cudaGetLastError();
     }
   }
+  {
+    int dev = 0, nsm = 0, coop = 0, b1 = 0, b2 = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_overlap_coop, TPB, 0);
+    ctx->coop_grid_tu = nsm * b1; ctx->coop_grid_ov = nsm * b2;
+    ctx->use_coop = coop && b1 > 0 && b2 > 0 && !getenv("DML_NO_COOP");
+    int gmax = std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_ov), 1);
+    CKC(ctx->coop_sums.ensure((size_t)gmax + 8, ctx->st));
+    CKC(ctx->part.ensure((size_t)2 * std::max(gmax, nblk(cap)) + 8, ctx->st));
+  }
   CKC(cudaMalloc(&ctx->sc, sizeof(DevScal)));
   CKC(cudaMallocHost(&ctx->hsc, sizeof(DevScal)));
   memset(ctx->hsc, 0, sizeof(DevScal));
@@ -507,16 +559,16 @@ void dml_destroy(dml_ctx *ctx) {
   cudaStreamSynchronize(ctx->st);
   prof_collect(ctx);
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
-  ctx->posm.release(); ctx->sorted_posm.release(); ctx->vel.release(); ctx->acel.release(); ctx->force.release(); ctx->epot.release();
+  ctx->posm.release(); ctx->sorted_posm.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
-  ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
+  ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
-  ctx->stage_d.release(); ctx->stage_i.release();
+  ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
   if (ctx->hsc) cudaFreeHost(ctx->hsc);
   if (ctx->st) cudaStreamDestroy(ctx->st);
@@ -566,7 +618,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   CKC(cudaMemcpyAsync(ctx->b_occ.p, bocc.data(), (size_t)ctx->cap * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->glen = (int)gord.size(); ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = b_amax;
-  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
   TRY(push_scal(ctx));
   LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
   CKC(cudaStreamSynchronize(ctx->st));
@@ -584,8 +636,12 @@ int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel
   if (flags) CKC(cudaMemcpyAsync(flags, ctx->stage_i.p + n, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
   if (vel) CKC(cudaMemcpyAsync(vel, ctx->vel.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   if (acel) CKC(cudaMemcpyAsync(acel, ctx->acel.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-  if (force) CKC(cudaMemcpyAsync(force, ctx->force.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-  if (epot) CKC(cudaMemcpyAsync(epot, ctx->epot.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (force || epot) {
+    CKC(ctx->stage_f.ensure(n3 + (size_t)n, ctx->st));
+    LAUNCH(K_PACK, k_unpack_fe, nblk(n), TPB, ctx->fe.p, ctx->stage_f.p, ctx->stage_f.p + n3, n);
+    if (force) CKC(cudaMemcpyAsync(force, ctx->stage_f.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (epot) CKC(cudaMemcpyAsync(epot, ctx->stage_f.p + n3, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  }
   if (pos_old) CKC(cudaMemcpyAsync(pos_old, ctx->pos_old.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   if (old_cg) CKC(cudaMemcpyAsync(old_cg, ctx->old_cg.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   if (uid) CKC(cudaMemcpyAsync(uid, ctx->uid.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
@@ -614,6 +670,7 @@ int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
   TRY(pull_scal(ctx));
   memset(c, 0, sizeof *c);
   if (ctx->hsc->listed) {
+    if (ctx->lazy_rows) { TRY(enq_materialize_rows(ctx)); }
     CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
     LAUNCH(K_MISC, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
     TRY(pull_scal(ctx));
@@ -642,7 +699,7 @@ int dml_fuerza(dml_ctx *ctx) {
 }
 int dml_ermak_a(dml_ctx *ctx) { TRY(enq_integrate(ctx, true)); return finish(ctx); }
 int dml_ermak_b(dml_ctx *ctx) {
-  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->force.p, ctx->ranv.p, ctx->ph, ctx->n);
+  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
   return finish(ctx);
 }
 int dml_cbrownian_hs(dml_ctx *ctx) { TRY(enq_integrate(ctx, false)); return finish(ctx); }
@@ -686,6 +743,7 @@ int dml_step(dml_ctx *ctx, int32_t nsteps) {
 
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) {
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
+  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   TRY(enq_sort_cells(ctx, 1));
   CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
   LAUNCH(K_MISC, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
@@ -702,6 +760,7 @@ int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos
 }
 
 int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) {
+  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("no neighbour list");
   std::vector<int> rs(n), rl(n), cols((size_t)std::max(ctx->hsc->cols_used, 1));
@@ -734,6 +793,7 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   if (off) CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), (size_t)off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->cols_used = off;
+  ctx->hsc->rows_pending = 0;
   ctx->hsc->listed = 1; ctx->hsc->rows_asym = 1; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption
   ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
   TRY(push_scal(ctx));

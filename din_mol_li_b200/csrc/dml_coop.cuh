@@ -1,0 +1,151 @@
+// dml_coop.cuh — persistent cooperative kernels: one launch per call site of dana's loop.
+//
+// test_update and overlap_moveback are chains of data-dependent phases (bin -> scan -> scatter -> order -> count ->
+// scan -> fill; init -> detect -> count -> alloc -> fill -> resolve -> apply).  As separate launches each phase costs
+// a launch whether or not it has work (the rebuild decision is taken on the device).  Here the grid is sized to the
+// machine (148 SMs x resident blocks), every phase is a grid-stride loop and phases are separated by grid.sync();
+// a step that needs no rebuild leaves after the first phase.  Launched with cudaLaunchCooperativeKernel.
+#pragma once
+#include <cooperative_groups.h>
+#include "dml_kernels.cuh"
+
+namespace dml {
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ int block_sum_int(int v, int *sh /*>=33*/) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) { int x = lane < nw ? sh[lane] : 0; x = __reduce_add_sync(0xffffffffu, x); if (lane == 0) sh[32] = x; }
+  __syncthreads();
+  return sh[32];
+}
+
+// Exclusive scan of in[0..n) into out[0..n) by the whole grid; one grid.sync inside.  Each block owns a contiguous
+// chunk (multiple of 1024).  total -> *total_out (written by block 0).  ZERO_IN clears in[] after reading.
+template <bool ZERO_IN>
+__device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ sums,
+                          int *__restrict__ total_out) {
+  __shared__ int sh[34];
+  __shared__ int wsum[8];
+  const int nb = gridDim.x;
+  const int chunk = (((n + nb - 1) / nb) + 1023) & ~1023;
+  const int b0 = min(n, (int)blockIdx.x * chunk), b1 = min(n, b0 + chunk);
+  int local = 0;
+  for (int i = b0 + threadIdx.x; i < b1; i += blockDim.x) local += in[i];
+  int tot = block_sum_int(local, sh);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+  grid.sync();
+  int pre = 0, all = 0;
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) { int v = sums[j]; all += v; if (j < (int)blockIdx.x) pre += v; }
+  int prefix = block_sum_int(pre, sh);
+  int total = block_sum_int(all, sh);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = total;
+  int carry = prefix;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = b0; base < b1; base += 1024) {
+    int idx = base + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = (idx + i < b1) ? in[idx + i] : 0; if (ZERO_IN && idx + i < b1) in[idx + i] = 0; }
+    int t = v[0] + v[1] + v[2] + v[3], x = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int q = lane < 8 ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, q, o); if (lane >= o) q += y; }
+      if (lane < 8) wsum[lane] = q;
+    }
+    __syncthreads();
+    int run = x - t + (w ? wsum[w - 1] : 0) + carry;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (idx + i < b1) out[idx + i] = run; run += v[i]; }
+    carry += wsum[7];
+  }
+}
+
+struct TUArgs {
+  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot; double4 *sorted_posm;
+  const int *slot_b; int *row_len, *row_cap, *row_start, *cols, *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
+};
+
+// test_update (Neighbor.F90:668-713) in one launch
+__global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  const int gsz = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+  DevScal *sc = A.sc;
+  // phase 0: do_pbc + per-block top-2 squared displacement
+  if (gt == 0) sc->halo_flag = 0;
+  double a1 = -1.0, a2 = -1.0;
+  for (int s = gt; s < A.n; s += gsz) { double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s); top2_merge(a1, a2, rd, -1.0); }
+  block_top2(a1, a2);
+  if (threadIdx.x == 0) { A.part[2 * blockIdx.x] = a1; A.part[2 * blockIdx.x + 1] = a2; }
+  grid.sync();
+  // phase 1: every block reduces the partials to the same decision (top-2 merging is order independent)
+  a1 = 1e-16; a2 = 1e-16;                                        // Neighbor.F90:643-644
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) top2_merge(a1, a2, A.part[2 * i], A.part[2 * i + 1]);
+  block_top2(a1, a2);
+  __shared__ int s_need;
+  if (threadIdx.x == 0) {
+    int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > A.nb_dcut);   // Neighbor.F90:697-710
+    s_need = need;
+  }
+  __syncthreads();
+  const bool need = s_need != 0;
+  grid.sync();                                                   // everybody has read sc->listed before block 0 updates it
+  if (gt == 0) {
+    sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; }
+  }
+  if (!(need || A.force_sort)) return;
+  // phase 2: binning
+  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.row_len, A.row_cap, sc, A.g, need, s);
+  grid.sync();
+  coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
+  grid.sync();
+  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_slot, need, s);
+  grid.sync();
+  if (gt == 0 && need) sc->rows_asym = sc->halo_flag;
+  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, c);
+  if (!need || A.lazy) return;
+  grid.sync();
+  // phases 3-5: rows (count, scan, fill) — update() + ngroup_cells, Neighbor.F90:608-633,465-548
+  d_rows<false>(A.sorted_posm, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, sc, A.g, A.nct, A.slack);
+  grid.sync();
+  coop_scan<false>(grid, A.row_cap, A.row_start, A.n, A.sums, &sc->cols_used);
+  grid.sync();
+  d_rows<true>(A.sorted_posm, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, sc, A.g, A.nct, A.slack);
+}
+
+struct OVArgs {
+  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; int *parent, *ovst, *comp_cnt, *comp_off,
+      *members, *roots; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass, stop_after_fill;
+};
+
+// overlap_moveback (dana.F90:849-943) in one launch (prob>=1); with stop_after_fill the host drives the recursion levels
+__global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.sc, A.n);
+  grid.sync();
+  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.parent, A.ovst, A.sc, A.g, A.n);
+  grid.sync();
+  p_ov_count(A.parent, A.ovst, A.comp_cnt, A.n);
+  grid.sync();
+  p_ov_alloc(A.parent, A.ovst, A.comp_cnt, A.comp_off, A.roots, A.sc, A.n);
+  grid.sync();
+  p_ov_fill(A.parent, A.ovst, A.comp_cnt, A.comp_off, A.members, A.n);
+  if (A.stop_after_fill) return;
+  grid.sync();
+  p_ov_resolve(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.ovst, A.roots, A.comp_cnt, A.comp_off, A.members, A.uid, A.rp_uovl,
+               A.sc, A.g, A.ph, A.step, A.guard_pass);
+  grid.sync();
+  p_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, A.sc, A.n);
+}
+
+} // namespace dml

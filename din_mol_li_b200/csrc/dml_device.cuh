@@ -62,6 +62,8 @@ struct DevScal {
   int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
   int rev_used;
   int glen, ghead, gtomb, b_amax;   // gcmc membership array (list order) and hs%b%amax
+  int rows_pending;                 // rows of the last rebuild not materialised yet (lazy build)
+  unsigned int ticket2;
   int rows_asym, rev_valid;         // rows may be asymmetric (halo cells / gcmc appends); transposed rows are current
   int listed;                       // hs%listed (Neighbor.F90:53)
   int cols_cap;                     // capacity of cols[] / rev_cols[]
@@ -85,12 +87,21 @@ struct Geo {
   double rcut2;      // rcut^2
 };
 
+// idnint(x) for the minimum image, bit-identical to round(): particles live inside the box, so |x| = |vd/box| < 1.5 and
+// the result is one of -1, 0, +1, decided by two comparisons (half away from zero: x>=0.5 -> 1, x<=-0.5 -> -1).
+// The software fp64 round() is only taken outside that range (never for in-box pairs), keeping the result exact in general.
+__device__ __forceinline__ double mic_axis(double v, double box, double one_box) {
+  const double x = v * one_box;
+  double k = (x >= 0.5 ? 1.0 : 0.0) - (x <= -0.5 ? 1.0 : 0.0);
+  if (fabs(x) >= 1.5) k = round(x);
+  return v - box * k;
+}
 // vdistance (Groups.F90:995-1016): a minus b, idnint minimum image on periodic axes, |.|^2 = (x²+y²)+z²
 __device__ __forceinline__ double dist2_idnint(const Geo &g, double ax, double ay, double az, double bx, double by, double bz) {
   double vx = ax - bx, vy = ay - by, vz = az - bz;
-  if (g.pbc[0]) vx = vx - g.box[0] * round(vx * g.one_box[0]);
-  if (g.pbc[1]) vy = vy - g.box[1] * round(vy * g.one_box[1]);
-  if (g.pbc[2]) vz = vz - g.box[2] * round(vz * g.one_box[2]);
+  if (g.pbc[0]) vx = mic_axis(vx, g.box[0], g.one_box[0]);
+  if (g.pbc[1]) vy = mic_axis(vy, g.box[1], g.one_box[1]);
+  if (g.pbc[2]) vz = mic_axis(vz, g.box[2], g.one_box[2]);
   return (vx * vx + vy * vy) + vz * vz;
 }
 
@@ -148,6 +159,33 @@ __constant__ int c_map[27][3] = {   // Cells.F90:28-36, stencil order fixes the 
   {0,0,0},{1,0,0},{1,1,0},{0,1,0},{-1,1,0},{1,0,-1},{1,1,-1},{0,1,-1},{-1,1,-1},
   {1,0,1},{1,1,1},{0,1,1},{-1,1,1},{0,0,1},{-1,0,0},{-1,-1,0},{0,-1,0},{1,-1,0},
   {-1,0,1},{-1,-1,1},{0,-1,1},{1,-1,1},{-1,0,-1},{-1,-1,-1},{0,-1,-1},{1,-1,-1},{0,0,-1}};
+
+// The same stencil for "one lane per stencil cell" code: constant memory would serialise a warp whose lanes index
+// different entries, so lane l decodes its own offset from two 64-bit literals (2 bits per component, value+1).
+__device__ __forceinline__ void map_of_lane(int l, int &dx, int &dy, int &dz) {
+  // entry e = (dx+1) | (dy+1)<<2 | (dz+1)<<4, 6 bits each; entries 0-9 in lo, 10-19 in mid, 20-26 in hi
+  const unsigned long long lo = 0ull
+    | (unsigned long long)(1 | 1 << 2 | 1 << 4) << 0   | (unsigned long long)(2 | 1 << 2 | 1 << 4) << 6
+    | (unsigned long long)(2 | 2 << 2 | 1 << 4) << 12  | (unsigned long long)(1 | 2 << 2 | 1 << 4) << 18
+    | (unsigned long long)(0 | 2 << 2 | 1 << 4) << 24  | (unsigned long long)(2 | 1 << 2 | 0 << 4) << 30
+    | (unsigned long long)(2 | 2 << 2 | 0 << 4) << 36  | (unsigned long long)(1 | 2 << 2 | 0 << 4) << 42
+    | (unsigned long long)(0 | 2 << 2 | 0 << 4) << 48  | (unsigned long long)(2 | 1 << 2 | 2 << 4) << 54;
+  const unsigned long long mid = 0ull
+    | (unsigned long long)(2 | 2 << 2 | 2 << 4) << 0   | (unsigned long long)(1 | 2 << 2 | 2 << 4) << 6
+    | (unsigned long long)(0 | 2 << 2 | 2 << 4) << 12  | (unsigned long long)(1 | 1 << 2 | 2 << 4) << 18
+    | (unsigned long long)(0 | 1 << 2 | 1 << 4) << 24  | (unsigned long long)(0 | 0 << 2 | 1 << 4) << 30
+    | (unsigned long long)(1 | 0 << 2 | 1 << 4) << 36  | (unsigned long long)(2 | 0 << 2 | 1 << 4) << 42
+    | (unsigned long long)(0 | 1 << 2 | 2 << 4) << 48  | (unsigned long long)(0 | 0 << 2 | 2 << 4) << 54;
+  const unsigned long long hi = 0ull
+    | (unsigned long long)(1 | 0 << 2 | 2 << 4) << 0   | (unsigned long long)(2 | 0 << 2 | 2 << 4) << 6
+    | (unsigned long long)(0 | 1 << 2 | 0 << 4) << 12  | (unsigned long long)(0 | 0 << 2 | 0 << 4) << 18
+    | (unsigned long long)(1 | 0 << 2 | 0 << 4) << 24  | (unsigned long long)(2 | 0 << 2 | 0 << 4) << 30
+    | (unsigned long long)(1 | 1 << 2 | 0 << 4) << 36;
+  unsigned long long w = l < 10 ? lo : (l < 20 ? mid : hi);
+  int sh = (l < 10 ? l : (l < 20 ? l - 10 : l - 20)) * 6;
+  int e = (int)(w >> sh) & 63;
+  dx = (e & 3) - 1; dy = ((e >> 2) & 3) - 1; dz = ((e >> 4) & 3) - 1;
+}
 
 // pair tables (dana.F90:87-100) and integrator constants, set per ctx before launches
 struct Phys {

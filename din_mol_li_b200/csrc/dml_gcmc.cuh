@@ -13,7 +13,7 @@
 namespace dml {
 
 struct GcmcArgs {
-  double4 *posm; double *vel, *acel, *force, *epot, *pos_old, *old_cg;
+  double4 *posm; double4 *fe; double *vel, *acel, *pos_old, *old_cg;
   int *uid, *slot_b, *b_occ;
   const int *cell_of_unused; const int *cell_start; const int *sorted_slot; const double4 *sorted_posm;
   int *row_start, *row_len, *row_cap, *cols; int cols_cap;
@@ -193,10 +193,10 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           double beta = sqrt(A.beta_kT / A.ph.mass[zt - 1]);
           // new atom copies the template (atom_asign, Groups.F90:484-502) BEFORE the draw touches anybody's velocity
           for (int k = 0; k < 3; ++k) {
-            A.vel[3 * ns + k] = A.vel[3 * tmpl + k]; A.force[3 * ns + k] = A.force[3 * tmpl + k]; A.acel[3 * ns + k] = A.acel[3 * tmpl + k];
+            A.vel[3 * ns + k] = A.vel[3 * tmpl + k]; A.acel[3 * ns + k] = A.acel[3 * tmpl + k];
             A.old_cg[3 * ns + k] = 1e8;
           }
-          A.epot[ns] = A.epot[tmpl];
+          st_rec(&A.fe[ns], ld_rec(&A.fe[tmpl]));             // force and epot of the template (atom_asign)
           A.pos_old[3 * ns] = rx; A.pos_old[3 * ns + 1] = ry; A.pos_old[3 * ns + 2] = rz;
           for (int k = 0; k < 3; ++k) A.vel[3 * last + k] = beta * rng.gauss();
           double4 pn = {rx, ry, rz, meta_as_double(with_disp((long long)zt | MF_REF | MF_GCMC, DISP_INF))};
@@ -331,7 +331,7 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   CKC(ctx->gpend.ensure((size_t)nadj + 8, ctx->st));
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && ctx->rp_nu == 0 && nadj > 0) FAIL("replay mode: call dml_set_replay_gcmc before gcmc_run");
   GcmcArgs A;
-  A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.force = ctx->force.p; A.epot = ctx->epot.p;
+  A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.fe = ctx->fe.p;
   A.pos_old = ctx->pos_old.p; A.old_cg = ctx->old_cg.p; A.uid = ctx->uid.p; A.slot_b = ctx->slot_b.p; A.b_occ = ctx->b_occ.p;
   A.cell_of_unused = nullptr; A.cell_start = ctx->cell_start.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
   A.row_start = ctx->row_start.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.cols = ctx->cols.p; A.cols_cap = (int)ctx->cols.cap;

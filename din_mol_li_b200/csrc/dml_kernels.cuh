@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(TPB) k_scan(int *__restrict__ in, int *__restr
                                               const DevScal *sc, int force, int guard_mode) {
   if (guard_mode == 0) { REBUILD_GUARD(sc, force); }
   else if (guard_mode == 1) { if (!(((volatile const DevScal *)sc)->rows_asym && !((volatile const DevScal *)sc)->rev_valid)) return; }
+  else if (guard_mode == 3) { if (!((volatile const DevScal *)sc)->rows_pending) return; }
   __shared__ int wsum[8];
   __shared__ int s_tile, s_prefix;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(&tickets[0], 1u);
@@ -83,48 +84,52 @@ __global__ void __launch_bounds__(TPB) k_scan(int *__restrict__ in, int *__restr
 // K1  test_update (Neighbor.F90:668-713): do_pbc (Groups.F90:1440-1467) + the two largest squared displacements
 //     (inq_dispmax, Neighbor.F90:635-666) in one streaming pass; k_top2_final takes the rebuild decision on the device.
 // ================================================================================================
-__global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ part,
-                                                  Geo g, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  double a1 = -1.0, a2 = -1.0;
-  if (s < n) {
-    double4 p = ld_rec(&posm[s]);
-    long long m = meta_of(p);
-    if (m & MF_TYPE) {
-      double po[3] = {pos_old[3 * s], pos_old[3 * s + 1], pos_old[3 * s + 2]};
-      double q[3] = {p.x, p.y, p.z};
-      bool ch = false;
+__device__ __forceinline__ double d_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, const Geo &g, int s) {
+  double4 p = ld_rec(&posm[s]);
+  long long m = meta_of(p);
+  if (!(m & MF_TYPE)) return -1.0;
+  double po[3] = {pos_old[3 * s], pos_old[3 * s + 1], pos_old[3 * s + 2]};
+  double q[3] = {p.x, p.y, p.z};
+  bool ch = false;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) if (g.pbc[k]) {
-        if (q[k] >= g.box[k]) { q[k] = q[k] - g.box[k]; po[k] = po[k] - g.box[k]; ch = true; }
-        else if (q[k] < 0.0) { q[k] = q[k] + g.box[k]; po[k] = po[k] + g.box[k]; ch = true; }
-      }
-      if (ch) {
-        p.x = q[0]; p.y = q[1]; p.z = q[2]; st_rec(&posm[s], p);
-        pos_old[3 * s] = po[0]; pos_old[3 * s + 1] = po[1]; pos_old[3 * s + 2] = po[2];
-      }
-      double vx = q[0] - po[0], vy = q[1] - po[1], vz = q[2] - po[2];
-      a1 = (vx * vx + vy * vy) + vz * vz;
-    }
+  for (int k = 0; k < 3; ++k) if (g.pbc[k]) {
+    if (q[k] >= g.box[k]) { q[k] = q[k] - g.box[k]; po[k] = po[k] - g.box[k]; ch = true; }
+    else if (q[k] < 0.0) { q[k] = q[k] + g.box[k]; po[k] = po[k] + g.box[k]; ch = true; }
   }
+  if (ch) {
+    p.x = q[0]; p.y = q[1]; p.z = q[2]; st_rec(&posm[s], p);
+    pos_old[3 * s] = po[0]; pos_old[3 * s + 1] = po[1]; pos_old[3 * s + 2] = po[2];
+  }
+  double vx = q[0] - po[0], vy = q[1] - po[1], vz = q[2] - po[2];
+  return (vx * vx + vy * vy) + vz * vz;
+}
+// block-wide top-2 of per-thread (a1,a2); result valid in thread 0
+__device__ __forceinline__ void block_top2(double &a1, double &a2) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
     top2_merge(a1, a2, b1, b2);
   }
-  __shared__ double s1[TPB / 32], s2[TPB / 32];
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __shared__ double s1[32], s2[32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
   if (lane == 0) { s1[w] = a1; s2[w] = a2; }
   __syncthreads();
   if (w == 0) {
-    a1 = lane < TPB / 32 ? s1[lane] : -1.0; a2 = lane < TPB / 32 ? s2[lane] : -1.0;
+    a1 = lane < nw ? s1[lane] : -1.0; a2 = lane < nw ? s2[lane] : -1.0;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
+    for (int o = 16; o > 0; o >>= 1) {
       double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
       top2_merge(a1, a2, b1, b2);
     }
-    if (lane == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
   }
+}
+__global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ part,
+                                                  Geo g, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double a1 = s < n ? d_pbc_disp(posm, pos_old, g, s) : -1.0, a2 = -1.0;
+  block_top2(a1, a2);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
 }
 __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, double nb_dcut) {
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
@@ -143,7 +148,7 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
     sc->d1 = a1; sc->d2 = a2;
     int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > nb_dcut);     // Neighbor.F90:697-710
     sc->need_rebuild = need;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; }
   }
 }
 
@@ -154,14 +159,10 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
 //     because both happen exactly when the list is rebuilt.  Invariant: cell_cnt and cell_cur are all zero
 //     between rebuilds (the scan clears cell_cnt, k_cell_order clears cell_cur).
 // ================================================================================================
-__global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                             int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, Geo g,
-                                             int n, int force) {
-  REBUILD_GUARD(sc, force);
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+__device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                      int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, const Geo &g,
+                                      bool rebuild, int s) {
   double4 p = ld_rec_nc(&posm[s]);
-  const bool rebuild = ((volatile const DevScal *)sc)->need_rebuild != 0;
   if (meta_of(p) & MF_TYPE) {
     int cx, cy, cz;
     if (cell_index(g, p.x, p.y, p.z, cx, cy, cz)) {
@@ -175,13 +176,17 @@ __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, i
     if (rebuild) { row_len[s] = 0; row_cap[s] = 0; }
   }
 }
-__global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
-                                                 const int *__restrict__ cell_start, int *__restrict__ cell_cur,
-                                                 int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force) {
+__global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                             int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, Geo g,
+                                             int n, int force) {
   REBUILD_GUARD(sc, force);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  const bool snapshot = ((volatile const DevScal *)sc)->need_rebuild != 0;
+  d_bin(posm, cell_of, cell_cnt, row_len, row_cap, sc, g, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
+}
+__device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
+                                          const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
+                                          bool snapshot, int s) {
   double4 p = ld_rec(&posm[s]);
   long long m = meta_of(p);
   if (m & MF_TYPE) {
@@ -190,14 +195,17 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
     if (snapshot) { pos_old[3 * s] = p.x; pos_old[3 * s + 1] = p.y; pos_old[3 * s + 2] = p.z; }
   } else if (snapshot && (m & MF_LIMBO)) { p.w = meta_as_double(0); st_rec(&posm[s], p); }
 }
-// one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
-__global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
-                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
-                             DevScal *__restrict__ sc, int ncell, int force) {
+__global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
+                                                 const int *__restrict__ cell_start, int *__restrict__ cell_cur,
+                                                 int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force) {
   REBUILD_GUARD(sc, force);
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag;
-  if (c >= ncell) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  d_scatter(posm, pos_old, cell_of, cell_start, cell_cur, sorted_slot, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
+}
+// one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
+__device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
+                                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm, int c) {
   cell_cur[c] = 0;
   int b = cell_start[c], e = cell_start[c + 1];
   for (int i = b + 1; i < e; ++i) {
@@ -207,6 +215,15 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
   }
   for (int i = b; i < e; ++i) { double4 p = ld_rec(&posm[sorted_slot[i]]); st_rec(&sorted_posm[i], p); }
 }
+__global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
+                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
+                             DevScal *__restrict__ sc, int ncell, int force) {
+  REBUILD_GUARD(sc, force);
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag;
+  if (c >= ncell) return;
+  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, c);
+}
 
 // ================================================================================================
 // K3  Verlet rows over linked cells      (ngroup_cells, Neighbor.F90:465-548; cell_pbc Cells.F90:378-404;
@@ -215,12 +232,13 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 //     come out in the reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
 // ================================================================================================
 template <bool FILL>
-__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
-                                              const int *__restrict__ cell_of, const int *__restrict__ cell_start,
-                                              int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                              int *__restrict__ cols, DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
-  REBUILD_GUARD(sc, 0);
+__device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
+                                       const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                                       int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
+                                       int *__restrict__ cols, DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
   const int lane = threadIdx.x & 31;
+  int mdx = 0, mdy = 0, mdz = 0;
+  if (lane < 27) map_of_lane(lane, mdx, mdy, mdz);
   const int nsorted = cell_start[ncell];              // number of binned particles
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   if (FILL && sc->cols_used > sc->cols_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); return; }
@@ -236,9 +254,10 @@ __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted
     int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
     int b = 0, e = 0;
     if (lane < 27) {
-      int nx = (c_map[lane][0] + cx - 1 + g.nc[0]) % g.nc[0] + 1;       // wraps every axis, z included
-      int ny = (c_map[lane][1] + cy - 1 + g.nc[1]) % g.nc[1] + 1;
-      int nz = (c_map[lane][2] + cz - 1 + g.nc[2]) % g.nc[2] + 1;
+      int nx = mdx + cx - 1, ny = mdy + cy - 1, nz = mdz + cz - 1;      // cell_pbc wraps every axis, z included (Cells.F90:387-391)
+      nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
+      ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
+      nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
       int nl = cell_lin(g, nx, ny, nz);
       b = cell_start[nl]; e = cell_start[nl + 1];
     }
@@ -262,6 +281,21 @@ __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted
         double rd = dist2_idnint(g, q.x, q.y, q.z, p.x, p.y, p.z);
         if (rd < g.rc_list2) cols[w++] = sorted_slot[u];
       }
+    }
+  }
+}
+template <bool FILL>
+__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
+                                              const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                                              int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
+                                              int *__restrict__ cols, DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
+  if (!((volatile const DevScal *)sc)->rows_pending) return;
+  d_rows<FILL>(sorted_posm, sorted_slot, cell_of, cell_start, row_len, row_cap, row_start, cols, sc, g, ncell, slack);
+  if (FILL) {                                         // the last block to finish marks the rows as materialised
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&sc->ticket2, 1u) == gridDim.x - 1) { sc->ticket2 = 0; sc->rows_pending = 0; }
     }
   }
 }
@@ -338,7 +372,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
                                                 const int *__restrict__ row_len, const int *__restrict__ cols,
                                                 const int *__restrict__ rev_start, const int *__restrict__ rev_len,
                                                 const int *__restrict__ rev_cols, const DevScal *__restrict__ sc,
-                                                const int *__restrict__ uid, double *__restrict__ force, double *__restrict__ epot,
+                                                const int *__restrict__ uid, double4 *__restrict__ fe,
                                                 Geo g, Phys ph, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
@@ -443,7 +477,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
       }
     }
   }
-  force[3 * s] = fx; force[3 * s + 1] = fy; force[3 * s + 2] = fz; epot[s] = ep;
+  st_rec(&fe[s], make_double4(fx, fy, fz, ep));        // force(3) + epot in one 256-bit store
 }
 
 // Production variant of the pair force: LANES lanes per ref particle share its row (n̄n ≈ 6 in solution), so the
@@ -468,7 +502,7 @@ template <int LANES>
 __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
     const double4 *__restrict__ posm, const int *__restrict__ row_start, const int *__restrict__ row_len,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-    const int *__restrict__ rev_cols, const DevScal *__restrict__ sc, double *__restrict__ force, double *__restrict__ epot,
+    const int *__restrict__ rev_cols, const DevScal *__restrict__ sc, double4 *__restrict__ fe,
     Geo g, Phys ph, int n) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
       }
     }
   }
-  if (act && sub == 0) { force[3 * s] = fx; force[3 * s + 1] = fy; force[3 * s + 2] = fz; epot[s] = ep; }
+  if (act && sub == 0) st_rec(&fe[s], make_double4(fx, fy, fz, ep));
 }
 
 // ================================================================================================
@@ -633,7 +667,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
 
 // ermak_b — dana.F90:1031-1052
 __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
-                                                 const double *__restrict__ force, const double *__restrict__ ranv, Phys ph, int n) {
+                                                 const double4 *__restrict__ fe, const double *__restrict__ ranv, Phys ph, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   long long m = meta_of(ld_rec_nc(&posm[s]));
@@ -641,9 +675,11 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
   int zt = (int)(m & MF_TYPE);
   if (zt == 2) return;
   double mass = ph.mass[zt - 1];
+  const double4 f4 = ld_rec_nc(&fe[s]);
+  const double fv[3] = {f4.x, f4.y, f4.z};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    double f = force[3 * s + k], a = acel[3 * s + k], v = vel[3 * s + k];
+    double f = fv[k], a = acel[3 * s + k], v = vel[3 * s + k];
     vel[3 * s + k] = ph.cc0 * v + ph.cc1mcc2 * a + ph.cc2 * f / mass + ranv[3 * s + k];
     acel[3 * s + k] = f / mass;
   }
@@ -659,15 +695,18 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
 // ================================================================================================
 constexpr int OV_MOVED = 1, OV_SKIP = 2, OV_TSHIFT = 2, OV_INVOLVED = 16, OV_ZERO = 32;
 
-__global__ void k_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
+__device__ __forceinline__ void p_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
                           int *__restrict__ comp_cnt, DevScal *__restrict__ sc, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
-  if (s >= n) return;
-  long long m = meta_of(ld_rec_nc(&posm[s]));
-  parent[s] = s; comp_cnt[s] = 0;
-  ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    long long m = meta_of(ld_rec_nc(&posm[s]));
+    parent[s] = s; comp_cnt[s] = 0;
+    ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
+  }
 }
+__global__ void k_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
+                          int *__restrict__ comp_cnt, DevScal *__restrict__ sc, int n) { p_ov_init(posm, parent, ovst, comp_cnt, sc, n); }
 __device__ __forceinline__ int uf_find(int *parent, int x) {
   for (;;) {
     int y = ((volatile int *)parent)[x];
@@ -686,69 +725,86 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
     if (old == a) return;
   }
 }
-__global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
+__device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const int *__restrict__ row_start, const int *__restrict__ row_len,
                                                    const int *__restrict__ cols, int *__restrict__ parent, int *__restrict__ ovst,
                                                    DevScal *__restrict__ sc, Geo g, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  double4 p1 = ld_rec_nc(&posm[s]);
-  long long m1 = meta_of(p1);
-  if (!(m1 & MF_REF)) return;
-  double o1[3] = {old_cg[3 * s], old_cg[3 * s + 1], old_cg[3 * s + 2]};
-  const float d1 = disp_of(m1);
-  const double rcut = sqrt(g.rcut2);
-  int b = row_start[s], len = row_len[s];
-  bool inv = false;
-  for (int jj = 0; jj < len; ++jj) {
-    int j = cols[b + jj];
-    double4 p2 = ld_rec_nc(&posm[j]);
-    long long m2 = meta_of(p2);
-    if (!(m2 & MF_TYPE)) continue;
-    // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
-    // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
-    double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
-    {
-      double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
-      if (rd_nn > thr * thr) continue;
+
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    double4 p1 = ld_rec_nc(&posm[s]);
+    long long m1 = meta_of(p1);
+    if (!(m1 & MF_REF)) continue;
+    double o1[3] = {old_cg[3 * s], old_cg[3 * s + 1], old_cg[3 * s + 2]};
+    const float d1 = disp_of(m1);
+    const double rcut = sqrt(g.rcut2);
+    int b = row_start[s], len = row_len[s];
+    bool inv = false;
+    for (int jj = 0; jj < len; ++jj) {
+      int j = cols[b + jj];
+      double4 p2 = ld_rec_nc(&posm[j]);
+      long long m2 = meta_of(p2);
+      if (!(m2 & MF_TYPE)) continue;
+      // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
+      // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
+      double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
+      {
+        double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
+        if (rd_nn > thr * thr) continue;
+      }
+      bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
+      if (m2 & MF_REF) {
+        double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
+        hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
+              dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
+        if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
+      }
+      inv = inv || hit;
     }
-    bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
-    if (m2 & MF_REF) {
-      double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
-      hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
-            dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
-      if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
-    }
-    inv = inv || hit;
+    if (inv) atomicOr(&ovst[s], OV_INVOLVED);
   }
-  if (inv) atomicOr(&ovst[s], OV_INVOLVED);
 }
-__global__ void k_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (!(ovst[s] & OV_INVOLVED)) return;
-  int r = uf_find(parent, s);
-  parent[s] = r;
-  atomicAdd(&comp_cnt[r], 1);
+__global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
+                                                   const int *__restrict__ row_start, const int *__restrict__ row_len,
+                                                   const int *__restrict__ cols, int *__restrict__ parent, int *__restrict__ ovst,
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, parent, ovst, sc, g, n); }
+__device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
+
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    if (!(ovst[s] & OV_INVOLVED)) continue;
+    int r = uf_find(parent, s);
+    parent[s] = r;
+    atomicAdd(&comp_cnt[r], 1);
+  }
+}
+__global__ void k_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) { p_ov_count(parent, ovst, comp_cnt, n); }
+__device__ __forceinline__ void p_ov_alloc(const int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt,
+                           int *__restrict__ comp_off, int *__restrict__ roots, DevScal *__restrict__ sc, int n) {
+
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    if (!(ovst[s] & OV_INVOLVED) || parent[s] != s) continue;
+    int c = comp_cnt[s];
+    comp_off[s] = atomicAdd(&sc->member_cursor, c);
+    comp_cnt[s] = 0;                                       // reused as the fill cursor
+    roots[atomicAdd(&sc->n_roots, 1)] = s;
+  }
 }
 __global__ void k_ov_alloc(const int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt,
-                           int *__restrict__ comp_off, int *__restrict__ roots, DevScal *__restrict__ sc, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (!(ovst[s] & OV_INVOLVED) || parent[s] != s) return;
-  int c = comp_cnt[s];
-  comp_off[s] = atomicAdd(&sc->member_cursor, c);
-  comp_cnt[s] = 0;                                       // reused as the fill cursor
-  roots[atomicAdd(&sc->n_roots, 1)] = s;
+                           int *__restrict__ comp_off, int *__restrict__ roots, DevScal *__restrict__ sc, int n) { p_ov_alloc(parent, ovst, comp_cnt, comp_off, roots, sc, n); }
+__device__ __forceinline__ void p_ov_fill(const int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt,
+                          const int *__restrict__ comp_off, int *__restrict__ members, int n) {
+
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    if (!(ovst[s] & OV_INVOLVED)) continue;
+    int r = parent[s];
+    members[comp_off[r] + atomicAdd(&comp_cnt[r], 1)] = s;
+  }
 }
 __global__ void k_ov_fill(const int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt,
-                          const int *__restrict__ comp_off, int *__restrict__ members, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (!(ovst[s] & OV_INVOLVED)) return;
-  int r = parent[s];
-  members[comp_off[r] + atomicAdd(&comp_cnt[r], 1)] = s;
-}
+                          const int *__restrict__ comp_off, int *__restrict__ members, int n) { p_ov_fill(parent, ovst, comp_cnt, comp_off, members, n); }
 // one thread per component: order the members by creation rank (once)
 __global__ void k_ov_sort(const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           int *__restrict__ members, const int *__restrict__ uid, const DevScal *__restrict__ sc) {
@@ -844,58 +900,68 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
 }
 // Fused variant (prob>=1: every metal contact deposits, nothing couples components): each component thread orders its
 // members and replays all recursion levels locally.  No host round trip, one launch.
-__global__ void k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
+__device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
                              const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                              int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= sc->n_roots) return;
-  int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
-  for (int i = b + 1; i < e; ++i) {                            // order by creation rank (= order of hs%ref%alist)
-    int s = members[i], key = uid[s], j = i - 1;
-    while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
-    members[j + 1] = s;
+
+  const int r_end = sc->n_roots;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < r_end; r += gridDim.x * blockDim.x) {
+    int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
+    for (int i = b + 1; i < e; ++i) {                            // order by creation rank (= order of hs%ref%alist)
+      int s = members[i], key = uid[s], j = i - 1;
+      while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
+      members[j + 1] = s;
+    }
+    OvAcc acc = {0, 0, 0, 0};
+    long long later = 0;
+    double z0 = sc->z0;
+    int pass = 0;
+    for (;; ++pass) {
+      long long ch0 = acc.ch;
+      bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
+                               (guard_pass > 0 && pass >= guard_pass) ? 1 : 0, z0, b, e, acc);
+      if (pass >= 1) later += acc.ch - ch0;
+      if (!again) break;
+    }
+    ov_flush(acc, sc);
+    if (later) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)later);
+    atomicMax(&sc->any_active, pass + 1);                        // deepest recursion level of this call
   }
-  OvAcc acc = {0, 0, 0, 0};
-  long long later = 0;
-  double z0 = sc->z0;
-  int pass = 0;
-  for (;; ++pass) {
-    long long ch0 = acc.ch;
-    bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
-                             (guard_pass > 0 && pass >= guard_pass) ? 1 : 0, z0, b, e, acc);
-    if (pass >= 1) later += acc.ch - ch0;
-    if (!again) break;
-  }
-  ov_flush(acc, sc);
-  if (later) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)later);
-  atomicMax(&sc->any_active, pass + 1);                        // deepest recursion level of this call
 }
+__global__ void k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
+                             const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                             const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
+                             int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) { p_ov_resolve(posm, old_cg, row_start, row_len, cols, ovst, roots, comp_cnt, comp_off, members, uid, rp_uovl, sc, g, ph, step, guard_pass); }
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
-__global__ void k_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
+__device__ __forceinline__ void p_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
                            const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s == 0) {                                                // choques2=max(choques2,choques-i), dana.F90:939-941
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                                                // choques2=max(choques2,choques-i), dana.F90:939-941
     if (sc->ch_later > sc->choques2) sc->choques2 = sc->ch_later;
     sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
   }
-  if (s >= n) return;
-  double4 p = ld_rec(&posm[s]);
-  long long m = meta_of(p);
-  if (!(m & MF_REF)) return;
-  int st = ovst[s];
-  long long nm = m;
-  if (st & OV_INVOLVED) {
-    nm = (m & ~(MF_TYPE | MF_SKIP)) | (long long)((st >> OV_TSHIFT) & 3) | ((st & OV_SKIP) ? MF_SKIP : 0);
-    if (st & OV_MOVED) { p.x = old_cg[3 * s]; p.y = old_cg[3 * s + 1]; p.z = old_cg[3 * s + 2]; }
-    if (st & OV_ZERO) {
-      vel[3 * s] = 0.0; vel[3 * s + 1] = 0.0; vel[3 * s + 2] = 0.0;
-      acel[3 * s] = 0.0; acel[3 * s + 1] = 0.0; acel[3 * s + 2] = 0.0;
-    }
-  } else nm = m | MF_SKIP;                                     // processed in the first pass, nothing in range
-  if (nm != m || (st & OV_MOVED)) { p.w = meta_as_double(nm); st_rec(&posm[s], p); }
+  const int s_end = n;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+    double4 p = ld_rec(&posm[s]);
+    long long m = meta_of(p);
+    if (!(m & MF_REF)) continue;
+    int st = ovst[s];
+    long long nm = m;
+    if (st & OV_INVOLVED) {
+      nm = (m & ~(MF_TYPE | MF_SKIP)) | (long long)((st >> OV_TSHIFT) & 3) | ((st & OV_SKIP) ? MF_SKIP : 0);
+      if (st & OV_MOVED) { p.x = old_cg[3 * s]; p.y = old_cg[3 * s + 1]; p.z = old_cg[3 * s + 2]; }
+      if (st & OV_ZERO) {
+        vel[3 * s] = 0.0; vel[3 * s + 1] = 0.0; vel[3 * s + 2] = 0.0;
+        acel[3 * s] = 0.0; acel[3 * s + 1] = 0.0; acel[3 * s + 2] = 0.0;
+      }
+    } else nm = m | MF_SKIP;                                     // processed in the first pass, nothing in range
+    if (nm != m || (st & OV_MOVED)) { p.w = meta_as_double(nm); st_rec(&posm[s], p); }
+  }
 }
+__global__ void k_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
+                           const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) { p_ov_apply(posm, vel, acel, old_cg, ovst, sc, n); }
 
 // ================================================================================================
 // K8  F -> CG promotion (dana.F90:228-236), calc_rho (521-549), maxz (776-794)
@@ -1001,6 +1067,12 @@ __global__ void k_unpack(const double4 *__restrict__ posm, double *__restrict__ 
   if (pos) { pos[3 * s] = p.x; pos[3 * s + 1] = p.y; pos[3 * s + 2] = p.z; }
   if (z) z[s] = (int)(m & MF_TYPE);
   if (flags) flags[s] = ((m & MF_REF) ? 1 : 0) | ((m & MF_GCMC) ? 2 : 0) | ((m & MF_SKIP) ? 4 : 0) | ((m & MF_LIMBO) ? 8 : 0);
+}
+__global__ void k_unpack_fe(const double4 *__restrict__ fe, double *__restrict__ force, double *__restrict__ epot, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double4 f = ld_rec_nc(&fe[s]);
+  force[3 * s] = f.x; force[3 * s + 1] = f.y; force[3 * s + 2] = f.z; epot[s] = f.w;
 }
 __global__ void k_count_members(const double4 *__restrict__ posm, DevScal *__restrict__ sc, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
