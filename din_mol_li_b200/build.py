@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdml.so")
 SRCS = ["dml.cu", "dana_host.cpp"]
-DEPS = ["dml.cu", "dana_host.cpp", os.path.join("..", "..", "include", "dml_host.h"), "dml_kernels.cuh", "dml_device.cuh", "dml_gcmc.cuh", os.path.join("..", "..", "include", "dml.h")]
+DEPS = ["dml.cu", "dml_coop.cuh", os.path.join("..", "..", "tools", "dana_host.cpp"), "dana_host.cpp", os.path.join("..", "..", "include", "dml_host.h"), "dml_kernels.cuh", "dml_device.cuh", "dml_gcmc.cuh", os.path.join("..", "..", "include", "dml.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
@@ -26,6 +26,14 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libdml.so")
     if verbose:
         print(log)
+    # C++ stand-in for the reference's main program, linked against the library (tools/dana_host.cpp)
+    exe = os.path.join(HERE, "dana_b200")
+    cmd = [NVCC, "-O2", "-std=c++17", "-o", exe, os.path.join(HERE, "..", "tools", "dana_host.cpp"), "-L" + HERE, "-ldml",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building dana_b200")
     return LIB
 
 

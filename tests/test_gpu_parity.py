@@ -107,3 +107,31 @@ def test_gcmc_fixture_on_device():
     c = ls.ctx.counters()
     assert c.gcmc_created > 0 and c.gcmc_destroyed > 0
     assert c.nat_sys == 594
+
+
+def test_dana_b200_driver_writes_reference_layout(tmp_path):
+    """tools/dana_host.cpp (C++ stand-in for dana's main program) runs tests/ermak through the C ABI with Philox noise and
+    writes Li.xyz in the reference's list-directed layout (same column structure as ref.xyz, atoms conserved)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "din_mol_li_b200", "dana_b200")
+    for f in ("entrada.ini", "movedor.ini"):
+        shutil.copy(os.path.join(GOLD, "ermak", f), tmp_path)
+    r = subprocess.run([exe, str(tmp_path), "--steps", "300"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(os.path.join(tmp_path, "Li.xyz")).read().split("\n")
+    ref = open(os.path.join(GOLD, "ermak", "ref.xyz")).read().split("\n")
+    assert lines[0] == ref[0]                                   # "        1204"
+    assert len(lines[1]) == len(ref[1]) and lines[1].startswith(" info:")
+    last = lines[-1207:-1]                                      # last frame
+    assert last[0] == ref[0]
+    assert all(len(a) == 93 for a in last[2:]) and all(len(a) == 93 for a in ref[2:1206])
+    # same initial configuration as the reference run: frame 0 of Li.xyz equals pos_inic of the oracle (same RNG, same rule)
+    d = O.read_case(os.path.join(GOLD, "ermak"))
+    o = O.Oracle(**d)
+    st = o.state()
+    frame0 = lines[2:2 + 1204]
+    p0 = np.array([[float(x) for x in ln.split()[1:4]] for ln in frame0])
+    assert np.array_equal(p0, st["pos"])
+    assert "vecinos actualizados" in r.stdout
