@@ -135,3 +135,36 @@ def test_dana_b200_driver_writes_reference_layout(tmp_path):
     p0 = np.array([[float(x) for x in ln.split()[1:4]] for ln in frame0])
     assert np.array_equal(p0, st["pos"])
     assert "vecinos actualizados" in r.stdout
+
+
+def _deposited(z):
+    return int((z >= 2).sum())
+
+
+@pytest.mark.parametrize("name,nsteps,nseeds", [("ermak", 2000, 5), ("gcmc", 1500, 5)])
+def test_long_run_observables_statistical(name, nsteps, nseeds):
+    """Production mode (Philox noise) against the oracle's own RNG: long-run observables agree within statistical error
+    (north_star criterion 4).  Observables: deposited atoms (CG+F), particles in the system, mean height of the ions."""
+    dep_o, dep_g, n_o, n_g, zm_o, zm_g = [], [], [], [], [], []
+    for k in range(nseeds):
+        d, o = case(name, idum=-104012 - 17 * k)
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=9000 + k)
+        ctx.step(nsteps)
+        c = ctx.counters()
+        g = ctx.download(c.n_slots)
+        alive = g["z"] > 0
+        dep_g.append(_deposited(g["z"][alive])); n_g.append(int(alive.sum())); zm_g.append(g["pos"][alive & (g["z"] == 1), 2].mean())
+        o.step(nsteps)
+        st = o.state()
+        dep_o.append(_deposited(st["z"])); n_o.append(len(st["z"])); zm_o.append(st["pos"][st["z"] == 1, 2].mean())
+        ctx.close()
+
+    def agree(a, b, what, floor):
+        a, b = np.array(a, float), np.array(b, float)
+        se = np.sqrt((a.var(ddof=1) + b.var(ddof=1)) / len(a)) + floor
+        assert abs(a.mean() - b.mean()) <= 4.5 * se, "%s: device %s vs oracle %s (se %.3g)" % (what, a, b, se)
+
+    agree(dep_g, dep_o, name + " deposited atoms", 1.0)
+    agree(n_g, n_o, name + " particles", 1.0)
+    agree(zm_g, zm_o, name + " mean ion height", 0.05)
+    assert np.mean(dep_g) > 5          # the comparison is not vacuous
