@@ -51,18 +51,20 @@ struct dml_ctx {
   bool profiling = false; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
   double prof_ms[32] = {0}; int64_t prof_n[32] = {0};
   // particle state
+  DBuf<float4> sorted_posf;                            // single-precision copy of the cell-sorted records (k_rows prefilter)
   DBuf<double4> posm, sorted_posm, fe;                 // fe = {force(3), epot}
   DBuf<double> vel, acel, pos_old, old_cg, ranv;
   DBuf<int> uid, slot_b;
   // cells
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, chain_pos;
   // rows
-  DBuf<int> row_start, row_len, row_cap, cols;
+  DBuf<int> row_start, row_len, row_cap, cols; DBuf<unsigned char> bq, rev_bq, halo_of, lane_cnt; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
+  bool rev_in_fuerza = true; // (re)build the transposed rows in front of the next pair-force call (else: right after a rebuild)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
-  int force_lanes = 2;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
+  int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
   DBuf<int> rev_cnt;
@@ -86,6 +88,7 @@ struct dml_ctx {
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 static int gcmc_run_impl(dml_ctx *ctx);
+static int enq_build_rev(dml_ctx *ctx);
 static int enq_sort_cells(dml_ctx *ctx, int force);
 static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
@@ -158,6 +161,14 @@ static int push_scal(dml_ctx *ctx) {
 
 static void set_box(dml_ctx *ctx, const double box[3]) {
   for (int k = 0; k < 3; ++k) { ctx->geo.box[k] = box[k]; ctx->geo.one_box[k] = 1.0 / box[k]; ctx->geo.half_box[k] = box[k] * .5; }
+  {
+    // fp32 error band of k_rows: coordinates up to L (+ one list radius outside the box) carry ulp(L)/2 each, the image shift
+    // another ulp; |d(d^2)| <= 2*sqrt(3)*rc*err + rounding of the products.  A factor 4 of slack on top.
+    double L = std::max(std::max(box[0], box[1]), box[2]) * 1.5 + 64.0;
+    double ulp = std::ldexp(1.0, (int)std::ceil(std::log2(L)) - 23);
+    double rl = ctx->cfg.rcut + ctx->cfg.nb_dcut;
+    ctx->geo.band2 = (float)(4.0 * (2.0 * 1.7321 * (rl + 1.0) * 3.0 * ulp + 1e-5 * rl * rl));
+  }
 }
 
 // cgroup_tessellate — Cells.F90:180-265 (host side: it depends only on the box and rcut+nb_dcut)
@@ -178,13 +189,19 @@ static void tessellate(dml_ctx *ctx) {
   if (nc[0] < 4 && nc[1] < 4 && nc[2] < 4) return;       // reference falls back to the O(N^2) list
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
+  g.lay_shift = 0; while (((g.nc[2] + 2) >> g.lay_shift) + 1 > LAY_MAX) g.lay_shift++;
+  g.nlay = ((g.nc[2] + 1) >> g.lay_shift) + 1;
   ctx->tessellated = true;
 }
 
 // single-pass scan (decoupled look-back).  guard_mode: 0 rebuild guard (| force), 1 transposed-rows guard, 2 always
 static int scan_excl(dml_ctx *ctx, int *in, int *out, int n, int *total_out, bool zero_in, int guard_mode, int force) {
   int nb = nblk(n, 1024);
-  CKC(ctx->scan_state.ensure((size_t)nb + 8, ctx->st));
+  if ((size_t)nb + 8 > ctx->scan_state.cap) {
+    // fresh (or grown) state must not carry epochs of an earlier context that owned the same memory
+    CKC(ctx->scan_state.ensure((size_t)nb + 1024, ctx->st));
+    CKC(cudaMemsetAsync(ctx->scan_state.p, 0, ctx->scan_state.cap * sizeof(unsigned long long), ctx->st));
+  }
   if (!ctx->scan_tickets) { CKC(cudaMalloc(&ctx->scan_tickets, 2 * sizeof(unsigned int))); CKC(cudaMemsetAsync(ctx->scan_tickets, 0, 2 * sizeof(unsigned int), ctx->st)); }
   unsigned int ep = ++ctx->scan_epoch;
   if ((ep & 0x3fffffffu) == 0) ep = ++ctx->scan_epoch;
@@ -201,12 +218,12 @@ static int ensure_particles(dml_ctx *ctx, int n) {
 // cell binning + counting sort; guarded on the device by need_rebuild | force
 static int enq_sort_cells(dml_ctx *ctx, int force) {
   int n = ctx->n, nct = ctx->nct;
-  LAUNCH(K_BIN, k_bin, nblk(n), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->row_len.p, ctx->row_cap.p, ctx->sc, ctx->geo, n, force);
+  LAUNCH(K_BIN, k_bin, nblk(n), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->row_len.p, ctx->row_cap.p, ctx->halo_of.p, ctx->sc, ctx->geo, n, force);
   TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, true, 0, force));
   LAUNCH(K_SCATTER, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
          ctx->sorted_slot.p, ctx->sc, n, force);
   LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
-         ctx->sorted_posm.p, ctx->sc, nct, force);
+         ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sc, nct, force);
   return 0;
 }
 
@@ -214,11 +231,11 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
   int nw = std::min(nblk(n * 32), 148 * 32);          // grid-stride over warps: an idle (guarded) launch stays cheap
-  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->lane_cnt.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 3, 0));
-  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->lane_cnt.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   return 0;
 }
 
@@ -238,20 +255,22 @@ static int enq_test_update(dml_ctx *ctx) {
   if (ctx->use_coop && n <= ctx->coop_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
-    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
-    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p;
+    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
+    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lane_cnt = ctx->lane_cnt.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
     A.nb_dcut = ctx->cfg.nb_dcut;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
     ctx->binned = true;
+    if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
     return 0;
   }
-  int nb = nblk(n);
+  int nb = std::min(nblk(n), 148 * 6);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->geo, n);
-  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->cfg.nb_dcut);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n);
+  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->lay.p, ctx->geo.nlay, ctx->cfg.nb_dcut);
   TRY(enq_sort_cells(ctx, force));
   if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
   ctx->binned = true;
   return 0;
 }
@@ -270,22 +289,29 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
   return 0;
 }
 
+// transposed rows, built on the device only when rows can be asymmetric (guarded launches, no-ops otherwise)
+static int enq_build_rev(dml_ctx *ctx) {
+  int n = ctx->n;
+  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p,
+         ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
+  TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
+  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
+         ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
+  LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
+  return 0;
+}
+
 static int enq_fuerza(dml_ctx *ctx) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
-  // transposed rows, built on the device only when rows can be asymmetric (guarded launches)
-  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p, ctx->sc, n);
-  TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
-  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
-         ctx->rev_cols.p, ctx->sc, n);
-  LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
+  if (ctx->rev_in_fuerza) { TRY(enq_build_rev(ctx)); if (ctx->cfg.reservoir != 3 && !ctx->lazy_rows) ctx->rev_in_fuerza = false; }
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
   else
   {
 #define FSUB(L) LAUNCH(K_FUERZA, (k_fuerza_sub<L>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
     switch (ctx->force_lanes) { case 1: FSUB(1); break; case 2: FSUB(2); break; case 4: FSUB(4); break; default: FSUB(8); break; }
 #undef FSUB
   }
@@ -299,7 +325,7 @@ static int enq_overlap(dml_ctx *ctx) {
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.row_start = ctx->row_start.p;
-    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.uid = ctx->uid.p;
     A.rp_uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
     A.n = n; A.guard_pass = ctx->ov_guard_pass; A.stop_after_fill = 0;
@@ -308,8 +334,8 @@ static int enq_overlap(dml_ctx *ctx) {
     return 0;
   }
   LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->sc, n);
-  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->parent.p,
-         ctx->ovst.p, ctx->sc, ctx->geo, n);
+  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
+         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
   LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
   LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
   LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
@@ -367,6 +393,7 @@ static int finish(dml_ctx *ctx) {
   if (used * 2 > ctx->cols.cap) {
     size_t want = used * 3 + 4096;
     CKC(ctx->cols.ensure(want, ctx->st, true)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st, false));
+    CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st, true)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st, false));
     ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
     ctx->hsc->rev_valid = 0;
     TRY(push_scal(ctx));
@@ -428,7 +455,7 @@ static int enq_step(dml_ctx *ctx) {
     TRY(gcmc_run_impl(ctx));
     TRY(enq_calc_rho(ctx));
   } else {
-    LAUNCH(K_PROMOTE, k_promote_rho, nblk(n), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, n);
+    LAUNCH(K_PROMOTE, k_promote_rho, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, n);
   }
   if (ctx->cfg.reservoir == 2) {
     if (!ctx->have_chunk) FAIL("reservoir 2: call dml_set_chunk_template before dml_step");
@@ -465,7 +492,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   set_box(ctx, cfg->box);
   for (int k = 0; k < 3; ++k) { ctx->geo.pbc[k] = cfg->pbc[k]; ctx->geo.nc[k] = 1; }
   double rl = cfg->rcut + cfg->nb_dcut;
-  ctx->geo.rc_list2 = rl * rl; ctx->geo.rcut2 = cfg->rcut * cfg->rcut;
+  ctx->geo.rc_list2 = rl * rl; ctx->geo.rcut2 = cfg->rcut * cfg->rcut; ctx->geo.bq_scale = 255.0 / rl;
   Phys &ph = ctx->ph; memset(&ph, 0, sizeof ph);
   for (int i = 0; i < 9; ++i) {
     ph.eps[i] = cfg->eps[i]; ph.r0[i] = cfg->r0[i]; ph.r0sq[i] = cfg->r0[i] * cfg->r0[i];
@@ -495,13 +522,18 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = atoi(e);
   if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
   size_t c3 = (size_t)cap * 3;
-  CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st));
+  CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
   CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
   CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
   CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
   CKC(ctx->row_start.ensure(cap + 1, ctx->st)); CKC(ctx->row_len.ensure(cap, ctx->st)); CKC(ctx->row_cap.ensure(cap, ctx->st));
   CKC(ctx->cols.ensure((size_t)cap * 48 + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
+  CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
+  CKC(ctx->lane_cnt.ensure((size_t)cap * 32, ctx->st));
+  CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
+  CKC(ctx->lay.ensure(2 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
   CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->rev_cnt.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(cudaMemsetAsync(ctx->row_cap.p, 0, (size_t)cap * sizeof(int), ctx->st));
@@ -559,11 +591,12 @@ void dml_destroy(dml_ctx *ctx) {
   cudaStreamSynchronize(ctx->st);
   prof_collect(ctx);
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
-  ctx->posm.release(); ctx->sorted_posm.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
+  ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->lane_cnt.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -787,14 +820,17 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   }
   rs[n] = off;
   CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
+  CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));   // caller's rows carry no build distances: never skip
   CKC(cudaMemcpyAsync(ctx->row_start.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_len.p, rl.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_cap.p, rc.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   if (off) CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), (size_t)off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->cols_used = off;
+  ctx->rev_in_fuerza = true;
   ctx->hsc->rows_pending = 0;
-  ctx->hsc->listed = 1; ctx->hsc->rows_asym = 1; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption
+  ctx->hsc->listed = 1; ctx->hsc->rows_asym = 2; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption
   ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
@@ -844,6 +880,12 @@ int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms,
   return 0;
 }
 int32_t dml_n_slots(dml_ctx *ctx) { return ctx->n; }
+int dml_set_strict_order(dml_ctx *ctx, int32_t on) {
+  ctx->cfg.strict_order = on ? 1 : 0;
+  CKC(cudaMemsetAsync(&ctx->sc->rev_valid, 0, sizeof(int), ctx->st));   // the two kernels use differently scoped transposed rows
+  ctx->rev_in_fuerza = true;
+  return 0;
+}
 int64_t dml_launch_count(dml_ctx *ctx) { return ctx->launches; }
 void *dml_stream(dml_ctx *ctx) { return (void *)ctx->st; }
 

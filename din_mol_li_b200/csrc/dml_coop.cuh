@@ -71,8 +71,8 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 }
 
 struct TUArgs {
-  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot; double4 *sorted_posm;
-  const int *slot_b; int *row_len, *row_cap, *row_start, *cols, *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
+  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot; double4 *sorted_posm; float4 *sorted_posf;
+  const int *slot_b; int *row_len, *row_cap, *row_start, *cols; unsigned char *bq, *halo_of, *lane_cnt; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
 };
 
 // test_update (Neighbor.F90:668-713) in one launch
@@ -82,8 +82,18 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   DevScal *sc = A.sc;
   // phase 0: do_pbc + per-block top-2 squared displacement
   if (gt == 0) sc->halo_flag = 0;
+  __shared__ unsigned int s_lay[LAY_MAX];
+  for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) s_lay[i] = 0u;
+  __syncthreads();
+  const int lay_old = sc->lay_cur;
   double a1 = -1.0, a2 = -1.0;
-  for (int s = gt; s < A.n; s += gsz) { double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s); top2_merge(a1, a2, rd, -1.0); }
+  for (int s = gt; s < A.n; s += gsz) {
+    double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s);
+    if (rd >= 0.0) lay_note(s_lay, A.g, A.posm[s].z, rd);
+    top2_merge(a1, a2, rd, -1.0);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&A.lay[(lay_old ^ 1) * LAY_MAX + i], s_lay[i]);
   block_top2(a1, a2);
   if (threadIdx.x == 0) { A.part[2 * blockIdx.x] = a1; A.part[2 * blockIdx.x + 1] = a2; }
   grid.sync();
@@ -101,30 +111,36 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   grid.sync();                                                   // everybody has read sc->listed before block 0 updates it
   if (gt == 0) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
+    sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
+    if (!need) sc->lay_cur = lay_old ^ 1;
     if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; }
+  }
+  if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
+    if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }
+    else { for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) A.lay[lay_old * LAY_MAX + i] = 0u; }
   }
   if (!(need || A.force_sort)) return;
   // phase 2: binning
-  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.row_len, A.row_cap, sc, A.g, need, s);
+  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.row_len, A.row_cap, A.halo_of, sc, A.g, need, s);
   grid.sync();
   coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
   grid.sync();
   for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_slot, need, s);
   grid.sync();
-  if (gt == 0 && need) sc->rows_asym = sc->halo_flag;
-  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, c);
+  if (gt == 0 && need) sc->rows_asym = sc->halo_flag ? 1 : 0;
+  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, A.sorted_posf, c);
   if (!need || A.lazy) return;
   grid.sync();
   // phases 3-5: rows (count, scan, fill) — update() + ngroup_cells, Neighbor.F90:608-633,465-548
-  d_rows<false>(A.sorted_posm, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, sc, A.g, A.nct, A.slack);
+  d_rows<false>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.lane_cnt, sc, A.g, A.nct, A.slack);
   grid.sync();
   coop_scan<false>(grid, A.row_cap, A.row_start, A.n, A.sums, &sc->cols_used);
   grid.sync();
-  d_rows<true>(A.sorted_posm, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, sc, A.g, A.nct, A.slack);
+  d_rows<true>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.lane_cnt, sc, A.g, A.nct, A.slack);
 }
 
 struct OVArgs {
-  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; int *parent, *ovst, *comp_cnt, *comp_off,
+  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
       *members, *roots; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass, stop_after_fill;
 };
 
@@ -133,7 +149,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
   p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.parent, A.ovst, A.sc, A.g, A.n);
+  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
   grid.sync();
   p_ov_count(A.parent, A.ovst, A.comp_cnt, A.n);
   grid.sync();

@@ -62,9 +62,14 @@ struct DevScal {
   int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
   int rev_used;
   int glen, ghead, gtomb, b_amax;   // gcmc membership array (list order) and hs%b%amax
+  double maxz_fac;                  // sum of |lohi| applied by maxz since the last test_update (z-dependent piston shift bound)
+  int lay_cur;                      // which of the two z-layer displacement tables is current
+  double dsum_tu;                   // sqrt(d1)+sqrt(d2) of the last test_update (0 right after a rebuild)
+  double maxz_disp;                 // bound of the displacement applied by maxz since the last test_update
+  unsigned int step_disp_bits;      // float bits: largest |pos-old_cg| of the last integrator call
   int rows_pending;                 // rows of the last rebuild not materialised yet (lazy build)
   unsigned int ticket2;
-  int rows_asym, rev_valid;         // rows may be asymmetric (halo cells / gcmc appends); transposed rows are current
+  int rows_asym, rev_valid;         // 0 symmetric rows, 1 asymmetric only through halo-cell particles, 2 general; transposed rows current
   int listed;                       // hs%listed (Neighbor.F90:53)
   int cols_cap;                     // capacity of cols[] / rev_cols[]
   long long nupd;                   // nupd_vlist (Neighbor.F90:110)
@@ -84,6 +89,9 @@ struct Geo {
   int hd[3];      // nc+2 (halo-inclusive extents, Cells.F90:248)
   int pbc[3];
   double rc_list2;   // (rcut+nb_dcut)^2
+  float band2;                       // half-width (in distance^2) of the band around rc_list^2 where fp32 cannot decide (k_rows)
+  int lay_shift, nlay;               // z-layer displacement table: layer = cell_z >> lay_shift
+  double bq_scale;   // 255/(rcut+nb_dcut): quantisation of build-time distances (dml_kernels.cuh, k_rows)
   double rcut2;      // rcut^2
 };
 

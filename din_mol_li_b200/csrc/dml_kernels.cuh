@@ -124,14 +124,54 @@ __device__ __forceinline__ void block_top2(double &a1, double &a2) {
     }
   }
 }
+// z-layer table of the largest displacement since the rows were built (float bits, order preserving for x>=0):
+// lets the pair-force kernel bound |move of i| + |move of j| locally instead of by the global top-2 (the piston shifts
+// particles near the ceiling far more than those near the electrode).
+constexpr int LAY_MAX = 1024;
+__device__ __forceinline__ int layer_of(const Geo &g, double z) {
+  int cz = (int)(z / g.cell[2]) + 1;
+  cz = cz < 0 ? 0 : (cz > g.nc[2] + 1 ? g.nc[2] + 1 : cz);
+  return cz >> g.lay_shift;
+}
+__device__ __forceinline__ void lay_note(unsigned int *s_lay, const Geo &g, double z, double rd) {
+  if (rd < 0.0) return;
+  float d = __double2float_ru(sqrt(rd)) * 1.000001f;
+  atomicMax(&s_lay[layer_of(g, z)], (unsigned int)__float_as_int(d));
+}
+// Largest quantised build-time distance that still has to be examined by a particle at height z looking for partners
+// within rmax: D - S <= rmax with S = bound of |move of i| + |move of j| since the rows were built (see k_fuerza_sub).
+__device__ __forceinline__ int skip_qmax(const Geo &g, const DevScal *__restrict__ sc, const unsigned int *__restrict__ lay, double z, double rmax) {
+  const int l = layer_of(g, z);
+  const unsigned int *lt = lay + sc->lay_cur * LAY_MAX;
+  unsigned int mx = 0u;
+#pragma unroll
+  for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldg(&lt[q])); }
+  const double since = sc->maxz_fac * fmax(z + 2.0 * g.cell[2] * (1 << g.lay_shift) - sc->z0, 0.0) +
+                       (double)__int_as_float((int)sc->step_disp_bits);
+  double S = fmin(2.0 * (double)__int_as_float((int)mx), sc->dsum_tu) + 2.0 * since;
+  if (since > g.cell[2]) return 255;                  // particles may have changed layer: no skipping
+  return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
+}
 __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ part,
-                                                  Geo g, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  double a1 = s < n ? d_pbc_disp(posm, pos_old, g, s) : -1.0, a2 = -1.0;
+                                                  unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, int n) {
+  // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
+  __shared__ unsigned int s_lay[LAY_MAX];
+  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) s_lay[i] = 0u;
+  __syncthreads();
+  double a1 = -1.0, a2 = -1.0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    double rd = d_pbc_disp(posm, pos_old, g, s);
+    if (rd >= 0.0) lay_note(s_lay, g, posm[s].z, rd);
+    top2_merge(a1, a2, rd, -1.0);
+  }
+  __syncthreads();
+  unsigned int *dst = lay + (sc->lay_cur ^ 1) * LAY_MAX;
+  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&dst[i], s_lay[i]);
   block_top2(a1, a2);
   if (threadIdx.x == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
 }
-__global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, double nb_dcut) {
+__global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
+                             double nb_dcut) {
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
   for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, part[2 * i], part[2 * i + 1]);
 #pragma unroll
@@ -140,6 +180,7 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
     top2_merge(a1, a2, b1, b2);
   }
   __shared__ double s1[32], s2[32];
+  __shared__ int s_need_sh;
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { s1[w] = a1; s2[w] = a2; }
   __syncthreads();
@@ -148,7 +189,19 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
     sc->d1 = a1; sc->d2 = a2;
     int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > nb_dcut);     // Neighbor.F90:697-710
     sc->need_rebuild = need;
+    sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
+    s_need_sh = need;
     if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; }
+  }
+  // z-layer tables: after a rebuild both are zero (displacements restart); otherwise the one just filled becomes current
+  // and the previous one is cleared for the next test_update
+  __syncthreads();
+  const int cur = sc->lay_cur;
+  if (s_need_sh) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) lay[i] = 0u; }
+  else {
+    for (int i = threadIdx.x; i < nlay; i += blockDim.x) lay[cur * LAY_MAX + i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) sc->lay_cur = cur ^ 1;
   }
 }
 
@@ -160,8 +213,8 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
 //     between rebuilds (the scan clears cell_cnt, k_cell_order clears cell_cur).
 // ================================================================================================
 __device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                      int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, const Geo &g,
-                                      bool rebuild, int s) {
+                                      int *__restrict__ row_len, int *__restrict__ row_cap, unsigned char *__restrict__ halo_of,
+                                      DevScal *__restrict__ sc, const Geo &g, bool rebuild, int s) {
   double4 p = ld_rec_nc(&posm[s]);
   if (meta_of(p) & MF_TYPE) {
     int cx, cy, cz;
@@ -169,20 +222,24 @@ __device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__r
       int lin = cell_lin(g, cx, cy, cz);
       cell_of[s] = lin;
       atomicAdd(&cell_cnt[lin], 1);
-      if (rebuild && (cx == 0 || cy == 0 || cz == 0 || cx == g.nc[0] + 1 || cy == g.nc[1] + 1 || cz == g.nc[2] + 1)) sc->halo_flag = 1;
+      if (rebuild) {
+        const bool halo = cx == 0 || cy == 0 || cz == 0 || cx == g.nc[0] + 1 || cy == g.nc[1] + 1 || cz == g.nc[2] + 1;
+        halo_of[s] = halo ? 1 : 0;
+        if (halo) sc->halo_flag = 1;
+      }
     } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
   } else {
     cell_of[s] = -1;
-    if (rebuild) { row_len[s] = 0; row_cap[s] = 0; }
+    if (rebuild) { row_len[s] = 0; row_cap[s] = 0; halo_of[s] = 0; }
   }
 }
 __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                             int *__restrict__ row_len, int *__restrict__ row_cap, DevScal *__restrict__ sc, Geo g,
-                                             int n, int force) {
+                                             int *__restrict__ row_len, int *__restrict__ row_cap, unsigned char *__restrict__ halo_of,
+                                             DevScal *__restrict__ sc, Geo g, int n, int force) {
   REBUILD_GUARD(sc, force);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  d_bin(posm, cell_of, cell_cnt, row_len, row_cap, sc, g, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
+  d_bin(posm, cell_of, cell_cnt, row_len, row_cap, halo_of, sc, g, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
 }
 __device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
                                           const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
@@ -205,7 +262,8 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
 }
 // one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
 __device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
-                                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm, int c) {
+                                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
+                                             float4 *__restrict__ sorted_posf, int c) {
   cell_cur[c] = 0;
   int b = cell_start[c], e = cell_start[c + 1];
   for (int i = b + 1; i < e; ++i) {
@@ -213,16 +271,21 @@ __device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, c
     while (j >= b) { int sj = sorted_slot[j]; if (slot_b[sj] >= key) break; sorted_slot[j + 1] = sj; --j; }
     sorted_slot[j + 1] = s;
   }
-  for (int i = b; i < e; ++i) { double4 p = ld_rec(&posm[sorted_slot[i]]); st_rec(&sorted_posm[i], p); }
+  for (int i = b; i < e; ++i) {
+    const int sl = sorted_slot[i];
+    double4 p = ld_rec(&posm[sl]); st_rec(&sorted_posm[i], p);
+    // single-precision copy for the candidate scan of k_rows; w carries the slot so the fill pass needs no second lookup
+    sorted_posf[i] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(sl));
+  }
 }
 __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
                              int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
-                             DevScal *__restrict__ sc, int ncell, int force) {
+                             float4 *__restrict__ sorted_posf, DevScal *__restrict__ sc, int ncell, int force) {
   REBUILD_GUARD(sc, force);
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag;
+  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag ? 1 : 0;
   if (c >= ncell) return;
-  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, c);
+  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, c);
 }
 
 // ================================================================================================
@@ -231,16 +294,38 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 //     the chain of cell map(:,l) and an exclusive prefix over the lanes (= stencil order) places its hits, so rows
 //     come out in the reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
 // ================================================================================================
+// Candidate test of k_rows.  The decision "rd < rc_list^2" must be the reference's fp64 one (vdistance, separately
+// rounded products), but almost every candidate is far from the boundary: a single-precision distance with a rigorous
+// error band decides those, and only candidates inside the band are re-evaluated in fp64 from the full record.
+__device__ __forceinline__ bool row_hit(const Geo &g, const double4 &p, float pxf, float pyf, float pzf, const float4 &q,
+                                        const double4 *__restrict__ sorted_posm, int u, float hbx, float hby, float rc2lo, float rc2hi,
+                                        double *rd_out) {
+  // hbx/hby = half box (0 on a non-periodic axis disables the image shift: |v| > 0 never triggers with hb = +inf)
+  float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+  if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+  if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+  const float d2 = vx * vx + vy * vy + vz * vz;
+  if (d2 > rc2hi) return false;
+  if (d2 < rc2lo && !rd_out) return true;
+  const double4 qd = ld_rec_nc(&sorted_posm[u]);
+  const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
+  if (rd_out) *rd_out = rd;
+  return rd < g.rc_list2;
+}
 template <bool FILL>
-__device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
+__device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                       const int *__restrict__ sorted_slot,
                                        const int *__restrict__ cell_of, const int *__restrict__ cell_start,
                                        int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                       int *__restrict__ cols, DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
+                                       int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned char *__restrict__ lane_cnt,
+                                       DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
   const int lane = threadIdx.x & 31;
   int mdx = 0, mdy = 0, mdz = 0;
   if (lane < 27) map_of_lane(lane, mdx, mdy, mdz);
   const int nsorted = cell_start[ncell];              // number of binned particles
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
+  const float rc2lo = (float)g.rc_list2 - g.band2, rc2hi = (float)g.rc_list2 + g.band2;
   if (FILL && sc->cols_used > sc->cols_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); return; }
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nsorted; t += nwarps) {
     double4 p = ld_rec_nc(&sorted_posm[t]);
@@ -251,6 +336,7 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
     }
     int lin = cell_of[s];
     if (lin < 0) continue;
+    const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
     int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
     int b = 0, e = 0;
     if (lane < 27) {
@@ -262,11 +348,26 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
       b = cell_start[nl]; e = cell_start[nl + 1];
     }
     int cnt = 0;
-    for (int u = b; u < e; ++u) {
-      if (u == t) continue;
-      double4 q = ld_rec_nc(&sorted_posm[u]);
-      double rd = dist2_idnint(g, q.x, q.y, q.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
-      if (rd < g.rc_list2) ++cnt;
+    if (!FILL) {
+      for (int u = b; u < e; ++u) {
+        if (u == t) continue;
+        const float4 q = __ldg(&sorted_posf[u]);
+        if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, nullptr)) ++cnt;
+      }
+    }
+    if (!FILL) lane_cnt[(size_t)t * 32 + lane] = (unsigned char)min(cnt, 255);   // one 32-byte sector per particle
+    if (FILL) {
+      // the per-lane hit counts of the first pass give the write offsets (prefix over the lanes = stencil order);
+      // a saturated count (>= 255 hits in one cell: dense metal) falls back to recounting
+      cnt = lane_cnt[(size_t)t * 32 + lane];
+      if (__any_sync(0xffffffffu, cnt == 255)) {
+        cnt = 0;
+        for (int u = b; u < e; ++u) {
+          if (u == t) continue;
+          const float4 q = __ldg(&sorted_posf[u]);
+          if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, nullptr)) ++cnt;
+        }
+      }
     }
     int incl = cnt;
 #pragma unroll
@@ -277,20 +378,27 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
       int w = row_start[s] + incl - cnt;
       for (int u = b; u < e; ++u) {
         if (u == t) continue;
-        double4 q = ld_rec_nc(&sorted_posm[u]);
-        double rd = dist2_idnint(g, q.x, q.y, q.z, p.x, p.y, p.z);
-        if (rd < g.rc_list2) cols[w++] = sorted_slot[u];
+        const float4 q = __ldg(&sorted_posf[u]);
+        double rd;
+        if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, &rd)) {
+          cols[w] = __float_as_int(q.w);
+          // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of k_fuerza_sub)
+          bq[w] = (unsigned char)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
+          ++w;
+        }
       }
     }
   }
 }
 template <bool FILL>
-__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const int *__restrict__ sorted_slot,
+__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                              const int *__restrict__ sorted_slot,
                                               const int *__restrict__ cell_of, const int *__restrict__ cell_start,
                                               int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                              int *__restrict__ cols, DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
+                                              int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned char *__restrict__ lane_cnt,
+                                              DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
-  d_rows<FILL>(sorted_posm, sorted_slot, cell_of, cell_start, row_len, row_cap, row_start, cols, sc, g, ncell, slack);
+  d_rows<FILL>(sorted_posm, sorted_posf, sorted_slot, cell_of, cell_start, row_len, row_cap, row_start, cols, bq, lane_cnt, sc, g, ncell, slack);
   if (FILL) {                                         // the last block to finish marks the rows as materialised
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -345,25 +453,32 @@ __device__ __forceinline__ bool pair_terms(const Geo &g, const Phys &ph, const d
 #define REV_GUARD(sc) if (!(((volatile const DevScal *)(sc))->rows_asym && !((volatile const DevScal *)(sc))->rev_valid)) return
 __global__ void k_rev_count(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
                             const double4 *__restrict__ posm, int *__restrict__ rev_len, int *__restrict__ rev_cnt,
-                            const DevScal *__restrict__ sc, int n) {
+                            const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   REV_GUARD(sc);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
+  if (halo_only && sc->rows_asym == 1 && !halo_of[s]) return;   // light mode: only rows of halo-cell particles are transposed
   if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
   int b = row_start[s], len = row_len[s];
   for (int jj = 0; jj < len; ++jj) atomicAdd(&rev_cnt[cols[b + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
 }
 __global__ void k_rev_fill(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
-                           int *__restrict__ rev_cols, const DevScal *__restrict__ sc, int n) {
+                           int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   REV_GUARD(sc);
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
+  if (halo_only && sc->rows_asym == 1 && !halo_of[s]) return;
   if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
   int b = row_start[s], len = row_len[s];
   // the scan cleared rev_len; it is rebuilt here as the fill cursor and ends as the row length
-  for (int jj = 0; jj < len; ++jj) { int j = cols[b + jj]; rev_cols[rev_start[j] + atomicAdd(&rev_len[j], 1)] = s; }
+  for (int jj = 0; jj < len; ++jj) {
+    int j = cols[b + jj];
+    int w = rev_start[j] + atomicAdd(&rev_len[j], 1);
+    rev_cols[w] = s; rev_bq[w] = bq[b + jj];
+  }
 }
 __global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
@@ -502,8 +617,9 @@ template <int LANES>
 __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
     const double4 *__restrict__ posm, const int *__restrict__ row_start, const int *__restrict__ row_len,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-    const int *__restrict__ rev_cols, const DevScal *__restrict__ sc, double4 *__restrict__ fe,
-    Geo g, Phys ph, int n) {
+    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
   bool act = s < n;
@@ -513,30 +629,44 @@ __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
   double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
   bool hit = false;
   if (act) {
-    const int asym = __ldg(&sc->rows_asym);
+    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
     const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+    const bool i_halo = asym == 1 && halo_of[s] != 0;
+    // Gather skip: an entry whose build-time distance D satisfies D - S > r0_max cannot be inside any cut-off, S being a
+    // bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
+    // around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
+    // integrator moved since.  qmax is the largest quantised D that still has to be looked at.
+    const int qmax = skip_qmax(g, sc, lay, p1.z, sqrt(ph.r0sq_max));
     const int npass = asym ? 2 : 1;
     for (int pass = 0; pass < npass; ++pass) {
-      const int *lst = pass == 0 ? cols + row_start[s] : rev_cols + rev_start[s];
+      const int off = pass == 0 ? row_start[s] : rev_start[s];
+      const int *lst = (pass == 0 ? cols : rev_cols) + off;
+      const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
       const int len = pass == 0 ? row_len[s] : rev_len[s];
-#pragma unroll 2
-      for (int jj = sub; jj < len; jj += LANES) {
-        const int j = __ldg(&lst[jj]);
-        const double4 p2 = ld_rec_nc(&posm[j]);
-        double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
-        if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
-        if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
-        const double dr2 = (vx * vx + vy * vy) + vz * vz;
-        if (dr2 > ph.r0sq_max) continue;
-        const long long m2 = meta_of(p2);
-        const int m = (int)(m2 & MF_TYPE);
-        if (m == 0) continue;                                        // limbo / removed
-        if (pass == 1 && !(m2 & MF_REF)) continue;                   // reverse visits come from row owners only
-        const int km = k3 + m - 1;
-        if (dr2 > ph.r0sq[km]) continue;
-        const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
-        const double w = (!asym && (m2 & MF_REF)) ? 2.0 : 1.0;       // exact doubling, then one rounding per add
-        fx += w * t.x; fy += w * t.y; fz += w * t.z; ep += w * t.w; hit = true;
+      for (int j0 = sub; j0 < len; j0 += 8 * LANES) {
+        unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { int jj = j0 + q * LANES; int b = jj < len ? (int)__ldg(&lq[jj]) : 1000; need |= (b <= qmax ? 1u : 0u) << q; }
+        while (need) {
+          const int q = __ffs(need) - 1; need &= need - 1;
+          const int j = __ldg(&lst[j0 + q * LANES]);
+          const double4 p2 = ld_rec_nc(&posm[j]);
+          double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
+          if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
+          if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
+          const double dr2 = (vx * vx + vy * vy) + vz * vz;
+          if (dr2 > ph.r0sq_max) continue;
+          const long long m2 = meta_of(p2);
+          const int m = (int)(m2 & MF_TYPE);
+          if (m == 0) continue;                                        // limbo / removed
+          if (pass == 1 && !(m2 & MF_REF)) continue;                   // reverse visits come from row owners only
+          const int km = k3 + m - 1;
+          if (dr2 > ph.r0sq[km]) continue;
+          const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
+          // weight 2 = own visit + the reverse visit by j, when j is a row owner that sees i (exact doubling, one rounding per add)
+          const double w = (pass == 0 && (m2 & MF_REF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
+          fx += w * t.x; fy += w * t.y; fz += w * t.z; ep += w * t.w; hit = true;
+        }
       }
     }
   }
@@ -555,19 +685,21 @@ __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
 // ================================================================================================
 // K4  integrators + boundary handling   (ermak_a dana.F90:974-1028, cbrownian_hs 798-846, atom_pbc 1187-1250)
 // ================================================================================================
-struct BlockAcc { long long tr, de; double msd, mv; };
+struct BlockAcc { long long tr, de; double msd, mv; float dmax; };
 
 __device__ __forceinline__ void block_flush(BlockAcc a, DevScal *sc) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a.tr += __shfl_xor_sync(0xffffffffu, a.tr, o); a.de += __shfl_xor_sync(0xffffffffu, a.de, o);
     a.msd += __shfl_xor_sync(0xffffffffu, a.msd, o); a.mv = fmax(a.mv, __shfl_xor_sync(0xffffffffu, a.mv, o));
+    a.dmax = fmaxf(a.dmax, __shfl_xor_sync(0xffffffffu, a.dmax, o));
   }
   if ((threadIdx.x & 31) == 0) {
     if (a.tr) atomicAdd((unsigned long long *)&sc->try_, (unsigned long long)a.tr);
     if (a.de) atomicAdd((unsigned long long *)&sc->depo, (unsigned long long)a.de);
     if (a.msd != 0.0) atomicAdd(&sc->msd_t, a.msd);
     if (a.mv > 0.0) atomicMax((unsigned long long *)&sc->max_vel, (unsigned long long)__double_as_longlong(a.mv));
+    if (a.dmax > 0.0f) atomicMax(&sc->step_disp_bits, (unsigned int)__float_as_int(a.dmax));
   }
 }
 
@@ -604,7 +736,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
                                                    const double *__restrict__ rp_upbc, DevScal *__restrict__ sc, Geo g, Phys ph,
                                                    unsigned int step, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  BlockAcc acc = {0, 0, 0.0, 0.0};
+  BlockAcc acc = {0, 0, 0.0, 0.0, 0.0f};
   if (s < n) {
     double4 p = ld_rec(&posm[s]);
     long long m = meta_of(p);
@@ -655,6 +787,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
         dx = dx - g.box[0] * round(dx * g.one_box[0]); dy = dy - g.box[1] * round(dy * g.one_box[1]);
         float df = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * 1.000001f;
         m = with_disp(m, (unsigned int)__float_as_int(df));
+        acc.dmax = fmaxf(acc.dmax, df);
       }
       p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
       st_rec(&posm[s], p);
@@ -727,7 +860,8 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
 }
 __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const int *__restrict__ row_start, const int *__restrict__ row_len,
-                                                   const int *__restrict__ cols, int *__restrict__ parent, int *__restrict__ ovst,
+                                                   const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                                                   const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
                                                    DevScal *__restrict__ sc, Geo g, int n) {
 
   const int s_end = n;
@@ -739,8 +873,10 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
     const float d1 = disp_of(m1);
     const double rcut = sqrt(g.rcut2);
     int b = row_start[s], len = row_len[s];
+    const int qmax = skip_qmax(g, sc, lay, p1.z, rcut);   // same build-distance skip as the pair force (covers new and old positions)
     bool inv = false;
     for (int jj = 0; jj < len; ++jj) {
+      if ((int)__ldg(&bq[b + jj]) > qmax) continue;
       int j = cols[b + jj];
       double4 p2 = ld_rec_nc(&posm[j]);
       long long m2 = meta_of(p2);
@@ -766,8 +902,9 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
 }
 __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const int *__restrict__ row_start, const int *__restrict__ row_len,
-                                                   const int *__restrict__ cols, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, parent, ovst, sc, g, n); }
+                                                   const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                                                   const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, bq, lay, parent, ovst, sc, g, n); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
@@ -805,17 +942,37 @@ __device__ __forceinline__ void p_ov_fill(const int *__restrict__ parent, const 
 }
 __global__ void k_ov_fill(const int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt,
                           const int *__restrict__ comp_off, int *__restrict__ members, int n) { p_ov_fill(parent, ovst, comp_cnt, comp_off, members, n); }
+// order the members [b,e) of a component by creation rank: insertion sort for the usual handful, heap sort beyond
+__device__ __forceinline__ void ov_sort_members(int *__restrict__ members, const int *__restrict__ uid, int b, int e) {
+  const int n = e - b;
+  if (n <= 32) {
+    for (int i = b + 1; i < e; ++i) {
+      int s = members[i], key = uid[s], j = i - 1;
+      while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
+      members[j + 1] = s;
+    }
+    return;
+  }
+  int *a = members + b;
+  auto sift = [&](int start, int end) {
+    int root = start;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child > end) break;
+      if (child + 1 <= end && uid[a[child]] < uid[a[child + 1]]) ++child;
+      if (uid[a[root]] < uid[a[child]]) { int t = a[root]; a[root] = a[child]; a[child] = t; root = child; } else break;
+    }
+  };
+  for (int st = (n - 2) / 2; st >= 0; --st) sift(st, n - 1);
+  for (int end = n - 1; end > 0; --end) { int t = a[end]; a[end] = a[0]; a[0] = t; sift(0, end - 1); }
+}
 // one thread per component: order the members by creation rank (once)
 __global__ void k_ov_sort(const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           int *__restrict__ members, const int *__restrict__ uid, const DevScal *__restrict__ sc) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sc->n_roots) return;
   int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
-  for (int i = b + 1; i < e; ++i) {
-    int s = members[i], key = uid[s], j = i - 1;
-    while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
-    members[j + 1] = s;
-  }
+  ov_sort_members(members, uid, b, e);
 }
 __device__ __forceinline__ void ov_pos(const double4 *posm, const double *old_cg, int a, int st, double q[3]) {
   if (st & OV_MOVED) { q[0] = old_cg[3 * a]; q[1] = old_cg[3 * a + 1]; q[2] = old_cg[3 * a + 2]; }
@@ -909,11 +1066,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
   const int r_end = sc->n_roots;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < r_end; r += gridDim.x * blockDim.x) {
     int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
-    for (int i = b + 1; i < e; ++i) {                            // order by creation rank (= order of hs%ref%alist)
-      int s = members[i], key = uid[s], j = i - 1;
-      while (j >= b && uid[members[j]] > key) { members[j + 1] = members[j]; --j; }
-      members[j + 1] = s;
-    }
+    ov_sort_members(members, uid, b, e);                       // order by creation rank (= order of hs%ref%alist)
     OvAcc acc = {0, 0, 0, 0};
     long long later = 0;
     double z0 = sc->z0;
@@ -983,18 +1136,17 @@ __global__ void k_promote(double4 *__restrict__ posm, DevScal *__restrict__ sc, 
 }
 // promotion + msd bookkeeping + calc_rho in one pass (reservoirs 1 and 2, where nothing runs between them)
 __global__ void __launch_bounds__(TPB) k_promote_rho(double4 *__restrict__ posm, DevScal *__restrict__ sc, double area, int use_z1, int n) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
   double z0 = sc->z0, zl = use_z1 ? sc->z1 : sc->zmax;
   int c = 0, dref = 0;
-  if (s < n) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     double4 p = ld_rec(&posm[s]);
     long long m = meta_of(p);
     if ((m & MF_REF) && (m & MF_TYPE) == 3) {
-      dref = 1;
+      dref++;
       m = (m & ~(MF_TYPE | MF_REF | MF_GCMC)) | 2;
       p.w = meta_as_double(m); st_rec(&posm[s], p);
     }
-    if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c = 1;
+    if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c++;
   }
   c = __reduce_add_sync(0xffffffffu, c); dref = __reduce_add_sync(0xffffffffu, dref);
   __shared__ int last;
@@ -1012,6 +1164,7 @@ __global__ void __launch_bounds__(TPB) k_promote_rho(double4 *__restrict__ posm,
     double vol = area * (zl - z0);
     sc->rho = gct / vol;
     sc->rho_count = 0; sc->n_involved = 0; sc->ticket = 0;
+    sc->step_disp_bits = 0u;                             // end of the step: the next integrator call records its own largest move
   }
 }
 __global__ void k_calc_rho(const double4 *__restrict__ posm, DevScal *__restrict__ sc, double area, int use_z1, int n) {
@@ -1032,6 +1185,7 @@ __global__ void k_calc_rho(const double4 *__restrict__ posm, DevScal *__restrict
     double vol = area * (zl - z0);                       // box(1)*box(2)*(z-z0)
     sc->rho = gct / vol;
     sc->rho_count = 0; sc->ticket = 0;
+    sc->step_disp_bits = 0u;
   }
 }
 __global__ void k_maxz(double4 *__restrict__ posm, DevScal *__restrict__ sc, double h_over_tau, int n) {
@@ -1042,7 +1196,11 @@ __global__ void k_maxz(double4 *__restrict__ posm, DevScal *__restrict__ sc, dou
     double4 p = ld_rec(&posm[s]);
     if ((meta_of(p) & MF_TYPE) && p.z > z0) { p.z = p.z - lohi * (p.z - z0); st_rec(&posm[s], p); }
   }
-  if (s == 0) sc->zmax = sc->zmax - lohi * (sc->zmax - z0);
+  if (s == 0) {
+    sc->maxz_disp += fabs(lohi) * fmax(sc->zmax - z0, 0.0) * 1.01;
+    sc->maxz_fac += fabs(lohi) * 1.01;   // |z shift| of any atom below the ceiling
+    sc->zmax = sc->zmax - lohi * (sc->zmax - z0);
+  }
 }
 
 // ================================================================================================

@@ -50,7 +50,7 @@ SYMBOLS = [
     "dml_ermak_b", "dml_cbrownian_hs", "dml_overlap_moveback", "dml_msd_book", "dml_promote", "dml_gcmc_run",
     "dml_calc_rho", "dml_maxz", "dml_bloques", "dml_set_chunk_template", "dml_step", "dml_get_cells",
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
-    "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_launch_count", "dml_stream",
+    "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_launch_count", "dml_stream",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def lib():
         L.dml_profile_get.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(C.c_int64), i32]
         L.dml_profile_kernel.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(dbl), C.POINTER(C.c_int64)]
         L.dml_n_slots.argtypes = [vp]
+        L.dml_set_strict_order.argtypes = [vp, i32]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -359,6 +360,9 @@ class Ctx:
                 return out
             out[name.value.decode()] = (ms.value, nl.value)
             kid += 1
+
+    def set_strict_order(self, on):
+        self._chk(lib().dml_set_strict_order(self.h, 1 if on else 0))
 
     def n_slots(self):
         return lib().dml_n_slots(self.h)

@@ -131,7 +131,8 @@ int dml_profile(dml_ctx *ctx, int32_t enable);
 int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset);
 /* per-kernel timing: kid = 0,1,2,... until the call returns 1; name points to a static string */
 int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches);
-int32_t dml_n_slots(dml_ctx *ctx);         /* hs%amax as known to the host side (no synchronisation) */
+int32_t dml_n_slots(dml_ctx *ctx);
+int dml_set_strict_order(dml_ctx *ctx, int32_t on);   /* switch dml_fuerza between reference summation order and production kernel */         /* hs%amax as known to the host side (no synchronisation) */
 int64_t dml_launch_count(dml_ctx *ctx);   /* kernels launched by this ctx so far */
 void *dml_stream(dml_ctx *ctx);           /* cudaStream_t used by every kernel of this ctx */
 
