@@ -7,10 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdml.so")
 SRCS = ["dml.cu", "dana_host.cpp"]
-DEPS = ["dml.cu", "dml_coop.cuh", os.path.join("..", "..", "tools", "dana_host.cpp"), "dana_host.cpp", os.path.join("..", "..", "include", "dml_host.h"), "dml_kernels.cuh", "dml_device.cuh", "dml_gcmc.cuh", os.path.join("..", "..", "include", "dml.h")]
+DEPS = ["dml.cu", "dml_coop.cuh", "dml_slab.cuh", os.path.join("..", "..", "tools", "dana_host.cpp"), "dana_host.cpp", os.path.join("..", "..", "include", "dml_host.h"), "dml_kernels.cuh", "dml_device.cuh", "dml_gcmc.cuh", os.path.join("..", "..", "include", "dml.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ldl"]
 
 
 def build(force=False, verbose=False):

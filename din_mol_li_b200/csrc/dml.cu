@@ -3,6 +3,7 @@
 #include "../../include/dml.h"
 #include "dml_kernels.cuh"
 #include "dml_coop.cuh"
+#include "dml_slab.cuh"
 namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos, DevScal *__restrict__ sc, int n); }
 #include <cmath>
 #include <cstdio>
@@ -60,6 +61,10 @@ struct dml_ctx {
   // rows
   DBuf<int> row_start, row_len, row_cap, cols; DBuf<unsigned char> bq, rev_bq, halo_of, lane_cnt; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
+  // slab decomposition (dml_slab.cuh)
+  ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
+  DBuf<int> send_lo, send_hi, slab_counts, pack_uid_lo, pack_uid_hi; DBuf<double4> pack_lo, pack_hi;
+  int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
   bool rev_in_fuerza = true; // (re)build the transposed rows in front of the next pair-force call (else: right after a rebuild)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates
@@ -596,6 +601,9 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
   ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
+  if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
+  ctx->send_lo.release(); ctx->send_hi.release(); ctx->slab_counts.release(); ctx->pack_uid_lo.release(); ctx->pack_uid_hi.release();
+  ctx->pack_lo.release(); ctx->pack_hi.release();
   ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->lane_cnt.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
@@ -853,6 +861,117 @@ int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng
   if (ng) CKC(cudaMemcpyAsync(ctx->rp_gg.p, gauss, (size_t)ng * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaStreamSynchronize(ctx->st));
   ctx->rp_nu = nu; ctx->rp_ng = ng;
+  return 0;
+}
+
+// ---- slab decomposition over NCCL (dml_slab.cuh) -----------------------------------------------------------------
+#define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { ctx->err = std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "nccl error"); return -1; } } while (0)
+
+int dml_comm_unique_id(void *id128) {
+  NcclApi *N = nccl_api();
+  if (!N) return -1;
+  ncclUniqueId id;
+  if (N->GetUniqueId(&id) != ncclSuccess) return -2;
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+int dml_comm_init(dml_ctx *ctx, const void *id128, int32_t rank, int32_t nranks) {
+  NcclApi *N = nccl_api();
+  if (!N) FAIL("libnccl.so.2 not found");
+  ncclUniqueId id; memcpy(&id, id128, sizeof id);
+  NCK(N->CommInitRank(&ctx->comm, nranks, id, rank));
+  ctx->rank = rank; ctx->nranks = nranks;
+  return 0;
+}
+// host-side planning: z cuts that give every slab the same number of particles (nranks+1 values, cuts[0]=-inf side = lo)
+int dml_slab_plan(int32_t n, const double *z, int32_t nranks, double lo, double hi, double *cuts) {
+  std::vector<double> zs(z, z + n);
+  std::sort(zs.begin(), zs.end());
+  cuts[0] = lo; cuts[nranks] = hi;
+  for (int k = 1; k < nranks; ++k) {
+    size_t i = (size_t)((double)n * k / nranks);
+    cuts[k] = n ? 0.5 * (zs[std::min<size_t>(i, n - 1)] + zs[i ? i - 1 : 0]) : lo + (hi - lo) * k / nranks;
+  }
+  return 0;
+}
+static int slab_exchange(dml_ctx *ctx, bool with_uid) {
+  NcclApi *N = nccl_api();
+  const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
+  if (has_lo && ctx->nsend_lo) LAUNCH(K_PACK, k_slab_pack, nblk(ctx->nsend_lo), TPB, ctx->posm.p, ctx->uid.p, ctx->send_lo.p, ctx->nsend_lo, ctx->pack_lo.p, with_uid ? ctx->pack_uid_lo.p : nullptr);
+  if (has_hi && ctx->nsend_hi) LAUNCH(K_PACK, k_slab_pack, nblk(ctx->nsend_hi), TPB, ctx->posm.p, ctx->uid.p, ctx->send_hi.p, ctx->nsend_hi, ctx->pack_hi.p, with_uid ? ctx->pack_uid_hi.p : nullptr);
+  NCK(N->GroupStart());
+  if (has_hi) {
+    if (ctx->nsend_hi) NCK(N->Send(ctx->pack_hi.p, (size_t)ctx->nsend_hi * 4, ncclDouble, ctx->rank + 1, ctx->comm, ctx->st));
+    if (ctx->nrecv_hi) NCK(N->Recv(ctx->posm.p + ctx->ghost_hi_first, (size_t)ctx->nrecv_hi * 4, ncclDouble, ctx->rank + 1, ctx->comm, ctx->st));
+    if (with_uid && ctx->nsend_hi) NCK(N->Send(ctx->pack_uid_hi.p, ctx->nsend_hi, ncclInt, ctx->rank + 1, ctx->comm, ctx->st));
+    if (with_uid && ctx->nrecv_hi) NCK(N->Recv(ctx->uid.p + ctx->ghost_hi_first, ctx->nrecv_hi, ncclInt, ctx->rank + 1, ctx->comm, ctx->st));
+  }
+  if (has_lo) {
+    if (ctx->nsend_lo) NCK(N->Send(ctx->pack_lo.p, (size_t)ctx->nsend_lo * 4, ncclDouble, ctx->rank - 1, ctx->comm, ctx->st));
+    if (ctx->nrecv_lo) NCK(N->Recv(ctx->posm.p + ctx->ghost_lo_first, (size_t)ctx->nrecv_lo * 4, ncclDouble, ctx->rank - 1, ctx->comm, ctx->st));
+    if (with_uid && ctx->nsend_lo) NCK(N->Send(ctx->pack_uid_lo.p, ctx->nsend_lo, ncclInt, ctx->rank - 1, ctx->comm, ctx->st));
+    if (with_uid && ctx->nrecv_lo) NCK(N->Recv(ctx->uid.p + ctx->ghost_lo_first, ctx->nrecv_lo, ncclInt, ctx->rank - 1, ctx->comm, ctx->st));
+  }
+  NCK(N->GroupEnd());
+  int ng = ctx->nrecv_lo + ctx->nrecv_hi;
+  if (ng) LAUNCH(K_PACK, k_slab_mark, nblk(ng), TPB, ctx->posm.p, with_uid ? ctx->slot_b.p : nullptr, with_uid ? ctx->halo_of.p : nullptr, ctx->n_owned, ng);
+  return 0;
+}
+// Selects the particles within one list radius of each face, exchanges them with rank-1 / rank+1 and appends the received
+// ones as ghost slots [n_owned, n_owned+n_ghost).  Call after dml_upload of the owned particles (zlo <= z < zhi).
+int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) {
+  NcclApi *N = nccl_api();
+  if (!ctx->comm || !N) FAIL("dml_slab_setup: call dml_comm_init first");
+  TRY(finish(ctx));
+  const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
+  int n = ctx->n_owned = ctx->n;
+  double w = ctx->cfg.rcut + ctx->cfg.nb_dcut;
+  CKC(ctx->send_lo.ensure(ctx->cap, ctx->st)); CKC(ctx->send_hi.ensure(ctx->cap, ctx->st)); CKC(ctx->slab_counts.ensure(8, ctx->st));
+  CKC(cudaMemsetAsync(ctx->slab_counts.p, 0, 8 * sizeof(int), ctx->st));
+  LAUNCH(K_PACK, k_slab_select, nblk(n), TPB, ctx->posm.p, ctx->send_lo.p, ctx->send_hi.p, ctx->slab_counts.p, zlo, zhi, w, has_lo ? 1 : 0, has_hi ? 1 : 0, n);
+  NCK(N->GroupStart());
+  if (has_hi) { NCK(N->Send(ctx->slab_counts.p + 1, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->slab_counts.p + 3, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); }
+  if (has_lo) { NCK(N->Send(ctx->slab_counts.p + 0, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->slab_counts.p + 2, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); }
+  NCK(N->GroupEnd());
+  int hc[4];
+  CKC(cudaMemcpyAsync(hc, ctx->slab_counts.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  ctx->nsend_lo = hc[0]; ctx->nsend_hi = hc[1]; ctx->nrecv_lo = has_lo ? hc[2] : 0; ctx->nrecv_hi = has_hi ? hc[3] : 0;
+  if (n + ctx->nrecv_lo + ctx->nrecv_hi > ctx->cap) FAIL("slot capacity exhausted by ghost particles (dml_config.capacity)");
+  ctx->ghost_lo_first = n; ctx->ghost_hi_first = n + ctx->nrecv_lo;
+  CKC(ctx->pack_lo.ensure((size_t)std::max(ctx->nsend_lo, 1), ctx->st)); CKC(ctx->pack_hi.ensure((size_t)std::max(ctx->nsend_hi, 1), ctx->st));
+  CKC(ctx->pack_uid_lo.ensure((size_t)std::max(ctx->nsend_lo, 1), ctx->st)); CKC(ctx->pack_uid_hi.ensure((size_t)std::max(ctx->nsend_hi, 1), ctx->st));
+  TRY(slab_exchange(ctx, true));
+  int ng = ctx->nrecv_lo + ctx->nrecv_hi;
+  // ghosts start with pos_old = pos and no velocity
+  if (ng) {
+    std::vector<double> tmp((size_t)ng * 4);
+    CKC(cudaMemcpyAsync(tmp.data(), ctx->posm.p + n, (size_t)ng * sizeof(double4), cudaMemcpyDeviceToHost, ctx->st));
+    CKC(cudaStreamSynchronize(ctx->st));
+    std::vector<double> po((size_t)ng * 3);
+    for (int i = 0; i < ng; ++i) for (int k = 0; k < 3; ++k) po[3 * (size_t)i + k] = tmp[4 * (size_t)i + k];
+    CKC(cudaMemcpyAsync(ctx->pos_old.p + (size_t)3 * n, po.data(), po.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CKC(cudaMemsetAsync(ctx->vel.p + (size_t)3 * n, 0, (size_t)ng * 3 * sizeof(double), ctx->st));
+    CKC(cudaMemsetAsync(ctx->acel.p + (size_t)3 * n, 0, (size_t)ng * 3 * sizeof(double), ctx->st));
+    CKC(cudaStreamSynchronize(ctx->st));
+  }
+  TRY(pull_scal(ctx));
+  ctx->n = n + ng;
+  ctx->hsc->n_slots = ctx->n; ctx->hsc->b_amax = ctx->n; ctx->hsc->nat_sys += ng; ctx->hsc->listed = 0; ctx->hsc->rows_pending = 0;
+  TRY(push_scal(ctx));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+// per-step refresh of the ghost positions from their owners (same lists as the last dml_slab_setup)
+int dml_slab_halo_exchange(dml_ctx *ctx) {
+  if (!ctx->comm) FAIL("dml_slab_halo_exchange: no communicator");
+  return slab_exchange(ctx, false);
+}
+int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nsend_lo, int32_t *nsend_hi) {
+  if (n_owned) *n_owned = ctx->n_owned;
+  if (n_ghost) *n_ghost = ctx->nrecv_lo + ctx->nrecv_hi;
+  if (nsend_lo) *nsend_lo = ctx->nsend_lo;
+  if (nsend_hi) *nsend_hi = ctx->nsend_hi;
   return 0;
 }
 

@@ -16,6 +16,9 @@ constexpr long long MF_REF = 4;     // member of hs%ref
 constexpr long long MF_GCMC = 8;    // member of gcmc
 constexpr long long MF_SKIP = 16;   // atom%skip
 constexpr long long MF_LIMBO = 32;  // slot parked on hs%limbo until the next full build
+constexpr long long MF_GHOST = 64;  // slab mode: copy of a particle owned by a neighbouring slab (no row, never integrated)
+constexpr long long MF_GREF = 128;  // slab mode: ghost that is a member of hs%ref on its owner (reverse visits exist there)
+constexpr long long MF_ANYREF = MF_REF | MF_GREF;
 
 // bits 32-63: float32 upper bound of |pos - old_cg| (minimum image) since the last integrator call, +inf when unknown.
 // It only feeds the exact-safe prefilter of k_ov_detect; all flag tests mask the low bits.

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
       double f[3], u;
       if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
       fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
-      if (!asym && (m2 & MF_REF)) { fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u; }
+      if (!asym && (m2 & MF_ANYREF)) { fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u; }
     }
     if (asym) {
       for (int jj = 0; jj < rvlen; ++jj) {
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
         double4 p2 = ld_rec_nc(&posm[j]);
         long long m2 = meta_of(p2);
         int m = (int)(m2 & MF_TYPE);
-        if (m == 0 || !(m2 & MF_REF)) continue;
+        if (m == 0 || !(m2 & MF_ANYREF)) continue;
         double f[3], u;
         if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
         fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
       double4 p2 = ld_rec_nc(&posm[j]);
       long long m2 = meta_of(p2);
       int m = (int)(m2 & MF_TYPE);
-      if (m == 0 || !(m2 & MF_REF)) continue;
+      if (m == 0 || !(m2 & MF_ANYREF)) continue;
       double f[3], u;
       if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
       if (nrev == KMAX) { overflow = true; break; }
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
           double4 p2 = ld_rec_nc(&posm[bj]);
           long long m2 = meta_of(p2);
           int m = (int)(m2 & MF_TYPE);
-          if (m == 0 || !(m2 & MF_REF)) continue;
+          if (m == 0 || !(m2 & MF_ANYREF)) continue;
           double f[3], u;
           if (!pair_terms(g, ph, p1, k, p2, m, f, u)) continue;
           fx = fx + f[0]; fy = fy + f[1]; fz = fz + f[2]; ep = ep + u;
@@ -659,12 +659,12 @@ __global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
           const long long m2 = meta_of(p2);
           const int m = (int)(m2 & MF_TYPE);
           if (m == 0) continue;                                        // limbo / removed
-          if (pass == 1 && !(m2 & MF_REF)) continue;                   // reverse visits come from row owners only
+          if (pass == 1 && !(m2 & MF_ANYREF)) continue;                // reverse visits come from row owners only
           const int km = k3 + m - 1;
           if (dr2 > ph.r0sq[km]) continue;
           const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
           // weight 2 = own visit + the reverse visit by j, when j is a row owner that sees i (exact doubling, one rounding per add)
-          const double w = (pass == 0 && (m2 & MF_REF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
+          const double w = (pass == 0 && (m2 & MF_ANYREF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
           fx += w * t.x; fy += w * t.y; fz += w * t.z; ep += w * t.w; hit = true;
         }
       }

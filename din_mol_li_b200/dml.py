@@ -50,7 +50,8 @@ SYMBOLS = [
     "dml_ermak_b", "dml_cbrownian_hs", "dml_overlap_moveback", "dml_msd_book", "dml_promote", "dml_gcmc_run",
     "dml_calc_rho", "dml_maxz", "dml_bloques", "dml_set_chunk_template", "dml_step", "dml_get_cells",
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
-    "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_launch_count", "dml_stream",
+    "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
+    "dml_slab_halo_exchange", "dml_slab_info", "dml_launch_count", "dml_stream",
 ]
 
 _lib = None
@@ -93,6 +94,12 @@ def lib():
         L.dml_profile_kernel.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(dbl), C.POINTER(C.c_int64)]
         L.dml_n_slots.argtypes = [vp]
         L.dml_set_strict_order.argtypes = [vp, i32]
+        L.dml_comm_unique_id.argtypes = [vp]
+        L.dml_comm_init.argtypes = [vp, vp, i32, i32]
+        L.dml_slab_plan.argtypes = [i32, vp, i32, dbl, dbl, vp]
+        L.dml_slab_setup.argtypes = [vp, dbl, dbl]
+        L.dml_slab_halo_exchange.argtypes = [vp]
+        L.dml_slab_info.argtypes = [vp] + [C.POINTER(i32)] * 4
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -121,6 +128,21 @@ def _i32(a):
 class HostRng(C.Structure):
     """dana's RNG state (include/dml_host.h)."""
     _fields_ = [("idum", C.c_int32), ("ix", C.c_int32), ("iy", C.c_int32), ("stored", C.c_int32), ("g", C.c_double), ("calls", C.c_uint64)]
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    rc = lib().dml_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise DmlError("ncclGetUniqueId failed (%d)" % rc)
+    return bytes(buf)
+
+
+def slab_plan(z, nranks, lo, hi):
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    cuts = np.empty(nranks + 1)
+    lib().dml_slab_plan(z.shape[0], _p(z), nranks, lo, hi, _p(cuts))
+    return cuts
 
 
 def host_pos_inic(idum, xi, yi, alto):
@@ -366,6 +388,23 @@ class Ctx:
 
     def n_slots(self):
         return lib().dml_n_slots(self.h)
+
+    # --- slab decomposition (one ctx per rank) ---
+    def comm_init(self, id128, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id128))
+        self._keep_id = buf
+        self._chk(lib().dml_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
+
+    def slab_setup(self, zlo, zhi):
+        self._chk(lib().dml_slab_setup(self.h, zlo, zhi))
+
+    def slab_halo_exchange(self):
+        self._chk(lib().dml_slab_halo_exchange(self.h))
+
+    def slab_info(self):
+        v = [C.c_int32() for _ in range(4)]
+        lib().dml_slab_info(self.h, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
 
     def launch_count(self):
         return lib().dml_launch_count(self.h)

@@ -125,6 +125,16 @@ int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, cons
 /* uniforms / gaussians consumed by the next dml_gcmc_run in order */
 int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss);
 
+/* Multi-GPU, one large box: z-slab decomposition with NCCL halo exchange (no counterpart in the reference, which is a
+ * serial program).  One ctx per rank.  Round-1 scope: ghost set-up, per-step halo refresh, list build and
+ * pair force on owned particles; migration / global rebuild decision / global piston are not implemented yet. */
+int dml_comm_unique_id(void *id128);                                   /* ncclGetUniqueId (rank 0), 128 bytes */
+int dml_comm_init(dml_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
+int dml_slab_plan(int32_t n, const double *z, int32_t nranks, double lo, double hi, double *cuts /*[nranks+1]*/);  /* host only */
+int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi);              /* after dml_upload of the owned particles */
+int dml_slab_halo_exchange(dml_ctx *ctx);                              /* refresh ghost positions (grouped ncclSend/ncclRecv) */
+int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nsend_lo, int32_t *nsend_hi);
+
 /* Timing helper for bench.py: device-side duration (ms) of the kernels of the named class accumulated since
  * the last call with reset!=0.  cls: 0 pair force, 1 list build, 2 integrator, 3 overlap, 4 all. */
 int dml_profile(dml_ctx *ctx, int32_t enable);

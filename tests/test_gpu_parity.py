@@ -2,6 +2,7 @@
 inputs.  Bit-exact for cells, neighbour rows, integrator/overlap/reservoir state; forces bit-exact in strict
 order and within 1e-12 relative in row order (BASELINE.json north_star)."""
 import os
+import sys
 import numpy as np
 import pytest
 from oracle import oracle as O
@@ -198,3 +199,17 @@ def test_production_force_kernel_with_gather_skip_matches_reference_order():
         ctx.ermak_b()
         ctx.test_update(); ctx.overlap_moveback(); ctx.test_update(); ctx.promote(); ctx.calc_rho(); ctx.maxz()
     assert checked > 30000 and nonzero > 50
+
+
+def test_slab_decomposition_two_gpus():
+    """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
+    1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", os.path.join(root, "tests", "slab_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") == 2
