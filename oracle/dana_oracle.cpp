@@ -1168,6 +1168,11 @@ int orc_threads(void) {
   return 1;
 #endif
 }
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
 void orc_rng_kat(int32_t idum, int n_ran, double *ran_out, int n_gas, double *gas_out) {
   Rng a; a.idum = idum; for (int i = 0; i < n_ran; ++i) ran_out[i] = a.ran();
   Rng b; b.idum = idum; for (int i = 0; i < n_gas; ++i) gas_out[i] = b.gasdev();

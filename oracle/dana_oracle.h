@@ -100,7 +100,8 @@ void  orc_trace_clear(void *h);
 int64_t orc_trace_size(void *h);
 void  orc_trace_get(void *h, int32_t *kind, int64_t *uid, double *val);
 
-int   orc_threads(void);                      /* threads the list build uses (OpenMP, like the reference) */
+int   orc_threads(void);
+void  orc_set_threads(int n);                 /* overrides OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */                      /* threads the list build uses (OpenMP, like the reference) */
 
 /* Stand-alone pieces (known-answer tests / generators) */
 void  orc_rng_kat(int32_t idum, int n_ran, double *ran_out, int n_gas, double *gas_out);

@@ -78,6 +78,7 @@ def lib():
         L.orc_trace_size.argtypes = [C.c_void_p]
         L.orc_trace_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
         L.orc_rng_kat.argtypes = [C.c_int32, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_pos_inic.argtypes = [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -257,6 +258,10 @@ def from_case(case_dir, **over):
 
 def threads():
     return lib().orc_threads()
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
 
 
 def rng_kat(idum, n_ran, n_gas):
