@@ -57,9 +57,9 @@ struct dml_ctx {
   DBuf<double> vel, acel, pos_old, old_cg, ranv;
   DBuf<int> uid, slot_b;
   // cells
-  DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, chain_pos;
+  DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_cell, chain_pos;
   // rows
-  DBuf<int> row_start, row_len, row_cap, cols; DBuf<unsigned char> bq, rev_bq, halo_of, lane_cnt; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<int> row_start, row_len, row_cap, cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned long long> bq8; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -69,6 +69,7 @@ struct dml_ctx {
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
+  int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
@@ -228,19 +229,19 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
   LAUNCH(K_SCATTER, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
          ctx->sorted_slot.p, ctx->sc, n, force);
   LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
-         ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sc, nct, force);
+         ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_cell.p, ctx->sc, nct, force);
   return 0;
 }
 
 // ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
-  int nw = std::min(nblk(n * 32), 148 * 32);          // grid-stride over warps: an idle (guarded) launch stays cheap
-  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->lane_cnt.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  int nw = std::min(nblk(n), 148 * 8);                // grid-stride over particles: an idle (guarded) launch stays cheap
+  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 3, 0));
-  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->cell_of.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->lane_cnt.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
+         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   return 0;
 }
 
@@ -260,8 +261,8 @@ static int enq_test_update(dml_ctx *ctx) {
   if (ctx->use_coop && n <= ctx->coop_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
-    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
-    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lane_cnt = ctx->lane_cnt.p; A.lay = ctx->lay.p;
+    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
+    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.bq8 = ctx->bq8.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
     A.nb_dcut = ctx->cfg.nb_dcut;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
@@ -271,8 +272,7 @@ static int enq_test_update(dml_ctx *ctx) {
   }
   int nb = std::min(nblk(n), 148 * 6);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n);
-  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->part.p, nb, ctx->sc, ctx->lay.p, ctx->geo.nlay, ctx->cfg.nb_dcut);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut);
   TRY(enq_sort_cells(ctx, force));
   if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
@@ -315,9 +315,12 @@ static int enq_fuerza(dml_ctx *ctx) {
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
   else
   {
-#define FSUB(L) LAUNCH(K_FUERZA, (k_fuerza_sub<L>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
-    switch (ctx->force_lanes) { case 1: FSUB(1); break; case 2: FSUB(2); break; case 4: FSUB(4); break; default: FSUB(8); break; }
+#define FSUB(L, B) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->bq8.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
+    switch (ctx->force_lanes) {
+      case 1: if (ctx->force_minb == 5) FSUB(1, 5); else if (ctx->force_minb == 3) FSUB(1, 3); else FSUB(1, 4); break;
+      case 2: FSUB(2, 5); break; case 4: FSUB(4, 5); break; default: FSUB(8, 5); break;
+    }
 #undef FSUB
   }
   return 0;
@@ -330,7 +333,7 @@ static int enq_overlap(dml_ctx *ctx) {
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.row_start = ctx->row_start.p;
-    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.bq8 = ctx->bq8.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.uid = ctx->uid.p;
     A.rp_uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
     A.n = n; A.guard_pass = ctx->ov_guard_pass; A.stop_after_fill = 0;
@@ -339,14 +342,14 @@ static int enq_overlap(dml_ctx *ctx) {
     return 0;
   }
   LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->sc, n);
-  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
+  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->lay.p,
          ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
   LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
   LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
   LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
   const double *uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr;
   if (ctx->cfg.prob >= 1.0) {
-    LAUNCH(K_OV_PASS, k_ov_resolve, nblk(n, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->ovst.p,
+    LAUNCH(K_OV_PASS, k_ov_resolve, nblk(n, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->lay.p, ctx->ovst.p,
            ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
            (unsigned int)ctx->step, ctx->ov_guard_pass);
   } else {
@@ -359,7 +362,7 @@ static int enq_overlap(dml_ctx *ctx) {
       for (int pass = 0;; ++pass) {
         CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
         LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
-               ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+               ctx->bq.p, ctx->bq8.p, ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
                (unsigned int)ctx->step, pass, (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
         TRY(pull_scal(ctx));
         if (!ctx->hsc->again) { CKC(cudaMemsetAsync(&ctx->sc->any_active, 0, sizeof(int), ctx->st)); ctx->hsc->any_active = pass + 1;
@@ -525,6 +528,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   ctx->lazy_rows = !cfg->integrador && cfg->reservoir != 3 && !getenv("DML_EAGER_ROWS");
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = atoi(e);
+  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 3 && v <= 5) ctx->force_minb = v; }
   if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
@@ -536,7 +540,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->cols.ensure((size_t)cap * 48 + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
-  CKC(ctx->lane_cnt.ensure((size_t)cap * 32, ctx->st));
+  CKC(ctx->bq8.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->bq8.p, 0, (size_t)cap * sizeof(unsigned long long), ctx->st));
+  CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
   CKC(ctx->lay.ensure(2 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
   CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
@@ -604,7 +609,7 @@ void dml_destroy(dml_ctx *ctx) {
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
   ctx->send_lo.release(); ctx->send_hi.release(); ctx->slab_counts.release(); ctx->pack_uid_lo.release(); ctx->pack_uid_hi.release();
   ctx->pack_lo.release(); ctx->pack_hi.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->lane_cnt.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->bq8.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -830,6 +835,7 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));   // caller's rows carry no build distances: never skip
+  CKC(cudaMemsetAsync(ctx->bq8.p, 0, ctx->bq8.cap * sizeof(unsigned long long), ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_start.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_len.p, rl.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->row_cap.p, rc.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));

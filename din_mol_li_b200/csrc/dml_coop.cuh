@@ -71,8 +71,8 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 }
 
 struct TUArgs {
-  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot; double4 *sorted_posm; float4 *sorted_posf;
-  const int *slot_b; int *row_len, *row_cap, *row_start, *cols; unsigned char *bq, *halo_of, *lane_cnt; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
+  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
+  const int *slot_b; int *row_len, *row_cap, *row_start, *cols; unsigned char *bq, *halo_of; unsigned long long *bq8; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
 };
 
 // test_update (Neighbor.F90:668-713) in one launch
@@ -128,19 +128,19 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_slot, need, s);
   grid.sync();
   if (gt == 0 && need) sc->rows_asym = sc->halo_flag ? 1 : 0;
-  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, A.sorted_posf, c);
+  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, c);
   if (!need || A.lazy) return;
   grid.sync();
   // phases 3-5: rows (count, scan, fill) — update() + ngroup_cells, Neighbor.F90:608-633,465-548
-  d_rows<false>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.lane_cnt, sc, A.g, A.nct, A.slack);
+  d_rows<false>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.bq8, sc, A.g, A.nct, A.slack);
   grid.sync();
   coop_scan<false>(grid, A.row_cap, A.row_start, A.n, A.sums, &sc->cols_used);
   grid.sync();
-  d_rows<true>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.cell_of, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.lane_cnt, sc, A.g, A.nct, A.slack);
+  d_rows<true>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.bq8, sc, A.g, A.nct, A.slack);
 }
 
 struct OVArgs {
-  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
+  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; const unsigned char *bq; const unsigned long long *bq8; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
       *members, *roots; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass, stop_after_fill;
 };
 
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
   p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
+  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.bq8, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
   grid.sync();
   p_ov_count(A.parent, A.ovst, A.comp_cnt, A.n);
   grid.sync();
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   p_ov_fill(A.parent, A.ovst, A.comp_cnt, A.comp_off, A.members, A.n);
   if (A.stop_after_fill) return;
   grid.sync();
-  p_ov_resolve(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.ovst, A.roots, A.comp_cnt, A.comp_off, A.members, A.uid, A.rp_uovl,
+  p_ov_resolve(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.bq8, A.lay, A.ovst, A.roots, A.comp_cnt, A.comp_off, A.members, A.uid, A.rp_uovl,
                A.sc, A.g, A.ph, A.step, A.guard_pass);
   grid.sync();
   p_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, A.sc, A.n);

@@ -78,7 +78,7 @@ struct DevScal {
   long long nupd;                   // nupd_vlist (Neighbor.F90:110)
   long long choques2, ch_later;     // dana.F90:941 bookkeeping
   long long overlap_passes;
-  int pad_;
+  unsigned int ticket3;             // last-block election of k_pbc_disp
 };
 
 enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,

@@ -48,25 +48,32 @@ __global__ void __launch_bounds__(TPB) k_scan(int *__restrict__ in, int *__restr
   }
   __syncthreads();
   const int T = wsum[7];
-  if (threadIdx.x == 0) {
+  if (w == 0) {
+    // decoupled look-back by one warp: 32 predecessors per poll (a single polling thread made a tile wait for a chain of
+    // dependent L2 round trips as long as its distance to the nearest finished predecessor)
     const unsigned long long ep = (unsigned long long)(epoch & 0x3fffffffu) << 34;
+    volatile unsigned long long *vs = (volatile unsigned long long *)state;
     int prefix = 0;
     if (tile == 0) {
-      ((volatile unsigned long long *)state)[0] = ep | (2ull << 32) | (unsigned int)T;
+      if (lane == 0) vs[0] = ep | (2ull << 32) | (unsigned int)T;
     } else {
-      ((volatile unsigned long long *)state)[tile] = ep | (1ull << 32) | (unsigned int)T;
-      __threadfence();
-      for (int j = tile - 1; j >= 0; --j) {
-        unsigned long long sv;
-        do { sv = ((volatile unsigned long long *)state)[j]; } while ((sv >> 34) != (ep >> 34) || ((sv >> 32) & 3ull) == 0);
-        prefix += (int)(unsigned int)sv;
-        if (((sv >> 32) & 3ull) == 2) break;
+      if (lane == 0) { vs[tile] = ep | (1ull << 32) | (unsigned int)T; __threadfence(); }
+      for (int j = tile - 1; j >= 0; j -= 32) {
+        const int idx = j - lane;
+        unsigned long long sv = 0ull;
+        if (idx >= 0) { do { sv = vs[idx]; } while ((sv >> 34) != (ep >> 34) || ((sv >> 32) & 3ull) == 0); }
+        const unsigned int incl = __ballot_sync(0xffffffffu, idx >= 0 && ((sv >> 32) & 3ull) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 32;          // nearest predecessor that already holds an inclusive prefix
+        prefix += __reduce_add_sync(0xffffffffu, (idx >= 0 && lane <= first) ? (int)(unsigned int)sv : 0);
+        if (incl) break;
       }
-      ((volatile unsigned long long *)state)[tile] = ep | (2ull << 32) | (unsigned int)(prefix + T);
+      if (lane == 0) vs[tile] = ep | (2ull << 32) | (unsigned int)(prefix + T);
     }
-    __threadfence();
-    s_prefix = prefix;
-    if (tile == (int)gridDim.x - 1 && total_out) *total_out = prefix + T;
+    if (lane == 0) {
+      __threadfence();
+      s_prefix = prefix;
+      if (tile == (int)gridDim.x - 1 && total_out) *total_out = prefix + T;
+    }
   }
   __syncthreads();
   int run = x - t + (w ? wsum[w - 1] : 0) + s_prefix;
@@ -152,28 +159,12 @@ __device__ __forceinline__ int skip_qmax(const Geo &g, const DevScal *__restrict
   if (since > g.cell[2]) return 255;                  // particles may have changed layer: no skipping
   return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
 }
-__global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ part,
-                                                  unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, int n) {
-  // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
-  __shared__ unsigned int s_lay[LAY_MAX];
-  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) s_lay[i] = 0u;
-  __syncthreads();
-  double a1 = -1.0, a2 = -1.0;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-    double rd = d_pbc_disp(posm, pos_old, g, s);
-    if (rd >= 0.0) lay_note(s_lay, g, posm[s].z, rd);
-    top2_merge(a1, a2, rd, -1.0);
-  }
-  __syncthreads();
-  unsigned int *dst = lay + (sc->lay_cur ^ 1) * LAY_MAX;
-  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&dst[i], s_lay[i]);
-  block_top2(a1, a2);
-  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
-}
-__global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
-                             double nb_dcut) {
+// Final step of test_update, run by ONE block: merges the per-block top-2 partials, takes the rebuild decision
+// (Neighbor.F90:697-710) and rotates the z-layer tables.
+__device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
+                                             double nb_dcut) {
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, part[2 * i], part[2 * i + 1]);
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, __ldcg(&part[2 * i]), __ldcg(&part[2 * i + 1]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
@@ -203,6 +194,41 @@ __global__ void k_top2_final(const double *__restrict__ part, int nb, DevScal *_
     __syncthreads();
     if (threadIdx.x == 0) sc->lay_cur = cur ^ 1;
   }
+}
+// finalize != 0: the last block to finish runs d_top2_final itself (single-GPU path, one launch less per test_update);
+// finalize == 0: the partials are left in part[] for the caller (slab mode merges them across ranks first).
+__global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *part,
+                                                  unsigned int *__restrict__ lay, DevScal *__restrict__ sc, Geo g, int n, int n_disp,
+                                                  int finalize, double nb_dcut) {
+  // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
+  __shared__ unsigned int s_lay[LAY_MAX];
+  __shared__ int s_last;
+  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) s_lay[i] = 0u;
+  __syncthreads();
+  double a1 = -1.0, a2 = -1.0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    double rd = d_pbc_disp(posm, pos_old, g, s);
+    if (rd >= 0.0) lay_note(s_lay, g, posm[s].z, rd);
+    if (s < n_disp) top2_merge(a1, a2, rd, -1.0);        // slab mode: ghosts are measured by their owners
+  }
+  __syncthreads();
+  unsigned int *dst = lay + (sc->lay_cur ^ 1) * LAY_MAX;
+  for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&dst[i], s_lay[i]);
+  block_top2(a1, a2);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
+  if (!finalize) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&sc->ticket3, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) sc->ticket3 = 0u;
+  __threadfence();
+  d_top2_final(part, (int)gridDim.x, sc, lay, g.nlay, nb_dcut);
+}
+__global__ void k_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
+                             double nb_dcut) {
+  d_top2_final(part, nb, sc, lay, nlay, nb_dcut);
 }
 
 // ================================================================================================
@@ -263,7 +289,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
 // one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
 __device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
                                              int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
-                                             float4 *__restrict__ sorted_posf, int c) {
+                                             float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, int c) {
   cell_cur[c] = 0;
   int b = cell_start[c], e = cell_start[c + 1];
   for (int i = b + 1; i < e; ++i) {
@@ -276,23 +302,23 @@ __device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, c
     double4 p = ld_rec(&posm[sl]); st_rec(&sorted_posm[i], p);
     // single-precision copy for the candidate scan of k_rows; w carries the slot so the fill pass needs no second lookup
     sorted_posf[i] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(sl));
+    sorted_cell[i] = c;                                // cell of the i-th sorted particle (k_rows: no gather through cell_of[slot])
   }
 }
 __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
                              int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
-                             float4 *__restrict__ sorted_posf, DevScal *__restrict__ sc, int ncell, int force) {
+                             float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, DevScal *__restrict__ sc, int ncell, int force) {
   REBUILD_GUARD(sc, force);
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag ? 1 : 0;
   if (c >= ncell) return;
-  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, c);
+  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, sorted_cell, c);
 }
 
 // ================================================================================================
 // K3  Verlet rows over linked cells      (ngroup_cells, Neighbor.F90:465-548; cell_pbc Cells.F90:378-404;
-//     vdistance Groups.F90:995-1016).  One warp per cell-sorted ref particle, one lane per stencil cell: lane l walks
-//     the chain of cell map(:,l) and an exclusive prefix over the lanes (= stencil order) places its hits, so rows
-//     come out in the reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
+//     vdistance Groups.F90:995-1016).  One thread per cell-sorted ref particle (see d_rows): rows come out in the
+//     reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
 // ================================================================================================
 // Candidate test of k_rows.  The decision "rd < rc_list^2" must be the reference's fp64 one (vdistance, separately
 // rounded products), but almost every candidate is far from the boundary: a single-precision distance with a rigorous
@@ -312,93 +338,75 @@ __device__ __forceinline__ bool row_hit(const Geo &g, const double4 &p, float px
   if (rd_out) *rd_out = rd;
   return rd < g.rc_list2;
 }
+// One thread per cell-sorted ref particle: the thread walks the 27 stencil cells in map order and every cell's segment in
+// chain order, which IS the reference's row order, so no prefix over lanes is needed and every lane of a warp tests its own
+// candidate (the earlier warp-per-particle kernel kept ~1/4 of the lanes busy).  Threads of a warp sit in the same or adjacent
+// cells, so their candidate loads hit the same lines.  FILL=false counts (row_len/row_cap), FILL=true writes cols/bq and the
+// 8-byte head of the build distances (bq8) that lets the consumers decide the gather skip from one coalesced load.
 template <bool FILL>
 __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                        const int *__restrict__ sorted_slot,
-                                       const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                                       const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
                                        int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                       int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned char *__restrict__ lane_cnt,
+                                       int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned long long *__restrict__ bq8,
                                        DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
-  const int lane = threadIdx.x & 31;
-  int mdx = 0, mdy = 0, mdz = 0;
-  if (lane < 27) map_of_lane(lane, mdx, mdy, mdz);
   const int nsorted = cell_start[ncell];              // number of binned particles
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int gsz = gridDim.x * blockDim.x;
   const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
   const float rc2lo = (float)g.rc_list2 - g.band2, rc2hi = (float)g.rc_list2 + g.band2;
   if (FILL && sc->cols_used > sc->cols_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); return; }
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nsorted; t += nwarps) {
-    double4 p = ld_rec_nc(&sorted_posm[t]);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsorted; t += gsz) {
+    const double4 p = ld_rec_nc(&sorted_posm[t]);
     const int s = sorted_slot[t];
     if (!(meta_of(p) & MF_REF)) {                     // rows exist only for ref atoms
-      if (!FILL && lane == 0) { row_len[s] = 0; row_cap[s] = 0; }
+      if (!FILL) { row_len[s] = 0; row_cap[s] = 0; }
       continue;
     }
-    int lin = cell_of[s];
-    if (lin < 0) continue;
+    const int lin = sorted_cell[t];
     const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
-    int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-    int b = 0, e = 0;
-    if (lane < 27) {
-      int nx = mdx + cx - 1, ny = mdy + cy - 1, nz = mdz + cz - 1;      // cell_pbc wraps every axis, z included (Cells.F90:387-391)
+    const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
+    int cnt = 0;
+    int w = FILL ? row_start[s] : 0;
+    unsigned long long head = ~0ull;
+#pragma unroll 1
+    for (int nab = 0; nab < 27; ++nab) {
+      int nx = c_map[nab][0] + cx - 1, ny = c_map[nab][1] + cy - 1, nz = c_map[nab][2] + cz - 1;   // cell_pbc wraps every axis, z included (Cells.F90:387-391)
       nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
       ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
       nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
-      int nl = cell_lin(g, nx, ny, nz);
-      b = cell_start[nl]; e = cell_start[nl + 1];
-    }
-    int cnt = 0;
-    if (!FILL) {
+      const int nl = cell_lin(g, nx, ny, nz);
+      const int b = __ldg(&cell_start[nl]), e = __ldg(&cell_start[nl + 1]);
       for (int u = b; u < e; ++u) {
         if (u == t) continue;
         const float4 q = __ldg(&sorted_posf[u]);
-        if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, nullptr)) ++cnt;
-      }
-    }
-    if (!FILL) lane_cnt[(size_t)t * 32 + lane] = (unsigned char)min(cnt, 255);   // one 32-byte sector per particle
-    if (FILL) {
-      // the per-lane hit counts of the first pass give the write offsets (prefix over the lanes = stencil order);
-      // a saturated count (>= 255 hits in one cell: dense metal) falls back to recounting
-      cnt = lane_cnt[(size_t)t * 32 + lane];
-      if (__any_sync(0xffffffffu, cnt == 255)) {
-        cnt = 0;
-        for (int u = b; u < e; ++u) {
-          if (u == t) continue;
-          const float4 q = __ldg(&sorted_posf[u]);
+        if (!FILL) {
           if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, nullptr)) ++cnt;
+        } else {
+          double rd;
+          if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, &rd)) {
+            cols[w] = __float_as_int(q.w);
+            // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
+            const int qb = min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
+            bq[w] = (unsigned char)qb;
+            if (cnt < 8) head = (head & ~(0xffull << (8 * cnt))) | ((unsigned long long)qb << (8 * cnt));
+            ++w; ++cnt;
+          }
         }
       }
     }
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    if (!FILL) {
-      if (lane == 31) { row_len[s] = incl; row_cap[s] = incl + slack; }
-    } else {
-      int w = row_start[s] + incl - cnt;
-      for (int u = b; u < e; ++u) {
-        if (u == t) continue;
-        const float4 q = __ldg(&sorted_posf[u]);
-        double rd;
-        if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, &rd)) {
-          cols[w] = __float_as_int(q.w);
-          // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of k_fuerza_sub)
-          bq[w] = (unsigned char)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
-          ++w;
-        }
-      }
-    }
+    if (!FILL) { row_len[s] = cnt; row_cap[s] = cnt + slack; }
+    else bq8[s] = head;
   }
 }
 template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                               const int *__restrict__ sorted_slot,
-                                              const int *__restrict__ cell_of, const int *__restrict__ cell_start,
+                                              const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
                                               int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                              int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned char *__restrict__ lane_cnt,
+                                              int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned long long *__restrict__ bq8,
                                               DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
-  d_rows<FILL>(sorted_posm, sorted_posf, sorted_slot, cell_of, cell_start, row_len, row_cap, row_start, cols, bq, lane_cnt, sc, g, ncell, slack);
+  d_rows<FILL>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, row_len, row_cap, row_start, cols, bq, bq8, sc, g, ncell, slack);
   if (FILL) {                                         // the last block to finish marks the rows as materialised
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -613,73 +621,94 @@ __device__ __noinline__ double4 lj_terms(double vx, double vy, double vz, double
   r.w = aux * .5;
   return r;
 }
-template <int LANES>
-__global__ void __launch_bounds__(TPB, 5) k_fuerza_sub(
+// One candidate of the production kernels: gather the record, cheap cut-off tests first, heavy math out of line.
+// pass 0 = own row, pass 1 = transposed row (reverse visits come from row owners only).
+struct FAcc { double fx, fy, fz, ep; bool hit; };
+__device__ __forceinline__ void fuerza_visit(const double4 *__restrict__ posm, const Geo &g, const Phys &ph, const double4 &p1, int k3,
+                                             int j, int pass, int asym, bool i_halo, FAcc &a) {
+  const double4 p2 = ld_rec_nc(&posm[j]);
+  double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
+  if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
+  if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
+  const double dr2 = (vx * vx + vy * vy) + vz * vz;
+  if (dr2 > ph.r0sq_max) return;
+  const long long m2 = meta_of(p2);
+  const int m = (int)(m2 & MF_TYPE);
+  if (m == 0) return;                                          // limbo / removed
+  if (pass == 1 && !(m2 & MF_ANYREF)) return;                  // reverse visits come from row owners only
+  const int km = k3 + m - 1;
+  if (dr2 > ph.r0sq[km]) return;
+  const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
+  // weight 2 = own visit + the reverse visit by j, when j is a row owner that sees i (exact doubling, one rounding per add)
+  const double w = (pass == 0 && (m2 & MF_ANYREF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
+  a.fx += w * t.x; a.fy += w * t.y; a.fz += w * t.z; a.ep += w * t.w; a.hit = true;
+}
+// Gather skip: an entry whose build-time distance D satisfies D - S > r0_max cannot be inside any cut-off, S being a
+// bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
+// around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
+// integrator moved since.  qmax is the largest quantised D that still has to be looked at.
+template <int LANES, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
     const double4 *__restrict__ posm, const int *__restrict__ row_start, const int *__restrict__ row_len,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+    const unsigned long long *__restrict__ bq8,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
     const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
   bool act = s < n;
+  // everything addressed by the slot alone is requested together (one memory round trip): record, row pointer/length and
+  // the first eight build-distance bytes of the row
   double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+  const int rs0 = act ? __ldg(&row_start[s]) : 0, rl0 = act ? __ldg(&row_len[s]) : 0;
+  const unsigned long long h8 = (act && LANES == 1) ? __ldg(&bq8[s]) : 0ull;
   const long long m1 = meta_of(p1);
   act = act && (m1 & MF_REF);
-  double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
-  bool hit = false;
+  FAcc a = {0.0, 0.0, 0.0, 0.0, false};
   if (act) {
     const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
     const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
     const bool i_halo = asym == 1 && halo_of[s] != 0;
-    // Gather skip: an entry whose build-time distance D satisfies D - S > r0_max cannot be inside any cut-off, S being a
-    // bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
-    // around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
-    // integrator moved since.  qmax is the largest quantised D that still has to be looked at.
     const int qmax = skip_qmax(g, sc, lay, p1.z, sqrt(ph.r0sq_max));
     const int npass = asym ? 2 : 1;
     for (int pass = 0; pass < npass; ++pass) {
-      const int off = pass == 0 ? row_start[s] : rev_start[s];
+      const int off = pass == 0 ? rs0 : rev_start[s];
       const int *lst = (pass == 0 ? cols : rev_cols) + off;
       const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
-      const int len = pass == 0 ? row_len[s] : rev_len[s];
-      for (int j0 = sub; j0 < len; j0 += 8 * LANES) {
+      const int len = pass == 0 ? rl0 : rev_len[s];
+      int jstart = sub;
+      if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first eight entries is already here
+        unsigned int need = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int b = (int)((h8 >> (8 * q)) & 255ull); need |= ((q < len && b <= qmax) ? 1u : 0u) << q; }
+        while (need) {
+          const int q = __ffs(need) - 1; need &= need - 1;
+          fuerza_visit(posm, g, ph, p1, k3, __ldg(&lst[q]), 0, asym, i_halo, a);
+        }
+        jstart = 8;
+      }
+      for (int j0 = jstart; j0 < len; j0 += 8 * LANES) {
         unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
 #pragma unroll
         for (int q = 0; q < 8; ++q) { int jj = j0 + q * LANES; int b = jj < len ? (int)__ldg(&lq[jj]) : 1000; need |= (b <= qmax ? 1u : 0u) << q; }
         while (need) {
           const int q = __ffs(need) - 1; need &= need - 1;
-          const int j = __ldg(&lst[j0 + q * LANES]);
-          const double4 p2 = ld_rec_nc(&posm[j]);
-          double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
-          if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
-          if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
-          const double dr2 = (vx * vx + vy * vy) + vz * vz;
-          if (dr2 > ph.r0sq_max) continue;
-          const long long m2 = meta_of(p2);
-          const int m = (int)(m2 & MF_TYPE);
-          if (m == 0) continue;                                        // limbo / removed
-          if (pass == 1 && !(m2 & MF_ANYREF)) continue;                // reverse visits come from row owners only
-          const int km = k3 + m - 1;
-          if (dr2 > ph.r0sq[km]) continue;
-          const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
-          // weight 2 = own visit + the reverse visit by j, when j is a row owner that sees i (exact doubling, one rounding per add)
-          const double w = (pass == 0 && (m2 & MF_ANYREF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
-          fx += w * t.x; fy += w * t.y; fz += w * t.z; ep += w * t.w; hit = true;
+          fuerza_visit(posm, g, ph, p1, k3, __ldg(&lst[j0 + q * LANES]), pass, asym, i_halo, a);
         }
       }
     }
   }
   if (LANES > 1) {
-    if (__any_sync(0xffffffffu, hit)) {
+    if (__any_sync(0xffffffffu, a.hit)) {
 #pragma unroll
       for (int o = LANES / 2; o > 0; o >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o);
-        fz += __shfl_xor_sync(0xffffffffu, fz, o); ep += __shfl_xor_sync(0xffffffffu, ep, o);
+        a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o); a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
+        a.fz += __shfl_xor_sync(0xffffffffu, a.fz, o); a.ep += __shfl_xor_sync(0xffffffffu, a.ep, o);
       }
     }
   }
-  if (act && sub == 0) st_rec(&fe[s], make_double4(fx, fy, fz, ep));
+  if (act && sub == 0) st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
 }
 
 // ================================================================================================
@@ -861,41 +890,54 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
 __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const int *__restrict__ row_start, const int *__restrict__ row_len,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                                                   const unsigned long long *__restrict__ bq8,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
                                                    DevScal *__restrict__ sc, Geo g, int n) {
-
   const int s_end = n;
+  const double rcut = sqrt(g.rcut2);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
-    double4 p1 = ld_rec_nc(&posm[s]);
-    long long m1 = meta_of(p1);
+    // one round trip for everything addressed by the slot alone
+    const double4 p1 = ld_rec_nc(&posm[s]);
+    const int b = __ldg(&row_start[s]), len = __ldg(&row_len[s]);
+    const unsigned long long h8 = __ldg(&bq8[s]);
+    const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
-    double o1[3] = {old_cg[3 * s], old_cg[3 * s + 1], old_cg[3 * s + 2]};
     const float d1 = disp_of(m1);
-    const double rcut = sqrt(g.rcut2);
-    int b = row_start[s], len = row_len[s];
     const int qmax = skip_qmax(g, sc, lay, p1.z, rcut);   // same build-distance skip as the pair force (covers new and old positions)
-    bool inv = false;
-    for (int jj = 0; jj < len; ++jj) {
-      if ((int)__ldg(&bq[b + jj]) > qmax) continue;
-      int j = cols[b + jj];
-      double4 p2 = ld_rec_nc(&posm[j]);
-      long long m2 = meta_of(p2);
-      if (!(m2 & MF_TYPE)) continue;
-      // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
-      // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
-      double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
-      {
-        double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
-        if (rd_nn > thr * thr) continue;
+    bool inv = false, have_o1 = false;
+    double o1[3] = {0.0, 0.0, 0.0};
+    for (int j0 = 0; j0 < len; j0 += 8) {
+      unsigned int need = 0u;
+      if (j0 == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int bb = (int)((h8 >> (8 * q)) & 255ull); need |= ((q < len && bb <= qmax) ? 1u : 0u) << q; }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { const int jj = j0 + q; const int bb = jj < len ? (int)__ldg(&bq[b + jj]) : 1000; need |= (bb <= qmax ? 1u : 0u) << q; }
       }
-      bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
-      if (m2 & MF_REF) {
-        double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
-        hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
-              dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
-        if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
+      while (need) {
+        const int q = __ffs(need) - 1; need &= need - 1;
+        const int j = __ldg(&cols[b + j0 + q]);
+        const double4 p2 = ld_rec_nc(&posm[j]);
+        const long long m2 = meta_of(p2);
+        if (!(m2 & MF_TYPE)) continue;
+        // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
+        // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
+        const double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
+        {
+          const double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
+          if (rd_nn > thr * thr) continue;
+        }
+        if (!have_o1) { o1[0] = old_cg[3 * s]; o1[1] = old_cg[3 * s + 1]; o1[2] = old_cg[3 * s + 2]; have_o1 = true; }
+        bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
+        if (m2 & MF_REF) {
+          const double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
+          hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
+                dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
+          if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
+        }
+        inv = inv || hit;
       }
-      inv = inv || hit;
     }
     if (inv) atomicOr(&ovst[s], OV_INVOLVED);
   }
@@ -903,8 +945,9 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
 __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const int *__restrict__ row_start, const int *__restrict__ row_len,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                                                   const unsigned long long *__restrict__ bq8,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, bq, lay, parent, ovst, sc, g, n); }
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, parent, ovst, sc, g, n); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
@@ -982,11 +1025,14 @@ __device__ __forceinline__ void ov_pos(const double4 *posm, const double *old_cg
 struct OvAcc { long long tr, de, ch, ch3; };
 __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                             const int *__restrict__ row_start, const int *__restrict__ row_len,
-                                            const int *__restrict__ cols, int *__restrict__ ovst, const int *__restrict__ members,
+                                            const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                                            const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay,
+                                            int *__restrict__ ovst, const int *__restrict__ members,
                                             const int *__restrict__ uid, const double *__restrict__ rp_uovl, DevScal *__restrict__ sc,
                                             const Geo &g, const Phys &ph, unsigned int step, int pass, int guard, double z0,
                                             int b, int e, OvAcc &acc) {
   bool again = false;
+  const double rcut = sqrt(g.rcut2);
   for (int i = b; i < e; ++i) {
     int a1 = members[i];
     int st1 = ((volatile int *)ovst)[a1];
@@ -994,8 +1040,14 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
     if (!((st1 >> OV_TSHIFT) & 3)) continue;
     st1 |= OV_SKIP;
     double q1[3]; ov_pos(posm, old_cg, a1, st1, q1);
-    int rb = row_start[a1], rl = row_len[a1];
+    const int rb = row_start[a1], rl = row_len[a1];
+    // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
+    // new/old combination, so skipping it here changes nothing and saves the dependent gathers of the replay
+    const unsigned long long h8 = bq8[a1];
+    const int qmax = skip_qmax(g, sc, lay, ld_rec_nc(&posm[a1]).z, rcut);
     for (int jj = 0; jj < rl; ++jj) {
+      const int bqv = jj < 8 ? (int)((h8 >> (8 * jj)) & 255ull) : (int)__ldg(&bq[rb + jj]);
+      if (bqv > qmax) continue;
       int a2 = cols[rb + jj];
       int st2 = ((volatile int *)ovst)[a2];
       int t2 = (st2 >> OV_TSHIFT) & 3;
@@ -1042,7 +1094,8 @@ __device__ __forceinline__ void ov_flush(const OvAcc &acc, DevScal *sc) {
 // Global-synchronous variant: one launch = one recursion level for every component (needed when prob<1, where a
 // failed deposition leaves skip=.false. without requesting another pass, so the pass count couples components).
 __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                          const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                          const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                          const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                           const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
                           DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
@@ -1050,7 +1103,7 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
   if (r >= sc->n_roots) return;
   int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
   OvAcc acc = {0, 0, 0, 0};
-  bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass, guard, sc->z0, b, e, acc);
+  bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, members, uid, rp_uovl, sc, g, ph, step, pass, guard, sc->z0, b, e, acc);
   ov_flush(acc, sc);
   if (pass >= 1 && acc.ch) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)acc.ch);
   if (again) sc->again = 1;
@@ -1058,7 +1111,8 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
 // Fused variant (prob>=1: every metal contact deposits, nothing couples components): each component thread orders its
 // members and replays all recursion levels locally.  No host round trip, one launch.
 __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                             const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                             const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                             const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                              int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
@@ -1073,7 +1127,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
     int pass = 0;
     for (;; ++pass) {
       long long ch0 = acc.ch;
-      bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
+      bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
                                (guard_pass > 0 && pass >= guard_pass) ? 1 : 0, z0, b, e, acc);
       if (pass >= 1) later += acc.ch - ch0;
       if (!again) break;
@@ -1084,10 +1138,11 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
   }
 }
 __global__ void k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                             const int *__restrict__ row_len, const int *__restrict__ cols, int *__restrict__ ovst,
+                             const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                             const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                              int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
-                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) { p_ov_resolve(posm, old_cg, row_start, row_len, cols, ovst, roots, comp_cnt, comp_off, members, uid, rp_uovl, sc, g, ph, step, guard_pass); }
+                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) { p_ov_resolve(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, roots, comp_cnt, comp_off, members, uid, rp_uovl, sc, g, ph, step, guard_pass); }
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
 __device__ __forceinline__ void p_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
                            const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) {

@@ -62,6 +62,17 @@ def test_lockstep_replay_bit_exact(name, nsteps):
         ls.step(check=True, tag="%s step %d" % (name, i + 1))
 
 
+@pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40), ("gcmc", 150)])
+def test_lockstep_replay_multi_launch_path(name, nsteps, monkeypatch):
+    """Same lock-step comparison with the persistent cooperative kernels switched off: the one-launch-per-phase path that
+    boxes above 65 536 slots take (bench.py's 100 k and 1 M workloads) must be bit-exact too."""
+    monkeypatch.setenv("DML_NO_COOP", "1")
+    d, o = case(name)
+    ls = P.Lockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s (multi-launch) step %d" % (name, i + 1))
+
+
 def test_brown_fixture_on_device():
     """The whole tests/brown case on the device in replay mode must end on the reference's ref.xyz."""
     d, o = case("brown")
