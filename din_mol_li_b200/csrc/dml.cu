@@ -59,7 +59,7 @@ struct dml_ctx {
   // cells
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_cell, chain_pos;
   // rows
-  DBuf<int> row_start, row_len, row_cap, cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned long long> bq8; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -67,7 +67,8 @@ struct dml_ctx {
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
   bool rev_in_fuerza = true; // (re)build the transposed rows in front of the next pair-force call (else: right after a rebuild)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
-  int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates
+  int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
+  int coop_tu_max_n = 262144;   // test_update has more and shorter phases: the one-launch form wins up to larger boxes
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
@@ -76,7 +77,7 @@ struct dml_ctx {
   DBuf<int> rev_cnt;
   DBuf<double> part;
   // overlap
-  DBuf<int> parent, ovst, comp_cnt, comp_off, members, roots;
+  DBuf<int> parent, ovst, comp_cnt, comp_off, members, roots, ov_head, ov_next;
   // gcmc
   DBuf<int> gorder, gpos, gcc, gpend, b_occ; int gorder_cap = 0;
   // replay
@@ -101,13 +102,13 @@ static int pull_scal(dml_ctx *ctx);
 
 enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
 // one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
-enum { K_SCAN = 0, K_PBC_BIN, K_TOP2, K_SCATTER, K_CELL_ORDER, K_ROWS_COUNT, K_ROWS_FILL, K_ROW_CAPS, K_FUERZA, K_INTEGRATE,
+enum { K_SCAN = 0, K_PBC_BIN, K_TOP2, K_SCATTER, K_CELL_ORDER, K_ROWS_COUNT, K_ROWS_FILL, K_OV_LINK, K_FUERZA, K_INTEGRATE,
        K_ERMAK_B, K_OV_INIT, K_OV_DETECT, K_OV_COUNT, K_OV_ALLOC, K_OV_FILL, K_OV_SORT, K_OV_PASS, K_OV_APPLY, K_PROMOTE,
        K_CALC_RHO, K_MAXZ, K_PACK, K_MISC, K_GCMC, K_REV, K_BIN, K_TU_COOP, K_OV_COOP, K_NKERN };
-static const char *const kern_name[K_NKERN] = {"scan", "pbc_disp", "top2_final", "scatter", "cell_order", "rows_count", "rows_fill",
-  "row_caps", "fuerza", "integrate", "ermak_b", "ov_init", "ov_detect", "ov_count", "ov_alloc", "ov_fill", "ov_sort", "ov_pass",
+static const char *const kern_name[K_NKERN] = {"scan", "pbc_disp", "top2_final", "scatter", "cell_order", "rows_count", "rows_build",
+  "ov_link", "fuerza", "integrate", "ermak_b", "ov_init", "ov_detect", "ov_count", "ov_alloc", "ov_fill", "ov_sort", "ov_pass",
   "ov_apply", "promote", "calc_rho", "maxz", "pack", "misc", "gcmc", "rev_rows", "bin", "test_update_coop", "overlap_coop"};
-static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_FORCE, CLS_INTEG,
+static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_LIST, CLS_LIST, CLS_LIST, CLS_OVERLAP, CLS_FORCE, CLS_INTEG,
   CLS_INTEG, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OVERLAP, CLS_OTHER,
   CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_OTHER, CLS_GCMC, CLS_LIST, CLS_LIST, CLS_LIST, CLS_OVERLAP};
 
@@ -186,7 +187,7 @@ static void tessellate(dml_ctx *ctx) {
     for (int k = 0; k < 3; ++k) if (!((double)(g.nc[k] + 1) >= g.box[k] / rc)) ok1 = false;
     if (ok1) {
       for (int k = 0; k < 3; ++k) if (!(rc < g.box[k] / (double)g.nc[k])) ok2 = false;
-      if (ok2) { for (int k = 0; k < 3; ++k) g.cell[k] = g.box[k] / (double)g.nc[k]; return; }
+      if (ok2) { for (int k = 0; k < 3; ++k) g.cell[k] = g.box[k] / (double)g.nc[k]; g.inv_cell2 = 1.0 / g.cell[2]; return; }
     }
   }
   int nc[3];
@@ -194,6 +195,7 @@ static void tessellate(dml_ctx *ctx) {
   for (int k = 0; k < 3; ++k) g.nc[k] = nc[k];
   if (nc[0] < 4 && nc[1] < 4 && nc[2] < 4) return;       // reference falls back to the O(N^2) list
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
+  g.inv_cell2 = 1.0 / g.cell[2];
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
   g.lay_shift = 0; while (((g.nc[2] + 2) >> g.lay_shift) + 1 > LAY_MAX) g.lay_shift++;
   g.nlay = ((g.nc[2] + 1) >> g.lay_shift) + 1;
@@ -224,11 +226,11 @@ static int ensure_particles(dml_ctx *ctx, int n) {
 // cell binning + counting sort; guarded on the device by need_rebuild | force
 static int enq_sort_cells(dml_ctx *ctx, int force) {
   int n = ctx->n, nct = ctx->nct;
-  LAUNCH(K_BIN, k_bin, nblk(n), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->row_len.p, ctx->row_cap.p, ctx->halo_of.p, ctx->sc, ctx->geo, n, force);
+  LAUNCH(K_BIN, k_bin, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->rh.p, ctx->halo_of.p, ctx->sc, ctx->geo, n, force);
   TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, true, 0, force));
-  LAUNCH(K_SCATTER, k_scatter, nblk(n), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
+  LAUNCH(K_SCATTER, k_scatter, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
          ctx->sorted_slot.p, ctx->sc, n, force);
-  LAUNCH(K_CELL_ORDER, k_cell_order, nblk(nct, 128), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
+  LAUNCH(K_CELL_ORDER, k_cell_order, std::min(nblk(nct, 128), 148 * 16), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
          ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_cell.p, ctx->sc, nct, force);
   return 0;
 }
@@ -237,11 +239,8 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
   int nw = std::min(nblk(n), 148 * 8);                // grid-stride over particles: an idle (guarded) launch stays cheap
-  LAUNCH(K_ROWS_COUNT, (k_rows<false>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
-  TRY(scan_excl(ctx, ctx->row_cap.p, ctx->row_start.p, n, &ctx->sc->cols_used, false, 3, 0));
-  LAUNCH(K_ROWS_FILL, (k_rows<true>), nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
-         ctx->row_len.p, ctx->row_cap.p, ctx->row_start.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  LAUNCH(K_ROWS_FILL, k_rows, nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
+         ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   return 0;
 }
 
@@ -258,11 +257,11 @@ static int enq_test_update(dml_ctx *ctx) {
     CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
   }
   int force = ctx->cfg.reservoir == 3 ? 1 : 0;       // gcmc_run needs the cells of the current positions every step
-  if (ctx->use_coop && n <= ctx->coop_max_n) {
+  if (ctx->use_coop && n <= ctx->coop_tu_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
     A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
-    A.slot_b = ctx->slot_b.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.row_start = ctx->row_start.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.bq8 = ctx->bq8.p; A.lay = ctx->lay.p;
+    A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
     A.nb_dcut = ctx->cfg.nb_dcut;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
@@ -297,10 +296,10 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
 // transposed rows, built on the device only when rows can be asymmetric (guarded launches, no-ops otherwise)
 static int enq_build_rev(dml_ctx *ctx) {
   int n = ctx->n;
-  LAUNCH(K_REV, k_rev_count, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p,
+  LAUNCH(K_REV, k_rev_count, std::min(nblk(n), 148 * 8), TPB, ctx->rh.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p,
          ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
-  LAUNCH(K_REV, k_rev_fill, nblk(n), TPB, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
+  LAUNCH(K_REV, k_rev_fill, std::min(nblk(n), 148 * 8), TPB, ctx->rh.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
          ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
   return 0;
@@ -311,14 +310,14 @@ static int enq_fuerza(dml_ctx *ctx) {
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   if (ctx->rev_in_fuerza) { TRY(enq_build_rev(ctx)); if (ctx->cfg.reservoir != 3 && !ctx->lazy_rows) ctx->rev_in_fuerza = false; }
   if (ctx->cfg.strict_order)
-    LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p,
+    LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
   else
   {
-#define FSUB(L, B) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B>), nblk(n * L), TPB, ctx->posm.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->bq8.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
+#define FSUB(L, B) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B>), nblk(n * L), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
     switch (ctx->force_lanes) {
-      case 1: if (ctx->force_minb == 5) FSUB(1, 5); else if (ctx->force_minb == 3) FSUB(1, 3); else FSUB(1, 4); break;
+      case 1: if (ctx->force_minb == 5) FSUB(1, 5); else if (ctx->force_minb == 3) FSUB(1, 3); else if (ctx->force_minb == 2) FSUB(1, 2); else FSUB(1, 4); break;
       case 2: FSUB(2, 5); break; case 4: FSUB(4, 5); break; default: FSUB(8, 5); break;
     }
 #undef FSUB
@@ -332,27 +331,28 @@ static int enq_overlap(dml_ctx *ctx) {
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
-    A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.row_start = ctx->row_start.p;
-    A.row_len = ctx->row_len.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.bq8 = ctx->bq8.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
-    A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.uid = ctx->uid.p;
+    A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
+    A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.ov_head = ctx->ov_head.p; A.ov_next = ctx->ov_next.p; A.uid = ctx->uid.p;
     A.rp_uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
-    A.n = n; A.guard_pass = ctx->ov_guard_pass; A.stop_after_fill = 0;
+    A.n = n; A.guard_pass = ctx->ov_guard_pass;
     LAUNCH_COOP(K_OV_COOP, k_overlap_coop, ctx->coop_grid_ov, A);
     ctx->have_rp_ovl = false;
     return 0;
   }
-  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->sc, n);
-  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->lay.p,
+  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
+  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
          ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
-  LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
-  LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
-  LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
   const double *uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr;
   if (ctx->cfg.prob >= 1.0) {
-    LAUNCH(K_OV_PASS, k_ov_resolve, nblk(n, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p, ctx->bq.p, ctx->bq8.p, ctx->lay.p, ctx->ovst.p,
-           ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+    LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
+    LAUNCH(K_OV_PASS, k_ov_resolve, std::min(nblk(n, 4), 148 * 4), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
+           ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->ov_head.p, ctx->ov_next.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
            (unsigned int)ctx->step, ctx->ov_guard_pass);
   } else {
+    LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
+    LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
+    LAUNCH(K_OV_FILL, k_ov_fill, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, n);
     // prob<1: a failed deposition leaves skip=.false. without asking for another pass, so whether that atom is looked at
     // again depends on the other components: keep the reference's global recursion levels (one launch + one flag read each)
     TRY(pull_scal(ctx));
@@ -361,8 +361,8 @@ static int enq_overlap(dml_ctx *ctx) {
       LAUNCH(K_OV_SORT, k_ov_sort, nblk(nroots, 128), 128, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, ctx->sc);
       for (int pass = 0;; ++pass) {
         CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
-        LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->row_start.p, ctx->row_len.p, ctx->cols.p,
-               ctx->bq.p, ctx->bq8.p, ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+        LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p,
+               ctx->bq.p, ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
                (unsigned int)ctx->step, pass, (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
         TRY(pull_scal(ctx));
         if (!ctx->hsc->again) { CKC(cudaMemsetAsync(&ctx->sc->any_active, 0, sizeof(int), ctx->st)); ctx->hsc->any_active = pass + 1;
@@ -397,9 +397,10 @@ static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
 static int finish(dml_ctx *ctx) {
   TRY(pull_scal(ctx));
   ctx->n = ctx->hsc->n_slots;
+  const size_t tail0 = (size_t)ctx->hsc->cols_tail0;
   size_t used = (size_t)std::max(ctx->hsc->cols_used, ctx->hsc->rev_used);
-  if (used * 2 > ctx->cols.cap) {
-    size_t want = used * 3 + 4096;
+  if (used > tail0 && (used - tail0) * 2 > ctx->cols.cap - tail0) {          // half of the tail region is in use
+    size_t want = tail0 + (used - tail0) * 3 + 4096;
     CKC(ctx->cols.ensure(want, ctx->st, true)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st, false));
     CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st, true)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st, false));
     ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
@@ -507,6 +508,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
     double x = cfg->r0[i], x2 = x * x, x4 = x2 * x2; ph.r0p6[i] = x2 * x4;
     ph.r0sq_max = std::max(ph.r0sq_max, ph.r0sq[i]);
   }
+  ph.r0_max = std::sqrt(ph.r0sq_max);
   for (int i = 0; i < 3; ++i) { ph.mass[i] = cfg->mass[i]; ph.sqrt_mass[i] = std::sqrt(cfg->mass[i]); }
   ph.h = cfg->h; ph.prob = cfg->prob; ph.tau = cfg->tau;
   {                                                       // set_ermak — dana.F90:947-971
@@ -527,8 +529,9 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   ctx->lazy_rows = !cfg->integrador && cfg->reservoir != 3 && !getenv("DML_EAGER_ROWS");
-  if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = atoi(e);
-  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 3 && v <= 5) ctx->force_minb = v; }
+  if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
+  if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
+  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 5) ctx->force_minb = v; }
   if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
@@ -536,25 +539,24 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
   CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
   CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
-  CKC(ctx->row_start.ensure(cap + 1, ctx->st)); CKC(ctx->row_len.ensure(cap, ctx->st)); CKC(ctx->row_cap.ensure(cap, ctx->st));
-  CKC(ctx->cols.ensure((size_t)cap * 48 + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
+  CKC(ctx->rh.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->rh.p, 0, (size_t)cap * sizeof(RowHead), ctx->st));
+  CKC(ctx->cols.ensure((size_t)cap * (ROW_W + 32) + 4096, ctx->st));   // region A (ROW_W per slot) + tail
+  CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
-  CKC(ctx->bq8.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->bq8.p, 0, (size_t)cap * sizeof(unsigned long long), ctx->st));
   CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
   CKC(ctx->lay.ensure(2 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
   CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->rev_cnt.p, 0, (size_t)cap * sizeof(int), ctx->st));
-  CKC(cudaMemsetAsync(ctx->row_cap.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(ctx->parent.ensure(cap, ctx->st)); CKC(ctx->ovst.ensure(cap, ctx->st)); CKC(ctx->comp_cnt.ensure(cap, ctx->st));
   CKC(ctx->comp_off.ensure(cap, ctx->st)); CKC(ctx->members.ensure(cap, ctx->st)); CKC(ctx->roots.ensure(cap, ctx->st));
+  CKC(ctx->ov_head.ensure(cap, ctx->st)); CKC(ctx->ov_next.ensure(cap, ctx->st));
   ctx->gorder_cap = 2 * cap + 2048;
   CKC(ctx->gorder.ensure((size_t)2 * ctx->gorder_cap, ctx->st)); CKC(ctx->gpos.ensure(cap, ctx->st));
   CKC(ctx->gcc.ensure((size_t)ctx->gorder_cap / 1024 + 8, ctx->st)); CKC(ctx->b_occ.ensure(cap, ctx->st));
   CKC(ctx->rp_gauss.ensure((size_t)cap * 6, ctx->st)); CKC(ctx->rp_upbc.ensure(cap, ctx->st)); CKC(ctx->rp_uovl.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)cap * sizeof(double4), ctx->st));
-  CKC(cudaMemsetAsync(ctx->row_len.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(cudaMemsetAsync(ctx->fe.p, 0, (size_t)cap * sizeof(double4), ctx->st));
   {
     // Keep the 32-byte particle records resident in the 126 MB L2 across the kernels of a step: every gather of the
@@ -591,6 +593,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   memset(ctx->hsc, 0, sizeof(DevScal));
   ctx->hsc->z0 = cfg->z0; ctx->hsc->z1 = cfg->z1; ctx->hsc->zmax = cfg->zmax;
   ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
+  ctx->hsc->cols_tail0 = ctx->hsc->cols_used = cap * ROW_W;
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
   return 0;
@@ -604,12 +607,12 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
   ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
-  ctx->row_start.release(); ctx->row_len.release(); ctx->row_cap.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
-  ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release();
+  ctx->rh.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
+  ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release(); ctx->ov_head.release(); ctx->ov_next.release();
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
   ctx->send_lo.release(); ctx->send_hi.release(); ctx->slab_counts.release(); ctx->pack_uid_lo.release(); ctx->pack_uid_hi.release();
   ctx->pack_lo.release(); ctx->pack_hi.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->bq8.release(); ctx->sorted_cell.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -718,7 +721,7 @@ int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
   if (ctx->hsc->listed) {
     if (ctx->lazy_rows) { TRY(enq_materialize_rows(ctx)); }
     CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
-    LAUNCH(K_MISC, k_sum_int, 64, TPB, ctx->row_len.p, ctx->n, &ctx->sc->list_entries);
+    LAUNCH(K_MISC, k_sum_rowlen, 64, TPB, ctx->rh.p, ctx->n, &ctx->sc->list_entries);
     TRY(pull_scal(ctx));
   }
   DevScal *h = ctx->hsc;
@@ -809,39 +812,39 @@ int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("no neighbour list");
-  std::vector<int> rs(n), rl(n), cols((size_t)std::max(ctx->hsc->cols_used, 1));
-  CKC(cudaMemcpyAsync(rs.data(), ctx->row_start.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
-  CKC(cudaMemcpyAsync(rl.data(), ctx->row_len.p, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  std::vector<RowHead> rh(n);
+  std::vector<int> cols((size_t)std::max(ctx->hsc->cols_used, 1));
+  CKC(cudaMemcpyAsync(rh.data(), ctx->rh.p, n * sizeof(RowHead), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaMemcpyAsync(cols.data(), ctx->cols.p, cols.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaStreamSynchronize(ctx->st));
   int rc = 0;
   for (int i = 0; i < n; ++i) {
-    nn[i] = rl[i];
-    for (int m = 0; m < rl[i]; ++m) { if (m >= width) { rc = 1; break; } rows[(size_t)i * width + m] = cols[rs[i] + m]; }
+    nn[i] = rh[i].len;
+    for (int m = 0; m < rh[i].len; ++m) { if (m >= width) { rc = 1; break; } rows[(size_t)i * width + m] = cols[rh[i].start + m]; }
   }
   return rc;
 }
 int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn, const int32_t *rows) {
   if (n > ctx->n) FAIL("dml_set_neighbors: n exceeds the number of slots");
-  std::vector<int> rs(n + 1), rl(ctx->n, 0), rc(ctx->n, 0), cols;
-  int off = 0;
+  // same layout as the device build: a row that fits (with the gcmc slack) sits in its slot's ROW_W entries, longer ones in the tail
+  const int tail0 = ctx->cap * ROW_W;
+  std::vector<RowHead> rh(ctx->n);
+  memset(rh.data(), 0, rh.size() * sizeof(RowHead));        // zero build distances: never skip
+  size_t off = (size_t)tail0;
   for (int i = 0; i < n; ++i) {
-    rs[i] = off; rl[i] = nn[i]; rc[i] = nn[i] + ctx->row_slack;
-    for (int m = 0; m < nn[i]; ++m) cols.push_back(rows[(size_t)i * width + m]);
-    for (int m = 0; m < ctx->row_slack; ++m) cols.push_back(-1);
-    off += rc[i];
+    rh[i].len = nn[i];
+    if (nn[i] + ctx->row_slack <= ROW_W) { rh[i].start = i * ROW_W; rh[i].cap = ROW_W; }
+    else { rh[i].start = (int)off; rh[i].cap = nn[i] + ctx->row_slack; off += (size_t)rh[i].cap; }
   }
-  rs[n] = off;
-  CKC(ctx->cols.ensure((size_t)off + 4096, ctx->st)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
+  CKC(ctx->cols.ensure(off + 4096, ctx->st, true)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
+  std::vector<int> cols(off, -1);
+  for (int i = 0; i < n; ++i) for (int m = 0; m < nn[i]; ++m) cols[(size_t)rh[i].start + m] = rows[(size_t)i * width + m];
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));   // caller's rows carry no build distances: never skip
-  CKC(cudaMemsetAsync(ctx->bq8.p, 0, ctx->bq8.cap * sizeof(unsigned long long), ctx->st));
-  CKC(cudaMemcpyAsync(ctx->row_start.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
-  CKC(cudaMemcpyAsync(ctx->row_len.p, rl.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
-  CKC(cudaMemcpyAsync(ctx->row_cap.p, rc.data(), ctx->n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
-  if (off) CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), (size_t)off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->rh.p, rh.data(), ctx->n * sizeof(RowHead), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
-  ctx->hsc->cols_used = off;
+  ctx->hsc->cols_used = (int)off;
   ctx->rev_in_fuerza = true;
   ctx->hsc->rows_pending = 0;
   ctx->hsc->listed = 1; ctx->hsc->rows_asym = 2; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption

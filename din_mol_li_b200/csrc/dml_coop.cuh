@@ -72,7 +72,7 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 
 struct TUArgs {
   double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
-  const int *slot_b; int *row_len, *row_cap, *row_start, *cols; unsigned char *bq, *halo_of; unsigned long long *bq8; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
+  const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
 };
 
 // test_update (Neighbor.F90:668-713) in one launch
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     if (!need) sc->lay_cur = lay_old ^ 1;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; sc->cols_used = sc->cols_tail0; }
   }
   if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
     if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   }
   if (!(need || A.force_sort)) return;
   // phase 2: binning
-  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.row_len, A.row_cap, A.halo_of, sc, A.g, need, s);
+  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.rh, A.halo_of, sc, A.g, need, s);
   grid.sync();
   coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
   grid.sync();
@@ -131,34 +131,25 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, c);
   if (!need || A.lazy) return;
   grid.sync();
-  // phases 3-5: rows (count, scan, fill) — update() + ngroup_cells, Neighbor.F90:608-633,465-548
-  d_rows<false>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.bq8, sc, A.g, A.nct, A.slack);
-  grid.sync();
-  coop_scan<false>(grid, A.row_cap, A.row_start, A.n, A.sums, &sc->cols_used);
-  grid.sync();
-  d_rows<true>(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.row_len, A.row_cap, A.row_start, A.cols, A.bq, A.bq8, sc, A.g, A.nct, A.slack);
+  // phase 3: rows in one pass — update() + ngroup_cells, Neighbor.F90:608-633,465-548
+  d_rows(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.rh, A.cols, A.bq, sc, A.g, A.nct, A.slack);
 }
 
 struct OVArgs {
-  double4 *posm; double *vel, *acel; const double *old_cg; const int *row_start, *row_len, *cols; const unsigned char *bq; const unsigned long long *bq8; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
-      *members, *roots; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass, stop_after_fill;
+  double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
+      *members, *roots, *ov_head, *ov_next; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass;
 };
 
-// overlap_moveback (dana.F90:849-943) in one launch (prob>=1); with stop_after_fill the host drives the recursion levels
+// overlap_moveback (dana.F90:849-943) in one launch (prob>=1)
 __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
-  p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.sc, A.n);
+  p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.ov_head, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.bq8, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
+  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
   grid.sync();
-  p_ov_count(A.parent, A.ovst, A.comp_cnt, A.n);
+  p_ov_link(A.parent, A.ovst, A.ov_head, A.ov_next, A.roots, A.sc, A.n);
   grid.sync();
-  p_ov_alloc(A.parent, A.ovst, A.comp_cnt, A.comp_off, A.roots, A.sc, A.n);
-  grid.sync();
-  p_ov_fill(A.parent, A.ovst, A.comp_cnt, A.comp_off, A.members, A.n);
-  if (A.stop_after_fill) return;
-  grid.sync();
-  p_ov_resolve(A.posm, A.old_cg, A.row_start, A.row_len, A.cols, A.bq, A.bq8, A.lay, A.ovst, A.roots, A.comp_cnt, A.comp_off, A.members, A.uid, A.rp_uovl,
+  p_ov_resolve(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.ovst, A.roots, A.ov_head, A.ov_next, A.members, A.uid, A.rp_uovl,
                A.sc, A.g, A.ph, A.step, A.guard_pass);
   grid.sync();
   p_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, A.sc, A.n);

@@ -43,6 +43,29 @@ __device__ __forceinline__ void st_rec(double4 *p, const double4 &r) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(r.x), "d"(r.y), "d"(r.z), "d"(r.w) : "memory");
 }
 
+// ---- row head: one 32-byte sector per slot ---------------------------------------------------------------------
+// Everything a consumer needs before it touches a row, fetched with the particle record in ONE memory round trip and written
+// by the list build as ONE full-sector store (three scattered 4-byte arrays cost three read-modify-write sectors per row):
+// the first 16 quantised build distances of the row (see k_rows / skip_qmax) and where the row lives.
+struct __align__(32) RowHead {
+  unsigned char bq[16];
+  int start;      // first entry in cols[] (slot*ROW_W, or a segment of the tail region for long rows)
+  int len;        // nn(i)   (Neighbor.F90:45)
+  int cap;        // entries that fit at start (gcmc appends, Neighbor.F90:295-314)
+  int pad;
+};
+__device__ __forceinline__ uint4 rh_bq16(const RowHead *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ int4 rh_meta(const RowHead *p) { return __ldg(reinterpret_cast<const int4 *>(p) + 1); }   // {start, len, cap, pad}
+__device__ __forceinline__ void rh_store(RowHead *p, const uint4 &b, int start, int len, int cap) {
+  reinterpret_cast<uint4 *>(p)[0] = b;
+  reinterpret_cast<int4 *>(p)[1] = make_int4(start, len, cap, 0);
+}
+// build-distance byte of entry jj of a row: the head holds the first 16, the tail array the rest (indexed like cols[])
+__device__ __forceinline__ int rh_byte(const uint4 &h, int jj) {
+  const unsigned int w = jj < 8 ? (jj < 4 ? h.x : h.y) : (jj < 12 ? h.z : h.w);
+  return (int)((w >> (8 * (jj & 3))) & 255u);
+}
+
 // ---- device-resident scalars (one struct in global memory; the host mirrors it on demand) --------------
 struct DevScal {
   double z0, z1, zmax, rho, rho0;
@@ -59,7 +82,8 @@ struct DevScal {
   int n_involved, n_roots, member_cursor;
   int n_slots;                   // hs%amax (device copy; gcmc may grow it)
   int nat_sys, nat_ref, nat_gcmc, nlimbo;
-  int cols_used;                 // bump pointer into cols[]
+  int cols_used;                 // bump pointer into the tail region of cols[] (rows longer than ROW_W, gcmc rows)
+  int cols_tail0;                // first entry of the tail region = capacity * ROW_W
   int next_uid;
   unsigned int ticket;
   int halo_flag;                 // some particle sits in a halo cell (rows may be asymmetric, see k_fuerza)
@@ -96,6 +120,7 @@ struct Geo {
   int lay_shift, nlay;               // z-layer displacement table: layer = cell_z >> lay_shift
   double bq_scale;   // 255/(rcut+nb_dcut): quantisation of build-time distances (dml_kernels.cuh, k_rows)
   double rcut2;      // rcut^2
+  double inv_cell2;  // 1/cell[2] (z-layer lookup only, see layer_of)
 };
 
 // idnint(x) for the minimum image, bit-identical to round(): particles live inside the box, so |x| = |vd/box| < 1.5 and
@@ -201,7 +226,7 @@ __device__ __forceinline__ void map_of_lane(int l, int &dx, int &dy, int &dz) {
 // pair tables (dana.F90:87-100) and integrator constants, set per ctx before launches
 struct Phys {
   double eps[9], r0[9], r0sq[9], r0p6[9];
-  double r0sq_max;                                    // largest cut-off squared of the table (cheap first test)
+  double r0sq_max, r0_max;                            // largest cut-off of the table, squared and plain (cheap first test, gather skip)
   double mass[3], sqrt_mass[3];
   double h, prob, tau;
   double cc0, cc1, cc2, sdr, sdv, crv1, crv2, skt;    // set_ermak, dana.F90:947-971

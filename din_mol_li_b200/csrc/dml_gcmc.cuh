@@ -16,7 +16,7 @@ struct GcmcArgs {
   double4 *posm; double4 *fe; double *vel, *acel, *pos_old, *old_cg;
   int *uid, *slot_b, *b_occ;
   const int *cell_of_unused; const int *cell_start; const int *sorted_slot; const double4 *sorted_posm;
-  int *row_start, *row_len, *row_cap, *cols; unsigned char *bq; unsigned long long *bq8; int cols_cap;
+  RowHead *rh; int *cols; unsigned char *bq; int cols_cap;
   int *gorder, *gpos, *gcc; int gorder_cap;
   int *pend;                       // slots inserted during this call, in insertion order
   const double *rp_u, *rp_g; int rp_nu, rp_ng;
@@ -239,19 +239,20 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
                   ++cnt;
                 }
                 if ((m & MF_REF) && !(rd > g.rc_list2)) {
-                  int len = A.row_len[s];
-                  if (len < A.row_cap[s]) {
-                    A.cols[A.row_start[s] + len] = ns; A.bq[A.row_start[s] + len] = 0; A.row_len[s] = len + 1;
-                    if (len < 8) A.bq8[s] &= ~(0xffull << (8 * len));   // appended entries carry no build distance: never skipped
+                  RowHead *h = &A.rh[s];
+                  const int len = h->len;
+                  if (len < h->cap) {
+                    A.cols[h->start + len] = ns; h->len = len + 1;
+                    if (len < 16) h->bq[len] = 0; else A.bq[h->start + len] = 0;   // appended entries carry no build distance: never skipped
                   }
                   else { sc->row_overflow++; atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
                 }
               }
             }
             if (ovf) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW);
-            A.row_start[ns] = base; A.row_len[ns] = cnt; A.row_cap[ns] = cnt + A.row_slack; A.bq8[ns] = 0ull;
+            rh_store(&A.rh[ns], make_uint4(0, 0, 0, 0), base, cnt, cnt + A.row_slack);   // zero build distances: nothing is ever skipped
             sc->cols_used = base + cnt + A.row_slack;
-          } else A.row_len[ns] = 0;
+          } else A.rh[ns].len = 0;
         }
       }
       __syncthreads();
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
         n = n - 1;
         A.gcc[A.gpos[s] / GB] -= 1;
         A.gorder[A.gpos[s]] = -1; sc->gtomb++;
-        A.row_len[s] = 0;
+        A.rh[s].len = 0;
         A.b_occ[A.slot_b[s]] = 0;
         double4 p = ld_rec(&A.posm[s]);
         p.w = meta_as_double(sc->listed ? MF_LIMBO : 0);
@@ -337,7 +338,7 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.fe = ctx->fe.p;
   A.pos_old = ctx->pos_old.p; A.old_cg = ctx->old_cg.p; A.uid = ctx->uid.p; A.slot_b = ctx->slot_b.p; A.b_occ = ctx->b_occ.p;
   A.cell_of_unused = nullptr; A.cell_start = ctx->cell_start.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
-  A.row_start = ctx->row_start.p; A.row_len = ctx->row_len.p; A.row_cap = ctx->row_cap.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.bq8 = ctx->bq8.p; A.cols_cap = (int)ctx->cols.cap;
+  A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.cols_cap = (int)ctx->cols.cap;
   A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;

@@ -136,7 +136,9 @@ __device__ __forceinline__ void block_top2(double &a1, double &a2) {
 // particles near the ceiling far more than those near the electrode).
 constexpr int LAY_MAX = 1024;
 __device__ __forceinline__ int layer_of(const Geo &g, double z) {
-  int cz = (int)(z / g.cell[2]) + 1;
+  // any monotone map of z onto slabs at least one list radius thick will do, as long as the table is filled and read with
+  // the same one: the inverse cell height saves the fp64 division of the exact cell index
+  int cz = (int)(z * g.inv_cell2) + 1;
   cz = cz < 0 ? 0 : (cz > g.nc[2] + 1 ? g.nc[2] + 1 : cz);
   return cz >> g.lay_shift;
 }
@@ -182,7 +184,7 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
     sc->need_rebuild = need;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     s_need_sh = need;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
   }
   // z-layer tables: after a rebuild both are zero (displacements restart); otherwise the one just filled becomes current
   // and the previous one is cleared for the next test_update
@@ -239,7 +241,7 @@ __global__ void k_top2_final(const double *part, int nb, DevScal *__restrict__ s
 //     between rebuilds (the scan clears cell_cnt, k_cell_order clears cell_cur).
 // ================================================================================================
 __device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                      int *__restrict__ row_len, int *__restrict__ row_cap, unsigned char *__restrict__ halo_of,
+                                      RowHead *__restrict__ rh, unsigned char *__restrict__ halo_of,
                                       DevScal *__restrict__ sc, const Geo &g, bool rebuild, int s) {
   double4 p = ld_rec_nc(&posm[s]);
   if (meta_of(p) & MF_TYPE) {
@@ -256,16 +258,16 @@ __device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__r
     } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
   } else {
     cell_of[s] = -1;
-    if (rebuild) { row_len[s] = 0; row_cap[s] = 0; halo_of[s] = 0; }
+    if (rebuild) { rh[s].len = 0; rh[s].cap = 0; halo_of[s] = 0; }
   }
 }
 __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
-                                             int *__restrict__ row_len, int *__restrict__ row_cap, unsigned char *__restrict__ halo_of,
+                                             RowHead *__restrict__ rh, unsigned char *__restrict__ halo_of,
                                              DevScal *__restrict__ sc, Geo g, int n, int force) {
-  REBUILD_GUARD(sc, force);
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  d_bin(posm, cell_of, cell_cnt, row_len, row_cap, halo_of, sc, g, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
+  REBUILD_GUARD(sc, force);                               // small persistent grid: a launch that has nothing to do stays cheap
+  const bool rebuild = ((volatile const DevScal *)sc)->need_rebuild != 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    d_bin(posm, cell_of, cell_cnt, rh, halo_of, sc, g, rebuild, s);
 }
 __device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
                                           const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
@@ -282,9 +284,9 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
                                                  const int *__restrict__ cell_start, int *__restrict__ cell_cur,
                                                  int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force) {
   REBUILD_GUARD(sc, force);
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  d_scatter(posm, pos_old, cell_of, cell_start, cell_cur, sorted_slot, ((volatile const DevScal *)sc)->need_rebuild != 0, s);
+  const bool snapshot = ((volatile const DevScal *)sc)->need_rebuild != 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    d_scatter(posm, pos_old, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s);
 }
 // one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
 __device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
@@ -309,10 +311,9 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
                              int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
                              float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, DevScal *__restrict__ sc, int ncell, int force) {
   REBUILD_GUARD(sc, force);
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag ? 1 : 0;
-  if (c >= ncell) return;
-  d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, sorted_cell, c);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag ? 1 : 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
+    d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, sorted_cell, c);
 }
 
 // ================================================================================================
@@ -320,104 +321,134 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 //     vdistance Groups.F90:995-1016).  One thread per cell-sorted ref particle (see d_rows): rows come out in the
 //     reference's order (stencil order x chain order).  FILL=false counts, FILL=true writes.
 // ================================================================================================
-// Candidate test of k_rows.  The decision "rd < rc_list^2" must be the reference's fp64 one (vdistance, separately
-// rounded products), but almost every candidate is far from the boundary: a single-precision distance with a rigorous
-// error band decides those, and only candidates inside the band are re-evaluated in fp64 from the full record.
-__device__ __forceinline__ bool row_hit(const Geo &g, const double4 &p, float pxf, float pyf, float pzf, const float4 &q,
-                                        const double4 *__restrict__ sorted_posm, int u, float hbx, float hby, float rc2lo, float rc2hi,
-                                        double *rd_out) {
-  // hbx/hby = half box (0 on a non-periodic axis disables the image shift: |v| > 0 never triggers with hb = +inf)
-  float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
-  if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
-  if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
-  const float d2 = vx * vx + vy * vy + vz * vz;
-  if (d2 > rc2hi) return false;
-  if (d2 < rc2lo && !rd_out) return true;
-  const double4 qd = ld_rec_nc(&sorted_posm[u]);
-  const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
-  if (rd_out) *rd_out = rd;
-  return rd < g.rc_list2;
-}
-// One thread per cell-sorted ref particle: the thread walks the 27 stencil cells in map order and every cell's segment in
-// chain order, which IS the reference's row order, so no prefix over lanes is needed and every lane of a warp tests its own
-// candidate (the earlier warp-per-particle kernel kept ~1/4 of the lanes busy).  Threads of a warp sit in the same or adjacent
-// cells, so their candidate loads hit the same lines.  FILL=false counts (row_len/row_cap), FILL=true writes cols/bq and the
-// 8-byte head of the build distances (bq8) that lets the consumers decide the gather skip from one coalesced load.
-template <bool FILL>
+// Row storage: slot s owns ROW_W entries at cols[s*ROW_W ..) ("region A").  A row that fits (length + gcmc slack <= ROW_W;
+// n̄n is about 6 in solution) lives there, so the build needs no count pass and no scan; longer rows (next to dense metal)
+// get a segment of the tail region [cols_tail0, cols_cap) by an atomic bump and are written by a second walk of the same
+// thread.  Where the row lives, its length and its first 16 build distances are the slot's RowHead (dml_device.cuh); the
+// build distances of entries 16.. of a long row are in bq[], indexed like cols[].
+constexpr int ROW_W = 16;
+
+// One thread per cell-sorted ref particle, two dense loops and no per-thread arrays (a queue or a table of cell ranges in local
+// memory costs more L2/DRAM traffic than the whole list):
+//  walk   one flat loop over the candidates in stencil order x chain order (which IS the reference's row order), single
+//         precision; a candidate below the upper edge of the fp32 error band is parked in the row's own storage (its sorted
+//         index, 4 bytes).  Lanes of a warp differ only in their total candidate count (~38 +- 6), and the next cell's range
+//         is fetched when a lane runs out of candidates.
+//  settle the parked candidates get the reference's exact fp64 test (vdistance, Groups.F90:995-1016; strict <,
+//         Neighbor.F90:515), the build-distance byte, and are compacted in place as slot ids.
+// About one candidate in seven is a hit: with the fp64 work inside the walk some lane of the warp would take the heavy path
+// in nearly every iteration with ~5 lanes active.
 __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                        const int *__restrict__ sorted_slot,
                                        const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                       int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                       int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned long long *__restrict__ bq8,
+                                       RowHead *__restrict__ rh,
+                                       int *__restrict__ cols, unsigned char *__restrict__ bq,
                                        DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
   const int nsorted = cell_start[ncell];              // number of binned particles
   const int gsz = gridDim.x * blockDim.x;
   const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
-  const float rc2lo = (float)g.rc_list2 - g.band2, rc2hi = (float)g.rc_list2 + g.band2;
-  if (FILL && sc->cols_used > sc->cols_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); return; }
+  const float rc2hi = (float)g.rc_list2 + g.band2;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsorted; t += gsz) {
     const double4 p = ld_rec_nc(&sorted_posm[t]);
     const int s = sorted_slot[t];
-    if (!(meta_of(p) & MF_REF)) {                     // rows exist only for ref atoms
-      if (!FILL) { row_len[s] = 0; row_cap[s] = 0; }
-      continue;
-    }
+    if (!(meta_of(p) & MF_REF)) { rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
     const int lin = sorted_cell[t];
     const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
     const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-    int cnt = 0;
-    int w = FILL ? row_start[s] : 0;
-    unsigned long long head = ~0ull;
-#pragma unroll 1
-    for (int nab = 0; nab < 27; ++nab) {
-      int nx = c_map[nab][0] + cx - 1, ny = c_map[nab][1] + cy - 1, nz = c_map[nab][2] + cz - 1;   // cell_pbc wraps every axis, z included (Cells.F90:387-391)
-      nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
-      ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
-      nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
-      const int nl = cell_lin(g, nx, ny, nz);
-      const int b = __ldg(&cell_start[nl]), e = __ldg(&cell_start[nl + 1]);
-      for (int u = b; u < e; ++u) {
-        if (u == t) continue;
-        const float4 q = __ldg(&sorted_posf[u]);
-        if (!FILL) {
-          if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, nullptr)) ++cnt;
-        } else {
-          double rd;
-          if (row_hit(g, p, pxf, pyf, pzf, q, sorted_posm, u, hbx, hby, rc2lo, rc2hi, &rd)) {
-            cols[w] = __float_as_int(q.w);
-            // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
-            const int qb = min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
-            bq[w] = (unsigned char)qb;
-            if (cnt < 8) head = (head & ~(0xffull << (8 * cnt))) | ((unsigned long long)qb << (8 * cnt));
-            ++w; ++cnt;
-          }
+    // Warm the caches before the walk: the walk is a chain of dependent loads (cell range -> candidate), one L2 round trip
+    // each.  Here the 27 cell ranges are requested together, then the first candidate line of every cell; their values only
+    // feed a checksum that is never true, the walk below then runs out of L1.  (Keeping the ranges in shared memory instead
+    // halves the instruction count but shrinks L1 below the working set of the block: measured, no gain.)
+    {
+      int b27[27];
+      unsigned int chk = 0u;
+#pragma unroll
+      for (int nab = 0; nab < 27; ++nab) {
+        int nx = c_map[nab][0] + cx - 1, ny = c_map[nab][1] + cy - 1, nz = c_map[nab][2] + cz - 1;
+        nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;
+        ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
+        nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
+        b27[nab] = __ldg(&cell_start[cell_lin(g, nx, ny, nz)]);
+      }
+#pragma unroll
+      for (int nab = 0; nab < 27; ++nab) chk += __float_as_uint(__ldg(&sorted_posf[min(b27[nab], nsorted - 1)].w));
+      if (chk == 0xdeadbeefu && pxf == -1.2345f) rh[s].pad = 1;       // never true: keeps the loads alive
+    }
+    int dst = s * ROW_W, lim = ROW_W, cnt = 0;
+    uint4 hb = make_uint4(0, 0, 0, 0);
+    for (int walk = 0; walk < 2; ++walk) {
+      // ---- walk ----
+      int npark = 0, nab = -1, u = 0, e = 0;
+      for (;;) {
+        while (u == e) {                                  // next stencil cell (empty ones are passed over)
+          if (++nab == 27) break;
+          int dx, dy, dz; map_of_lane(nab, dx, dy, dz);
+          int nx = dx + cx - 1, ny = dy + cy - 1, nz = dz + cz - 1;     // cell_pbc wraps every axis, z included (Cells.F90:387-391)
+          nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
+          ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
+          nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
+          const int nl = cell_lin(g, nx, ny, nz);
+          u = __ldg(&cell_start[nl]); e = __ldg(&cell_start[nl + 1]);
+        }
+        if (nab == 27) break;
+        if (u != t) {
+          const float4 q = __ldg(&sorted_posf[u]);
+          float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+          if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+          if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+          if (vx * vx + vy * vy + vz * vz <= rc2hi) { if (npark < lim) cols[dst + npark] = u; ++npark; }
+        }
+        ++u;
+      }
+      // ---- settle (the lanes of the warp are together again here) ----
+      cnt = 0; hb = make_uint4(0, 0, 0, 0);
+      const int nset = min(npark, lim);
+      for (int i = 0; i < nset; ++i) {
+        const int uq = cols[dst + i];
+        const double4 qd = ld_rec_nc(&sorted_posm[uq]);
+        const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
+        if (rd < g.rc_list2) {
+          cols[dst + cnt] = sorted_slot[uq];               // cnt <= i: compaction in place
+          // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
+          const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
+          if (cnt < 16) {
+            const unsigned int sh = qb << (8 * (cnt & 3));
+            if (cnt < 8) { if (cnt < 4) hb.x |= sh; else hb.y |= sh; } else { if (cnt < 12) hb.z |= sh; else hb.w |= sh; }
+          } else bq[dst + cnt] = (unsigned char)qb;
+          ++cnt;
         }
       }
+      if (walk == 0 && npark > 0 && npark <= ROW_W) {      // leave no partly written sector behind: pad to the next 8 entries
+        for (int i = npark; i < ((npark + 7) & ~7); ++i) cols[dst + i] = -1;
+      }
+      if (walk == 1 || npark + slack <= ROW_W) break;
+      // long row (next to dense metal): a segment of the tail region sized for every parked candidate, second walk fills it;
+      // the first 16 build distances stay in the slot's own bytes (see ROW_W)
+      const int need = npark + slack;
+      const int tb = atomicAdd(&sc->cols_used, need);
+      if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); cnt = 0; dst = s * ROW_W; lim = ROW_W; break; }
+      dst = tb; lim = need;
     }
-    if (!FILL) { row_len[s] = cnt; row_cap[s] = cnt + slack; }
-    else bq8[s] = head;
+    rh_store(&rh[s], hb, dst, cnt, lim);                  // one full-sector store per row
   }
 }
-template <bool FILL>
 __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                               const int *__restrict__ sorted_slot,
                                               const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                              int *__restrict__ row_len, int *__restrict__ row_cap, const int *__restrict__ row_start,
-                                              int *__restrict__ cols, unsigned char *__restrict__ bq, unsigned long long *__restrict__ bq8,
+                                              RowHead *__restrict__ rh,
+                                              int *__restrict__ cols, unsigned char *__restrict__ bq,
                                               DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
-  d_rows<FILL>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, row_len, row_cap, row_start, cols, bq, bq8, sc, g, ncell, slack);
-  if (FILL) {                                         // the last block to finish marks the rows as materialised
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(&sc->ticket2, 1u) == gridDim.x - 1) { sc->ticket2 = 0; sc->rows_pending = 0; }
-    }
+  d_rows(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack);
+  __syncthreads();                                      // the last block to finish marks the rows as materialised
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sc->ticket2, 1u) == gridDim.x - 1) { sc->ticket2 = 0; sc->rows_pending = 0; }
   }
 }
-__global__ void k_sum_int(const int *__restrict__ v, int n, long long *__restrict__ out) {
+__global__ void k_sum_rowlen(const RowHead *__restrict__ rh, int n, long long *__restrict__ out) {
   long long a = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a += v[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a += rh[i].len;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
   if ((threadIdx.x & 31) == 0 && a) atomicAdd((unsigned long long *)out, (unsigned long long)a);
@@ -459,40 +490,43 @@ __device__ __forceinline__ bool pair_terms(const Geo &g, const Phys &ph, const d
 // Transposed rows: rev(i) = { j : i in row(j) }.  Needed when rows can be asymmetric (a particle in a halo cell is
 // never found as a candidate, Cells.F90:248 + cell_pbc wrap; incremental gcmc appends use <= instead of <).
 #define REV_GUARD(sc) if (!(((volatile const DevScal *)(sc))->rows_asym && !((volatile const DevScal *)(sc))->rev_valid)) return
-__global__ void k_rev_count(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
+__global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                             const double4 *__restrict__ posm, int *__restrict__ rev_len, int *__restrict__ rev_cnt,
                             const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   REV_GUARD(sc);
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
-  if (halo_only && sc->rows_asym == 1 && !halo_of[s]) return;   // light mode: only rows of halo-cell particles are transposed
-  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
-  int b = row_start[s], len = row_len[s];
-  for (int jj = 0; jj < len; ++jj) atomicAdd(&rev_cnt[cols[b + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
+  const bool light = halo_only && sc->rows_asym == 1;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
+    if (light && !halo_of[s]) continue;                 // light mode: only rows of halo-cell particles are transposed
+    if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) continue;
+    const int4 m = rh_meta(&rh[s]);
+    for (int jj = 0; jj < m.y; ++jj) atomicAdd(&rev_cnt[cols[m.x + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
+  }
 }
-__global__ void k_rev_fill(const int *__restrict__ row_start, const int *__restrict__ row_len, const int *__restrict__ cols,
+__global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
                            const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   REV_GUARD(sc);
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  if (halo_only && sc->rows_asym == 1 && !halo_of[s]) return;
-  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
-  int b = row_start[s], len = row_len[s];
-  // the scan cleared rev_len; it is rebuilt here as the fill cursor and ends as the row length
-  for (int jj = 0; jj < len; ++jj) {
-    int j = cols[b + jj];
-    int w = rev_start[j] + atomicAdd(&rev_len[j], 1);
-    rev_cols[w] = s; rev_bq[w] = bq[b + jj];
+  const bool light = halo_only && sc->rows_asym == 1;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    if (light && !halo_of[s]) continue;
+    if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) continue;
+    const int4 m = rh_meta(&rh[s]);
+    const uint4 h = rh_bq16(&rh[s]);
+    // the scan cleared rev_len; it is rebuilt here as the fill cursor and ends as the row length
+    for (int jj = 0; jj < m.y; ++jj) {
+      int j = cols[m.x + jj];
+      int w = rev_start[j] + atomicAdd(&rev_len[j], 1);
+      rev_cols[w] = s; rev_bq[w] = (unsigned char)(jj < 16 ? rh_byte(h, jj) : (int)bq[m.x + jj]);
+    }
   }
 }
 __global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
 template <bool STRICT>
-__global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm, const int *__restrict__ row_start,
-                                                const int *__restrict__ row_len, const int *__restrict__ cols,
+__global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
+                                                const int *__restrict__ cols,
                                                 const int *__restrict__ rev_start, const int *__restrict__ rev_len,
                                                 const int *__restrict__ rev_cols, const DevScal *__restrict__ sc,
                                                 const int *__restrict__ uid, double4 *__restrict__ fe,
@@ -504,7 +538,8 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
   if (!(m1 & MF_REF)) return;
   int k = (int)(m1 & MF_TYPE);
   const int asym = sc->rows_asym;
-  int b = row_start[s], len = row_len[s];
+  const int4 rm = rh_meta(&rh[s]);
+  int b = rm.x, len = rm.y;
   const int *rv = asym ? rev_cols + rev_start[s] : cols + b;
   int rvlen = asym ? rev_len[s] : len;
   double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
@@ -621,12 +656,25 @@ __device__ __noinline__ double4 lj_terms(double vx, double vy, double vz, double
   r.w = aux * .5;
   return r;
 }
-// One candidate of the production kernels: gather the record, cheap cut-off tests first, heavy math out of line.
+// ---- build-distance heads -------------------------------------------------------------------------------------------
+// need16(): bit q set <=> entry q (< len, < 16) of the row has a quantised build distance <= qmax, i.e. has to be looked at.
+// Byte-wise SIMD compares on the four words of the 16-byte head; the 4 compare bytes of a word are squeezed to a nibble.
+__device__ __forceinline__ unsigned int need16(const uint4 &h, int len, int qmax) {
+  const unsigned int q4 = (unsigned int)qmax * 0x01010101u;
+  const unsigned int w[4] = {h.x, h.y, h.z, h.w};
+  unsigned int need = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned int m = __vcmpleu4(w[i], q4) & 0x01010101u;         // 1 per byte whose value is <= qmax
+    need |= (((m * 0x01020408u) >> 24) & 0xfu) << (4 * i);
+  }
+  return len >= 16 ? need : (need & ((1u << len) - 1u));
+}
+// Pair term of the production kernels once the partner's record is here: cheap cut-off tests first, heavy math out of line.
 // pass 0 = own row, pass 1 = transposed row (reverse visits come from row owners only).
 struct FAcc { double fx, fy, fz, ep; bool hit; };
-__device__ __forceinline__ void fuerza_visit(const double4 *__restrict__ posm, const Geo &g, const Phys &ph, const double4 &p1, int k3,
-                                             int j, int pass, int asym, bool i_halo, FAcc &a) {
-  const double4 p2 = ld_rec_nc(&posm[j]);
+__device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const double4 &p1, int k3, const double4 &p2,
+                                            int pass, int asym, bool i_halo, FAcc &a) {
   double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
   if (vx > g.half_box[0]) vx = vx - g.box[0]; else if (vx < -g.half_box[0]) vx = vx + g.box[0];   // dana.F90:1098-1106
   if (vy > g.half_box[1]) vy = vy - g.box[1]; else if (vy < -g.half_box[1]) vy = vy + g.box[1];
@@ -649,20 +697,20 @@ __device__ __forceinline__ void fuerza_visit(const double4 *__restrict__ posm, c
 // integrator moved since.  qmax is the largest quantised D that still has to be looked at.
 template <int LANES, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
-    const double4 *__restrict__ posm, const int *__restrict__ row_start, const int *__restrict__ row_len,
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-    const unsigned long long *__restrict__ bq8,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
     const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
   bool act = s < n;
-  // everything addressed by the slot alone is requested together (one memory round trip): record, row pointer/length and
-  // the first eight build-distance bytes of the row
+  // everything addressed by the slot alone is requested together (one memory round trip, two sectors): the particle
+  // record and the row head (where the row lives, its length, its first sixteen build distances)
   double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-  const int rs0 = act ? __ldg(&row_start[s]) : 0, rl0 = act ? __ldg(&row_len[s]) : 0;
-  const unsigned long long h8 = (act && LANES == 1) ? __ldg(&bq8[s]) : 0ull;
+  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
+  const int rs0 = rm.x, rl0 = rm.y;
+  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
   const long long m1 = meta_of(p1);
   act = act && (m1 & MF_REF);
   FAcc a = {0.0, 0.0, 0.0, 0.0, false};
@@ -670,7 +718,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
     const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
     const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
     const bool i_halo = asym == 1 && halo_of[s] != 0;
-    const int qmax = skip_qmax(g, sc, lay, p1.z, sqrt(ph.r0sq_max));
+    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
     const int npass = asym ? 2 : 1;
     for (int pass = 0; pass < npass; ++pass) {
       const int off = pass == 0 ? rs0 : rev_start[s];
@@ -678,23 +726,26 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
       const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
       const int len = pass == 0 ? rl0 : rev_len[s];
       int jstart = sub;
-      if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first eight entries is already here
-        unsigned int need = 0u;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { const int b = (int)((h8 >> (8 * q)) & 255ull); need |= ((q < len && b <= qmax) ? 1u : 0u) << q; }
+      if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first sixteen entries is already here
+        unsigned int need = need16(h16, len, qmax);
         while (need) {
           const int q = __ffs(need) - 1; need &= need - 1;
-          fuerza_visit(posm, g, ph, p1, k3, __ldg(&lst[q]), 0, asym, i_halo, a);
+          fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[q])]), 0, asym, i_halo, a);
         }
-        jstart = 8;
+        jstart = 16;
       }
       for (int j0 = jstart; j0 < len; j0 += 8 * LANES) {
         unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { int jj = j0 + q * LANES; int b = jj < len ? (int)__ldg(&lq[jj]) : 1000; need |= (b <= qmax ? 1u : 0u) << q; }
+        for (int q = 0; q < 8; ++q) {
+          const int jj = j0 + q * LANES;
+          int b = 1000;
+          if (jj < len) b = (pass == 0 && jj < 16) ? rh_byte(h16, jj) : (int)__ldg(&lq[jj]);
+          need |= (b <= qmax ? 1u : 0u) << q;
+        }
         while (need) {
           const int q = __ffs(need) - 1; need &= need - 1;
-          fuerza_visit(posm, g, ph, p1, k3, __ldg(&lst[j0 + q * LANES]), pass, asym, i_halo, a);
+          fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[j0 + q * LANES])]), pass, asym, i_halo, a);
         }
       }
     }
@@ -858,17 +909,17 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
 constexpr int OV_MOVED = 1, OV_SKIP = 2, OV_TSHIFT = 2, OV_INVOLVED = 16, OV_ZERO = 32;
 
 __device__ __forceinline__ void p_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
-                          int *__restrict__ comp_cnt, DevScal *__restrict__ sc, int n) {
+                          int *__restrict__ comp_cnt, int *__restrict__ ov_head, DevScal *__restrict__ sc, int n) {
   if (blockIdx.x == 0 && threadIdx.x == 0) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
   const int s_end = n;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
     long long m = meta_of(ld_rec_nc(&posm[s]));
-    parent[s] = s; comp_cnt[s] = 0;
+    parent[s] = s; comp_cnt[s] = 0; ov_head[s] = -1;
     ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
   }
 }
 __global__ void k_ov_init(const double4 *__restrict__ posm, int *__restrict__ parent, int *__restrict__ ovst,
-                          int *__restrict__ comp_cnt, DevScal *__restrict__ sc, int n) { p_ov_init(posm, parent, ovst, comp_cnt, sc, n); }
+                          int *__restrict__ comp_cnt, int *__restrict__ ov_head, DevScal *__restrict__ sc, int n) { p_ov_init(posm, parent, ovst, comp_cnt, ov_head, sc, n); }
 __device__ __forceinline__ int uf_find(int *parent, int x) {
   for (;;) {
     int y = ((volatile int *)parent)[x];
@@ -888,9 +939,8 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
   }
 }
 __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
-                                                   const int *__restrict__ row_start, const int *__restrict__ row_len,
+                                                   const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                                                   const unsigned long long *__restrict__ bq8,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
                                                    DevScal *__restrict__ sc, Geo g, int n) {
   const int s_end = n;
@@ -898,25 +948,25 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
     // one round trip for everything addressed by the slot alone
     const double4 p1 = ld_rec_nc(&posm[s]);
-    const int b = __ldg(&row_start[s]), len = __ldg(&row_len[s]);
-    const unsigned long long h8 = __ldg(&bq8[s]);
+    const int4 rm = rh_meta(&rh[s]);
+    const int b = rm.x, len = rm.y;
+    const uint4 h16 = rh_bq16(&rh[s]);
     const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
     const float d1 = disp_of(m1);
     const int qmax = skip_qmax(g, sc, lay, p1.z, rcut);   // same build-distance skip as the pair force (covers new and old positions)
     bool inv = false, have_o1 = false;
     double o1[3] = {0.0, 0.0, 0.0};
-    for (int j0 = 0; j0 < len; j0 += 8) {
-      unsigned int need = 0u;
-      if (j0 == 0) {
+    for (int j0 = 0; j0 < len; j0 += 16) {
+      unsigned int need;
+      if (j0 == 0) need = need16(h16, len, qmax);
+      else {
+        need = 0u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { const int bb = (int)((h8 >> (8 * q)) & 255ull); need |= ((q < len && bb <= qmax) ? 1u : 0u) << q; }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { const int jj = j0 + q; const int bb = jj < len ? (int)__ldg(&bq[b + jj]) : 1000; need |= (bb <= qmax ? 1u : 0u) << q; }
+        for (int q = 0; q < 16; ++q) { const int jj = j0 + q; const int bb = jj < len ? (int)__ldg(&bq[b + jj]) : 1000; need |= (bb <= qmax ? 1u : 0u) << q; }
       }
       while (need) {
-        const int q = __ffs(need) - 1; need &= need - 1;
+        const int q = __ffs(need) - 1; need &= need - 1u;
         const int j = __ldg(&cols[b + j0 + q]);
         const double4 p2 = ld_rec_nc(&posm[j]);
         const long long m2 = meta_of(p2);
@@ -943,11 +993,10 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
   }
 }
 __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
-                                                   const int *__restrict__ row_start, const int *__restrict__ row_len,
+                                                   const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                                                   const unsigned long long *__restrict__ bq8,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, parent, ovst, sc, g, n); }
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
@@ -1024,9 +1073,9 @@ __device__ __forceinline__ void ov_pos(const double4 *posm, const double *old_cg
 // one reference pass (one recursion level) over the members [b,e) of one component; returns "again"
 struct OvAcc { long long tr, de, ch, ch3; };
 __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
-                                            const int *__restrict__ row_start, const int *__restrict__ row_len,
+                                            const RowHead *__restrict__ rh,
                                             const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                                            const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay,
+                                            const unsigned int *__restrict__ lay,
                                             int *__restrict__ ovst, const int *__restrict__ members,
                                             const int *__restrict__ uid, const double *__restrict__ rp_uovl, DevScal *__restrict__ sc,
                                             const Geo &g, const Phys &ph, unsigned int step, int pass, int guard, double z0,
@@ -1040,14 +1089,14 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
     if (!((st1 >> OV_TSHIFT) & 3)) continue;
     st1 |= OV_SKIP;
     double q1[3]; ov_pos(posm, old_cg, a1, st1, q1);
-    const int rb = row_start[a1], rl = row_len[a1];
+    const int4 rm = rh_meta(&rh[a1]);
+    const uint4 h16 = rh_bq16(&rh[a1]);
+    const int rb = rm.x, rl = rm.y;
     // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
     // new/old combination, so skipping it here changes nothing and saves the dependent gathers of the replay
-    const unsigned long long h8 = bq8[a1];
     const int qmax = skip_qmax(g, sc, lay, ld_rec_nc(&posm[a1]).z, rcut);
     for (int jj = 0; jj < rl; ++jj) {
-      const int bqv = jj < 8 ? (int)((h8 >> (8 * jj)) & 255ull) : (int)__ldg(&bq[rb + jj]);
-      if (bqv > qmax) continue;
+      if ((jj < 16 ? rh_byte(h16, jj) : (int)__ldg(&bq[rb + jj])) > qmax) continue;
       int a2 = cols[rb + jj];
       int st2 = ((volatile int *)ovst)[a2];
       int t2 = (st2 >> OV_TSHIFT) & 3;
@@ -1093,9 +1142,9 @@ __device__ __forceinline__ void ov_flush(const OvAcc &acc, DevScal *sc) {
 }
 // Global-synchronous variant: one launch = one recursion level for every component (needed when prob<1, where a
 // failed deposition leaves skip=.false. without requesting another pass, so the pass count couples components).
-__global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                          const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                          const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
+__global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const RowHead *__restrict__ rh,
+                          const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                          const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                           const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
                           DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
@@ -1103,46 +1152,145 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
   if (r >= sc->n_roots) return;
   int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
   OvAcc acc = {0, 0, 0, 0};
-  bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, members, uid, rp_uovl, sc, g, ph, step, pass, guard, sc->z0, b, e, acc);
+  bool again = ov_one_pass(posm, old_cg, rh, cols, bq, lay, ovst, members, uid, rp_uovl, sc, g, ph, step, pass, guard, sc->z0, b, e, acc);
   ov_flush(acc, sc);
   if (pass >= 1 && acc.ch) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)acc.ch);
   if (again) sc->again = 1;
 }
-// Fused variant (prob>=1: every metal contact deposits, nothing couples components): each component thread orders its
-// members and replays all recursion levels locally.  No host round trip, one launch.
-__device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                             const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                             const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
-                             const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
+// prob>=1 path (every metal contact deposits, nothing couples components): the members of a component are chained into a
+// list hanging off its root (one kernel instead of count / allocate / fill), and one WARP per component replays all
+// recursion levels locally.  No host round trip.
+__device__ __forceinline__ void p_ov_link(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ ov_head,
+                                          int *__restrict__ ov_next, int *__restrict__ roots, DevScal *__restrict__ sc, int n) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    if (!(ovst[s] & OV_INVOLVED)) continue;
+    const int r = uf_find(parent, s);
+    ov_next[s] = atomicExch(&ov_head[r], s);
+    if (r == s) roots[atomicAdd(&sc->n_roots, 1)] = s;
+  }
+}
+__global__ void k_ov_link(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ ov_head, int *__restrict__ ov_next,
+                          int *__restrict__ roots, DevScal *__restrict__ sc, int n) { p_ov_link(parent, ovst, ov_head, ov_next, roots, sc, n); }
+
+// One warp per component.  Members are visited in ascending creation rank (= order of hs%ref%alist) like the reference;
+// inside a visit the lanes take one row entry each.  That is exact because the entries of one row are independent given the
+// states at the start of the visit (they are distinct atoms, and an entry only changes its own state), except for the `exit`
+// at the first metal contact, which is applied with a ballot: entries behind it are ignored, entries before it act.
+__device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const RowHead *__restrict__ rh,
+                             const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                             const unsigned int *__restrict__ lay, int *__restrict__ ovst,
+                             const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
                              int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
-
+  const unsigned int FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int r_end = sc->n_roots;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < r_end; r += gridDim.x * blockDim.x) {
-    int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
-    ov_sort_members(members, uid, b, e);                       // order by creation rank (= order of hs%ref%alist)
+  const double rcut = sqrt(g.rcut2), z0 = sc->z0;
+  volatile int *vst = (volatile int *)ovst;
+  for (int r = wid; r < r_end; r += nw) {
+    const int root = roots[r];
+    // ---- collect the members (list walk, uniform) and order them by creation rank ----
+    int mine = -1, cnt = 0;
+    for (int cur = ov_head[root]; cur >= 0; cur = ov_next[cur]) { if (cnt == lane) mine = cur; ++cnt; }
+    const bool big = cnt > 32;
+    int sorted = -1, base = 0;
+    if (!big) {
+      const int myuid = mine >= 0 ? uid[mine] : 0x7fffffff;
+      int rank = 0;
+      for (int i = 0; i < cnt; ++i) rank += (__shfl_sync(FULL, myuid, i) < myuid) ? 1 : 0;
+      for (int i = 0; i < cnt; ++i) { const int rk = __shfl_sync(FULL, rank, i), mv = __shfl_sync(FULL, mine, i); if (rk == lane) sorted = mv; }
+    } else {                                               // rare: spill to the scratch array, one lane sorts
+      if (lane == 0) {
+        base = atomicAdd(&sc->member_cursor, cnt);
+        int i = 0;
+        for (int cur = ov_head[root]; cur >= 0; cur = ov_next[cur]) members[base + i++] = cur;
+        ov_sort_members(members, uid, base, base + cnt);
+      }
+      base = __shfl_sync(FULL, base, 0);
+      __syncwarp();
+    }
     OvAcc acc = {0, 0, 0, 0};
     long long later = 0;
-    double z0 = sc->z0;
     int pass = 0;
     for (;; ++pass) {
-      long long ch0 = acc.ch;
-      bool again = ov_one_pass(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, members, uid, rp_uovl, sc, g, ph, step, pass,
-                               (guard_pass > 0 && pass >= guard_pass) ? 1 : 0, z0, b, e, acc);
+      const int guard = (guard_pass > 0 && pass >= guard_pass) ? 1 : 0;
+      const long long ch0 = acc.ch;
+      bool again = false;
+      for (int i = 0; i < cnt; ++i) {
+        const int a1 = big ? ((volatile int *)members)[base + i] : __shfl_sync(FULL, sorted, i);
+        int st1 = vst[a1];
+        if (st1 & OV_SKIP) continue;
+        if (!((st1 >> OV_TSHIFT) & 3)) continue;
+        st1 |= OV_SKIP;
+        double q1[3]; ov_pos(posm, old_cg, a1, st1, q1);
+        const int4 rm = rh_meta(&rh[a1]);
+        const uint4 h16 = rh_bq16(&rh[a1]);
+        const int rb = rm.x, rl = rm.y;
+        // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
+        // new/old combination, so skipping it here changes nothing
+        const int qmax = skip_qmax(g, sc, lay, ld_rec_nc(&posm[a1]).z, rcut);
+        bool stop = false;
+        for (int j0 = 0; j0 < rl && !stop; j0 += 32) {
+          const int jj = j0 + lane;
+          bool in = false;
+          int a2 = -1, st2 = 0, t2 = 0;
+          double q2[3] = {0.0, 0.0, 0.0};
+          if (jj < rl && (jj < 16 ? rh_byte(h16, jj) : (int)__ldg(&bq[rb + jj])) <= qmax) {
+            a2 = __ldg(&cols[rb + jj]);
+            st2 = vst[a2];
+            t2 = (st2 >> OV_TSHIFT) & 3;                            // 0 = limbo (dana.F90:881-883)
+            if (t2) { ov_pos(posm, old_cg, a2, st2, q2); in = !(dist2_idnint(g, q1[0], q1[1], q1[2], q2[0], q2[1], q2[2]) > g.rcut2); }
+          }
+          const unsigned int cgm = __ballot_sync(FULL, in && t2 == 2);
+          const int first = cgm ? __ffs(cgm) - 1 : 32;              // first contact with metal: the reference leaves the row there
+          const bool mob = in && t2 != 2 && lane < first;
+          bool unsolv = false;
+          if (mob && (ph.piston || guard)) {                        // unsolvable pair guard (dana.F90:920-927)
+            if (q2[0] == old_cg[3 * a2] && q2[1] == old_cg[3 * a2 + 1] && q2[2] == old_cg[3 * a2 + 2] &&
+                q1[0] == old_cg[3 * a1] && q1[1] == old_cg[3 * a1 + 1] && q1[2] == old_cg[3 * a1 + 2]) unsolv = true;
+          }
+          const bool mv = mob && !unsolv;
+          // o2 goes back to its previous position; velocities are zeroed when the state is applied
+          if (mv) ovst[a2] = (st2 | OV_MOVED | OV_ZERO) & ~OV_SKIP;
+          acc.ch3 += __popc(__ballot_sync(FULL, mob && unsolv));
+          const int nm = __popc(__ballot_sync(FULL, mv));
+          acc.ch += nm;
+          if (nm) again = true;
+          if (cgm) {                                                 // deposition attempt (uniform over the warp)
+            acc.tr++;
+            double ne;
+            if (ph.rng_mode == 1) ne = rp_uovl ? rp_uovl[a1] : 0.0;
+            else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
+            if (ne < ph.prob) {
+              acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
+              if (q1[2] > z0 && lane == 0) atomicCAS(&sc->err, 0, DML_E_SUPERO_Z0);
+            } else { st1 |= OV_MOVED; st1 &= ~OV_SKIP; }
+            stop = true;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ovst[a1] = st1;
+        __syncwarp();
+      }
       if (pass >= 1) later += acc.ch - ch0;
       if (!again) break;
     }
-    ov_flush(acc, sc);
-    if (later) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)later);
-    atomicMax(&sc->any_active, pass + 1);                        // deepest recursion level of this call
+    if (lane == 0) {
+      ov_flush(acc, sc);
+      if (later) atomicAdd((unsigned long long *)&sc->ch_later, (unsigned long long)later);
+      atomicMax(&sc->any_active, pass + 1);                        // deepest recursion level of this call
+    }
   }
 }
-__global__ void k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const int *__restrict__ row_start,
-                             const int *__restrict__ row_len, const int *__restrict__ cols, const unsigned char *__restrict__ bq,
-                             const unsigned long long *__restrict__ bq8, const unsigned int *__restrict__ lay, int *__restrict__ ovst,
-                             const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
+__global__ void __launch_bounds__(128) k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const RowHead *__restrict__ rh,
+                             const int *__restrict__ cols, const unsigned char *__restrict__ bq,
+                             const unsigned int *__restrict__ lay, int *__restrict__ ovst,
+                             const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
                              int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
-                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) { p_ov_resolve(posm, old_cg, row_start, row_len, cols, bq, bq8, lay, ovst, roots, comp_cnt, comp_off, members, uid, rp_uovl, sc, g, ph, step, guard_pass); }
+                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
+  p_ov_resolve(posm, old_cg, rh, cols, bq, lay, ovst, roots, ov_head, ov_next, members, uid, rp_uovl, sc, g, ph, step, guard_pass);
+}
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
 __device__ __forceinline__ void p_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
                            const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) {
