@@ -64,6 +64,9 @@ struct dml_ctx {
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
   DBuf<int> send_lo, send_hi, slab_counts, pack_uid_lo, pack_uid_hi; DBuf<double4> pack_lo, pack_hi;
+  double zlo = 0.0, zhi = 0.0; int slab_holes = 0; bool slab_ready = false;     // slab bounds, holes in the owned region
+  DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
+  DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
   bool rev_in_fuerza = true; // (re)build the transposed rows in front of the next pair-force call (else: right after a rebuild)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
@@ -612,6 +615,9 @@ void dml_destroy(dml_ctx *ctx) {
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
   ctx->send_lo.release(); ctx->send_hi.release(); ctx->slab_counts.release(); ctx->pack_uid_lo.release(); ctx->pack_uid_hi.release();
   ctx->pack_lo.release(); ctx->pack_hi.release();
+  ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
+  ctx->mig_ri.release(); ctx->cnt_own.release(); ctx->cnt_all.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
+  ctx->top2_own.release(); ctx->top2_all.release();
   ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
@@ -926,18 +932,16 @@ static int slab_exchange(dml_ctx *ctx, bool with_uid) {
   if (ng) LAUNCH(K_PACK, k_slab_mark, nblk(ng), TPB, ctx->posm.p, with_uid ? ctx->slot_b.p : nullptr, with_uid ? ctx->halo_of.p : nullptr, ctx->n_owned, ng);
   return 0;
 }
-// Selects the particles within one list radius of each face, exchanges them with rank-1 / rank+1 and appends the received
-// ones as ghost slots [n_owned, n_owned+n_ghost).  Call after dml_upload of the owned particles (zlo <= z < zhi).
-int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) {
+// Selects the owned particles within one list radius of each face, exchanges them with rank-1 / rank+1 and appends the
+// received ones as ghost slots [n_owned, n_owned+n_ghost).  One host synchronisation (the four counts).
+static int slab_refresh_ghosts(dml_ctx *ctx) {
   NcclApi *N = nccl_api();
-  if (!ctx->comm || !N) FAIL("dml_slab_setup: call dml_comm_init first");
-  TRY(finish(ctx));
   const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
-  int n = ctx->n_owned = ctx->n;
-  double w = ctx->cfg.rcut + ctx->cfg.nb_dcut;
+  const int n = ctx->n_owned;
+  const double w = ctx->cfg.rcut + ctx->cfg.nb_dcut;
   CKC(ctx->send_lo.ensure(ctx->cap, ctx->st)); CKC(ctx->send_hi.ensure(ctx->cap, ctx->st)); CKC(ctx->slab_counts.ensure(8, ctx->st));
-  CKC(cudaMemsetAsync(ctx->slab_counts.p, 0, 8 * sizeof(int), ctx->st));
-  LAUNCH(K_PACK, k_slab_select, nblk(n), TPB, ctx->posm.p, ctx->send_lo.p, ctx->send_hi.p, ctx->slab_counts.p, zlo, zhi, w, has_lo ? 1 : 0, has_hi ? 1 : 0, n);
+  CKC(cudaMemsetAsync(ctx->slab_counts.p, 0, 4 * sizeof(int), ctx->st));
+  LAUNCH(K_PACK, k_slab_select, nblk(n), TPB, ctx->posm.p, ctx->send_lo.p, ctx->send_hi.p, ctx->slab_counts.p, ctx->zlo, ctx->zhi, w, has_lo ? 1 : 0, has_hi ? 1 : 0, n);
   NCK(N->GroupStart());
   if (has_hi) { NCK(N->Send(ctx->slab_counts.p + 1, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->slab_counts.p + 3, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); }
   if (has_lo) { NCK(N->Send(ctx->slab_counts.p + 0, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->slab_counts.p + 2, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); }
@@ -951,25 +955,136 @@ int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) {
   CKC(ctx->pack_lo.ensure((size_t)std::max(ctx->nsend_lo, 1), ctx->st)); CKC(ctx->pack_hi.ensure((size_t)std::max(ctx->nsend_hi, 1), ctx->st));
   CKC(ctx->pack_uid_lo.ensure((size_t)std::max(ctx->nsend_lo, 1), ctx->st)); CKC(ctx->pack_uid_hi.ensure((size_t)std::max(ctx->nsend_hi, 1), ctx->st));
   TRY(slab_exchange(ctx, true));
-  int ng = ctx->nrecv_lo + ctx->nrecv_hi;
-  // ghosts start with pos_old = pos and no velocity
-  if (ng) {
-    std::vector<double> tmp((size_t)ng * 4);
-    CKC(cudaMemcpyAsync(tmp.data(), ctx->posm.p + n, (size_t)ng * sizeof(double4), cudaMemcpyDeviceToHost, ctx->st));
-    CKC(cudaStreamSynchronize(ctx->st));
-    std::vector<double> po((size_t)ng * 3);
-    for (int i = 0; i < ng; ++i) for (int k = 0; k < 3; ++k) po[3 * (size_t)i + k] = tmp[4 * (size_t)i + k];
-    CKC(cudaMemcpyAsync(ctx->pos_old.p + (size_t)3 * n, po.data(), po.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-    CKC(cudaMemsetAsync(ctx->vel.p + (size_t)3 * n, 0, (size_t)ng * 3 * sizeof(double), ctx->st));
-    CKC(cudaMemsetAsync(ctx->acel.p + (size_t)3 * n, 0, (size_t)ng * 3 * sizeof(double), ctx->st));
+  const int ng = ctx->nrecv_lo + ctx->nrecv_hi;
+  // ghosts start with pos_old = old_cg = pos, no velocity and no row
+  if (ng) LAUNCH(K_PACK, k_slab_ghost_init, nblk(ng), TPB, ctx->posm.p, ctx->pos_old.p, ctx->old_cg.p, ctx->vel.p, ctx->acel.p, ctx->rh.p, n, ng);
+  ctx->n = n + ng;
+  return 0;
+}
+int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) {
+  NcclApi *N = nccl_api();
+  if (!ctx->comm || !N) FAIL("dml_slab_setup: call dml_comm_init first");
+  TRY(finish(ctx));
+  ctx->zlo = zlo; ctx->zhi = zhi;
+  const int n = ctx->n_owned = ctx->n;
+  {                                                        // holes of the uploaded arrays (z == 0 slots)
+    CKC(ctx->slab_counts.ensure(8, ctx->st)); CKC(ctx->mig_holes.ensure(ctx->cap, ctx->st));
+    CKC(cudaMemsetAsync(ctx->slab_counts.p, 0, 8 * sizeof(int), ctx->st));
+    LAUNCH(K_PACK, k_slab_holes, nblk(n), TPB, ctx->posm.p, ctx->mig_holes.p, ctx->slab_counts.p, n);
+    CKC(cudaMemcpyAsync(&ctx->slab_holes, ctx->slab_counts.p + 6, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
     CKC(cudaStreamSynchronize(ctx->st));
   }
+  TRY(slab_refresh_ghosts(ctx));
+  const int ng = ctx->n - n;
   TRY(pull_scal(ctx));
-  ctx->n = n + ng;
   ctx->hsc->n_slots = ctx->n; ctx->hsc->b_amax = ctx->n; ctx->hsc->nat_sys += ng; ctx->hsc->listed = 0; ctx->hsc->rows_pending = 0;
   TRY(push_scal(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
+  ctx->slab_ready = true;
   return 0;
+}
+// Particles that left [zlo, zhi) move to the neighbouring slab with their full state; arrivals refill the holes.
+static int slab_migrate(dml_ctx *ctx) {
+  NcclApi *N = nccl_api();
+  const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
+  const int n = ctx->n_owned;
+  CKC(ctx->mig_list_lo.ensure(ctx->cap, ctx->st)); CKC(ctx->mig_list_hi.ensure(ctx->cap, ctx->st)); CKC(ctx->mig_rc.ensure(2, ctx->st));
+  CKC(ctx->mig_holes.ensure(ctx->cap, ctx->st));
+  CKC(cudaMemsetAsync(ctx->slab_counts.p + 4, 0, 4 * sizeof(int), ctx->st));
+  CKC(cudaMemsetAsync(ctx->mig_rc.p, 0, 2 * sizeof(int), ctx->st));
+  LAUNCH(K_PACK, k_slab_mig_select, nblk(n), TPB, ctx->posm.p, ctx->mig_list_lo.p, ctx->mig_list_hi.p, ctx->slab_counts.p, ctx->zlo, ctx->zhi,
+         has_lo ? 1 : 0, has_hi ? 1 : 0, n);
+  NCK(N->GroupStart());
+  if (has_hi) { NCK(N->Send(ctx->slab_counts.p + 5, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->mig_rc.p + 1, 1, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); }
+  if (has_lo) { NCK(N->Send(ctx->slab_counts.p + 4, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->mig_rc.p + 0, 1, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); }
+  NCK(N->GroupEnd());
+  int hs[2], hr[2];
+  CKC(cudaMemcpyAsync(hs, ctx->slab_counts.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaMemcpyAsync(hr, ctx->mig_rc.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  const int nsl = hs[0], nsh = hs[1], nrl = has_lo ? hr[0] : 0, nrh = has_hi ? hr[1] : 0;
+  if (nsl + nsh + nrl + nrh == 0) return 0;
+  const int nholes = ctx->slab_holes + nsl + nsh, narr = nrl + nrh;
+  if (n + std::max(0, narr - nholes) > ctx->cap) FAIL("slot capacity exhausted by migrating particles (dml_config.capacity)");
+  CKC(ctx->mig_sd_lo.ensure((size_t)std::max(nsl, 1) * MIG_D, ctx->st)); CKC(ctx->mig_sd_hi.ensure((size_t)std::max(nsh, 1) * MIG_D, ctx->st));
+  CKC(ctx->mig_si_lo.ensure((size_t)std::max(nsl, 1), ctx->st)); CKC(ctx->mig_si_hi.ensure((size_t)std::max(nsh, 1), ctx->st));
+  CKC(ctx->mig_rd.ensure((size_t)std::max(narr, 1) * MIG_D, ctx->st)); CKC(ctx->mig_ri.ensure((size_t)std::max(narr, 1), ctx->st));
+  if (nsl) LAUNCH(K_PACK, k_slab_mig_pack, nblk(nsl), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->uid.p, ctx->rh.p, ctx->mig_list_lo.p, nsl, ctx->mig_sd_lo.p, ctx->mig_si_lo.p);
+  if (nsh) LAUNCH(K_PACK, k_slab_mig_pack, nblk(nsh), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->uid.p, ctx->rh.p, ctx->mig_list_hi.p, nsh, ctx->mig_sd_hi.p, ctx->mig_si_hi.p);
+  LAUNCH(K_PACK, k_slab_holes, nblk(n), TPB, ctx->posm.p, ctx->mig_holes.p, ctx->slab_counts.p, n);
+  NCK(N->GroupStart());
+  if (nsh) { NCK(N->Send(ctx->mig_sd_hi.p, (size_t)nsh * MIG_D, ncclDouble, ctx->rank + 1, ctx->comm, ctx->st)); NCK(N->Send(ctx->mig_si_hi.p, nsh, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); }
+  if (nrh) { NCK(N->Recv(ctx->mig_rd.p + (size_t)nrl * MIG_D, (size_t)nrh * MIG_D, ncclDouble, ctx->rank + 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->mig_ri.p + nrl, nrh, ncclInt, ctx->rank + 1, ctx->comm, ctx->st)); }
+  if (nsl) { NCK(N->Send(ctx->mig_sd_lo.p, (size_t)nsl * MIG_D, ncclDouble, ctx->rank - 1, ctx->comm, ctx->st)); NCK(N->Send(ctx->mig_si_lo.p, nsl, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); }
+  if (nrl) { NCK(N->Recv(ctx->mig_rd.p, (size_t)nrl * MIG_D, ncclDouble, ctx->rank - 1, ctx->comm, ctx->st)); NCK(N->Recv(ctx->mig_ri.p, nrl, ncclInt, ctx->rank - 1, ctx->comm, ctx->st)); }
+  NCK(N->GroupEnd());
+  if (narr) LAUNCH(K_PACK, k_slab_mig_unpack, nblk(narr), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->uid.p, ctx->slot_b.p,
+                   ctx->fe.p, ctx->rh.p, ctx->halo_of.p, ctx->mig_rd.p, ctx->mig_ri.p, narr, 0, ctx->mig_holes.p, nholes, n);
+  ctx->slab_holes = std::max(0, nholes - narr);
+  ctx->n_owned = n + std::max(0, narr - nholes);
+  return 0;
+}
+// test_update (Neighbor.F90:668-713) on the decomposed box: global decision, migration + ghost re-selection + rows at a rebuild
+static int slab_test_update(dml_ctx *ctx) {
+  NcclApi *N = nccl_api();
+  tessellate(ctx);
+  if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction");
+  int n = ctx->n, nct = ctx->nct;
+  if ((size_t)nct + 2 > ctx->cell_start.cap) {
+    CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
+    CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, ctx->cell_cnt.cap * sizeof(int), ctx->st));
+    CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
+  }
+  const int nb = std::min(nblk(n), 148 * 6);
+  CKC(ctx->part.ensure((size_t)2 * nb, ctx->st)); CKC(ctx->top2_own.ensure(2, ctx->st)); CKC(ctx->top2_all.ensure((size_t)2 * ctx->nranks, ctx->st));
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 0, ctx->cfg.nb_dcut);
+  LAUNCH(K_TOP2, k_top2_local, 1, 256, ctx->part.p, nb, ctx->top2_own.p);
+  NCK(N->AllGather(ctx->top2_own.p, ctx->top2_all.p, 2, ncclDouble, ctx->comm, ctx->st));
+  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->top2_all.p, ctx->nranks, ctx->sc, ctx->lay.p, ctx->geo.nlay, ctx->cfg.nb_dcut);
+  TRY(pull_scal(ctx));
+  if (ctx->hsc->need_rebuild) {
+    TRY(slab_migrate(ctx));
+    TRY(slab_refresh_ghosts(ctx));
+    TRY(pull_scal(ctx));
+    ctx->hsc->n_slots = ctx->n; ctx->hsc->b_amax = ctx->n;
+    TRY(push_scal(ctx));
+    TRY(enq_sort_cells(ctx, 0));
+    TRY(enq_materialize_rows(ctx));
+    ctx->rev_in_fuerza = true;
+  }
+  ctx->binned = true;
+  return 0;
+}
+// promotion + calc_rho with the global census
+static int slab_promote_rho(dml_ctx *ctx) {
+  NcclApi *N = nccl_api();
+  if (!ctx->cnt_own.p) { CKC(ctx->cnt_own.ensure(4, ctx->st)); CKC(cudaMemsetAsync(ctx->cnt_own.p, 0, 4 * sizeof(int), ctx->st)); }
+  CKC(ctx->cnt_all.ensure((size_t)4 * ctx->nranks, ctx->st));
+  LAUNCH(K_PROMOTE, k_slab_promote_count, std::min(nblk(ctx->n_owned), 148 * 8), TPB, ctx->posm.p, ctx->sc, ctx->cnt_own.p, ctx->n_owned);
+  NCK(N->AllGather(ctx->cnt_own.p, ctx->cnt_all.p, 4, ncclInt, ctx->comm, ctx->st));
+  LAUNCH(K_PROMOTE, k_slab_rho_final, 1, 1, ctx->cnt_all.p, ctx->nranks, ctx->cnt_own.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1]);
+  return 0;
+}
+// nsteps iterations of dana's loop body (dana.F90:173-265; Ermak integrator + piston) on the decomposed box
+int dml_slab_step(dml_ctx *ctx, int32_t nsteps) {
+  if (!ctx->comm || !ctx->slab_ready) FAIL("dml_slab_step: call dml_comm_init and dml_slab_setup first");
+  if (!ctx->cfg.integrador || ctx->cfg.reservoir != 1) FAIL("dml_slab_step: the decomposed box runs the Ermak integrator with the piston reservoir");
+  for (int i = 0; i < nsteps; ++i) {
+    const int ng = ctx->n - ctx->n_owned;
+    if (ng) LAUNCH(K_PACK, k_slab_ghost_save, nblk(ng), TPB, ctx->posm.p, ctx->old_cg.p, ctx->n_owned, ng);
+    TRY(enq_integrate(ctx, true));
+    TRY(slab_exchange(ctx, false));
+    TRY(enq_fuerza(ctx));
+    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
+    TRY(slab_test_update(ctx));
+    TRY(enq_overlap(ctx));
+    TRY(slab_exchange(ctx, false));
+    TRY(slab_test_update(ctx));
+    TRY(slab_promote_rho(ctx));
+    TRY(enq_maxz(ctx));
+    ctx->t = ctx->t + ctx->cfg.h;
+  }
+  return finish(ctx);
 }
 // per-step refresh of the ghost positions from their owners (same lists as the last dml_slab_setup)
 int dml_slab_halo_exchange(dml_ctx *ctx) {

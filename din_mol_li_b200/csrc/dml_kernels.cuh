@@ -975,12 +975,14 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
         // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
         const double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
         {
-          const double thr = (rcut + (double)d1 + ((m2 & MF_REF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
+          // (slab mode: a ghost that is mobile on its owner, MF_GREF, carries an infinite bound and its old_cg was saved
+          //  when the step started, so it joins the conflict graph like a ref atom)
+          const double thr = (rcut + (double)d1 + ((m2 & MF_ANYREF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
           if (rd_nn > thr * thr) continue;
         }
         if (!have_o1) { o1[0] = old_cg[3 * s]; o1[1] = old_cg[3 * s + 1]; o1[2] = old_cg[3 * s + 2]; have_o1 = true; }
         bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
-        if (m2 & MF_REF) {
+        if (m2 & MF_ANYREF) {
           const double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
           hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
                 dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
@@ -1224,12 +1226,43 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
         if (!((st1 >> OV_TSHIFT) & 3)) continue;
         st1 |= OV_SKIP;
         double q1[3]; ov_pos(posm, old_cg, a1, st1, q1);
+        const double4 rec1 = ld_rec_nc(&posm[a1]);
+        if (meta_of(rec1) & MF_GHOST) {
+          // Slab mode: a1 is owned by the neighbouring slab and has no row here.  Its visit (it comes in creation-rank order
+          // like everybody else) acts on the owned members of the component that are in range — the same pair decisions its
+          // owner takes from the same inputs; its contacts with metal are the owner's business.
+          for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int mi = i0 + lane;
+            const int a2 = mi < cnt ? (big ? ((volatile int *)members)[base + mi] : (i0 == 0 ? sorted : -1)) : -1;
+            bool mv = false, unsolv = false;
+            if (a2 >= 0 && a2 != a1 && !(meta_of(ld_rec_nc(&posm[a2])) & MF_GHOST)) {
+              const int st2 = vst[a2];
+              if ((st2 >> OV_TSHIFT) & 3) {
+                double q2[3]; ov_pos(posm, old_cg, a2, st2, q2);
+                if (!(dist2_idnint(g, q1[0], q1[1], q1[2], q2[0], q2[1], q2[2]) > g.rcut2)) {
+                  if ((ph.piston || guard) &&
+                      q2[0] == old_cg[3 * a2] && q2[1] == old_cg[3 * a2 + 1] && q2[2] == old_cg[3 * a2 + 2] &&
+                      q1[0] == old_cg[3 * a1] && q1[1] == old_cg[3 * a1 + 1] && q1[2] == old_cg[3 * a1 + 2]) unsolv = true;
+                  else { mv = true; ovst[a2] = (st2 | OV_MOVED | OV_ZERO) & ~OV_SKIP; }
+                }
+              }
+            }
+            acc.ch3 += __popc(__ballot_sync(FULL, unsolv));
+            const int nm = __popc(__ballot_sync(FULL, mv));
+            acc.ch += nm;
+            if (nm) again = true;
+          }
+          __syncwarp();
+          if (lane == 0) ovst[a1] = st1;
+          __syncwarp();
+          continue;
+        }
         const int4 rm = rh_meta(&rh[a1]);
         const uint4 h16 = rh_bq16(&rh[a1]);
         const int rb = rm.x, rl = rm.y;
         // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
         // new/old combination, so skipping it here changes nothing
-        const int qmax = skip_qmax(g, sc, lay, ld_rec_nc(&posm[a1]).z, rcut);
+        const int qmax = skip_qmax(g, sc, lay, rec1.z, rcut);
         bool stop = false;
         for (int j0 = 0; j0 < rl && !stop; j0 += 32) {
           const int jj = j0 + lane;

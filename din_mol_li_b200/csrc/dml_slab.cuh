@@ -7,9 +7,17 @@
 // ncclSend/ncclRecv on the ctx stream (NVLink 5 / NVSwitch: every peer is equidistant, so slab k <-> GPU k is arbitrary).
 // NCCL is resolved with dlopen at the first comm call: the library itself has no link-time NCCL dependency.
 //
-// Round-1 scope: set-up (ghost selection + exchange), per-step halo refresh, and the list build / pair force on top of
-// them — validated against the single-GPU result (same pair sets, forces within 1e-12).  Particle migration at
-// rebuild, the global rebuild decision and the global piston are the next step.
+// dml_slab_step runs dana's loop body (Ermak + piston, the configuration of BASELINE config 4) on the decomposed box:
+//   - the rebuild decision is global: every rank reduces its own two largest squared displacements, the pairs are
+//     all-gathered and every rank merges them to the same decision (top-2 merging is order independent);
+//   - at a rebuild the particles that left the slab migrate to the neighbour (full state), holes are refilled, ghosts are
+//     re-selected and the rows rebuilt;
+//   - rho of the piston is global (all-gather of the per-rank counts), maxz is then the same arithmetic on every copy;
+//   - overlap_moveback treats ghosts that are mobile on their owner as full participants of the conflict components, visited
+//     in creation-rank order like everybody else (their visit acts on the owned atoms in range), so both sides of a face
+//     replay the same pair decisions from the same inputs; what a rank cannot see (third atoms beyond its halo) makes the
+//     multi-GPU trajectory an approximation of the single-GPU one — validated on observables.
+// Noise is Philox keyed by (seed; creation rank, step), i.e. independent of the decomposition.
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -23,6 +31,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -35,9 +44,9 @@ static NcclApi *nccl_api() {
 #define SYM(f, name) *(void **)(&a.f) = dlsym(a.h, name)
   SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
   SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
-  SYM(GetErrorString, "ncclGetErrorString");
+  SYM(GetErrorString, "ncclGetErrorString"); SYM(AllGather, "ncclAllGather");
 #undef SYM
-  if (!a.GetUniqueId || !a.CommInitRank || !a.Send || !a.Recv || !a.GroupStart || !a.GroupEnd) { a.h = nullptr; return nullptr; }
+  if (!a.GetUniqueId || !a.CommInitRank || !a.Send || !a.Recv || !a.GroupStart || !a.GroupEnd || !a.AllGather) { a.h = nullptr; return nullptr; }
   return &a;
 }
 
@@ -67,11 +76,116 @@ __global__ void k_slab_mark(double4 *__restrict__ posm, int *__restrict__ slot_b
   int s = first + i;
   double4 p = ld_rec(&posm[s]);
   long long m = meta_of(p);
-  long long nm = (m & MF_TYPE) | MF_GHOST | ((m & (MF_REF | MF_GREF)) ? MF_GREF : 0);
+  long long nm = (m & (MF_TYPE | MF_SKIP)) | MF_GHOST | ((m & (MF_REF | MF_GREF)) ? MF_GREF : 0);
   p.w = meta_as_double(with_disp(nm, DISP_INF));
   st_rec(&posm[s], p);
   if (slot_b) slot_b[s] = s;
   if (halo_of) halo_of[s] = 0;
+}
+
+// ---- migration at a rebuild ------------------------------------------------------------------------------------
+constexpr int MIG_D = 13;     // doubles per migrant: record (4), vel (3), acel (3), old_cg (3)
+__global__ void k_slab_mig_select(const double4 *__restrict__ posm, int *__restrict__ send_lo, int *__restrict__ send_hi,
+                                  int *__restrict__ counts, double zlo, double zhi, int has_lo, int has_hi, int n_owned) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_owned) return;
+  double4 p = ld_rec_nc(&posm[s]);
+  if (!(meta_of(p) & MF_TYPE)) return;
+  if (has_lo && p.z < zlo) send_lo[atomicAdd(&counts[4], 1)] = s;
+  else if (has_hi && p.z >= zhi) send_hi[atomicAdd(&counts[5], 1)] = s;
+}
+// full state of the leavers into the send buffers; their slots become holes
+__global__ void k_slab_mig_pack(double4 *__restrict__ posm, const double *__restrict__ vel, const double *__restrict__ acel,
+                                const double *__restrict__ old_cg, const int *__restrict__ uid, RowHead *__restrict__ rh,
+                                const int *__restrict__ list, int cnt, double *__restrict__ out_d, int *__restrict__ out_i) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const int s = list[i];
+  const double4 p = ld_rec(&posm[s]);
+  double *o = out_d + (size_t)i * MIG_D;
+  o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = p.w;
+  for (int k = 0; k < 3; ++k) { o[4 + k] = vel[3 * s + k]; o[7 + k] = acel[3 * s + k]; o[10 + k] = old_cg[3 * s + k]; }
+  out_i[i] = uid[s];
+  st_rec(&posm[s], make_double4(0.0, 0.0, 0.0, meta_as_double(0)));
+  rh[s].len = 0; rh[s].cap = 0;
+}
+__global__ void k_slab_holes(const double4 *__restrict__ posm, int *__restrict__ holes, int *__restrict__ counts, int n_owned) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_owned) return;
+  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_TYPE)) holes[atomicAdd(&counts[6], 1)] = s;
+}
+// arrivals take the holes first, then the slots behind the owned region
+__global__ void k_slab_mig_unpack(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel, double *__restrict__ pos_old,
+                                  double *__restrict__ old_cg, int *__restrict__ uid, int *__restrict__ slot_b, double4 *__restrict__ fe,
+                                  RowHead *__restrict__ rh, unsigned char *__restrict__ halo_of,
+                                  const double *__restrict__ in_d, const int *__restrict__ in_i, int cnt, int first,
+                                  const int *__restrict__ holes, int nholes, int n_owned) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const int q = first + i;                                   // rank among all arrivals of this rebuild
+  const int s = q < nholes ? holes[q] : n_owned + (q - nholes);
+  const double *o = in_d + (size_t)i * MIG_D;
+  const long long m = with_disp(__double_as_longlong(o[3]) & 0xffffffffll, DISP_INF);
+  st_rec(&posm[s], make_double4(o[0], o[1], o[2], meta_as_double(m)));
+  for (int k = 0; k < 3; ++k) { vel[3 * s + k] = o[4 + k]; acel[3 * s + k] = o[7 + k]; old_cg[3 * s + k] = o[10 + k]; pos_old[3 * s + k] = o[k]; }
+  uid[s] = in_i[i]; slot_b[s] = s; halo_of[s] = 0;
+  st_rec(&fe[s], make_double4(0.0, 0.0, 0.0, 0.0));
+  rh[s].len = 0; rh[s].cap = 0;
+}
+// fresh ghosts: pos_old = old_cg = pos, no velocity, no row
+__global__ void k_slab_ghost_init(const double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ old_cg,
+                                  double *__restrict__ vel, double *__restrict__ acel, RowHead *__restrict__ rh, int first, int cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const int s = first + i;
+  const double4 p = ld_rec_nc(&posm[s]);
+  const double q[3] = {p.x, p.y, p.z};
+  for (int k = 0; k < 3; ++k) { pos_old[3 * s + k] = q[k]; old_cg[3 * s + k] = q[k]; vel[3 * s + k] = 0.0; acel[3 * s + k] = 0.0; }
+  rh[s].len = 0; rh[s].cap = 0;
+}
+// previous positions of the ghosts = where they are when the step starts (their owners' old_cg of this step)
+__global__ void k_slab_ghost_save(const double4 *__restrict__ posm, double *__restrict__ old_cg, int first, int cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const int s = first + i;
+  const double4 p = ld_rec_nc(&posm[s]);
+  old_cg[3 * s] = p.x; old_cg[3 * s + 1] = p.y; old_cg[3 * s + 2] = p.z;
+}
+// own two largest squared displacements out of the per-block partials (one block)
+__global__ void k_top2_local(const double *__restrict__ part, int nb, double *__restrict__ out) {
+  double a1 = -1.0, a2 = -1.0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, part[2 * i], part[2 * i + 1]);
+  block_top2(a1, a2);
+  if (threadIdx.x == 0) { out[0] = a1; out[1] = a2; }
+}
+// F -> CG promotion (dana.F90:228-236) and the census of calc_rho (521-549) over the OWNED particles; the counts of all
+// ranks are gathered and k_slab_rho_final turns them into the same rho everywhere
+__global__ void __launch_bounds__(TPB) k_slab_promote_count(double4 *__restrict__ posm, DevScal *__restrict__ sc, int *__restrict__ out, int n_owned) {
+  const double z0 = sc->z0, zl = sc->zmax;
+  int c = 0, dref = 0, nref = 0;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_owned; s += gridDim.x * blockDim.x) {
+    double4 p = ld_rec(&posm[s]);
+    long long m = meta_of(p);
+    if ((m & MF_REF) && (m & MF_TYPE) == 3) {
+      dref++;
+      m = (m & ~(MF_TYPE | MF_REF | MF_GCMC)) | 2;
+      p.w = meta_as_double(m); st_rec(&posm[s], p);
+    }
+    if (m & MF_REF) nref++;
+    if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c++;
+  }
+  c = __reduce_add_sync(0xffffffffu, c); dref = __reduce_add_sync(0xffffffffu, dref); nref = __reduce_add_sync(0xffffffffu, nref);
+  if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(&out[0], c); if (dref) atomicAdd(&out[1], dref); if (nref) atomicAdd(&out[2], nref); }
+}
+__global__ void k_slab_rho_final(const int *__restrict__ gathered, int nranks, int *__restrict__ own, DevScal *__restrict__ sc, double area) {
+  long long c = 0, dref = 0, nref = 0;
+  for (int r = 0; r < nranks; ++r) { c += gathered[4 * r]; dref += gathered[4 * r + 1]; nref += gathered[4 * r + 2]; }
+  sc->msd_t = sc->msd_t / (double)(nref + dref);          // dana.F90:201-202 (before the promotion loop; local sum, global count)
+  sc->msd_max = fmax(sc->msd_max, sc->msd_t);
+  sc->nat_ref -= own[1];
+  sc->rho = (double)c / (area * (sc->zmax - sc->z0));
+  sc->step_disp_bits = 0u;
+  own[0] = own[1] = own[2] = own[3] = 0;
 }
 
 } // namespace dml

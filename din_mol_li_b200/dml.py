@@ -51,7 +51,7 @@ SYMBOLS = [
     "dml_calc_rho", "dml_maxz", "dml_bloques", "dml_set_chunk_template", "dml_step", "dml_get_cells",
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
-    "dml_slab_halo_exchange", "dml_slab_info", "dml_launch_count", "dml_stream",
+    "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
 ]
 
 _lib = None
@@ -99,6 +99,7 @@ def lib():
         L.dml_slab_plan.argtypes = [i32, vp, i32, dbl, dbl, vp]
         L.dml_slab_setup.argtypes = [vp, dbl, dbl]
         L.dml_slab_halo_exchange.argtypes = [vp]
+        L.dml_slab_step.argtypes = [vp, i32]
         L.dml_slab_info.argtypes = [vp] + [C.POINTER(i32)] * 4
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
@@ -400,6 +401,10 @@ class Ctx:
 
     def slab_halo_exchange(self):
         self._chk(lib().dml_slab_halo_exchange(self.h))
+
+    def slab_step(self, n=1):
+        """dana's loop body on the decomposed box (every rank calls it with the same n)."""
+        self._chk(lib().dml_slab_step(self.h, n))
 
     def slab_info(self):
         v = [C.c_int32() for _ in range(4)]

@@ -126,13 +126,16 @@ int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, cons
 int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss);
 
 /* Multi-GPU, one large box: z-slab decomposition with NCCL halo exchange (no counterpart in the reference, which is a
- * serial program).  One ctx per rank.  Round-1 scope: ghost set-up, per-step halo refresh, list build and
- * pair force on owned particles; migration / global rebuild decision / global piston are not implemented yet. */
+ * serial program).  One ctx per rank, every rank makes the same calls in the same order.
+ * dml_slab_step = dml_step for the decomposed box (Ermak integrator + piston reservoir): global rebuild decision, particle
+ * migration and ghost re-selection at a rebuild, global rho for the piston, cross-face overlap resolution.  Counters
+ * (try, depo, choques) are per rank; nupd_vlist, rho and zmax are the same on every rank. */
 int dml_comm_unique_id(void *id128);                                   /* ncclGetUniqueId (rank 0), 128 bytes */
 int dml_comm_init(dml_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
 int dml_slab_plan(int32_t n, const double *z, int32_t nranks, double lo, double hi, double *cuts /*[nranks+1]*/);  /* host only */
 int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi);              /* after dml_upload of the owned particles */
 int dml_slab_halo_exchange(dml_ctx *ctx);                              /* refresh ghost positions (grouped ncclSend/ncclRecv) */
+int dml_slab_step(dml_ctx *ctx, int32_t nsteps);                       /* dana.F90:173-265 on the decomposed box */
 int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nsend_lo, int32_t *nsend_hi);
 
 /* Timing helper for bench.py: device-side duration (ms) of the kernels of the named class accumulated since

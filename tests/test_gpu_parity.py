@@ -224,3 +224,18 @@ def test_slab_decomposition_two_gpus():
                         "--master-port", "29617", os.path.join(root, "tests", "slab_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") == 2
+
+
+def test_slab_step_two_gpus():
+    """dml_slab_step (global rebuild decision, migration, ghost re-selection, global piston, cross-face overlap rule) against
+    dml_step on one GPU: tests/slab_step_check.py under torchrun, 2 ranks, 200 steps.  Needs two GPUs on the box."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SLAB_STEPS="200")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29619", os.path.join(root, "tests", "slab_step_check.py")], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") == 2
