@@ -266,7 +266,7 @@ static int enq_test_update(dml_ctx *ctx) {
     A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
     A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
-    A.nb_dcut = ctx->cfg.nb_dcut;
+    A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
     ctx->binned = true;
     if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
@@ -274,7 +274,7 @@ static int enq_test_update(dml_ctx *ctx) {
   }
   int nb = std::min(nblk(n), 148 * 6);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
   TRY(enq_sort_cells(ctx, force));
   if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
@@ -308,9 +308,15 @@ static int enq_build_rev(dml_ctx *ctx) {
   return 0;
 }
 
-static int enq_fuerza(dml_ctx *ctx) {
+static int enq_qtab(dml_ctx *ctx) {
+  LAUNCH(K_MISC, k_qtab, 1, 256, ctx->lay.p, ctx->sc, ctx->geo, ctx->ph.r0_max, ctx->cfg.rcut);
+  return 0;
+}
+// fused = called from the step sequence, where the integrator / test_update that ran just before refreshed the skip tables
+static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  (void)fused;
   if (ctx->rev_in_fuerza) { TRY(enq_build_rev(ctx)); if (ctx->cfg.reservoir != 3 && !ctx->lazy_rows) ctx->rev_in_fuerza = false; }
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
@@ -329,9 +335,10 @@ static int enq_fuerza(dml_ctx *ctx) {
 }
 
 // overlap_moveback (dana.F90:849-943)
-static int enq_overlap(dml_ctx *ctx) {
+static int enq_overlap(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  if (!fused) TRY(enq_qtab(ctx));
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
@@ -455,11 +462,11 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
 static int enq_step(dml_ctx *ctx) {
   int n = ctx->n;
   if (ctx->cfg.integrador) {
-    TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx));
+    TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
     LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
   } else TRY(enq_integrate(ctx, false));
   TRY(enq_test_update(ctx));
-  TRY(enq_overlap(ctx));
+  TRY(enq_overlap(ctx, true));
   TRY(enq_test_update(ctx));
   if (ctx->cfg.reservoir == 3) {
     LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
@@ -549,7 +556,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
   CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
-  CKC(ctx->lay.ensure(2 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
+  CKC(ctx->lay.ensure(3 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0xff, 3 * LAY_MAX * sizeof(unsigned int), ctx->st));   // 2 displacement tables + the skip tables (k_qtab)
+  CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
   CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->rev_cnt.p, 0, (size_t)cap * sizeof(int), ctx->st));
   CKC(ctx->parent.ensure(cap, ctx->st)); CKC(ctx->ovst.ensure(cap, ctx->st)); CKC(ctx->comp_cnt.ensure(cap, ctx->st));
@@ -909,7 +917,7 @@ int dml_slab_plan(int32_t n, const double *z, int32_t nranks, double lo, double 
   }
   return 0;
 }
-static int slab_exchange(dml_ctx *ctx, bool with_uid) {
+static int slab_exchange(dml_ctx *ctx, bool with_uid, bool measure = false) {
   NcclApi *N = nccl_api();
   const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
   if (has_lo && ctx->nsend_lo) LAUNCH(K_PACK, k_slab_pack, nblk(ctx->nsend_lo), TPB, ctx->posm.p, ctx->uid.p, ctx->send_lo.p, ctx->nsend_lo, ctx->pack_lo.p, with_uid ? ctx->pack_uid_lo.p : nullptr);
@@ -929,7 +937,8 @@ static int slab_exchange(dml_ctx *ctx, bool with_uid) {
   }
   NCK(N->GroupEnd());
   int ng = ctx->nrecv_lo + ctx->nrecv_hi;
-  if (ng) LAUNCH(K_PACK, k_slab_mark, nblk(ng), TPB, ctx->posm.p, with_uid ? ctx->slot_b.p : nullptr, with_uid ? ctx->halo_of.p : nullptr, ctx->n_owned, ng);
+  if (ng) LAUNCH(K_PACK, k_slab_mark, nblk(ng), TPB, ctx->posm.p, with_uid ? ctx->slot_b.p : nullptr, with_uid ? ctx->halo_of.p : nullptr, ctx->n_owned, ng,
+                 measure ? ctx->old_cg.p : nullptr, ctx->sc, ctx->geo);
   return 0;
 }
 // Selects the owned particles within one list radius of each face, exchanges them with rank-1 / rank+1 and appends the
@@ -1037,10 +1046,10 @@ static int slab_test_update(dml_ctx *ctx) {
   }
   const int nb = std::min(nblk(n), 148 * 6);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st)); CKC(ctx->top2_own.ensure(2, ctx->st)); CKC(ctx->top2_all.ensure((size_t)2 * ctx->nranks, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 0, ctx->cfg.nb_dcut);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 0, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
   LAUNCH(K_TOP2, k_top2_local, 1, 256, ctx->part.p, nb, ctx->top2_own.p);
   NCK(N->AllGather(ctx->top2_own.p, ctx->top2_all.p, 2, ncclDouble, ctx->comm, ctx->st));
-  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->top2_all.p, ctx->nranks, ctx->sc, ctx->lay.p, ctx->geo.nlay, ctx->cfg.nb_dcut);
+  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->top2_all.p, ctx->nranks, ctx->sc, ctx->lay.p, ctx->geo, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
   TRY(pull_scal(ctx));
   if (ctx->hsc->need_rebuild) {
     TRY(slab_migrate(ctx));
@@ -1073,12 +1082,12 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) {
     const int ng = ctx->n - ctx->n_owned;
     if (ng) LAUNCH(K_PACK, k_slab_ghost_save, nblk(ng), TPB, ctx->posm.p, ctx->old_cg.p, ctx->n_owned, ng);
     TRY(enq_integrate(ctx, true));
-    TRY(slab_exchange(ctx, false));
-    TRY(enq_fuerza(ctx));
+    TRY(slab_exchange(ctx, false, true));                 // ghosts at their new positions; their moves enter the skip bound
+    TRY(enq_fuerza(ctx, true));
     LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
     TRY(slab_test_update(ctx));
-    TRY(enq_overlap(ctx));
-    TRY(slab_exchange(ctx, false));
+    TRY(enq_overlap(ctx, true));
+    TRY(slab_exchange(ctx, false, true));
     TRY(slab_test_update(ctx));
     TRY(slab_promote_rho(ctx));
     TRY(enq_maxz(ctx));

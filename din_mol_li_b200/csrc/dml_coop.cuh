@@ -72,7 +72,7 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 
 struct TUArgs {
   double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
-  const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut;
+  const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut, rmax_f, rmax_o;
 };
 
 // test_update (Neighbor.F90:668-713) in one launch
@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
     if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }
     else { for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) A.lay[lay_old * LAY_MAX + i] = 0u; }
+    __threadfence();
+    __syncthreads();
+    d_qtab(A.lay, sc, A.g, A.rmax_f, A.rmax_o);                  // skip tables for the consumers that follow
   }
   if (!(need || A.force_sort)) return;
   // phase 2: binning

@@ -103,6 +103,7 @@ struct DevScal {
   long long choques2, ch_later;     // dana.F90:941 bookkeeping
   long long overlap_passes;
   unsigned int ticket3;             // last-block election of k_pbc_disp
+  unsigned int ticket4;             // last-block election of k_integrate
 };
 
 enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,

@@ -149,6 +149,8 @@ __device__ __forceinline__ void lay_note(unsigned int *s_lay, const Geo &g, doub
 }
 // Largest quantised build-time distance that still has to be examined by a particle at height z looking for partners
 // within rmax: D - S <= rmax with S = bound of |move of i| + |move of j| since the rows were built (see k_fuerza_sub).
+// Largest quantised build-time distance that still has to be examined by a particle at height z looking for partners
+// within rmax: D - S <= rmax with S = bound of |move of i| + |move of j| since the rows were built (see k_fuerza_sub).
 __device__ __forceinline__ int skip_qmax(const Geo &g, const DevScal *__restrict__ sc, const unsigned int *__restrict__ lay, double z, double rmax) {
   const int l = layer_of(g, z);
   const unsigned int *lt = lay + sc->lay_cur * LAY_MAX;
@@ -161,10 +163,45 @@ __device__ __forceinline__ int skip_qmax(const Geo &g, const DevScal *__restrict
   if (since > g.cell[2]) return 255;                  // particles may have changed layer: no skipping
   return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
 }
+// The same bound tabulated per z-layer for overlap_moveback (table 1, rmax = rcut; table 0 holds the pair-force value).  The
+// single block that finishes test_update refreshes it (d_top2_final), so the overlap kernels that follow read one byte where
+// every thread would evaluate the formula; a stand-alone dml_overlap_moveback call refreshes it with k_qtab first. table 0 for the pair force (rmax = largest
+// cut-off of the pair table), table 1 for overlap_moveback (rmax = rcut).  The bound of a layer uses the top of the layer where
+// the per-particle formula used z, so it is never smaller.  The tables live behind the two displacement tables of lay[].
+__device__ __forceinline__ int skip_qtab(const Geo &g, const unsigned int *__restrict__ lay, double z, int which) {
+  const unsigned char *qt = reinterpret_cast<const unsigned char *>(lay + 2 * LAY_MAX) + which * LAY_MAX;
+  return (int)__ldg(&qt[layer_of(g, z)]);
+}
+// Executed by one block.  sc is read around L1 (the block may hold a stale line of it from earlier in its kernel).
+__device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const DevScal *sc, const Geo &g, double rmax_f, double rmax_o) {
+  volatile const DevScal *v = sc;
+  unsigned char *qt = reinterpret_cast<unsigned char *>(lay + 2 * LAY_MAX);
+  const unsigned int *lt = lay + v->lay_cur * LAY_MAX;
+  const double thick = g.cell[2] * (double)(1 << g.lay_shift);
+  const double maxz_fac = v->maxz_fac, z0 = v->z0, zmax = v->zmax, dsum = v->dsum_tu;
+  const double sdisp = (double)__int_as_float((int)v->step_disp_bits);
+  for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
+    unsigned int mx = 0u;
+#pragma unroll
+    for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldcg(&lt[q])); }
+    double ztop = thick * (double)(l + 1);             // every particle of layer l sits below ...
+    if (l == g.nlay - 1) ztop = fmax(ztop, zmax);      // ... except in the last one, which also takes what is above the box (up to the ceiling)
+    const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
+    const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
+    int qf = 255, qo = 255;
+    if (!(since > g.cell[2])) {                        // else particles may have changed layer: no skipping
+      qf = (int)fmin(255.0, ceil((rmax_f * 1.000001 + S) * g.bq_scale) + 1.0);
+      qo = (int)fmin(255.0, ceil((rmax_o * 1.000001 + S) * g.bq_scale) + 1.0);
+    }
+    qt[l] = (unsigned char)qf; qt[LAY_MAX + l] = (unsigned char)qo;
+  }
+}
+__global__ void k_qtab(unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, double rmax_f, double rmax_o) { d_qtab(lay, sc, g, rmax_f, rmax_o); }
 // Final step of test_update, run by ONE block: merges the per-block top-2 partials, takes the rebuild decision
 // (Neighbor.F90:697-710) and rotates the z-layer tables.
-__device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
-                                             double nb_dcut) {
+__device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, const Geo &g,
+                                             double nb_dcut, double rmax_f, double rmax_o) {
+  const int nlay = g.nlay;
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
   for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, __ldcg(&part[2 * i]), __ldcg(&part[2 * i + 1]));
 #pragma unroll
@@ -196,12 +233,15 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
     __syncthreads();
     if (threadIdx.x == 0) sc->lay_cur = cur ^ 1;
   }
+  __threadfence();
+  __syncthreads();
+  d_qtab(lay, sc, g, rmax_f, rmax_o);                  // the skip tables the next consumers (overlap_moveback, pair force) will read
 }
 // finalize != 0: the last block to finish runs d_top2_final itself (single-GPU path, one launch less per test_update);
 // finalize == 0: the partials are left in part[] for the caller (slab mode merges them across ranks first).
 __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *part,
                                                   unsigned int *__restrict__ lay, DevScal *__restrict__ sc, Geo g, int n, int n_disp,
-                                                  int finalize, double nb_dcut) {
+                                                  int finalize, double nb_dcut, double rmax_f, double rmax_o) {
   // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
   __shared__ unsigned int s_lay[LAY_MAX];
   __shared__ int s_last;
@@ -219,18 +259,17 @@ __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, do
   block_top2(a1, a2);
   if (threadIdx.x == 0) { part[2 * blockIdx.x] = a1; part[2 * blockIdx.x + 1] = a2; }
   if (!finalize) return;
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&sc->ticket3, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&sc->ticket3, 1u) == gridDim.x - 1) ? 1 : 0; }
   __syncthreads();
   if (!s_last) return;
   if (threadIdx.x == 0) sc->ticket3 = 0u;
   __threadfence();
-  d_top2_final(part, (int)gridDim.x, sc, lay, g.nlay, nb_dcut);
+  d_top2_final(part, (int)gridDim.x, sc, lay, g, nb_dcut, rmax_f, rmax_o);
 }
-__global__ void k_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, int nlay,
-                             double nb_dcut) {
-  d_top2_final(part, nb, sc, lay, nlay, nb_dcut);
+__global__ void k_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, Geo g,
+                             double nb_dcut, double rmax_f, double rmax_o) {
+  d_top2_final(part, nb, sc, lay, g, nb_dcut, rmax_f, rmax_o);
 }
 
 // ================================================================================================
@@ -954,7 +993,7 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
     const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
     const float d1 = disp_of(m1);
-    const int qmax = skip_qmax(g, sc, lay, p1.z, rcut);   // same build-distance skip as the pair force (covers new and old positions)
+    const int qmax = skip_qtab(g, lay, p1.z, 1);          // same build-distance skip as the pair force (covers new and old positions)
     bool inv = false, have_o1 = false;
     double o1[3] = {0.0, 0.0, 0.0};
     for (int j0 = 0; j0 < len; j0 += 16) {
@@ -1096,7 +1135,7 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
     const int rb = rm.x, rl = rm.y;
     // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
     // new/old combination, so skipping it here changes nothing and saves the dependent gathers of the replay
-    const int qmax = skip_qmax(g, sc, lay, ld_rec_nc(&posm[a1]).z, rcut);
+    const int qmax = skip_qtab(g, lay, ld_rec_nc(&posm[a1]).z, 1);
     for (int jj = 0; jj < rl; ++jj) {
       if ((jj < 16 ? rh_byte(h16, jj) : (int)__ldg(&bq[rb + jj])) > qmax) continue;
       int a2 = cols[rb + jj];
@@ -1262,7 +1301,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
         const int rb = rm.x, rl = rm.y;
         // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
         // new/old combination, so skipping it here changes nothing
-        const int qmax = skip_qmax(g, sc, lay, rec1.z, rcut);
+        const int qmax = skip_qtab(g, lay, rec1.z, 1);
         bool stop = false;
         for (int j0 = 0; j0 < rl && !stop; j0 += 32) {
           const int jj = j0 + lane;

@@ -69,18 +69,35 @@ __global__ void k_slab_pack(const double4 *__restrict__ posm, const int *__restr
   st_rec(&out_p[i], ld_rec_nc(&posm[s]));
   if (out_uid) out_uid[i] = uid[s];
 }
-// received records become ghosts: keep position and element, drop the owner's membership flags
-__global__ void k_slab_mark(double4 *__restrict__ posm, int *__restrict__ slot_b, unsigned char *__restrict__ halo_of, int first, int cnt) {
+// received records become ghosts: keep position, element and skip flag, drop the owner's membership flags.  With old_cg
+// (refresh inside a step) the move of the ghost since the step started is measured: it goes into the record (prefilter of
+// k_ov_detect) and into step_disp_bits, because the gather-skip bound must cover the ghosts' moves as well as the local ones.
+__global__ void k_slab_mark(double4 *__restrict__ posm, int *__restrict__ slot_b, unsigned char *__restrict__ halo_of, int first, int cnt,
+                            const double *__restrict__ old_cg, DevScal *__restrict__ sc, Geo g) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cnt) return;
-  int s = first + i;
-  double4 p = ld_rec(&posm[s]);
-  long long m = meta_of(p);
-  long long nm = (m & (MF_TYPE | MF_SKIP)) | MF_GHOST | ((m & (MF_REF | MF_GREF)) ? MF_GREF : 0);
-  p.w = meta_as_double(with_disp(nm, DISP_INF));
-  st_rec(&posm[s], p);
-  if (slot_b) slot_b[s] = s;
-  if (halo_of) halo_of[s] = 0;
+  float df = 0.0f;
+  if (i < cnt) {
+    int s = first + i;
+    double4 p = ld_rec(&posm[s]);
+    long long m = meta_of(p);
+    long long nm = (m & (MF_TYPE | MF_SKIP)) | MF_GHOST | ((m & (MF_REF | MF_GREF)) ? MF_GREF : 0);
+    unsigned int bits = DISP_INF;
+    if (old_cg) {
+      double dx = p.x - old_cg[3 * s], dy = p.y - old_cg[3 * s + 1], dz = p.z - old_cg[3 * s + 2];
+      dx = dx - g.box[0] * round(dx * g.one_box[0]); dy = dy - g.box[1] * round(dy * g.one_box[1]);
+      df = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * 1.000001f;
+      bits = (unsigned int)__float_as_int(df);
+    }
+    p.w = meta_as_double(with_disp(nm, bits));
+    st_rec(&posm[s], p);
+    if (slot_b) slot_b[s] = s;
+    if (halo_of) halo_of[s] = 0;
+  }
+  if (old_cg) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) df = fmaxf(df, __shfl_xor_sync(0xffffffffu, df, o));
+    if ((threadIdx.x & 31) == 0 && df > 0.0f) atomicMax(&sc->step_disp_bits, (unsigned int)__float_as_int(df));
+  }
 }
 
 // ---- migration at a rebuild ------------------------------------------------------------------------------------
