@@ -68,10 +68,10 @@ struct dml_ctx {
   DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
   DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
-  bool rev_in_fuerza = true; // (re)build the transposed rows in front of the next pair-force call (else: right after a rebuild)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
-  int coop_tu_max_n = 262144;   // test_update has more and shorter phases: the one-launch form wins up to larger boxes
+  int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
+                                // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
@@ -269,7 +269,6 @@ static int enq_test_update(dml_ctx *ctx) {
     A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
     ctx->binned = true;
-    if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
     return 0;
   }
   int nb = std::min(nblk(n), 148 * 6);
@@ -277,7 +276,6 @@ static int enq_test_update(dml_ctx *ctx) {
   LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
   TRY(enq_sort_cells(ctx, force));
   if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
-  if (ctx->cfg.integrador && !ctx->rev_in_fuerza) TRY(enq_build_rev(ctx));
   ctx->binned = true;
   return 0;
 }
@@ -317,7 +315,7 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   (void)fused;
-  if (ctx->rev_in_fuerza) { TRY(enq_build_rev(ctx)); if (ctx->cfg.reservoir != 3 && !ctx->lazy_rows) ctx->rev_in_fuerza = false; }
+  TRY(enq_build_rev(ctx));                              // guarded on the device: no-ops unless rows are asymmetric and the transposed rows stale
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
@@ -859,7 +857,6 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->cols_used = (int)off;
-  ctx->rev_in_fuerza = true;
   ctx->hsc->rows_pending = 0;
   ctx->hsc->listed = 1; ctx->hsc->rows_asym = 2; ctx->hsc->rev_valid = 0;   // caller's rows: make no symmetry assumption
   ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
@@ -1059,8 +1056,7 @@ static int slab_test_update(dml_ctx *ctx) {
     TRY(push_scal(ctx));
     TRY(enq_sort_cells(ctx, 0));
     TRY(enq_materialize_rows(ctx));
-    ctx->rev_in_fuerza = true;
-  }
+    }
   ctx->binned = true;
   return 0;
 }
@@ -1135,7 +1131,6 @@ int32_t dml_n_slots(dml_ctx *ctx) { return ctx->n; }
 int dml_set_strict_order(dml_ctx *ctx, int32_t on) {
   ctx->cfg.strict_order = on ? 1 : 0;
   CKC(cudaMemsetAsync(&ctx->sc->rev_valid, 0, sizeof(int), ctx->st));   // the two kernels use differently scoped transposed rows
-  ctx->rev_in_fuerza = true;
   return 0;
 }
 int64_t dml_launch_count(dml_ctx *ctx) { return ctx->launches; }
