@@ -74,6 +74,8 @@ struct dml_ctx {
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
+  bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
+                             // kernel takes exactly the sum of the two, 77 us vs 38 + 39 us at 1 M, so the default keeps them apart)
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
@@ -314,18 +316,27 @@ static int enq_qtab(dml_ctx *ctx) {
 static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
-  (void)fused;
+  // fused: called from the step sequence — the production kernel also applies ermak_b (see k_fuerza_sub<.., FUSEB>)
   TRY(enq_build_rev(ctx));                              // guarded on the device: no-ops unless rows are asymmetric and the transposed rows stale
   if (ctx->cfg.strict_order)
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
   else
   {
-#define FSUB(L, B) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B>), nblk(n * L), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
-    switch (ctx->force_lanes) {
-      case 1: if (ctx->force_minb == 5) FSUB(1, 5); else if (ctx->force_minb == 3) FSUB(1, 3); else if (ctx->force_minb == 2) FSUB(1, 2); else FSUB(1, 4); break;
-      case 2: FSUB(2, 5); break; case 4: FSUB(4, 5); break; default: FSUB(8, 5); break;
+#define FSUB(L, B, F) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B, F>), nblk(n * L), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p)
+    if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 4) FSUB(1, 4, true); else FSUB(1, 3, true); }
+    else if (ctx->force_lanes == 1 && ctx->force_minb >= 9) {      // 128-thread blocks: register budgets between the 256-thread steps
+#define FSUB128(B) LAUNCH(K_FUERZA, (k_fuerza_sub<1, B, false, 128>), nblk(n, 128), 128, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p)
+      if (ctx->force_minb == 9) FSUB128(9); else if (ctx->force_minb == 10) FSUB128(10); else FSUB128(11);
+#undef FSUB128
+    }
+    else switch (ctx->force_lanes) {
+      case 1: if (ctx->force_minb == 5) FSUB(1, 5, false); else if (ctx->force_minb == 3) FSUB(1, 3, false); else if (ctx->force_minb == 2) FSUB(1, 2, false); else FSUB(1, 4, false); break;
+      case 2: FSUB(2, 5, false); break; case 4: FSUB(4, 5, false); break; default: FSUB(8, 5, false); break;
     }
 #undef FSUB
   }
@@ -461,7 +472,8 @@ static int enq_step(dml_ctx *ctx) {
   int n = ctx->n;
   if (ctx->cfg.integrador) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
-    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
+    if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
+      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
   } else TRY(enq_integrate(ctx, false));
   TRY(enq_test_update(ctx));
   TRY(enq_overlap(ctx, true));
@@ -539,8 +551,9 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ctx->lazy_rows = !cfg->integrador && cfg->reservoir != 3 && !getenv("DML_EAGER_ROWS");
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
-  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 5) ctx->force_minb = v; }
-  if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; }
+  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
+  if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
+  if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; if (v != 1) ctx->fuse_ermak_b = false; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
@@ -1080,7 +1093,8 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) {
     TRY(enq_integrate(ctx, true));
     TRY(slab_exchange(ctx, false, true));                 // ghosts at their new positions; their moves enter the skip bound
     TRY(enq_fuerza(ctx, true));
-    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
+    if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
+      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
     TRY(slab_test_update(ctx));
     TRY(enq_overlap(ctx, true));
     TRY(slab_exchange(ctx, false, true));

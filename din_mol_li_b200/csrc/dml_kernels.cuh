@@ -734,13 +734,16 @@ __device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const 
 // bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
 // around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
 // integrator moved since.  qmax is the largest quantised D that still has to be looked at.
-template <int LANES, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
+// FUSEB: the thread that holds the finished force of a particle also does its ermak_b update (dana.F90:1031-1052) — same
+// arithmetic as k_ermak_b, one pass less over records and forces; vel/acel/ranv are requested with the first round trip.
+template <int LANES, int MINB, bool FUSEB, int BS = TPB>
+__global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
     const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n,
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
   bool act = s < n;
@@ -750,6 +753,11 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
   const int rs0 = rm.x, rl0 = rm.y;
   const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
+  double bv[3] = {0.0, 0.0, 0.0}, ba[3] = {0.0, 0.0, 0.0}, br[3] = {0.0, 0.0, 0.0};
+  if (FUSEB && act) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { bv[k] = vel[3 * s + k]; ba[k] = acel[3 * s + k]; br[k] = __ldg(&ranv[3 * s + k]); }
+  }
   const long long m1 = meta_of(p1);
   act = act && (m1 & MF_REF);
   FAcc a = {0.0, 0.0, 0.0, 0.0, false};
@@ -798,7 +806,21 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
       }
     }
   }
-  if (act && sub == 0) st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
+  if (act && sub == 0) {
+    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
+    if (FUSEB) {
+      const int zt = (int)(m1 & MF_TYPE);
+      if (zt != 2) {
+        const double mass = ph.mass[zt - 1];
+        const double fv[3] = {a.fx, a.fy, a.fz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          vel[3 * s + k] = ph.cc0 * bv[k] + ph.cc1mcc2 * ba[k] + ph.cc2 * fv[k] / mass + br[k];
+          acel[3 * s + k] = fv[k] / mass;
+        }
+      }
+    }
+  }
 }
 
 // ================================================================================================

@@ -212,6 +212,24 @@ def test_production_force_kernel_with_gather_skip_matches_reference_order():
     assert checked > 30000 and nonzero > 50
 
 
+def test_fused_ermak_b_is_bit_identical(monkeypatch):
+    """With DML_FUSE_ERMAK_B dml_step applies ermak_b inside the production pair-force kernel instead of launching k_ermak_b
+    after it.  Same arithmetic on the same forces: every array must be bit-identical after a Philox run of tests/ermak."""
+    d, o = case("ermak")
+    out = []
+    for fuse in (False, True):
+        if fuse:
+            monkeypatch.setenv("DML_FUSE_ERMAK_B", "1")
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=4711)
+        ctx.step(300)
+        n = ctx.counters().n_slots
+        out.append(ctx.download(n))
+        ctx.close()
+    for k in ("pos", "vel", "acel", "force", "epot", "z", "flags"):
+        assert np.array_equal(out[0][k], out[1][k]), k
+    assert np.abs(out[0]["vel"]).sum() > 0
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
