@@ -4,6 +4,7 @@
 #include "dml_kernels.cuh"
 #include "dml_coop.cuh"
 #include "dml_slab.cuh"
+#include "dml_observe.cuh"
 namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ gorder, const int *__restrict__ gpos, DevScal *__restrict__ sc, int n); }
 #include <cmath>
 #include <cstdio>
@@ -68,6 +69,7 @@ struct dml_ctx {
   DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
   DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
+  bool rows_legacy = false; // DML_ROWS_LEGACY=1: 27-cell ordered walk for every row (the fast walk needs >= 3 cells per axis)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
@@ -76,6 +78,9 @@ struct dml_ctx {
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
                              // kernel takes exactly the sum of the two, 77 us vs 38 + 39 us at 1 M, so the default keeps them apart)
+  int force_pf = 0, force_pf_ahead = 148 * TPB, force_ppt = 1;   // DML_FORCE_PF / DML_FORCE_PPT: see k_fuerza_sub, k_fuerza_ppt
+  bool force_wq = false;      // DML_FORCE_WQ=1: warp-queue pair-force kernel (k_fuerza_wq)
+  bool force_batch = false;   // DML_FORCE_BATCH=1: batched index/record requests in the production pair-force kernel
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
@@ -87,6 +92,9 @@ struct dml_ctx {
   DBuf<int> gorder, gpos, gcc, gpend, b_occ; int gorder_cap = 0;
   // replay
   DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
+  // output reductions and observables (dml_observe.cuh)
+  DBuf<double> obs_part, obs_out; DBuf<unsigned long long> obs_counts; DBuf<int> gr_cell_of, gr_cnt, gr_start; DBuf<double4> gr_sorted;
+  unsigned int *obs_ticket = nullptr;
   // staging
   DBuf<double> stage_d, stage_f; DBuf<int> stage_i;
   DevScal *sc = nullptr; DevScal *hsc = nullptr;    // device / pinned host mirror
@@ -202,6 +210,7 @@ static void tessellate(dml_ctx *ctx) {
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
   g.inv_cell2 = 1.0 / g.cell[2];
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
+  g.rows_fast = (nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3 && ctx->cap < (1 << 26) && !ctx->rows_legacy) ? 1 : 0;
   g.lay_shift = 0; while (((g.nc[2] + 2) >> g.lay_shift) + 1 > LAY_MAX) g.lay_shift++;
   g.nlay = ((g.nc[2] + 1) >> g.lay_shift) + 1;
   ctx->tessellated = true;
@@ -325,12 +334,28 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   {
 #define FSUB(L, B, F) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B, F>), nblk(n * L), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p)
-    if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 4) FSUB(1, 4, true); else FSUB(1, 3, true); }
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B))
+#define FPPT(P, B) LAUNCH(K_FUERZA, (k_fuerza_ppt<P, B>), nblk(n, TPB * P), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->force_pf)
+#define FWQ(B) LAUNCH(K_FUERZA, (k_fuerza_wq<B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
+    if (ctx->force_wq && ctx->force_lanes == 1 && ctx->force_ppt == 1 && !ctx->force_batch && !(fused && ctx->fuse_ermak_b)) {
+      if (ctx->force_minb == 5) FWQ(5); else if (ctx->force_minb == 3) FWQ(3); else if (ctx->force_minb >= 6) FWQ(6); else FWQ(4);
+    }
+    else if (ctx->force_ppt == 2 && !(fused && ctx->fuse_ermak_b)) { if (ctx->force_minb >= 4) FPPT(2, 4); else if (ctx->force_minb == 3) FPPT(2, 3); else FPPT(2, 2); }
+    else if (ctx->force_ppt == 4 && !(fused && ctx->fuse_ermak_b)) { if (ctx->force_minb >= 3) FPPT(4, 3); else FPPT(4, 2); }
+    else if (ctx->force_batch && ctx->force_lanes == 1 && !(fused && ctx->fuse_ermak_b) && ctx->force_minb <= 5) {
+#define FSUBB(B) LAUNCH(K_FUERZA, (k_fuerza_sub<1, B, false, TPB, true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B))
+      if (ctx->force_minb == 5) FSUBB(5); else if (ctx->force_minb == 3) FSUBB(3); else if (ctx->force_minb == 2) FSUBB(2); else FSUBB(4);
+#undef FSUBB
+    }
+    else if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 4) FSUB(1, 4, true); else FSUB(1, 3, true); }
     else if (ctx->force_lanes == 1 && ctx->force_minb >= 9) {      // 128-thread blocks: register budgets between the 256-thread steps
 #define FSUB128(B) LAUNCH(K_FUERZA, (k_fuerza_sub<1, B, false, 128>), nblk(n, 128), 128, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p)
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B) / 2)
       if (ctx->force_minb == 9) FSUB128(9); else if (ctx->force_minb == 10) FSUB128(10); else FSUB128(11);
 #undef FSUB128
     }
@@ -339,6 +364,8 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
       case 2: FSUB(2, 5, false); break; case 4: FSUB(4, 5, false); break; default: FSUB(8, 5, false); break;
     }
 #undef FSUB
+#undef FPPT
+#undef FWQ
   }
   return 0;
 }
@@ -553,6 +580,11 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
+  if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
+  if (const char *e = getenv("DML_FORCE_WQ")) ctx->force_wq = atoi(e) != 0;
+  if (const char *e = getenv("DML_FORCE_BATCH")) ctx->force_batch = atoi(e) != 0;
+  if (const char *e = getenv("DML_FORCE_PF")) ctx->force_pf = atoi(e) & 31;
+  if (const char *e = getenv("DML_FORCE_PPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->force_ppt = v; }
   if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; if (v != 1) ctx->fuse_ermak_b = false; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
@@ -605,6 +637,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_overlap_coop, TPB, 0);
     ctx->coop_grid_tu = nsm * b1; ctx->coop_grid_ov = nsm * b2;
+    if (const char *e = getenv("DML_COOP_TU_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b1) ctx->coop_grid_tu = nsm * v; }   // blocks per SM of k_test_update_coop
+    if (const char *e = getenv("DML_COOP_OV_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b2) ctx->coop_grid_ov = nsm * v; }
     ctx->use_coop = coop && b1 > 0 && b2 > 0 && !getenv("DML_NO_COOP");
     int gmax = std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_ov), 1);
     CKC(ctx->coop_sums.ensure((size_t)gmax + 8, ctx->st));
@@ -641,6 +675,8 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
+  ctx->obs_part.release(); ctx->obs_out.release(); ctx->obs_counts.release(); ctx->gr_cell_of.release(); ctx->gr_cnt.release(); ctx->gr_start.release();
+  ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
@@ -1115,6 +1151,81 @@ int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nse
   if (n_ghost) *n_ghost = ctx->nrecv_lo + ctx->nrecv_hi;
   if (nsend_lo) *nsend_lo = ctx->nsend_lo;
   if (nsend_hi) *nsend_hi = ctx->nsend_hi;
+  return 0;
+}
+
+
+// ---- output reductions and observables ---------------------------------------------------------------
+int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *temp, int32_t *n_mobile) {
+  const int n = ctx->n;
+  const int nb = std::min(nblk(n, OBS_TPB), 148 * 4);
+  CKC(ctx->obs_part.ensure((size_t)4 * 148 * 4, ctx->st)); CKC(ctx->obs_out.ensure(4, ctx->st));
+  if (!ctx->obs_ticket) { CKC(cudaMalloc(&ctx->obs_ticket, sizeof(unsigned int))); CKC(cudaMemsetAsync(ctx->obs_ticket, 0, sizeof(unsigned int), ctx->st)); }
+  LAUNCH(K_MISC, k_salida_sums, nb, OBS_TPB, ctx->posm.p, ctx->fe.p, ctx->vel.p, ctx->ph, n, ctx->obs_part.p, ctx->obs_ticket, ctx->obs_out.p);
+  double out[4];
+  CKC(cudaMemcpyAsync(out, ctx->obs_out.p, sizeof(out), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  if (energia) *energia = out[0];
+  if (energia_ref) *energia_ref = out[1];
+  if (temp) *temp = out[2] / (out[3] * 3.0 * ctx->cfg.kB_ui);          // kion, dana.F90:1374
+  if (n_mobile) *n_mobile = (int32_t)out[3];
+  return 0;
+}
+
+int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int32_t type_mask, int64_t *counts) {
+  if (nbins < 1 || nbins > OBS_MAX_BINS || !(zhi > zlo) || !counts) FAIL("dml_density_profile: need 1 <= nbins <= 8192, zhi > zlo and an output array");
+  const int n = ctx->n;
+  CKC(ctx->obs_counts.ensure(OBS_MAX_BINS, ctx->st));
+  CKC(cudaMemsetAsync(ctx->obs_counts.p, 0, (size_t)nbins * sizeof(unsigned long long), ctx->st));
+  const double dz = (zhi - zlo) / (double)nbins;
+  prof_begin(ctx, K_MISC);
+  k_density_profile<<<std::min(nblk(n, OBS_TPB), 148 * 2), OBS_TPB, (size_t)nbins * sizeof(unsigned int), ctx->st>>>(ctx->posm.p, n, zlo, dz, nbins, type_mask,
+                                                                                                                  ctx->obs_counts.p);
+  prof_end(ctx);
+  CKC(cudaMemcpyAsync(counts, ctx->obs_counts.p, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  CKC(cudaGetLastError());
+  return 0;
+}
+
+int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t *counts, int32_t *n_selected) {
+  if (nbins < 1 || nbins > OBS_MAX_BINS || !(rmax > 0.0) || !counts) FAIL("dml_gr: need 1 <= nbins <= 8192, rmax > 0 and an output array");
+  const int n = ctx->n;
+  TRY(pull_scal(ctx));
+  GrGrid gg;
+  const double span[3] = {ctx->geo.box[0], ctx->geo.box[1], std::max(ctx->geo.box[2], ctx->hsc->zmax)};
+  for (int k = 0; k < 3; ++k) {
+    gg.nc[k] = std::max(1, (int)(span[k] / rmax));
+    gg.nc[k] = std::min(gg.nc[k], 512);
+    gg.cell[k] = span[k] / (double)gg.nc[k];
+  }
+  for (int k = 0; k < 2; ++k)
+    if (ctx->geo.pbc[k] && gg.nc[k] < 3) FAIL("dml_gr: rmax too large for the periodic box (need box >= 3 rmax in x and y)");
+  const int nct = gg.nc[0] * gg.nc[1] * gg.nc[2];
+  CKC(ctx->gr_cell_of.ensure(std::max(n, 1), ctx->st)); CKC(ctx->gr_sorted.ensure(std::max(n, 1), ctx->st));
+  CKC(ctx->gr_cnt.ensure((size_t)nct + 2, ctx->st)); CKC(ctx->gr_start.ensure((size_t)nct + 2, ctx->st));
+  CKC(ctx->obs_counts.ensure(OBS_MAX_BINS, ctx->st));
+  CKC(cudaMemsetAsync(ctx->obs_counts.p, 0, (size_t)nbins * sizeof(unsigned long long), ctx->st));
+  CKC(cudaMemsetAsync(ctx->gr_cnt.p, 0, ((size_t)nct + 2) * sizeof(int), ctx->st));
+  int *nsel = ctx->gr_cnt.p + nct + 1;
+  const int nb = std::min(nblk(n, OBS_TPB), 148 * 8);
+  LAUNCH(K_MISC, k_gr_bin, nb, OBS_TPB, ctx->posm.p, n, gg, type_mask, ctx->gr_cell_of.p, ctx->gr_cnt.p, nsel);
+  TRY(scan_excl(ctx, ctx->gr_cnt.p, ctx->gr_start.p, nct, ctx->gr_start.p + nct, true, 2, 1));   // clears gr_cnt: reused as the fill cursor
+  LAUNCH(K_MISC, k_gr_scatter, nb, OBS_TPB, ctx->posm.p, n, ctx->gr_cell_of.p, ctx->gr_start.p, ctx->gr_cnt.p, ctx->gr_sorted.p);
+  int hsel = 0;
+  CKC(cudaMemcpyAsync(&hsel, nsel, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  if (hsel > 0) {
+    const double dr_bin = rmax / (double)nbins;
+    prof_begin(ctx, K_MISC);
+    k_gr_pairs<<<nblk(hsel, OBS_TPB), OBS_TPB, (size_t)nbins * sizeof(unsigned int), ctx->st>>>(ctx->gr_sorted.p, hsel, ctx->gr_start.p, gg, ctx->geo,
+                                                                                              rmax * rmax, dr_bin, nbins, ctx->obs_counts.p);
+    prof_end(ctx);
+  }
+  CKC(cudaMemcpyAsync(counts, ctx->obs_counts.p, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  CKC(cudaGetLastError());
+  if (n_selected) *n_selected = hsel;
   return 0;
 }
 

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) s_lay[i] = 0u;
   __syncthreads();
   const int lay_old = sc->lay_cur;
+  const int was_listed = sc->listed;                             // read before the first grid.sync: block 0 rewrites it right after
   double a1 = -1.0, a2 = -1.0;
   for (int s = gt; s < A.n; s += gsz) {
     double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s);
@@ -103,12 +104,11 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   block_top2(a1, a2);
   __shared__ int s_need;
   if (threadIdx.x == 0) {
-    int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > A.nb_dcut);   // Neighbor.F90:697-710
+    int need = (!was_listed) || (sqrt(a1) + sqrt(a2) > A.nb_dcut);   // Neighbor.F90:697-710
     s_need = need;
   }
   __syncthreads();
   const bool need = s_need != 0;
-  grid.sync();                                                   // everybody has read sc->listed before block 0 updates it
   if (gt == 0) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;

@@ -122,6 +122,7 @@ struct Geo {
   double bq_scale;   // 255/(rcut+nb_dcut): quantisation of build-time distances (dml_kernels.cuh, k_rows)
   double rcut2;      // rcut^2
   double inv_cell2;  // 1/cell[2] (z-layer lookup only, see layer_of)
+  int rows_fast;     // every axis has >= 3 cells: d_rows may merge the x-neighbours of a stencil row (dml_kernels.cuh)
 };
 
 // idnint(x) for the minimum image, bit-identical to round(): particles live inside the box, so |x| = |vd/box| < 1.5 and

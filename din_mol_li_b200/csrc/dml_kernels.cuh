@@ -377,98 +377,216 @@ constexpr int ROW_W = 16;
 //         Neighbor.F90:515), the build-distance byte, and are compacted in place as slot ids.
 // About one candidate in seven is a hit: with the fp64 work inside the walk some lane of the warp would take the heavy path
 // in nearly every iteration with ~5 lanes active.
+// Ordered walk + settle of one particle into cols[dst .. dst+lim): the reference's enumeration (27 stencil cells in map order x
+// chain order).  Returns the number of parked candidates; cnt / hb describe the finished row when npark <= lim.
+struct RowOut { int npark, cnt; uint4 hb; };
+__device__ __forceinline__ RowOut rows_ordered_into(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                                    const int *__restrict__ sorted_slot, const int *__restrict__ cell_start,
+                                                    int *__restrict__ cols, unsigned char *__restrict__ bq, const Geo &g,
+                                                    const double4 &p, int t, int cx, int cy, int cz, int dst, int lim, bool pad) {
+  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
+  const float rc2hi = (float)g.rc_list2 + g.band2;
+  const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
+  // ---- walk ----
+  int npark = 0, nab = -1, u = 0, e = 0;
+  for (;;) {
+    while (u == e) {                                  // next stencil cell (empty ones are passed over)
+      if (++nab == 27) break;
+      int dx, dy, dz; map_of_lane(nab, dx, dy, dz);
+      int nx = dx + cx - 1, ny = dy + cy - 1, nz = dz + cz - 1;     // cell_pbc wraps every axis, z included (Cells.F90:387-391)
+      nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
+      ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
+      nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
+      const int nl = cell_lin(g, nx, ny, nz);
+      u = __ldg(&cell_start[nl]); e = __ldg(&cell_start[nl + 1]);
+    }
+    if (nab == 27) break;
+    if (u != t) {
+      const float4 q = __ldg(&sorted_posf[u]);
+      float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+      if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+      if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+      if (vx * vx + vy * vy + vz * vz <= rc2hi) { if (npark < lim) cols[dst + npark] = u; ++npark; }
+    }
+    ++u;
+  }
+  // ---- settle: the reference's exact fp64 test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515) ----
+  RowOut o; o.npark = npark; o.cnt = 0; o.hb = make_uint4(0, 0, 0, 0);
+  const int nset = min(npark, lim);
+  for (int i = 0; i < nset; ++i) {
+    const int uq = cols[dst + i];
+    const double4 qd = ld_rec_nc(&sorted_posm[uq]);
+    const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
+    if (rd < g.rc_list2) {
+      const int cnt = o.cnt;
+      cols[dst + cnt] = sorted_slot[uq];               // cnt <= i: compaction in place
+      // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
+      const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
+      if (cnt < 16) {
+        const unsigned int sh = qb << (8 * (cnt & 3));
+        if (cnt < 8) { if (cnt < 4) o.hb.x |= sh; else o.hb.y |= sh; } else { if (cnt < 12) o.hb.z |= sh; else o.hb.w |= sh; }
+      } else bq[dst + cnt] = (unsigned char)qb;
+      o.cnt = cnt + 1;
+    }
+  }
+  if (pad && npark > 0 && npark <= ROW_W) {            // leave no partly written sector behind: pad to the next 8 entries
+    for (int i = npark; i < ((npark + 7) & ~7); ++i) cols[dst + i] = -1;
+  }
+  return o;
+}
+
+// inverse of the stencil map: nab_of(dx,dy,dz) = position of the offset in Cells.F90:28-36 (5 bits per entry, one word per dz)
+constexpr int MAP27[27][3] = {
+  {0,0,0},{1,0,0},{1,1,0},{0,1,0},{-1,1,0},{1,0,-1},{1,1,-1},{0,1,-1},{-1,1,-1},
+  {1,0,1},{1,1,1},{0,1,1},{-1,1,1},{0,0,1},{-1,0,0},{-1,-1,0},{0,-1,0},{1,-1,0},
+  {-1,0,1},{-1,-1,1},{0,-1,1},{1,-1,1},{-1,0,-1},{-1,-1,-1},{0,-1,-1},{1,-1,-1},{0,0,-1}};
+__host__ __device__ constexpr unsigned long long inv_map_word(int dzp) {
+  unsigned long long w = 0ull;
+  for (int n = 0; n < 27; ++n)
+    if (MAP27[n][2] + 1 == dzp) w |= (unsigned long long)n << (5 * ((MAP27[n][1] + 1) * 3 + (MAP27[n][0] + 1)));
+  return w;
+}
+constexpr unsigned long long INV_MAP_W0 = inv_map_word(0), INV_MAP_W1 = inv_map_word(1), INV_MAP_W2 = inv_map_word(2);
+__device__ __forceinline__ int nab_of(int dx, int dy, int dz) {
+  constexpr unsigned long long w0 = INV_MAP_W0, w1 = INV_MAP_W1, w2 = INV_MAP_W2;
+  const unsigned long long w = dz < 0 ? w0 : (dz == 0 ? w1 : w2);
+  return (int)((w >> (5 * ((dy + 1) * 3 + dx + 1))) & 31ull);
+}
+
+// One thread per cell-sorted ref particle.
+//  fast path (every axis has >= 3 cells): ncu on the 27-cell walk showed 53 % of the kernel's instructions in the "next stencil
+//    cell" step, executed 105 times per warp with 8 lanes active.  The three x-neighbours of a stencil row are contiguous in the
+//    cell-sorted arrays, so the walk visits 9 segments (plus the periodic wrap cell at the box edge) instead of 27 cells, in
+//    single precision, parking candidates below the upper edge of the fp32 error band in shared memory.  The parked ones get
+//    the reference's exact fp64 test and are inserted by key = (stencil position, sorted index) — the reference's row order
+//    (stencil order x chain order, Neighbor.F90:497-540) — into the at most ROW_W entries of the row.
+//  long rows (next to dense metal; more than ROW_W parked) and boxes with fewer than 3 cells on an axis (where the reference
+//    visits a cell twice) take the ordered 27-cell walk, the former into a segment of the tail region.
+constexpr int KEY_SHIFT = 26, KEY_MASK = (1 << KEY_SHIFT) - 1;
 __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                        const int *__restrict__ sorted_slot,
                                        const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
                                        RowHead *__restrict__ rh,
                                        int *__restrict__ cols, unsigned char *__restrict__ bq,
                                        DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
+  __shared__ int s_key[ROW_W][TPB];
+  __shared__ int s_seg[18][TPB];
+  __shared__ unsigned char s_qb[ROW_W][TPB];
+  const int tid = threadIdx.x;
   const int nsorted = cell_start[ncell];              // number of binned particles
   const int gsz = gridDim.x * blockDim.x;
   const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
   const float rc2hi = (float)g.rc_list2 + g.band2;
+  const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;     // below this the fp32 distance is inside the list radius for sure
+  const float bqs = __double2float_rd(g.bq_scale * 0.999999);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsorted; t += gsz) {
     const double4 p = ld_rec_nc(&sorted_posm[t]);
     const int s = sorted_slot[t];
     if (!(meta_of(p) & MF_REF)) { rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
     const int lin = sorted_cell[t];
-    const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
     const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-    // Warm the caches before the walk: the walk is a chain of dependent loads (cell range -> candidate), one L2 round trip
-    // each.  Here the 27 cell ranges are requested together, then the first candidate line of every cell; their values only
-    // feed a checksum that is never true, the walk below then runs out of L1.  (Keeping the ranges in shared memory instead
-    // halves the instruction count but shrinks L1 below the working set of the block: measured, no gain.)
-    {
-      int b27[27];
-      unsigned int chk = 0u;
+    int npark = 0;
+    bool done = false;
+    if (g.rows_fast) {
+      const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
+      // cell_pbc wraps the centre like any other cell (a particle binned in a halo cell looks around the wrapped cell)
+      const int ecx = (cx - 1 < 0 ? cx - 1 + g.nc[0] : (cx - 1 >= g.nc[0] ? cx - 1 - g.nc[0] : cx - 1)) + 1;
+      const int ecy = (cy - 1 < 0 ? cy - 1 + g.nc[1] : (cy - 1 >= g.nc[1] ? cy - 1 - g.nc[1] : cy - 1)) + 1;
+      const int ecz = (cz - 1 < 0 ? cz - 1 + g.nc[2] : (cz - 1 >= g.nc[2] ? cz - 1 - g.nc[2] : cz - 1)) + 1;
+      const bool edge = ecx == 1 || ecx == g.nc[0];
+      const int xa = max(ecx - 1, 1), xb = min(ecx + 1, g.nc[0]), xw = ecx == 1 ? g.nc[0] : 1;
+      int rowy[3], rowz[3];                               // wrapped neighbour rows, as offsets into cell_start
 #pragma unroll
-      for (int nab = 0; nab < 27; ++nab) {
-        int nx = c_map[nab][0] + cx - 1, ny = c_map[nab][1] + cy - 1, nz = c_map[nab][2] + cz - 1;
-        nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;
+      for (int d = 0; d < 3; ++d) {
+        int ny = ecy - 2 + d, nz = ecz - 2 + d;
         ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
         nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
-        b27[nab] = __ldg(&cell_start[cell_lin(g, nx, ny, nz)]);
+        rowy[d] = g.hd[0] * ny; rowz[d] = g.hd[0] * g.hd[1] * nz;
       }
+      for (int round = 0; round < (edge ? 2 : 1); ++round) {   // round 1: the periodic wrap cell of a particle at the box edge
+        // the nine segment ranges are requested together (18 loads in flight) and kept in shared memory: the walk below then
+        // advances with two shared-memory reads instead of recomputing a wrapped cell index
+        const int x0 = round ? xw : xa, x1 = (round ? xw : xb) + 1;
 #pragma unroll
-      for (int nab = 0; nab < 27; ++nab) chk += __float_as_uint(__ldg(&sorted_posf[min(b27[nab], nsorted - 1)].w));
-      if (chk == 0xdeadbeefu && pxf == -1.2345f) rh[s].pad = 1;       // never true: keeps the loads alive
-    }
-    int dst = s * ROW_W, lim = ROW_W, cnt = 0;
-    uint4 hb = make_uint4(0, 0, 0, 0);
-    for (int walk = 0; walk < 2; ++walk) {
-      // ---- walk ----
-      int npark = 0, nab = -1, u = 0, e = 0;
-      for (;;) {
-        while (u == e) {                                  // next stencil cell (empty ones are passed over)
-          if (++nab == 27) break;
-          int dx, dy, dz; map_of_lane(nab, dx, dy, dz);
-          int nx = dx + cx - 1, ny = dy + cy - 1, nz = dz + cz - 1;     // cell_pbc wraps every axis, z included (Cells.F90:387-391)
-          nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;   // |offset| <= 2 < nc, one conditional add == mod
-          ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
-          nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
-          const int nl = cell_lin(g, nx, ny, nz);
-          u = __ldg(&cell_start[nl]); e = __ldg(&cell_start[nl + 1]);
+        for (int idx = 0; idx < 9; ++idx) {
+          const int row = rowy[idx % 3] + rowz[idx / 3];
+          s_seg[2 * idx][tid] = __ldg(&cell_start[row + x0]); s_seg[2 * idx + 1][tid] = __ldg(&cell_start[row + x1]);
         }
-        if (nab == 27) break;
-        if (u != t) {
-          const float4 q = __ldg(&sorted_posf[u]);
+        int seg = 0, u = s_seg[0][tid], e = s_seg[1][tid];
+        for (;;) {
+          while (u == e) { if (++seg == 9) break; u = s_seg[2 * seg][tid]; e = s_seg[2 * seg + 1][tid]; }
+          if (seg == 9) break;
+          if (u != t) {
+            const float4 q = __ldg(&sorted_posf[u]);
+            float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+            if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+            if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+            const float d2 = vx * vx + vy * vy + vz * vz;
+            if (d2 <= rc2hi) {
+              // parked word: sorted index | segment << 26 | round << 30 | "inside the list radius for sure" << 31
+              if (npark < ROW_W) s_key[npark][tid] = u | (seg << KEY_SHIFT) | (round << 30) | (d2 < rc2lo ? (int)0x80000000 : 0);
+              ++npark;
+            }
+          }
+          ++u;
+        }
+      }
+      if (npark + slack <= ROW_W) {
+        // ---- settle: exact test only inside the fp32 error band, key, insertion in row order ----
+        int cnt = 0;
+        for (int i = 0; i < npark; ++i) {
+          const int wd = s_key[i][tid];
+          const int uq = wd & KEY_MASK, sg = (wd >> KEY_SHIFT) & 15;
+          const float4 q = __ldg(&sorted_posf[uq]);
           float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
           if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
           if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
-          if (vx * vx + vy * vy + vz * vz <= rc2hi) { if (npark < lim) cols[dst + npark] = u; ++npark; }
+          const float d2 = vx * vx + vy * vy + vz * vz;
+          bool hit = wd < 0;
+          if (!hit) {                                      // the reference's test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515)
+            const double4 qd = ld_rec_nc(&sorted_posm[uq]);
+            hit = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z) < g.rc_list2;
+          }
+          if (hit) {
+            const int dzs = sg / 3, dys = sg - 3 * dzs;    // 0..2
+            int ddx;
+            if (wd & (1 << 30)) ddx = ecx == 1 ? -1 : 1;
+            else {
+              const int row = rowy[0] * (dys == 0) + rowy[1] * (dys == 1) + rowy[2] * (dys == 2) + rowz[0] * (dzs == 0) + rowz[1] * (dzs == 1) + rowz[2] * (dzs == 2);
+              ddx = uq >= __ldg(&cell_start[row + ecx + 1]) ? 1 : (uq >= __ldg(&cell_start[row + ecx]) ? 0 : -1);
+            }
+            const int key = (nab_of(ddx, dys - 1, dzs - 1) << KEY_SHIFT) | uq;
+            // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
+            const unsigned char qb = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
+            int j = cnt;
+            while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; s_qb[j][tid] = s_qb[j - 1][tid]; --j; }
+            s_key[j][tid] = key; s_qb[j][tid] = qb; ++cnt;
+          }
         }
-        ++u;
-      }
-      // ---- settle (the lanes of the warp are together again here) ----
-      cnt = 0; hb = make_uint4(0, 0, 0, 0);
-      const int nset = min(npark, lim);
-      for (int i = 0; i < nset; ++i) {
-        const int uq = cols[dst + i];
-        const double4 qd = ld_rec_nc(&sorted_posm[uq]);
-        const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);   // vdistance(vd,aj,ai)
-        if (rd < g.rc_list2) {
-          cols[dst + cnt] = sorted_slot[uq];               // cnt <= i: compaction in place
-          // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
-          const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
-          if (cnt < 16) {
-            const unsigned int sh = qb << (8 * (cnt & 3));
-            if (cnt < 8) { if (cnt < 4) hb.x |= sh; else hb.y |= sh; } else { if (cnt < 12) hb.z |= sh; else hb.w |= sh; }
-          } else bq[dst + cnt] = (unsigned char)qb;
-          ++cnt;
+        const int dst = s * ROW_W;
+        uint4 hb = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < cnt; ++i) {
+          cols[dst + i] = sorted_slot[s_key[i][tid] & KEY_MASK];
+          const unsigned int sh = (unsigned int)s_qb[i][tid] << (8 * (i & 3));
+          if (i < 8) { if (i < 4) hb.x |= sh; else hb.y |= sh; } else { if (i < 12) hb.z |= sh; else hb.w |= sh; }
         }
+        for (int i = cnt; i < ((cnt + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
+        rh_store(&rh[s], hb, dst, cnt, ROW_W);              // one full-sector store per row
+        done = true;
       }
-      if (walk == 0 && npark > 0 && npark <= ROW_W) {      // leave no partly written sector behind: pad to the next 8 entries
-        for (int i = npark; i < ((npark + 7) & ~7); ++i) cols[dst + i] = -1;
-      }
-      if (walk == 1 || npark + slack <= ROW_W) break;
-      // long row (next to dense metal): a segment of the tail region sized for every parked candidate, second walk fills it;
-      // the first 16 build distances stay in the slot's own bytes (see ROW_W)
-      const int need = npark + slack;
-      const int tb = atomicAdd(&sc->cols_used, need);
-      if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); cnt = 0; dst = s * ROW_W; lim = ROW_W; break; }
-      dst = tb; lim = need;
+    } else {
+      const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, s * ROW_W, ROW_W, true);
+      npark = o.npark;
+      if (npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); done = true; }
     }
-    rh_store(&rh[s], hb, dst, cnt, lim);                  // one full-sector store per row
+    if (done) continue;
+    // long row (next to dense metal): a segment of the tail region sized for every parked candidate, filled by the ordered walk;
+    // the first 16 build distances stay in the slot's own bytes (see ROW_W)
+    const int need = npark + slack;
+    const int tb = atomicAdd(&sc->cols_used, need);
+    if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); continue; }
+    const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, tb, need, false);
+    rh_store(&rh[s], o.hb, tb, o.cnt, need);
   }
 }
 __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
@@ -736,14 +854,80 @@ __device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const 
 // integrator moved since.  qmax is the largest quantised D that still has to be looked at.
 // FUSEB: the thread that holds the finished force of a particle also does its ermak_b update (dana.F90:1031-1052) — same
 // arithmetic as k_ermak_b, one pass less over records and forces; vel/acel/ranv are requested with the first round trip.
-template <int LANES, int MINB, bool FUSEB, int BS = TPB>
+// Row walk of one ref particle whose record, row head and skip bound are already in registers (shared by the kernels below).
+template <int LANES, bool BATCH = false, bool SKIPHEAD = false>
+__device__ __forceinline__ void fuerza_row(const double4 *__restrict__ posm, const int *__restrict__ cols, const int *__restrict__ rev_start,
+                                           const int *__restrict__ rev_len, const int *__restrict__ rev_cols,
+                                           const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+                                           const Geo &g, const Phys &ph, const double4 &p1, int k3, int s, int sub, int rs0, int rl0,
+                                           const uint4 &h16, int qmax, int asym, bool i_halo, FAcc &a) {
+  const int npass = asym ? 2 : 1;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int off = pass == 0 ? rs0 : rev_start[s];
+    const int *lst = (pass == 0 ? cols : rev_cols) + off;
+    const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
+    const int len = pass == 0 ? rl0 : rev_len[s];
+    int jstart = sub;
+    if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first sixteen entries is already here
+      unsigned int need = SKIPHEAD ? 0u : need16(h16, len, qmax);
+      if (BATCH && need && (off & 3) == 0) {
+        // The block lives as long as its slowest thread, and a thread that needs K entries used to pay 2K dependent round
+        // trips (index, record, index, record, ...).  Here the indices of entries 0-7 come back together (two 16-byte loads,
+        // one sector) and the records are requested two at a time: 1 + ceil(K/2) round trips.
+        const int4 *l4 = reinterpret_cast<const int4 *>(lst);
+        const int4 ca = (need & 0x0fu) ? __ldg(l4) : make_int4(0, 0, 0, 0);
+        const int4 cb = (need & 0xf0u) ? __ldg(l4 + 1) : make_int4(0, 0, 0, 0);
+        unsigned int lo = need & 0xffu;
+        need &= ~0xffu;
+        while (lo) {
+          const int q0 = __ffs(lo) - 1; lo &= lo - 1;
+          const bool two = lo != 0u;
+          const int q1 = two ? __ffs(lo) - 1 : q0; lo &= lo - 1;
+          const int4 s0 = q0 < 4 ? ca : cb, s1 = q1 < 4 ? ca : cb;
+          const int j0 = (q0 & 2) ? ((q0 & 1) ? s0.w : s0.z) : ((q0 & 1) ? s0.y : s0.x);
+          const int j1 = (q1 & 2) ? ((q1 & 1) ? s1.w : s1.z) : ((q1 & 1) ? s1.y : s1.x);
+          const double4 r0 = ld_rec_nc(&posm[j0]);
+          const double4 r1 = ld_rec_nc(&posm[j1]);
+          fuerza_pair(g, ph, p1, k3, r0, 0, asym, i_halo, a);
+          if (two) fuerza_pair(g, ph, p1, k3, r1, 0, asym, i_halo, a);
+        }
+      }
+      while (need) {
+        const int q = __ffs(need) - 1; need &= need - 1;
+        fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[q])]), 0, asym, i_halo, a);
+      }
+      jstart = 16;
+    }
+    for (int j0 = jstart; j0 < len; j0 += 8 * LANES) {
+      unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int jj = j0 + q * LANES;
+        int b = 1000;
+        if (jj < len) b = (pass == 0 && jj < 16) ? rh_byte(h16, jj) : (int)__ldg(&lq[jj]);
+        need |= (b <= qmax ? 1u : 0u) << q;
+      }
+      while (need) {
+        const int q = __ffs(need) - 1; need &= need - 1;
+        fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[j0 + q * LANES])]), pass, asym, i_halo, a);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// pf: L2 prefetch switches (DML_FORCE_PF).  The kernel is bound by memory latency, not bandwidth (ncu: long-scoreboard stalls,
+// 3 TB/s of DRAM traffic): bit 0 asks L2 for the record and row head of the particle that the thread taking this block's place
+// will own (slot + pf_ahead, pf_ahead = threads resident on the device), bit 1 for the first sector of this particle's own row
+// in region A (its address depends on the slot alone) while record and head are still on their way.
+template <int LANES, int MINB, bool FUSEB, int BS = TPB, bool BATCH = false>
 __global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
     const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
     const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n,
-    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv) {
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, int pf, int pf_ahead) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = gt / LANES, sub = gt % LANES;
   bool act = s < n;
@@ -753,6 +937,11 @@ __global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
   const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
   const int rs0 = rm.x, rl0 = rm.y;
   const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
+  if (pf && sub == 0) {
+    if ((pf & 2) && act) prefetch_l2(&cols[(size_t)s * ROW_W]);
+    if ((pf & 1) && s + pf_ahead < n) { prefetch_l2(&posm[s + pf_ahead]); prefetch_l2(&rh[s + pf_ahead]); }
+    if ((pf & 4) && s + pf_ahead < n) prefetch_l2(&cols[(size_t)(s + pf_ahead) * ROW_W]);
+  }
   double bv[3] = {0.0, 0.0, 0.0}, ba[3] = {0.0, 0.0, 0.0}, br[3] = {0.0, 0.0, 0.0};
   if (FUSEB && act) {
 #pragma unroll
@@ -765,37 +954,9 @@ __global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
     const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
     const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
     const bool i_halo = asym == 1 && halo_of[s] != 0;
-    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
-    const int npass = asym ? 2 : 1;
-    for (int pass = 0; pass < npass; ++pass) {
-      const int off = pass == 0 ? rs0 : rev_start[s];
-      const int *lst = (pass == 0 ? cols : rev_cols) + off;
-      const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
-      const int len = pass == 0 ? rl0 : rev_len[s];
-      int jstart = sub;
-      if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first sixteen entries is already here
-        unsigned int need = need16(h16, len, qmax);
-        while (need) {
-          const int q = __ffs(need) - 1; need &= need - 1;
-          fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[q])]), 0, asym, i_halo, a);
-        }
-        jstart = 16;
-      }
-      for (int j0 = jstart; j0 < len; j0 += 8 * LANES) {
-        unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int jj = j0 + q * LANES;
-          int b = 1000;
-          if (jj < len) b = (pass == 0 && jj < 16) ? rh_byte(h16, jj) : (int)__ldg(&lq[jj]);
-          need |= (b <= qmax ? 1u : 0u) << q;
-        }
-        while (need) {
-          const int q = __ffs(need) - 1; need &= need - 1;
-          fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[j0 + q * LANES])]), pass, asym, i_halo, a);
-        }
-      }
-    }
+    // pf bits 3,4: diagnostics for tools/perf_probe.py only (wrong forces): 8 = rows taken as empty, 16 = no skip bound (look at all)
+    const int qmax = (pf & 16) ? 255 : skip_qmax(g, sc, lay, p1.z, ph.r0_max);
+    fuerza_row<LANES, BATCH>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, sub, rs0, (pf & 8) ? 0 : rl0, h16, qmax, asym, i_halo, a);
   }
   if (LANES > 1) {
     if (__any_sync(0xffffffffu, a.hit)) {
@@ -820,6 +981,131 @@ __global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
         }
       }
     }
+  }
+}
+
+// Warp-queue form of the production kernel (DML_FORCE_WQ, default on).  ncu on the thread-per-particle kernel: a warp makes
+// 1.7 trips through the gather loop with 5 lanes active, every trip two dependent memory round trips (index, record) of about
+// a microsecond each under load, so a warp lives 4.5 round trips of which only the first streams.  Here the needed head
+// entries of the 32 particles of a warp (about 9) are renumbered 0..T-1 by a prefix sum over the lanes and handed out one per
+// lane: all indices travel together, then all records.  A lane that finds its pair inside the cut-off parks the term in shared
+// memory (ordered by entry number, i.e. by owner and row position); the owners then add their terms in row order, so the result
+// is bit-identical to the thread-per-particle kernel.  More than WQ_HITS terms in one warp (next to dense metal): the warp falls
+// back to the serial walk.  Entries beyond the row head and transposed rows keep the serial walk.
+constexpr int WQ_HITS = 32;
+template <int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_fuerza_wq(
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
+    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
+    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
+  __shared__ double4 s_hit[TPB / 32][WQ_HITS];
+  __shared__ unsigned char s_own[TPB / 32][WQ_HITS];
+  const unsigned int full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  bool act = s < n;
+  const double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
+  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
+  const long long m1 = meta_of(p1);
+  act = act && (m1 & MF_REF);
+  const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
+  int pk = 0, qmax = 0;
+  unsigned int need = 0u;
+  if (act) {
+    pk = ((int)(m1 & MF_TYPE) - 1) * 3;                // k3 in bits 0-3, i_halo in bit 4
+    if (asym == 1 && halo_of[s] != 0) pk |= 16;
+    qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
+    need = need16(h16, rm.y, qmax);
+  }
+  const int cnt = __popc(need);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
+  const int base = incl - cnt;
+  const int T = __shfl_sync(full, incl, 31);
+  FAcc a = {0.0, 0.0, 0.0, 0.0, false};
+  int nh = 0;
+  bool overflow = false;
+  for (int e0 = 0; e0 < T; e0 += 32) {                 // warp-uniform
+    const int e = e0 + lane;
+    const bool on = e < T;
+    int owner = 0;                                     // last lane whose first entry number is <= e
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1) {
+      const int cand = owner + st;
+      const int b = __shfl_sync(full, base, cand & 31);
+      if (b <= e) owner = cand;
+    }
+    unsigned int nm = __shfl_sync(full, need, owner);
+    const int kth = e - __shfl_sync(full, base, owner);
+    const double ox = __shfl_sync(full, p1.x, owner), oy = __shfl_sync(full, p1.y, owner), oz = __shfl_sync(full, p1.z, owner);
+    const int ors = __shfl_sync(full, rm.x, owner), opk = __shfl_sync(full, pk, owner);
+    FAcc t = {0.0, 0.0, 0.0, 0.0, false};
+    if (on) {
+      for (int i = 0; i < kth; ++i) nm &= nm - 1;      // kth-th needed entry of the owner (kth < 16, usually 0 or 1)
+      const int q = __ffs(nm) - 1;
+      const int j = __ldg(&cols[ors + q]);
+      fuerza_pair(g, ph, make_double4(ox, oy, oz, 0.0), opk & 15, ld_rec_nc(&posm[j]), 0, asym, (opk & 16) != 0, t);
+    }
+    const unsigned int hm = __ballot_sync(full, t.hit);
+    if (hm) {
+      if (nh + __popc(hm) > WQ_HITS) { overflow = true; break; }
+      if (t.hit) {
+        const int pos = nh + __popc(hm & ((1u << lane) - 1u));
+        s_hit[w][pos] = make_double4(t.fx, t.fy, t.fz, t.ep); s_own[w][pos] = (unsigned char)owner;
+      }
+      nh += __popc(hm);
+    }
+  }
+  __syncwarp();
+  if (!overflow) {
+    for (int h = 0; h < nh; ++h) {
+      if ((int)s_own[w][h] == lane) { const double4 c = s_hit[w][h]; a.fx += c.x; a.fy += c.y; a.fz += c.z; a.ep += c.w; a.hit = true; }
+    }
+  }
+  if (act) {
+    const int k3 = pk & 15; const bool i_halo = (pk & 16) != 0;
+    if (overflow) fuerza_row<1, false, false>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
+    else if (rm.y > 16 || asym) fuerza_row<1, false, true>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
+    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
+  }
+}
+
+// PPT particles per thread (slots s, s + blockDim, ...): the records and row heads of all of them are requested before the
+// first one is worked on, so a thread keeps PPT x 64 bytes in flight during the streaming part instead of 64 (DML_FORCE_PPT).
+template <int PPT, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_fuerza_ppt(
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
+    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
+    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n, int pf) {
+  const int s0 = blockIdx.x * (blockDim.x * PPT) + threadIdx.x;
+  double4 p[PPT]; int4 rm[PPT]; uint4 h[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int s = s0 + k * blockDim.x;
+    const bool in = s < n;
+    p[k] = in ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+    rm[k] = in ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
+    h[k] = in ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
+    if ((pf & 2) && in) prefetch_l2(&cols[(size_t)s * ROW_W]);
+  }
+  const int asym = __ldg(&sc->rows_asym);
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int s = s0 + k * blockDim.x;
+    const long long m1 = meta_of(p[k]);
+    if (s >= n || !(m1 & MF_REF)) continue;
+    FAcc a = {0.0, 0.0, 0.0, 0.0, false};
+    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+    const bool i_halo = asym == 1 && halo_of[s] != 0;
+    const int qmax = skip_qmax(g, sc, lay, p[k].z, ph.r0_max);
+    fuerza_row<1>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p[k], k3, s, 0, rm[k].x, rm[k].y, h[k], qmax, asym, i_halo, a);
+    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
   }
 }
 

@@ -52,6 +52,7 @@ SYMBOLS = [
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
     "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
+    "dml_salida_sums", "dml_density_profile", "dml_gr",
 ]
 
 _lib = None
@@ -101,6 +102,9 @@ def lib():
         L.dml_slab_halo_exchange.argtypes = [vp]
         L.dml_slab_step.argtypes = [vp, i32]
         L.dml_slab_info.argtypes = [vp] + [C.POINTER(i32)] * 4
+        L.dml_salida_sums.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i32)]
+        L.dml_density_profile.argtypes = [vp, dbl, dbl, i32, i32, vp]
+        L.dml_gr.argtypes = [vp, dbl, i32, i32, vp, C.POINTER(i32)]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -330,6 +334,26 @@ class Ctx:
 
     def step(self, n=1):
         self._chk(lib().dml_step(self.h, n))
+
+    # --- output reductions and observables (salida/kion sums, rho(z), g(r)) ---
+    def salida_sums(self):
+        """energia (sum of epot over sys, dana.F90:1160), energia over hs%ref only, temp (kion, dana.F90:1342-1376), j."""
+        e, er, t, j = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+        self._chk(lib().dml_salida_sums(self.h, C.byref(e), C.byref(er), C.byref(t), C.byref(j)))
+        return e.value, er.value, t.value, j.value
+
+    def density_profile(self, zlo, zhi, nbins, types=(1,)):
+        """counts[b] of particles of the given elements (1 Li, 2 CG, 3 F) per z bin."""
+        out = np.zeros(nbins, np.int64)
+        self._chk(lib().dml_density_profile(self.h, float(zlo), float(zhi), int(nbins), sum(1 << t for t in types), _p(out)))
+        return out
+
+    def gr(self, rmax, nbins, types=(1,)):
+        """Pair-distance histogram (unordered pairs, vdistance minimum image) of the given elements; returns (counts, n_selected)."""
+        out = np.zeros(nbins, np.int64)
+        ns = C.c_int32()
+        self._chk(lib().dml_gr(self.h, float(rmax), int(nbins), sum(1 << t for t in types), _p(out), C.byref(ns)))
+        return out, ns.value
 
     # --- inspection / parity ---
     def cells(self, n=None):

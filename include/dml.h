@@ -114,6 +114,18 @@ int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos
  * between call sites (reservoir 2 uses the template given to dml_set_chunk_template). */
 int dml_step(dml_ctx *ctx, int32_t nsteps);
 
+/* Output path on the device: what salida() needs without downloading the frame.
+ * dml_salida_sums: energia = sum of epot over sys (src/dana.F90:1155-1163), temp = kion(sys) (src/dana.F90:1342-1376:
+ * sum of m*v.v over the non-CG atoms / (j*3*kB_ui)), n_mobile = j.  energia_ref sums hs%ref only (CG atoms keep whatever
+ * epot they had when they were promoted: the reference never zeroes them).  Sums are re-associated
+ * (fixed tree): equal from run to run, within 1e-12 relative of the reference's serial loop.
+ * dml_density_profile: counts[b] = particles of the selected elements (type_mask bit z: 1 Li, 2 CG, 3 F) with
+ * int((z-zlo)/((zhi-zlo)/nbins)) == b.  dml_gr: counts[b] = unordered pairs of selected particles with
+ * int(|vdistance|/(rmax/nbins)) == b and |vdistance|^2 < rmax^2 (vdistance: src/Groups.F90:995-1016).  Integer results. */
+int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *temp, int32_t *n_mobile);
+int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int32_t type_mask, int64_t *counts /*[nbins]*/);
+int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t *counts /*[nbins]*/, int32_t *n_selected);
+
 /* Parity / inspection */
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz /*[n][3], halo-inclusive 0..nc+1*/, int32_t *chain_pos /*[n]*/);
 int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn /*[n]*/, int32_t *rows /*[n][width], slot ids*/);

@@ -230,6 +230,27 @@ def test_fused_ermak_b_is_bit_identical(monkeypatch):
     assert np.abs(out[0]["vel"]).sum() > 0
 
 
+@pytest.mark.parametrize("env", ["DML_FORCE_WQ=1", "DML_FORCE_BATCH=1", "DML_FORCE_PPT=2", "DML_FORCE_PF=3", "DML_FORCE_WQ=1,DML_FORCE_MINB=3"])
+def test_pair_force_kernel_variants_bit_identical(env, monkeypatch):
+    """The alternative schedules of the production pair-force kernel (warp queue, batched requests, two particles per thread,
+    L2 prefetch) add the same terms in the same order as the default one: a Philox run of tests/ermak (deposit grows, so
+    cut-off hits, CG partners and long rows occur) must end bit-identical in every array."""
+    d, o = case("ermak")
+    out = []
+    for variant in ("", env):
+        for kv in [x for x in variant.split(",") if x]:
+            k, v = kv.split("=")
+            monkeypatch.setenv(k, v)
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=4711)
+        ctx.step(400)
+        n = ctx.counters().n_slots
+        out.append(ctx.download(n))
+        ctx.close()
+    for k in ("pos", "vel", "acel", "force", "epot", "z", "flags"):
+        assert np.array_equal(out[0][k], out[1][k]), k
+    assert np.abs(out[0]["force"]).sum() > 0
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""

@@ -22,10 +22,10 @@ for w in $what; do
       timeout 300 python bench.py --impl reference --steps 10 --warmup 1 > $out/bench_ref_$tag.json 2>> $out/bench_$tag.err
       echo "bench ref rc=$?"; cut -c1-300 $out/bench_ref_$tag.json ;;
     launches)
-      timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 600 --csv --log-file $out/launches_$tag.csv \
+      timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches_$tag.csv \
         python bench.py --steps 3 --warmup 3 --no-cpu --ermak-particles 0 --ensemble-replicas 0 > $out/launches_$tag.log 2>&1
       echo "launches rc=$?"
-      timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 600 --csv --log-file $out/launches_ermak1m_$tag.csv \
+      timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches_ermak1m_$tag.csv \
         python tools/perf_probe.py ermak:1000000 --steps 4 --out $out/probe_ncu_scratch.jsonl > $out/launches_ermak1m_$tag.log 2>&1
       echo "launches ermak rc=$?" ;;
     ncu)
@@ -36,7 +36,7 @@ for w in $what; do
         -o $out/ncu_brown100k_$tag python bench.py --steps 3 --warmup 3 --no-cpu --ermak-particles 0 --ensemble-replicas 0 > $out/ncu_brown100k_$tag.log 2>&1
       echo "ncu brown rc=$?" ;;
     probe)
-      timeout 600 python tools/perf_probe.py brown:100000 ermak:1000000 --steps 30 --variants "${PROBE_VARIANTS:-default}" --out $out/probe_$tag.jsonl > $out/probe_$tag.log 2>&1
+      timeout 900 python tools/perf_probe.py ${PROBE_WL:-brown:100000 ermak:1000000} --steps 30 --variants "${PROBE_VARIANTS:-default}" --out $out/probe_$tag.jsonl > $out/probe_$tag.log 2>&1
       echo "probe rc=$?"; tail -4 $out/probe_$tag.log | cut -c1-900 ;;
   esac
 done
