@@ -74,7 +74,7 @@ struct dml_ctx {
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
-  bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
+  bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
                              // kernel takes exactly the sum of the two, 77 us vs 38 + 39 us at 1 M, so the default keeps them apart)
@@ -308,6 +308,14 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
 // transposed rows, built on the device only when rows can be asymmetric (guarded launches, no-ops otherwise)
 static int enq_build_rev(dml_ctx *ctx) {
   int n = ctx->n;
+  if (ctx->use_coop && ctx->coop_grid_rev > 0) {
+    RevArgs A;
+    A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.posm = ctx->posm.p; A.rev_start = ctx->rev_start.p; A.rev_len = ctx->rev_len.p; A.rev_cnt = ctx->rev_cnt.p;
+    A.rev_cols = ctx->rev_cols.p; A.bq = ctx->bq.p; A.rev_bq = ctx->rev_bq.p; A.halo_of = ctx->halo_of.p; A.halo_only = ctx->cfg.strict_order ? 0 : 1;
+    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.n = n;
+    LAUNCH_COOP(K_REV, k_rev_coop, ctx->coop_grid_rev, A);
+    return 0;
+  }
   LAUNCH(K_REV, k_rev_count, std::min(nblk(n), 148 * 8), TPB, ctx->rh.p, ctx->cols.p, ctx->posm.p, ctx->rev_len.p, ctx->rev_cnt.p,
          ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
@@ -637,10 +645,11 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_overlap_coop, TPB, 0);
     ctx->coop_grid_tu = nsm * b1; ctx->coop_grid_ov = nsm * b2;
+    { int b3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_rev_coop, TPB, 0); ctx->coop_grid_rev = getenv("DML_NO_REV_COOP") ? 0 : nsm * std::min(b3, 4); }
     if (const char *e = getenv("DML_COOP_TU_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b1) ctx->coop_grid_tu = nsm * v; }   // blocks per SM of k_test_update_coop
     if (const char *e = getenv("DML_COOP_OV_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b2) ctx->coop_grid_ov = nsm * v; }
     ctx->use_coop = coop && b1 > 0 && b2 > 0 && !getenv("DML_NO_COOP");
-    int gmax = std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_ov), 1);
+    int gmax = std::max(std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_ov), ctx->coop_grid_rev), 1);
     CKC(ctx->coop_sums.ensure((size_t)gmax + 8, ctx->st));
     CKC(ctx->part.ensure((size_t)2 * std::max(gmax, nblk(cap)) + 8, ctx->st));
   }

@@ -647,10 +647,9 @@ __device__ __forceinline__ bool pair_terms(const Geo &g, const Phys &ph, const d
 // Transposed rows: rev(i) = { j : i in row(j) }.  Needed when rows can be asymmetric (a particle in a halo cell is
 // never found as a candidate, Cells.F90:248 + cell_pbc wrap; incremental gcmc appends use <= instead of <).
 #define REV_GUARD(sc) if (!(((volatile const DevScal *)(sc))->rows_asym && !((volatile const DevScal *)(sc))->rev_valid)) return
-__global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restrict__ cols,
+__device__ __forceinline__ void p_rev_count(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                             const double4 *__restrict__ posm, int *__restrict__ rev_len, int *__restrict__ rev_cnt,
                             const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
-  REV_GUARD(sc);
   const bool light = halo_only && sc->rows_asym == 1;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
@@ -660,11 +659,16 @@ __global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restric
     for (int jj = 0; jj < m.y; ++jj) atomicAdd(&rev_cnt[cols[m.x + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
   }
 }
-__global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
+__global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restrict__ cols,
+                            const double4 *__restrict__ posm, int *__restrict__ rev_len, int *__restrict__ rev_cnt,
+                            const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
+  REV_GUARD(sc);
+  p_rev_count(rh, cols, posm, rev_len, rev_cnt, halo_of, halo_only, sc, n);
+}
+__device__ __forceinline__ void p_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
                            const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
-  REV_GUARD(sc);
   const bool light = halo_only && sc->rows_asym == 1;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     if (light && !halo_of[s]) continue;
@@ -678,6 +682,13 @@ __global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict
       rev_cols[w] = s; rev_bq[w] = (unsigned char)(jj < 16 ? rh_byte(h, jj) : (int)bq[m.x + jj]);
     }
   }
+}
+__global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
+                           const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
+                           int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
+  REV_GUARD(sc);
+  p_rev_fill(rh, cols, posm, rev_start, rev_len, rev_cols, bq, rev_bq, halo_of, halo_only, sc, n);
 }
 __global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
