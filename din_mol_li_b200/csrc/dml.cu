@@ -710,13 +710,27 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   if (old_cg) TRY(upload_d(ctx, ctx->old_cg.p, old_cg, n3));
   if (!vel) CKC(cudaMemsetAsync(ctx->vel.p, 0, n3 * sizeof(double), ctx->st));
   if (!acel) CKC(cudaMemsetAsync(ctx->acel.p, 0, n3 * sizeof(double), ctx->st));
+  ctx->n = n; ctx->binned = false;
+  if (ctx->cfg.reservoir != 3) {
+    // No gcmc group to keep in list order: creation ranks, b indices, their occupancy and the two running maxima are filled in
+    // on the device (k_upload_book), so the call is copies + three small kernels and one synchronisation.
+    if (uid) CKC(cudaMemcpyAsync(ctx->uid.p, uid, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+    if (slot_b) CKC(cudaMemcpyAsync(ctx->slot_b.p, slot_b, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+    CKC(cudaMemsetAsync(ctx->b_occ.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
+    TRY(pull_scal(ctx));
+    ctx->hsc->glen = 0; ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = 0;
+    ctx->hsc->n_slots = n; ctx->hsc->next_uid = 0; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+    TRY(push_scal(ctx));
+    LAUNCH(K_MISC, k_upload_book, nblk(n), TPB, ctx->posm.p, ctx->uid.p, ctx->slot_b.p, ctx->b_occ.p, ctx->sc, n, ctx->cap, uid ? 0 : 1, slot_b ? 0 : 1);
+    TRY(pull_scal(ctx));                                  // surfaces an out-of-range slot_b (DML_E_CAPACITY) and refreshes the host mirror
+    return 0;
+  }
   std::vector<int> tmp;
   int mx = -1;
   if (uid) { CKC(cudaMemcpyAsync(ctx->uid.p, uid, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); for (int i = 0; i < n; ++i) mx = std::max(mx, uid[i]); }
   else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; mx = n - 1; CKC(cudaMemcpyAsync(ctx->uid.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
   if (slot_b) CKC(cudaMemcpyAsync(ctx->slot_b.p, slot_b, n * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   else { tmp.resize(n); for (int i = 0; i < n; ++i) tmp[i] = i; CKC(cudaMemcpyAsync(ctx->slot_b.p, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->st)); CKC(cudaStreamSynchronize(ctx->st)); }
-  ctx->n = n; ctx->binned = false;
   // gcmc membership in list order (= creation order) and occupancy of the b index (Groups.F90:1083-1093)
   std::vector<std::pair<int, int>> gm;
   std::vector<int> bocc(ctx->cap, 0), gpos(ctx->cap, 0), gord;

@@ -1833,6 +1833,34 @@ __global__ void k_count_members(const double4 *__restrict__ posm, DevScal *__res
   a = __reduce_add_sync(0xffffffffu, a); r = __reduce_add_sync(0xffffffffu, r); gq = __reduce_add_sync(0xffffffffu, gq); l = __reduce_add_sync(0xffffffffu, l);
   if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(&sc->nat_sys, a); if (r) atomicAdd(&sc->nat_ref, r); if (gq) atomicAdd(&sc->nat_gcmc, gq); if (l) atomicAdd(&sc->nlimbo, l); }
 }
+// dml_upload without a gcmc group: member counts (k_count_members), default creation ranks / b indices, occupancy of the b index
+// (Groups.F90:1083-1093) and the running maxima hs%b%amax and next creation rank, in one pass over the uploaded slots.
+__global__ void k_upload_book(const double4 *__restrict__ posm, int *__restrict__ uid, int *__restrict__ slot_b, int *__restrict__ b_occ,
+                              DevScal *__restrict__ sc, int n, int cap, int gen_uid, int gen_sb) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  int a = 0, r = 0, l = 0, amax = 0, nuid = 0;
+  if (s < n) {
+    const long long m = meta_of(ld_rec_nc(&posm[s]));
+    a = (m & MF_TYPE) ? 1 : 0; r = (m & MF_REF) ? 1 : 0; l = (m & MF_LIMBO) ? 1 : 0;
+    if (gen_uid) uid[s] = s;
+    if (gen_sb) slot_b[s] = s;
+    nuid = (gen_uid ? s : uid[s]) + 1;
+    if (a) {
+      const int sb = gen_sb ? s : slot_b[s];
+      if (sb < 0 || sb >= cap) atomicCAS(&sc->err, 0, DML_E_CAPACITY);
+      else { b_occ[sb] = 1; amax = sb + 1; }
+    }
+  }
+  a = __reduce_add_sync(0xffffffffu, a); r = __reduce_add_sync(0xffffffffu, r); l = __reduce_add_sync(0xffffffffu, l);
+  amax = __reduce_max_sync(0xffffffffu, amax); nuid = __reduce_max_sync(0xffffffffu, nuid);
+  if ((threadIdx.x & 31) == 0) {
+    if (a) atomicAdd(&sc->nat_sys, a);
+    if (r) atomicAdd(&sc->nat_ref, r);
+    if (l) atomicAdd(&sc->nlimbo, l);
+    if (amax) atomicMax(&sc->b_amax, amax);
+    if (nuid) atomicMax(&sc->next_uid, nuid);
+  }
+}
 // chain position of every particle inside its cell (inspection only)
 __global__ void k_msd_book(DevScal *__restrict__ sc) {      // dana.F90:201-202
   sc->msd_t = sc->msd_t / sc->nat_ref;
