@@ -104,10 +104,24 @@ module dml_cuda
     integer(c_int) function dml_reset_try_depo(ctx) bind(C, name='dml_reset_try_depo')
       import; type(c_ptr), value :: ctx
     end function
+    ! salida()/kion() sums on the device (dana.F90:1155-1163, 1342-1376): no frame download for E.dat / T.dat
+    integer(c_int) function dml_salida_sums(ctx, energia, energia_ref, temp, n_mobile) bind(C, name='dml_salida_sums')
+      import; type(c_ptr), value :: ctx; real(c_double), intent(out) :: energia, energia_ref, temp
+      integer(c_int32_t), intent(out) :: n_mobile
+    end function
+    ! observables: counts(nbins) are integer(8); type_mask bit z selects element z (1 Li, 2 CG, 3 F)
+    integer(c_int) function dml_density_profile(ctx, zlo, zhi, nbins, type_mask, counts) bind(C, name='dml_density_profile')
+      import; type(c_ptr), value :: ctx; real(c_double), value :: zlo, zhi; integer(c_int32_t), value :: nbins, type_mask
+      integer(c_int64_t), intent(out) :: counts(*)
+    end function
+    integer(c_int) function dml_gr(ctx, rmax, nbins, type_mask, counts, n_selected) bind(C, name='dml_gr')
+      import; type(c_ptr), value :: ctx; real(c_double), value :: rmax; integer(c_int32_t), value :: nbins, type_mask
+      integer(c_int64_t), intent(out) :: counts(*); integer(c_int32_t), intent(out) :: n_selected
+    end function
   end interface
   public :: dml_create, dml_destroy, dml_last_error, dml_upload, dml_download, dml_test_update, dml_fuerza, dml_ermak_a, &
             dml_ermak_b, dml_cbrownian_hs, dml_overlap_moveback, dml_msd_book, dml_promote, dml_gcmc_run, dml_calc_rho, &
-            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo
+            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo, dml_salida_sums, dml_density_profile, dml_gr
 
 contains
 

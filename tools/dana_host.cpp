@@ -128,6 +128,7 @@ int main(int argc, char **argv) {
   FILE *fxyz = fopen((dir + "/Li.xyz").c_str(), "w"), *fe = fopen((dir + "/E.dat").c_str(), "w"), *ft = fopen((dir + "/T.dat").c_str(), "w"),
        *fr = fopen((dir + "/rho.dat").c_str(), "w"), *ftry = fopen((dir + "/try.dat").c_str(), "w"), *fd = fopen((dir + "/depo.dat").c_str(), "w");
   std::vector<double> P, V, EP; std::vector<int32_t> Z, FL, UID;
+  const bool device_sums = getenv("DANA_DEVICE_SUMS") != nullptr;   // E.dat / T.dat from dml_salida_sums instead of the host loop
   auto salida = [&](double t) -> int {                      // dana.F90:1143-1183 (+kion 1342-1376), atoms in sys%alist order
     dml_counters k; if (dml_get_counters(ctx, &k)) return 1;
     int ns = k.n_slots;
@@ -145,8 +146,15 @@ int main(int argc, char **argv) {
       energia += EP[i];
       if (Z[i] != 2) { jm++; vdac += ((V[3 * i] * V[3 * i] + V[3 * i + 1] * V[3 * i + 1]) + V[3 * i + 2] * V[3 * i + 2]) * 6.94; }
     }
+    double temp_out = vdac / (jm * 3.0 * c.kB_ui);
+    if (device_sums) {                                        // E.dat / T.dat from the device reductions (dml_salida_sums); the host loop above stays as the check
+      double e_dev = 0, e_ref = 0, t_dev = 0; int32_t j_dev = 0;
+      if (dml_salida_sums(ctx, &e_dev, &e_ref, &t_dev, &j_dev)) return 1;
+      if (j_dev != jm || std::fabs(e_dev - energia) > 1e-9 * std::max(1.0, std::fabs(energia))) { fprintf(stderr, "dml_salida_sums disagrees with the host sums\n"); return 1; }
+      energia = e_dev; temp_out = t_dev;
+    }
     fprintf(fe, "%s%s\n", fort_real(t).c_str(), fort_real(energia).c_str());
-    fprintf(ft, "%s%s\n", fort_real(t).c_str(), fort_real(vdac / (jm * 3.0 * c.kB_ui)).c_str());
+    fprintf(ft, "%s%s\n", fort_real(t).c_str(), fort_real(temp_out).c_str());
     fprintf(fr, "%s%s\n", fort_real(t).c_str(), fort_real(s.rho).c_str());
     fprintf(ftry, "%s%12lld\n", fort_real(t).c_str(), (long long)k.try_);
     fprintf(fd, "%s%12lld\n", fort_real(t).c_str(), (long long)k.depo);
