@@ -69,6 +69,7 @@ struct dml_ctx {
   DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
   DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
+  int rows_lanes = 1;       // DML_ROWS_LANES: lanes per particle in the fast row build (1, 2 or 4)
   bool rows_legacy = false; // DML_ROWS_LEGACY=1: 27-cell ordered walk for every row (the fast walk needs >= 3 cells per axis)
   bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
@@ -210,7 +211,7 @@ static void tessellate(dml_ctx *ctx) {
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
   g.inv_cell2 = 1.0 / g.cell[2];
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
-  g.rows_fast = (nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3 && ctx->cap < (1 << 26) && !ctx->rows_legacy) ? 1 : 0;
+  g.rows_fast = (nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3 && ctx->cap < (1 << 26) && !ctx->rows_legacy) ? ctx->rows_lanes : 0;
   g.lay_shift = 0; while (((g.nc[2] + 2) >> g.lay_shift) + 1 > LAY_MAX) g.lay_shift++;
   g.nlay = ((g.nc[2] + 1) >> g.lay_shift) + 1;
   ctx->tessellated = true;
@@ -252,7 +253,7 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 // ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
-  int nw = std::min(nblk(n), 148 * 8);                // grid-stride over particles: an idle (guarded) launch stays cheap
+  int nw = std::min(nblk(n * std::max(ctx->geo.rows_fast, 1)), 148 * 8);   // grid-stride over particles: an idle (guarded) launch stays cheap
   LAUNCH(K_ROWS_FILL, k_rows, nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
          ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   return 0;
@@ -589,6 +590,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
+  if (const char *e = getenv("DML_ROWS_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->rows_lanes = v; }
   if (const char *e = getenv("DML_FORCE_WQ")) ctx->force_wq = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_BATCH")) ctx->force_batch = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_PF")) ctx->force_pf = atoi(e) & 31;

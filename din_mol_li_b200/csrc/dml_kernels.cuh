@@ -365,7 +365,7 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 // get a segment of the tail region [cols_tail0, cols_cap) by an atomic bump and are written by a second walk of the same
 // thread.  Where the row lives, its length and its first 16 build distances are the slot's RowHead (dml_device.cuh); the
 // build distances of entries 16.. of a long row are in bq[], indexed like cols[].
-constexpr int ROW_W = 16;
+constexpr int ROW_W = 24;   // Poisson(5.8) neighbours in solution: P(n > 16) = 1.2e-4 left a dozen rows per 100 k particles on the serial ordered walk (a 28 us tail of the 70 us kernel, ncu: SMs active 57 % of the time); P(n > 24) = 3e-9
 
 // One thread per cell-sorted ref particle, two dense loops and no per-thread arrays (a queue or a table of cell ranges in local
 // memory costs more L2/DRAM traffic than the whole list):
@@ -463,6 +463,16 @@ __device__ __forceinline__ int nab_of(int dx, int dy, int dz) {
 //  long rows (next to dense metal; more than ROW_W parked) and boxes with fewer than 3 cells on an axis (where the reference
 //    visits a cell twice) take the ordered 27-cell walk, the former into a segment of the tail region.
 constexpr int KEY_SHIFT = 26, KEY_MASK = (1 << KEY_SHIFT) - 1;
+// build-distance bytes of the row being settled live in the thread's own words of the segment table (free once the walk is over)
+#define SQB(i) (reinterpret_cast<unsigned char *>(&s_seg[(i) >> 2][tid])[(i) & 3])
+template <int L>
+__device__ __forceinline__ void d_rows_ml(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                          const int *__restrict__ sorted_slot,
+                                          const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
+                                          RowHead *__restrict__ rh,
+                                          int *__restrict__ cols, unsigned char *__restrict__ bq,
+                                          DevScal *__restrict__ sc, const Geo &g, int ncell, int slack,
+                                          int (*s_key)[TPB], int (*s_seg)[TPB]);
 __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                        const int *__restrict__ sorted_slot,
                                        const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
@@ -471,8 +481,9 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
                                        DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
   __shared__ int s_key[ROW_W][TPB];
   __shared__ int s_seg[18][TPB];
-  __shared__ unsigned char s_qb[ROW_W][TPB];
   const int tid = threadIdx.x;
+  if (g.rows_fast == 2) { d_rows_ml<2>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack, s_key, s_seg); return; }
+  if (g.rows_fast == 4) { d_rows_ml<4>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack, s_key, s_seg); return; }
   const int nsorted = cell_start[ncell];              // number of binned particles
   const int gsz = gridDim.x * blockDim.x;
   const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
@@ -559,16 +570,16 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
             // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
             const unsigned char qb = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
             int j = cnt;
-            while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; s_qb[j][tid] = s_qb[j - 1][tid]; --j; }
-            s_key[j][tid] = key; s_qb[j][tid] = qb; ++cnt;
+            while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; SQB(j) = SQB(j - 1); --j; }
+            s_key[j][tid] = key; SQB(j) = qb; ++cnt;
           }
         }
         const int dst = s * ROW_W;
         uint4 hb = make_uint4(0, 0, 0, 0);
         for (int i = 0; i < cnt; ++i) {
           cols[dst + i] = sorted_slot[s_key[i][tid] & KEY_MASK];
-          const unsigned int sh = (unsigned int)s_qb[i][tid] << (8 * (i & 3));
-          if (i < 8) { if (i < 4) hb.x |= sh; else hb.y |= sh; } else { if (i < 12) hb.z |= sh; else hb.w |= sh; }
+          const unsigned int sh = (unsigned int)SQB(i) << (8 * (i & 3));
+          if (i < 8) { if (i < 4) hb.x |= sh; else hb.y |= sh; } else if (i < 16) { if (i < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + i] = SQB(i);
         }
         for (int i = cnt; i < ((cnt + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
         rh_store(&rh[s], hb, dst, cnt, ROW_W);              // one full-sector store per row
@@ -589,6 +600,158 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
     rh_store(&rh[s], o.hb, tb, o.cnt, need);
   }
 }
+// L lanes per particle (L = 2 or 4, all in one warp): a 100 k box gives one thread per particle only 5 warps per scheduler and the
+// kernel is a chain of dependent L1/L2 round trips, so the nine (or eighteen) segments of a particle are dealt out to L lanes.
+// Every lane walks and settles its own segments into its own shared-memory column exactly like the single-lane path; the row
+// position of a hit is its position in the lane's sorted column plus the number of smaller keys in the other lanes' columns.
+template <int L>
+__device__ __forceinline__ void d_rows_ml(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                          const int *__restrict__ sorted_slot,
+                                          const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
+                                          RowHead *__restrict__ rh,
+                                          int *__restrict__ cols, unsigned char *__restrict__ bq,
+                                          DevScal *__restrict__ sc, const Geo &g, int ncell, int slack,
+                                          int (*s_key)[TPB], int (*s_seg)[TPB]) {
+  const int tid = threadIdx.x, lane = tid & 31, sub = tid & (L - 1);
+  const unsigned int gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (lane & ~(L - 1));
+  const int nsorted = cell_start[ncell];
+  const int gsz = (gridDim.x * blockDim.x) / L;
+  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
+  const float rc2hi = (float)g.rc_list2 + g.band2;
+  const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;
+  const float bqs = __double2float_rd(g.bq_scale * 0.999999);
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / L; t < nsorted; t += gsz) {
+    const double4 p = ld_rec_nc(&sorted_posm[t]);
+    const int s = sorted_slot[t];
+    if (!(meta_of(p) & MF_REF)) { if (sub == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }
+    const int lin = sorted_cell[t];
+    const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
+    const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
+    const int ecx = (cx - 1 < 0 ? cx - 1 + g.nc[0] : (cx - 1 >= g.nc[0] ? cx - 1 - g.nc[0] : cx - 1)) + 1;
+    const int ecy = (cy - 1 < 0 ? cy - 1 + g.nc[1] : (cy - 1 >= g.nc[1] ? cy - 1 - g.nc[1] : cy - 1)) + 1;
+    const int ecz = (cz - 1 < 0 ? cz - 1 + g.nc[2] : (cz - 1 >= g.nc[2] ? cz - 1 - g.nc[2] : cz - 1)) + 1;
+    const bool edge = ecx == 1 || ecx == g.nc[0];
+    const int xa = max(ecx - 1, 1), xb = min(ecx + 1, g.nc[0]), xw = ecx == 1 ? g.nc[0] : 1;
+    int ry0, ry1, ry2, rz0, rz1, rz2;
+    {
+      int a = ecy - 2, b = ecy - 1, c = ecy, d = ecz - 2, e = ecz - 1, f = ecz;
+      a = (a < 0 ? a + g.nc[1] : a) + 1; b += 1; c = (c >= g.nc[1] ? c - g.nc[1] : c) + 1;
+      d = (d < 0 ? d + g.nc[2] : d) + 1; e += 1; f = (f >= g.nc[2] ? f - g.nc[2] : f) + 1;
+      ry0 = g.hd[0] * a; ry1 = g.hd[0] * b; ry2 = g.hd[0] * c;
+      const int hz = g.hd[0] * g.hd[1];
+      rz0 = hz * d; rz1 = hz * e; rz2 = hz * f;
+    }
+    // own segments: v = sub, sub+L, ... over the 9 (edge: 18) virtual segments; v >= 9 is the wrap cell of stencil row v-9
+    const int nv = edge ? 18 : 9;
+    int nown = 0;
+    for (int v = sub; v < nv; v += L, ++nown) {
+      const int rnd = v >= 9 ? 1 : 0, idx = v - 9 * rnd, dz = idx / 3, dy = idx - 3 * dz;
+      const int row = (dy == 0 ? ry0 : (dy == 1 ? ry1 : ry2)) + (dz == 0 ? rz0 : (dz == 1 ? rz1 : rz2));
+      s_seg[2 * nown][tid] = __ldg(&cell_start[row + (rnd ? xw : xa)]);
+      s_seg[2 * nown + 1][tid] = __ldg(&cell_start[row + (rnd ? xw : xb) + 1]);
+    }
+    int npark = 0;
+    if (nown > 0) {
+      int j = 0, u = s_seg[0][tid], e = s_seg[1][tid];
+      for (;;) {
+        while (u == e) { if (++j == nown) break; u = s_seg[2 * j][tid]; e = s_seg[2 * j + 1][tid]; }
+        if (j == nown) break;
+        if (u != t) {
+          const float4 q = __ldg(&sorted_posf[u]);
+          float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+          if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+          if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+          const float d2 = vx * vx + vy * vy + vz * vz;
+          if (d2 <= rc2hi) {
+            const int v = sub + j * L, rnd = v >= 9 ? 1 : 0;
+            if (npark < ROW_W) s_key[npark][tid] = u | ((v - 9 * rnd) << KEY_SHIFT) | (rnd << 30) | (d2 < rc2lo ? (int)0x80000000 : 0);
+            ++npark;
+          }
+        }
+        ++u;
+      }
+    }
+    int ntot = npark;
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) ntot += __shfl_xor_sync(gmask, ntot, o);
+    if (ntot + slack <= ROW_W) {
+      // ---- settle own column ----
+      int cnt = 0;
+      for (int i = 0; i < npark; ++i) {
+        const int wd = s_key[i][tid];
+        const int uq = wd & KEY_MASK, sg = (wd >> KEY_SHIFT) & 15;
+        const float4 q = __ldg(&sorted_posf[uq]);
+        float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+        if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+        if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+        const float d2 = vx * vx + vy * vy + vz * vz;
+        bool hit = wd < 0;
+        if (!hit) {
+          const double4 qd = ld_rec_nc(&sorted_posm[uq]);
+          hit = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z) < g.rc_list2;
+        }
+        if (hit) {
+          const int dzs = sg / 3, dys = sg - 3 * dzs;
+          int ddx;
+          if (wd & (1 << 30)) ddx = ecx == 1 ? -1 : 1;
+          else {
+            const int row = (dys == 0 ? ry0 : (dys == 1 ? ry1 : ry2)) + (dzs == 0 ? rz0 : (dzs == 1 ? rz1 : rz2));
+            ddx = uq >= __ldg(&cell_start[row + ecx + 1]) ? 1 : (uq >= __ldg(&cell_start[row + ecx]) ? 0 : -1);
+          }
+          const int key = (nab_of(ddx, dys - 1, dzs - 1) << KEY_SHIFT) | uq;
+          const unsigned char qb = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
+          int j = cnt;
+          while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; SQB(j) = SQB(j - 1); --j; }
+          s_key[j][tid] = key; SQB(j) = qb; ++cnt;
+        }
+      }
+      __syncwarp(gmask);
+      // ---- merge by rank: position = own index + smaller keys in the other lanes' columns ----
+      int cnts[L];
+#pragma unroll
+      for (int o = 0; o < L; ++o) cnts[o] = __shfl_sync(gmask, cnt, (lane & ~(L - 1)) + o);
+      int total = 0;
+#pragma unroll
+      for (int o = 0; o < L; ++o) total += cnts[o];
+      const int dst = s * ROW_W, tbase = tid & ~(L - 1);
+      uint4 hb = make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < cnt; ++i) {
+        const int key = s_key[i][tid];
+        int rank = i;
+#pragma unroll
+        for (int o = 0; o < L; ++o) {
+          if (o == sub) continue;
+          for (int m = 0; m < cnts[o]; ++m) rank += s_key[m][tbase + o] < key ? 1 : 0;
+        }
+        cols[dst + rank] = sorted_slot[key & KEY_MASK];
+        const unsigned int sh = (unsigned int)SQB(i) << (8 * (rank & 3));
+        if (rank < 8) { if (rank < 4) hb.x |= sh; else hb.y |= sh; } else if (rank < 16) { if (rank < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + rank] = SQB(i);
+      }
+#pragma unroll
+      for (int o = 1; o < L; o <<= 1) {
+        hb.x |= __shfl_xor_sync(gmask, hb.x, o); hb.y |= __shfl_xor_sync(gmask, hb.y, o);
+        hb.z |= __shfl_xor_sync(gmask, hb.z, o); hb.w |= __shfl_xor_sync(gmask, hb.w, o);
+      }
+      if (sub == 0) {
+        for (int i = total; i < ((total + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
+        rh_store(&rh[s], hb, dst, total, ROW_W);
+      }
+      __syncwarp(gmask);                                  // the columns are reused by the next particle of the group
+      continue;
+    }
+    // long row: ordered 27-cell walk by the first lane into a segment of the tail region (see d_rows)
+    if (sub == 0) {
+      const int need = ntot + slack;
+      const int tb = atomicAdd(&sc->cols_used, need);
+      if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); }
+      else {
+        const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, tb, need, false);
+        rh_store(&rh[s], o.hb, tb, o.cnt, need);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                               const int *__restrict__ sorted_slot,
                                               const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
