@@ -453,6 +453,97 @@ __device__ __forceinline__ int nab_of(int dx, int dy, int dz) {
   return (int)((w >> (5 * ((dy + 1) * 3 + dx + 1))) & 31ull);
 }
 
+// Long row (next to dense metal: an ion over a two-layer bcc electrode sees ~90 CG atoms) built by a whole warp: lane l < 27 owns
+// stencil cell l of the map (Cells.F90:28-36), counts its fp32 candidates, an exclusive prefix over the lanes gives every cell's
+// place in the row (stencil order x chain order), a second walk parks the candidates there, and the fp64 test + compaction run
+// 32 entries at a time with ballots.  One thread doing this alone (what the thread-per-particle pass would do) takes ~10 k
+// dependent instructions per row: measured 326 us instead of 163 us of test_update per step on the 1 M box with the CG slab.
+__device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                               const int *__restrict__ sorted_slot, const int *__restrict__ sorted_cell,
+                                               const int *__restrict__ cell_start, RowHead *__restrict__ rh,
+                                               int *__restrict__ cols, unsigned char *__restrict__ bq,
+                                               DevScal *__restrict__ sc, const Geo &g, int slack, int t) {
+  const unsigned int full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const double4 p = ld_rec_nc(&sorted_posm[t]);
+  const int s = sorted_slot[t];
+  const int lin = sorted_cell[t];
+  const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
+  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
+  const float rc2hi = (float)g.rc_list2 + g.band2;
+  const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
+  int b = 0, e = 0;
+  if (lane < 27) {
+    int dx, dy, dz; map_of_lane(lane, dx, dy, dz);
+    int nx = dx + cx - 1, ny = dy + cy - 1, nz = dz + cz - 1;     // cell_pbc wraps every axis, z included (Cells.F90:387-391)
+    nx = (nx < 0 ? nx + g.nc[0] : (nx >= g.nc[0] ? nx - g.nc[0] : nx)) + 1;
+    ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
+    nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
+    const int nl = cell_lin(g, nx, ny, nz);
+    b = __ldg(&cell_start[nl]); e = __ldg(&cell_start[nl + 1]);
+  }
+  int tb = 0, npark = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int c = 0;
+    int off = 0;
+    if (pass == 1) {
+      // place of this lane's cell in the row
+      int incl = npark;                                     // npark holds the lane's own count of pass 0 here
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
+      off = incl - npark;
+      npark = __shfl_sync(full, incl, 31);
+      const int need = npark + slack;
+      if (lane == 0) tb = atomicAdd(&sc->cols_used, need);
+      tb = __shfl_sync(full, tb, 0);
+      if (tb + need > sc->cols_cap) {
+        if (lane == 0) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); }
+        return;
+      }
+    }
+    for (int u = b; u < e; ++u) {
+      if (u == t) continue;
+      const float4 q = __ldg(&sorted_posf[u]);
+      float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
+      if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
+      if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+      if (vx * vx + vy * vy + vz * vz <= rc2hi) { if (pass == 1) cols[tb + off + c] = u; ++c; }
+    }
+    if (pass == 0) npark = c;
+  }
+  __syncwarp();
+  // settle: the reference's exact test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515), ordered compaction in place
+  int cnt = 0;
+  uint4 hb = make_uint4(0, 0, 0, 0);
+  for (int i0 = 0; i0 < npark; i0 += 32) {
+    const int i = i0 + lane;
+    bool hit = false; int slot = -1; unsigned int qb = 0u;
+    if (i < npark) {
+      const int uq = cols[tb + i];
+      const double4 qd = ld_rec_nc(&sorted_posm[uq]);
+      const double rd = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z);
+      if (rd < g.rc_list2) { hit = true; slot = sorted_slot[uq]; qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999)); }
+    }
+    const unsigned int hm = __ballot_sync(full, hit);
+    __syncwarp();                                           // every lane has read its parked entry before the row is overwritten
+    if (hit) {
+      const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
+      cols[tb + pos] = slot;
+      if (pos < 16) {
+        const unsigned int sh = qb << (8 * (pos & 3));
+        if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else { if (pos < 12) hb.z |= sh; else hb.w |= sh; }
+      } else bq[tb + pos] = (unsigned char)qb;
+    }
+    cnt += __popc(hm);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    hb.x |= __shfl_xor_sync(full, hb.x, o); hb.y |= __shfl_xor_sync(full, hb.y, o);
+    hb.z |= __shfl_xor_sync(full, hb.z, o); hb.w |= __shfl_xor_sync(full, hb.w, o);
+  }
+  if (lane == 0) rh_store(&rh[s], hb, tb, cnt, npark + slack);
+}
+
 // One thread per cell-sorted ref particle.
 //  fast path (every axis has >= 3 cells): ncu on the 27-cell walk showed 53 % of the kernel's instructions in the "next stencil
 //    cell" step, executed 105 times per warp with 8 lanes active.  The three x-neighbours of a stencil row are contiguous in the
@@ -490,10 +581,17 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
   const float rc2hi = (float)g.rc_list2 + g.band2;
   const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;     // below this the fp32 distance is inside the list radius for sure
   const float bqs = __double2float_rd(g.bq_scale * 0.999999);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nsorted; t += gsz) {
+  __shared__ int s_long[TPB];
+  __shared__ int s_nlong;
+  for (int tbase = blockIdx.x * blockDim.x; tbase < nsorted; tbase += gsz) {   // block-uniform trip count: the long rows of a trip are built by whole warps below
+    if (tid == 0) s_nlong = 0;
+    __syncthreads();
+    const int t = tbase + tid;
+    if (t < nsorted) {
     const double4 p = ld_rec_nc(&sorted_posm[t]);
     const int s = sorted_slot[t];
-    if (!(meta_of(p) & MF_REF)) { rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
+    if (!(meta_of(p) & MF_REF)) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0);   // rows exist only for ref atoms
+    else {
     const int lin = sorted_cell[t];
     const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
     int npark = 0;
@@ -590,14 +688,14 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
       npark = o.npark;
       if (npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); done = true; }
     }
-    if (done) continue;
-    // long row (next to dense metal): a segment of the tail region sized for every parked candidate, filled by the ordered walk;
-    // the first 16 build distances stay in the slot's own bytes (see ROW_W)
-    const int need = npark + slack;
-    const int tb = atomicAdd(&sc->cols_used, need);
-    if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); continue; }
-    const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, tb, need, false);
-    rh_store(&rh[s], o.hb, tb, o.cnt, need);
+    if (!done) s_long[atomicAdd(&s_nlong, 1)] = t;        // long row (next to dense metal): built by a warp, see rows_long_warp
+    }
+    }
+    __syncthreads();
+    const int nlong = s_nlong;
+    for (int i = tid >> 5; i < nlong; i += TPB / 32)
+      rows_long_warp(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, slack, s_long[i]);
+    __syncthreads();
   }
 }
 // L lanes per particle (L = 2 or 4, all in one warp): a 100 k box gives one thread per particle only 5 warps per scheduler and the

@@ -251,6 +251,48 @@ def test_pair_force_kernel_variants_bit_identical(env, monkeypatch):
     assert np.abs(out[0]["force"]).sum() > 0
 
 
+def _slab_oracle():
+    """Two atomic layers of bcc metal (CG, a = 3.51 A) under ions placed by the reference's pos_inic rule: every ion within a list
+    radius of the electrode has a row of 60-90 entries, far beyond the 24 that fit a slot's own row storage."""
+    a = 3.51
+    nx = 24
+    xi = yi = nx * a
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(nx), np.arange(1), indexing="ij"), -1).reshape(-1, 3).astype(float)
+    cg = np.concatenate([g * a + [0.9, 0.9, 0.5], (g + 0.5) * a + [0.9, 0.9, 0.5]])
+    ions, _ = O.pos_inic(-104012, xi, yi, 100.0)
+    ions = ions + [0.0, 0.0, 5.7]
+    pos = np.concatenate([cg, ions])
+    z = np.concatenate([np.full(len(cg), 2, np.int32), np.ones(len(ions), np.int32)])
+    return O.Oracle(idum=-31, xi=xi, yi=yi, z0=60.0, zmax=110.0, h=1e-2, nb_dcut=10.0, integrador=1, reservoir=1, init_xyz=pos, init_z=z)
+
+
+def test_long_rows_next_to_dense_metal():
+    """Rows longer than a slot's own storage are built by a whole warp (rows_long_warp): same entries in the same order as the
+    reference's serial walk, at t = 0 and after every rebuild of a replayed run over the electrode (forces from CG partners,
+    depositions on contact, hard-sphere move-backs)."""
+    o = _slab_oracle()
+    ctx = P.ctx_from_oracle(o)
+    ctx.test_update()
+    a = P.oracle_slot_arrays(o)
+    n = len(a["z"])
+    nn, rows, _ = o.rows(width=256)
+    gnn, grows = ctx.neighbors(n, width=256)
+    assert nn.max() > 40 and (nn > 24).sum() > 15                   # the long-row path is exercised
+    assert np.array_equal(gnn, nn[:n])
+    assert P.rows_as_lists(gnn, grows, 0) == P.rows_as_lists(nn[:n], rows, 1)
+    ctx.close()
+    ls = P.Lockstep(o, strict=1)
+    nupd0 = o.scalars().nupd
+    for i in range(120):
+        ls.step(check=True, tag="slab step %d" % (i + 1))
+        if i % 20 == 19:
+            nn, rows, _ = o.rows(width=256)
+            n = o.scalars().hs_amax
+            gnn, grows = ls.ctx.neighbors(n, width=256)
+            assert P.rows_as_lists(gnn, grows, 0) == P.rows_as_lists(nn[:n], rows, 1), "rows differ after step %d" % (i + 1)
+    assert o.scalars().nupd > nupd0 + 2                             # several device-side rebuilds happened
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
