@@ -612,6 +612,8 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
         nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
         rowy[d] = g.hd[0] * ny; rowz[d] = g.hd[0] * g.hd[1] * nz;
       }
+      const float bxf = g.pbc[0] ? (float)g.box[0] : 0.0f, byf = g.pbc[1] ? (float)g.box[1] : 0.0f;
+      const float sy0 = ecy - 2 < 0 ? -byf : 0.0f, sy2 = ecy >= g.nc[1] ? byf : 0.0f;
       for (int round = 0; round < (edge ? 2 : 1); ++round) {   // round 1: the periodic wrap cell of a particle at the box edge
         // the nine segment ranges are requested together (18 loads in flight) and kept in shared memory: the walk below then
         // advances with two shared-memory reads instead of recomputing a wrapped cell index
@@ -621,15 +623,24 @@ __device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, 
           const int row = rowy[idx % 3] + rowz[idx / 3];
           s_seg[2 * idx][tid] = __ldg(&cell_start[row + x0]); s_seg[2 * idx + 1][tid] = __ldg(&cell_start[row + x1]);
         }
+        // minimum image without branches: all candidates of a segment sit in the same periodic image relative to the particle
+        // (the x-neighbours of round 0 are inside the box, the wrap cell of round 1 one box length away; a stencil row that
+        // wrapped in y is one box length away in y), so the shift is a per-segment constant.  It is the operation the branchy
+        // form applies whenever the pair can be inside the list radius (cells are at least one list radius wide).
+        const float sx = round ? (ecx == 1 ? -bxf : bxf) : 0.0f;
         int seg = 0, u = s_seg[0][tid], e = s_seg[1][tid];
+        float sy = sy0;                                     // segments 0,3,6 look at row ecy-1, 1,4,7 at ecy, 2,5,8 at ecy+1
         for (;;) {
-          while (u == e) { if (++seg == 9) break; u = s_seg[2 * seg][tid]; e = s_seg[2 * seg + 1][tid]; }
+          while (u == e) {
+            if (++seg == 9) break;
+            u = s_seg[2 * seg][tid]; e = s_seg[2 * seg + 1][tid];
+            const int dy = seg - 3 * (seg / 3);
+            sy = dy == 0 ? sy0 : (dy == 1 ? 0.0f : sy2);
+          }
           if (seg == 9) break;
           if (u != t) {
             const float4 q = __ldg(&sorted_posf[u]);
-            float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
-            if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
-            if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
+            const float vx = (q.x - pxf) + sx, vy = (q.y - pyf) + sy, vz = q.z - pzf;
             const float d2 = vx * vx + vy * vy + vz * vz;
             if (d2 <= rc2hi) {
               // parked word: sorted index | segment << 26 | round << 30 | "inside the list radius for sure" << 31
