@@ -75,6 +75,8 @@ struct dml_ctx {
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
+  int tu_fused = 0;         // what the last test_update launch folded in (bit 0 k_ov_init, bit 1 k_ov_apply)
+  bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
@@ -262,7 +264,8 @@ static int enq_materialize_rows(dml_ctx *ctx) {
 // test_update (Neighbor.F90:668-713) enqueued without any host round trip: the rebuild decision is taken by
 // k_top2_final on the device and the rebuild kernels (update + ngroup_cells, Neighbor.F90:608-633,465-548) are
 // always launched but return immediately when no rebuild is due.
-static int enq_test_update(dml_ctx *ctx) {
+static int enq_test_update(dml_ctx *ctx, int fuse = 0) {
+  ctx->tu_fused = 0;
   tessellate(ctx);
   if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction: the reference's O(N^2) ngroup_verlet path is not implemented on the device");
   int n = ctx->n, nct = ctx->nct;
@@ -279,6 +282,9 @@ static int enq_test_update(dml_ctx *ctx) {
     A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
     A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
+    A.fuse = ctx->no_tu_fuse ? 0 : fuse; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p; A.ov_head = ctx->ov_head.p;
+    A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p;
+    ctx->tu_fused = A.fuse;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
     ctx->binned = true;
     return 0;
@@ -380,7 +386,11 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
 }
 
 // overlap_moveback (dana.F90:849-943)
-static int enq_overlap(dml_ctx *ctx, bool fused = false) {
+// inside dml_step the two test_update launches around overlap_moveback can carry its first and last pass over the slots
+static bool tu_can_fuse(const dml_ctx *ctx) { return ctx->use_coop && ctx->n <= ctx->coop_tu_max_n && !ctx->no_tu_fuse; }
+static bool ov_is_multi_launch(const dml_ctx *ctx) { return !(ctx->use_coop && ctx->n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0); }
+
+static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false, bool defer_apply = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   if (!fused) TRY(enq_qtab(ctx));
@@ -395,7 +405,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false) {
     ctx->have_rp_ovl = false;
     return 0;
   }
-  LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
+  if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
          ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
   const double *uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr;
@@ -425,7 +435,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false) {
       }
     }
   }
-  LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, ctx->sc, n);
+  if (!defer_apply) LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, ctx->sc, n);
   ctx->have_rp_ovl = false;
   return 0;
 }
@@ -511,9 +521,10 @@ static int enq_step(dml_ctx *ctx) {
     if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
       LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
   } else TRY(enq_integrate(ctx, false));
-  TRY(enq_test_update(ctx));
-  TRY(enq_overlap(ctx, true));
-  TRY(enq_test_update(ctx));
+  const bool fz = tu_can_fuse(ctx) && ov_is_multi_launch(ctx);   // k_ov_init rides on the first test_update, k_ov_apply on the second
+  TRY(enq_test_update(ctx, fz ? 1 : 0));
+  TRY(enq_overlap(ctx, true, fz, fz));
+  TRY(enq_test_update(ctx, fz ? 2 : 0));
   if (ctx->cfg.reservoir == 3) {
     LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
     TRY(enq_promote(ctx));
@@ -590,6 +601,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
+  if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
   if (const char *e = getenv("DML_ROWS_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->rows_lanes = v; }
   if (const char *e = getenv("DML_FORCE_WQ")) ctx->force_wq = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_BATCH")) ctx->force_batch = atoi(e) != 0;

@@ -73,6 +73,9 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 struct TUArgs {
   double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
   const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut, rmax_f, rmax_o;
+  // neighbours of the call inside dml_step folded into the first pass over the slots: fuse bit 0 = the initialisation of the
+  // overlap_moveback that follows (k_ov_init), bit 1 = the write-back of the overlap_moveback that came before (k_ov_apply)
+  int fuse; int *parent, *ovst, *comp_cnt, *ov_head; double *vel, *acel; const double *old_cg;
 };
 
 // test_update (Neighbor.F90:668-713) in one launch
@@ -88,8 +91,19 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   const int lay_old = sc->lay_cur;
   const int was_listed = sc->listed;                             // read before the first grid.sync: block 0 rewrites it right after
   double a1 = -1.0, a2 = -1.0;
+  if (gt == 0 && (A.fuse & 2)) {                                 // k_ov_apply's bookkeeping (dana.F90:939-941)
+    if (sc->ch_later > sc->choques2) sc->choques2 = sc->ch_later;
+    sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
+  }
+  if (gt == 0 && (A.fuse & 1)) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
   for (int s = gt; s < A.n; s += gsz) {
+    if (A.fuse & 2) d_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, s);
     double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s);
+    if (A.fuse & 1) {
+      const long long m = meta_of(ld_rec(&A.posm[s]));
+      A.parent[s] = s; A.comp_cnt[s] = 0; A.ov_head[s] = -1;
+      A.ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
+    }
     if (rd >= 0.0) lay_note(s_lay, A.g, A.posm[s].z, rd);
     top2_merge(a1, a2, rd, -1.0);
   }

@@ -1955,29 +1955,30 @@ __global__ void __launch_bounds__(128) k_ov_resolve(const double4 *__restrict__ 
   p_ov_resolve(posm, old_cg, rh, cols, bq, lay, ovst, roots, ov_head, ov_next, members, uid, rp_uovl, sc, g, ph, step, guard_pass);
 }
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
+__device__ __forceinline__ void d_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
+                                           const double *__restrict__ old_cg, const int *__restrict__ ovst, int s) {
+  double4 p = ld_rec(&posm[s]);
+  long long m = meta_of(p);
+  if (!(m & MF_REF)) return;
+  int st = ovst[s];
+  long long nm = m;
+  if (st & OV_INVOLVED) {
+    nm = (m & ~(MF_TYPE | MF_SKIP)) | (long long)((st >> OV_TSHIFT) & 3) | ((st & OV_SKIP) ? MF_SKIP : 0);
+    if (st & OV_MOVED) { p.x = old_cg[3 * s]; p.y = old_cg[3 * s + 1]; p.z = old_cg[3 * s + 2]; }
+    if (st & OV_ZERO) {
+      vel[3 * s] = 0.0; vel[3 * s + 1] = 0.0; vel[3 * s + 2] = 0.0;
+      acel[3 * s] = 0.0; acel[3 * s + 1] = 0.0; acel[3 * s + 2] = 0.0;
+    }
+  } else nm = m | MF_SKIP;                                     // processed in the first pass, nothing in range
+  if (nm != m || (st & OV_MOVED)) { p.w = meta_as_double(nm); st_rec(&posm[s], p); }
+}
 __device__ __forceinline__ void p_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
                            const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {                                                // choques2=max(choques2,choques-i), dana.F90:939-941
     if (sc->ch_later > sc->choques2) sc->choques2 = sc->ch_later;
     sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
   }
-  const int s_end = n;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
-    double4 p = ld_rec(&posm[s]);
-    long long m = meta_of(p);
-    if (!(m & MF_REF)) continue;
-    int st = ovst[s];
-    long long nm = m;
-    if (st & OV_INVOLVED) {
-      nm = (m & ~(MF_TYPE | MF_SKIP)) | (long long)((st >> OV_TSHIFT) & 3) | ((st & OV_SKIP) ? MF_SKIP : 0);
-      if (st & OV_MOVED) { p.x = old_cg[3 * s]; p.y = old_cg[3 * s + 1]; p.z = old_cg[3 * s + 2]; }
-      if (st & OV_ZERO) {
-        vel[3 * s] = 0.0; vel[3 * s + 1] = 0.0; vel[3 * s + 2] = 0.0;
-        acel[3 * s] = 0.0; acel[3 * s + 1] = 0.0; acel[3 * s + 2] = 0.0;
-      }
-    } else nm = m | MF_SKIP;                                     // processed in the first pass, nothing in range
-    if (nm != m || (st & OV_MOVED)) { p.w = meta_as_double(nm); st_rec(&posm[s], p); }
-  }
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) d_ov_apply(posm, vel, acel, old_cg, ovst, s);
 }
 __global__ void k_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
                            const double *__restrict__ old_cg, const int *__restrict__ ovst, DevScal *__restrict__ sc, int n) { p_ov_apply(posm, vel, acel, old_cg, ovst, sc, n); }

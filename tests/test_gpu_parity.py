@@ -293,6 +293,31 @@ def test_long_rows_next_to_dense_metal():
     assert o.scalars().nupd > nupd0 + 2                             # several device-side rebuilds happened
 
 
+@pytest.mark.parametrize("name,nsteps", [("ermak", 400), ("brown", 150)])
+def test_step_with_folded_overlap_passes_bit_identical(name, nsteps, monkeypatch):
+    """Inside dml_step the first and last pass of overlap_moveback over the slots (k_ov_init, k_ov_apply) ride on the two
+    test_update launches around it (boxes above the cooperative-overlap size, i.e. bench.py's).  Forced here on the small fixtures:
+    the Philox trajectory must be bit-identical with and without the folding."""
+    d, o = case(name)
+    monkeypatch.setenv("DML_COOP_MAX_N", "100")              # multi-launch overlap_moveback ...
+    monkeypatch.setenv("DML_COOP_TU_MAX_N", "4194304")       # ... between one-launch test_updates
+    out = []
+    for nofuse in (False, True):
+        if nofuse:
+            monkeypatch.setenv("DML_NO_TU_FUSE", "1")
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=2024)
+        if name == "brown":
+            ch = P.ChunkTemplate(d["chunk_xyz"], o.scalars().zmax, o.params.dist + 3.2)
+            ctx.set_chunk_template(ch.pos, ch.pos_old, ch.dist, P.RHOMEDIA)
+        ctx.step(nsteps)
+        c = ctx.counters()
+        out.append((ctx.download(c.n_slots), c.choques, c.choques2, c.overlap_passes, c.nupd_vlist))
+        ctx.close()
+    for k in ("pos", "vel", "acel", "pos_old", "z", "flags"):
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    assert out[0][1:] == out[1][1:] and out[0][1] > 0
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
