@@ -1415,16 +1415,19 @@ __device__ __forceinline__ void block_flush(BlockAcc a, DevScal *sc) {
 
 // atom_pbc — dana.F90:1187-1250.  Returns depos.  The deposition uniform is drawn only when z<=0.
 struct RngSrc { int mode; unsigned long long seed; unsigned int id, step; const double *rp; int slot; };
-__device__ __forceinline__ bool atom_pbc_dev(const Geo &g, const Phys &ph, double zmax, double q[3], double po[3], const double og[3],
-                                             double v[3], long long &meta, const RngSrc &rs, BlockAcc &acc) {
+// pos_old is only touched when the particle crosses a periodic face (a few per thousand per step) and, under Ermak, vel only when
+// it bounces off the ceiling: both are read / written on demand (pos_old_s points at the slot's three doubles, wrote_v reports the
+// bounce), which takes 72 of the 236 bytes per particle out of the streaming pass.
+__device__ __forceinline__ bool atom_pbc_dev(const Geo &g, const Phys &ph, double zmax, double q[3], double *__restrict__ pos_old_s, const double og[3],
+                                             double v[3], long long &meta, const RngSrc &rs, BlockAcc &acc, bool &wrote_v) {
   bool depos = false;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    if (q[j] > g.box[j]) { q[j] = q[j] - g.box[j]; po[j] = po[j] - g.box[j]; }
-    if (q[j] < 0.0) { q[j] = q[j] + g.box[j]; po[j] = po[j] + g.box[j]; }
+    if (q[j] > g.box[j]) { q[j] = q[j] - g.box[j]; pos_old_s[j] = pos_old_s[j] - g.box[j]; }
+    if (q[j] < 0.0) { q[j] = q[j] + g.box[j]; pos_old_s[j] = pos_old_s[j] + g.box[j]; }
   }
   if (q[2] > zmax) {
-    if (ph.integrador) { q[2] = q[2] - 2 * (q[2] - zmax); v[2] = -v[2]; }
+    if (ph.integrador) { q[2] = q[2] - 2 * (q[2] - zmax); v[2] = -v[2]; wrote_v = true; }
     else { q[0] = og[0]; q[1] = og[1]; q[2] = og[2]; }
   }
   acc.msd += v[0] * v[0] * ph.h * ph.h;
@@ -1453,7 +1456,6 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
     if (m & MF_REF) {
       double q[3] = {p.x, p.y, p.z}, og[3] = {p.x, p.y, p.z};
       double v[3] = {vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]};
-      double po[3] = {pos_old[3 * s], pos_old[3 * s + 1], pos_old[3 * s + 2]};
       old_cg[3 * s] = og[0]; old_cg[3 * s + 1] = og[1]; old_cg[3 * s + 2] = og[2];
       int zt = (int)(m & MF_TYPE);
       double gs[6];
@@ -1487,7 +1489,8 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
       }
       double zmax = sc->zmax;
       RngSrc rs = {ph.rng_mode, ph.seed, (unsigned int)uid[s], step, rp_upbc, s};
-      bool depos = atom_pbc_dev(g, ph, zmax, q, po, og, v, m, rs, acc);
+      bool wrote_v = !ERMAK;                               // the Brownian step always rewrites vel
+      bool depos = atom_pbc_dev(g, ph, zmax, q, pos_old + 3 * (size_t)s, og, v, m, rs, acc, wrote_v);
       if (!depos) {
         if (!ERMAK) acc.mv = fmax(acc.mv, (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
         m &= ~MF_SKIP;
@@ -1501,8 +1504,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
       }
       p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
       st_rec(&posm[s], p);
-      vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2];
-      pos_old[3 * s] = po[0]; pos_old[3 * s + 1] = po[1]; pos_old[3 * s + 2] = po[2];
+      if (wrote_v) { vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2]; }
     }
   }
   block_flush(acc, sc);
