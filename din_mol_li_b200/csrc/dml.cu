@@ -98,6 +98,7 @@ struct dml_ctx {
   // output reductions and observables (dml_observe.cuh)
   DBuf<double> obs_part, obs_out; DBuf<unsigned long long> obs_counts; DBuf<int> gr_cell_of, gr_cnt, gr_start; DBuf<double4> gr_sorted;
   unsigned int *obs_ticket = nullptr;
+  DBuf<int> snap_uid; DBuf<unsigned char> snap_mb; DBuf<int4> mc_out; DBuf<int> mc_count; bool have_snap = false;   // dml_membership_changes
   // staging
   DBuf<double> stage_d, stage_f; DBuf<int> stage_i;
   DevScal *sc = nullptr; DevScal *hsc = nullptr;    // device / pinned host mirror
@@ -700,12 +701,21 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->obs_part.release(); ctx->obs_out.release(); ctx->obs_counts.release(); ctx->gr_cell_of.release(); ctx->gr_cnt.release(); ctx->gr_start.release();
   ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
+  ctx->snap_uid.release(); ctx->snap_mb.release(); ctx->mc_out.release(); ctx->mc_count.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
   if (ctx->hsc) cudaFreeHost(ctx->hsc);
   if (ctx->st) cudaStreamDestroy(ctx->st);
   delete ctx;
+}
+
+// snapshot of who occupies every slot and of its group membership (dml_membership_changes reports against it)
+static int member_snapshot(dml_ctx *ctx) {
+  CKC(ctx->snap_uid.ensure(ctx->cap, ctx->st)); CKC(ctx->snap_mb.ensure(ctx->cap, ctx->st));
+  LAUNCH(K_MISC, k_member_snap, std::min(nblk(ctx->cap, OBS_TPB), 148 * 8), OBS_TPB, ctx->posm.p, ctx->uid.p, ctx->n, ctx->cap, ctx->snap_uid.p, ctx->snap_mb.p);
+  ctx->have_snap = true;
+  return 0;
 }
 
 int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, const double *acel, const double *pos_old,
@@ -736,6 +746,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
     ctx->hsc->n_slots = n; ctx->hsc->next_uid = 0; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
     TRY(push_scal(ctx));
     LAUNCH(K_MISC, k_upload_book, nblk(n), TPB, ctx->posm.p, ctx->uid.p, ctx->slot_b.p, ctx->b_occ.p, ctx->sc, n, ctx->cap, uid ? 0 : 1, slot_b ? 0 : 1);
+    TRY(member_snapshot(ctx));
     TRY(pull_scal(ctx));                                  // surfaces an out-of-range slot_b (DML_E_CAPACITY) and refreshes the host mirror
     return 0;
   }
@@ -768,6 +779,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
   TRY(push_scal(ctx));
   LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
+  TRY(member_snapshot(ctx));
   CKC(cudaStreamSynchronize(ctx->st));
   return 0;
 }
@@ -1263,6 +1275,32 @@ int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t 
   CKC(cudaStreamSynchronize(ctx->st));
   CKC(cudaGetLastError());
   if (n_selected) *n_selected = hsel;
+  return 0;
+}
+
+int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int32_t *kind, int32_t *uid_now, int32_t *z_now, int32_t *n_changes) {
+  if (!n_changes || max_changes < 0) FAIL("dml_membership_changes: n_changes is required");
+  if (!ctx->have_snap) { TRY(member_snapshot(ctx)); *n_changes = 0; CKC(cudaStreamSynchronize(ctx->st)); return 0; }
+  CKC(ctx->mc_out.ensure((size_t)std::max(max_changes, 1), ctx->st)); CKC(ctx->mc_count.ensure(1, ctx->st));
+  CKC(cudaMemsetAsync(ctx->mc_count.p, 0, sizeof(int), ctx->st));
+  LAUNCH(K_MISC, k_member_diff, std::min(nblk(ctx->cap, OBS_TPB), 148 * 8), OBS_TPB, ctx->posm.p, ctx->uid.p, ctx->n, ctx->cap, ctx->snap_uid.p, ctx->snap_mb.p,
+         max_changes, ctx->mc_out.p, ctx->mc_count.p);
+  int cnt = 0;
+  CKC(cudaMemcpyAsync(&cnt, ctx->mc_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  *n_changes = cnt;
+  const int m = std::min(cnt, (int)max_changes);
+  if (m > 0) {
+    std::vector<int4> rec(m);
+    CKC(cudaMemcpy(rec.data(), ctx->mc_out.p, (size_t)m * sizeof(int4), cudaMemcpyDeviceToHost));
+    std::sort(rec.begin(), rec.end(), [](const int4 &a, const int4 &b) { return a.x < b.x; });   // ascending slot
+    for (int i = 0; i < m; ++i) {
+      if (slot) slot[i] = rec[i].x;
+      if (kind) kind[i] = rec[i].y;
+      if (uid_now) uid_now[i] = rec[i].z;
+      if (z_now) z_now[i] = rec[i].w;
+    }
+  }
   return 0;
 }
 

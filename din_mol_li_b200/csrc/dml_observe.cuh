@@ -153,4 +153,44 @@ __global__ void __launch_bounds__(OBS_TPB) k_gr_pairs(const double4 *__restrict_
   for (int b = threadIdx.x; b < nbins; b += blockDim.x) if (hist[b]) atomicAdd(&counts[b], (unsigned long long)hist[b]);
 }
 
+
+// ---- host object model sync: what changed in sys / hs%ref / gcmc membership since the last snapshot -----------
+// The reference keeps membership in pointer lists (Groups.F90 atom / group / igroup); the device changes it in four places
+// (gcmc insertion and deletion dana.F90:655-706, chunk blocks 716-773, Li -> F on deposition 1236-1240, F -> CG promotion 228-236).
+// Instead of instrumenting each of them, the slot's occupant (creation rank) and a membership byte are snapshotted and compared.
+constexpr int MC_NEW = 1, MC_GONE = 2, MC_ELEMENT = 4, MC_LEFT_REF = 8, MC_LEFT_GCMC = 16;
+__device__ __forceinline__ int member_byte(long long m) {       // element | ref << 2 | gcmc << 3; 0 = empty slot (or parked on limbo)
+  const int zt = (int)(m & MF_TYPE);
+  if (zt == 0 || (m & MF_GHOST)) return 0;
+  return zt | ((m & MF_REF) ? 4 : 0) | ((m & MF_GCMC) ? 8 : 0);
+}
+__global__ void __launch_bounds__(OBS_TPB) k_member_snap(const double4 *__restrict__ posm, const int *__restrict__ uid, int n, int cap,
+                                                        int *__restrict__ snap_uid, unsigned char *__restrict__ snap_mb) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+    const int mb = s < n ? member_byte(meta_of(ld_rec_nc(&posm[s]))) : 0;
+    snap_mb[s] = (unsigned char)mb; snap_uid[s] = mb ? uid[s] : -1;
+  }
+}
+__global__ void __launch_bounds__(OBS_TPB) k_member_diff(const double4 *__restrict__ posm, const int *__restrict__ uid, int n, int cap,
+                                                        int *__restrict__ snap_uid, unsigned char *__restrict__ snap_mb,
+                                                        int max_out, int4 *__restrict__ out, int *__restrict__ count) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+    const int mb = s < n ? member_byte(meta_of(ld_rec_nc(&posm[s]))) : 0;
+    const int u = mb ? uid[s] : -1;
+    const int omb = snap_mb[s], ou = snap_uid[s];
+    int kind = 0;
+    if (mb && (!omb || ou != u)) kind |= MC_NEW;
+    if (omb && (!mb || ou != u)) kind |= MC_GONE;
+    if (mb && omb && ou == u) {
+      if ((mb & 3) != (omb & 3)) kind |= MC_ELEMENT;
+      if ((omb & 4) && !(mb & 4)) kind |= MC_LEFT_REF;
+      if ((omb & 8) && !(mb & 8)) kind |= MC_LEFT_GCMC;
+    }
+    if (kind) {
+      const int k = atomicAdd(count, 1);
+      if (k < max_out) { out[k] = make_int4(s, kind, u, mb & 3); snap_mb[s] = (unsigned char)mb; snap_uid[s] = u; }   // unreported slots stay pending
+    }
+  }
+}
+
 } // namespace dml

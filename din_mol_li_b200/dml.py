@@ -52,7 +52,7 @@ SYMBOLS = [
     "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
     "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
-    "dml_salida_sums", "dml_density_profile", "dml_gr",
+    "dml_salida_sums", "dml_density_profile", "dml_gr", "dml_membership_changes",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def lib():
         L.dml_salida_sums.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i32)]
         L.dml_density_profile.argtypes = [vp, dbl, dbl, i32, i32, vp]
         L.dml_gr.argtypes = [vp, dbl, i32, i32, vp, C.POINTER(i32)]
+        L.dml_membership_changes.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(i32)]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -354,6 +355,15 @@ class Ctx:
         ns = C.c_int32()
         self._chk(lib().dml_gr(self.h, float(rmax), int(nbins), sum(1 << t for t in types), _p(out), C.byref(ns)))
         return out, ns.value
+
+    def membership_changes(self, max_changes=65536):
+        """(slot, kind, uid_now, z_now) arrays of the slots whose occupant / membership changed since the previous call (or upload);
+        kind bits: 1 new occupant, 2 previous occupant gone, 4 element changed, 8 left hs%ref, 16 left gcmc."""
+        sl, kd, ud, zn = (np.zeros(max_changes, np.int32) for _ in range(4))
+        n = C.c_int32()
+        self._chk(lib().dml_membership_changes(self.h, max_changes, _p(sl), _p(kd), _p(ud), _p(zn), C.byref(n)))
+        m = min(n.value, max_changes)
+        return sl[:m], kd[:m], ud[:m], zn[:m], n.value
 
     # --- inspection / parity ---
     def cells(self, n=None):

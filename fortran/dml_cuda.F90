@@ -114,6 +114,13 @@ module dml_cuda
       import; type(c_ptr), value :: ctx; real(c_double), value :: zlo, zhi; integer(c_int32_t), value :: nbins, type_mask
       integer(c_int64_t), intent(out) :: counts(*)
     end function
+    ! host object model sync: slots whose occupant / element / membership changed since the previous call (kind bits: 1 new atom,
+    ! 2 previous atom gone, 4 element changed, 8 left hs%ref, 16 left gcmc) -> attach / detach_all / setz exactly those atoms
+    integer(c_int) function dml_membership_changes(ctx, max_changes, slot, kind, uid_now, z_now, n_changes) &
+        bind(C, name='dml_membership_changes')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: max_changes
+      integer(c_int32_t), intent(out) :: slot(*), kind(*), uid_now(*), z_now(*), n_changes
+    end function
     integer(c_int) function dml_gr(ctx, rmax, nbins, type_mask, counts, n_selected) bind(C, name='dml_gr')
       import; type(c_ptr), value :: ctx; real(c_double), value :: rmax; integer(c_int32_t), value :: nbins, type_mask
       integer(c_int64_t), intent(out) :: counts(*); integer(c_int32_t), intent(out) :: n_selected
@@ -121,7 +128,7 @@ module dml_cuda
   end interface
   public :: dml_create, dml_destroy, dml_last_error, dml_upload, dml_download, dml_test_update, dml_fuerza, dml_ermak_a, &
             dml_ermak_b, dml_cbrownian_hs, dml_overlap_moveback, dml_msd_book, dml_promote, dml_gcmc_run, dml_calc_rho, &
-            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo, dml_salida_sums, dml_density_profile, dml_gr
+            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo, dml_salida_sums, dml_density_profile, dml_gr, dml_membership_changes
 
 contains
 

@@ -126,6 +126,16 @@ int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *
 int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int32_t type_mask, int64_t *counts /*[nbins]*/);
 int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t *counts /*[nbins]*/, int32_t *n_selected);
 
+/* Host object model sync: the reference keeps membership in pointer lists (src/Groups.F90 atom/group/igroup);
+ * the device changes it in gcmc_run (insert src/dana.F90:655-674, delete 703-706), bloques (716-773), atom_pbc /
+ * overlap_moveback (Li -> F, 1236-1240, 905-910) and the promotion loop (F -> CG, 228-236).  This call reports every slot whose
+ * occupant or membership differs from the previous call (the first one compares with dml_upload), in ascending slot order, so
+ * the Fortran side can attach / detach / setz exactly those atoms instead of re-reading the whole system.
+ * kind bits: 1 a new atom occupies the slot (uid_now = its creation rank, z_now its element), 2 the previous occupant is gone,
+ * 4 element changed (z_now), 8 left hs%ref, 16 left the gcmc group.  *n_changes = records found; at most max_changes are returned
+ * (the snapshot advances only for slots reported in full: if *n_changes > max_changes, call again for the rest). */
+int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int32_t *kind, int32_t *uid_now, int32_t *z_now, int32_t *n_changes);
+
 /* Parity / inspection */
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz /*[n][3], halo-inclusive 0..nc+1*/, int32_t *chain_pos /*[n]*/);
 int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn /*[n]*/, int32_t *rows /*[n][width], slot ids*/);

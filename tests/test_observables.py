@@ -107,3 +107,63 @@ def test_gr_total_pairs_property_at_scale():
     assert 2 * int(counts.sum()) == int(c.list_entries)
     assert counts[: int(3.2 / (13.2 / 512))].sum() == 0          # pos_inic keeps every pair at >= 3.2 A
     ctx.close()
+
+
+def _member_bytes(a):
+    """element | ref << 2 | gcmc << 3 per slot, 0 for empty / limbo slots (same rule as member_byte in dml_observe.cuh)."""
+    alive = (a["z"] > 0) & ((a["flags"] & 8) == 0)
+    mb = np.where(alive, a["z"] | ((a["flags"] & 1) << 2) | (((a["flags"] >> 1) & 1) << 3), 0)
+    return mb.astype(np.int64), np.where(alive, a["uid"], -1).astype(np.int64)
+
+
+def _expected_changes(prev, now):
+    n = max(len(prev[0]), len(now[0]))
+    pad = lambda x, fill: np.concatenate([x, np.full(n - len(x), fill, np.int64)])
+    omb, ou, mb, u = pad(prev[0], 0), pad(prev[1], -1), pad(now[0], 0), pad(now[1], -1)
+    kind = np.zeros(n, np.int64)
+    kind |= np.where((mb > 0) & ((omb == 0) | (ou != u)), 1, 0)
+    kind |= np.where((omb > 0) & ((mb == 0) | (ou != u)), 2, 0)
+    same = (mb > 0) & (omb > 0) & (ou == u)
+    kind |= np.where(same & ((mb & 3) != (omb & 3)), 4, 0)
+    kind |= np.where(same & ((omb & 4) > 0) & ((mb & 4) == 0), 8, 0)
+    kind |= np.where(same & ((omb & 8) > 0) & ((mb & 8) == 0), 16, 0)
+    sl = np.flatnonzero(kind)
+    return sl, kind[sl], u[sl], mb[sl] & 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nsteps,every", [("gcmc", 400, 40), ("brown", 120, 30), ("ermak", 300, 60)])
+def test_membership_changes_follow_the_oracle(name, nsteps, every):
+    """dml_membership_changes (host object model sync) in a replayed run: the slots it reports between two calls are
+    exactly those whose occupant (creation rank), element or group membership changed in the ORACLE's lists over the same steps:
+    gcmc insertions / deletions with index reuse, chunk blocks, Li -> F depositions, F -> CG promotions."""
+    import parity as P
+    d = O.read_case(os.path.join(GOLD, name))
+    o = O.Oracle(**d)
+    ls = P.Lockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
+    sl, kd, ud, zn, tot = ls.ctx.membership_changes()
+    assert tot == 0                                               # nothing changed since the upload
+    prev = _member_bytes(P.oracle_slot_arrays(o))
+    seen = 0
+    for i in range(nsteps):
+        ls.step(check=False)
+        if (i + 1) % every == 0:
+            now = _member_bytes(P.oracle_slot_arrays(o))
+            esl, ekd, eud, ezn = _expected_changes(prev, now)
+            sl, kd, ud, zn, tot = ls.ctx.membership_changes()
+            assert tot == len(esl) and np.array_equal(sl, esl) and np.array_equal(kd, ekd)
+            assert np.array_equal(ud, eud) and np.array_equal(zn, ezn)
+            seen += tot
+            prev = now
+    assert seen > 5
+    # a call with too small arrays keeps the unreported slots pending
+    for i in range(every):
+        ls.step(check=False)
+    now = _member_bytes(P.oracle_slot_arrays(o))
+    esl, _, _, _ = _expected_changes(prev, now)
+    if len(esl) >= 2:
+        sl1, _, _, _, tot1 = ls.ctx.membership_changes(max_changes=1)
+        sl2, _, _, _, tot2 = ls.ctx.membership_changes()
+        assert tot1 == len(esl) and tot2 == len(esl) - 1
+        assert sorted(list(sl1) + list(sl2)) == list(esl)
+    ls.ctx.close()
