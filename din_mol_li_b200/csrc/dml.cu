@@ -82,6 +82,8 @@ struct dml_ctx {
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
                              // kernel takes exactly the sum of the two, 77 us vs 38 + 39 us at 1 M, so the default keeps them apart)
   int force_pf = 0, force_pf_ahead = 148 * TPB, force_ppt = 1;   // DML_FORCE_PF / DML_FORCE_PPT: see k_fuerza_sub, k_fuerza_ppt
+  bool force_lean = false;    // DML_FORCE_LEAN=1: two-pass pair force (lean streaming pass + worklist pass), see k_fuerza_lean
+  DBuf<int> wl; int *wl_count = nullptr;
   bool force_wq = false;      // DML_FORCE_WQ=1: warp-queue pair-force kernel (k_fuerza_wq)
   bool force_batch = false;   // DML_FORCE_BATCH=1: batched index/record requests in the production pair-force kernel
   int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
@@ -355,7 +357,21 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->force_pf)
 #define FWQ(B) LAUNCH(K_FUERZA, (k_fuerza_wq<B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
-    if (ctx->force_wq && ctx->force_lanes == 1 && ctx->force_ppt == 1 && !ctx->force_batch && !(fused && ctx->fuse_ermak_b)) {
+    if (ctx->force_lean && ctx->force_lanes == 1) {
+      const bool fb = fused && ctx->fuse_ermak_b;
+      if (!ctx->wl_count) { CKC(cudaMalloc(&ctx->wl_count, 2 * sizeof(int))); CKC(cudaMemsetAsync(ctx->wl_count, 0, 2 * sizeof(int), ctx->st)); }
+      CKC(ctx->wl.ensure((size_t)ctx->cap + 32, ctx->st));
+      const int gw = 148 * 6;
+#define FLEAN(F) do { \
+      LAUNCH(K_FUERZA, (k_fuerza_lean<F>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->rev_len.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
+             ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->wl.p, ctx->wl_count); \
+      LAUNCH(K_FUERZA, (k_fuerza_work<F, 4>), gw, TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, \
+             ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->wl.p, ctx->wl_count, \
+             (unsigned int *)(ctx->wl_count + 1)); } while (0)
+      if (fb) FLEAN(true); else FLEAN(false);
+#undef FLEAN
+    }
+    else if (ctx->force_wq && ctx->force_lanes == 1 && ctx->force_ppt == 1 && !ctx->force_batch && !(fused && ctx->fuse_ermak_b)) {
       if (ctx->force_minb == 5) FWQ(5); else if (ctx->force_minb == 3) FWQ(3); else if (ctx->force_minb >= 6) FWQ(6); else FWQ(4);
     }
     else if (ctx->force_ppt == 2 && !(fused && ctx->fuse_ermak_b)) { if (ctx->force_minb >= 4) FPPT(2, 4); else if (ctx->force_minb == 3) FPPT(2, 3); else FPPT(2, 2); }
@@ -604,6 +620,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
   if (const char *e = getenv("DML_ROWS_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->rows_lanes = v; }
+  if (const char *e = getenv("DML_FORCE_LEAN")) ctx->force_lean = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_WQ")) ctx->force_wq = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_BATCH")) ctx->force_batch = atoi(e) != 0;
   if (const char *e = getenv("DML_FORCE_PF")) ctx->force_pf = atoi(e) & 31;
@@ -701,6 +718,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->obs_part.release(); ctx->obs_out.release(); ctx->obs_counts.release(); ctx->gr_cell_of.release(); ctx->gr_cnt.release(); ctx->gr_start.release();
   ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
+  ctx->wl.release(); if (ctx->wl_count) cudaFree(ctx->wl_count);
   ctx->snap_uid.release(); ctx->snap_mb.release(); ctx->mc_out.release(); ctx->mc_count.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();

@@ -1357,6 +1357,103 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_wq(
   }
 }
 
+// Two-pass form of the production pair force (DML_FORCE_LEAN).  The probes of DESIGN.md §6 split the one-kernel form into ~27 us of
+// streaming at half occupancy (the gather code costs 64 registers) and ~13 us of dependent gathers.  Here the first pass only
+// streams: record + row head in, skip decision, and for a particle none of whose entries can be inside a cut-off (most of them) the
+// zero force out — with FUSEB also its ermak_b update (dana.F90:1031-1052), the arithmetic of k_ermak_b with force 0 — while the
+// others go to a worklist (warp-aggregated append).  The second pass runs the usual row walk for the worklist only.  Same terms in
+// the same order as k_fuerza_sub, hence bit-identical.
+template <bool FUSEB>
+__global__ void __launch_bounds__(TPB) k_fuerza_lean(
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const int *__restrict__ rev_len,
+    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n,
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv,
+    int *__restrict__ wl, int *__restrict__ wl_count) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool act = s < n;
+  const double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
+  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
+  const long long m1 = meta_of(p1);
+  act = act && (m1 & MF_REF);
+  bool work = false;
+  if (act) {
+    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
+    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
+    work = need16(h16, rm.y, qmax) != 0u || rm.y > 16;   // entries beyond the head carry their bytes elsewhere: second pass
+    if (asym == 2) work = true;
+    else if (asym == 1 && (halo_of[s] != 0 || rev_len[s] != 0)) work = true;
+  }
+  const unsigned int wm = __ballot_sync(0xffffffffu, work);
+  if (wm) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(wl_count, __popc(wm));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (work) wl[base + __popc(wm & ((1u << lane) - 1u))] = s;
+  }
+  if (act && !work) {
+    st_rec(&fe[s], make_double4(0.0, 0.0, 0.0, 0.0));
+    if (FUSEB) {
+      const int zt = (int)(m1 & MF_TYPE);
+      if (zt != 2) {
+        const double mass = ph.mass[zt - 1];
+        const double fz = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double bv = vel[3 * s + k], ba = acel[3 * s + k], br = __ldg(&ranv[3 * s + k]);
+          vel[3 * s + k] = ph.cc0 * bv + ph.cc1mcc2 * ba + ph.cc2 * fz / mass + br;
+          acel[3 * s + k] = fz / mass;
+        }
+      }
+    }
+  }
+}
+template <bool FUSEB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_fuerza_work(
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
+    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
+    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph,
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv,
+    const int *__restrict__ wl, int *__restrict__ wl_count, unsigned int *__restrict__ ticket) {
+  const int nw = *((volatile int *)wl_count);
+  const int asym = __ldg(&sc->rows_asym);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) {
+    const int s = wl[i];
+    const double4 p1 = ld_rec_nc(&posm[s]);
+    const int4 rm = rh_meta(&rh[s]);
+    const uint4 h16 = rh_bq16(&rh[s]);
+    const long long m1 = meta_of(p1);
+    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+    const bool i_halo = asym == 1 && halo_of[s] != 0;
+    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
+    FAcc a = {0.0, 0.0, 0.0, 0.0, false};
+    fuerza_row<1, false, false>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
+    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
+    if (FUSEB) {
+      const int zt = (int)(m1 & MF_TYPE);
+      if (zt != 2) {
+        const double mass = ph.mass[zt - 1];
+        const double fv[3] = {a.fx, a.fy, a.fz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double bv = vel[3 * s + k], ba = acel[3 * s + k], br = __ldg(&ranv[3 * s + k]);
+          vel[3 * s + k] = ph.cc0 * bv + ph.cc1mcc2 * ba + ph.cc2 * fv[k] / mass + br;
+          acel[3 * s + k] = fv[k] / mass;
+        }
+      }
+    }
+  }
+  __syncthreads();                                       // the last block to finish empties the worklist for the next call
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *wl_count = 0; }
+  }
+}
+
 // PPT particles per thread (slots s, s + blockDim, ...): the records and row heads of all of them are requested before the
 // first one is worked on, so a thread keeps PPT x 64 bytes in flight during the streaming part instead of 64 (DML_FORCE_PPT).
 template <int PPT, int MINB>
