@@ -761,7 +761,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
     CKC(cudaMemsetAsync(ctx->b_occ.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
     TRY(pull_scal(ctx));
     ctx->hsc->glen = 0; ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = 0;
-    ctx->hsc->n_slots = n; ctx->hsc->next_uid = 0; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+    ctx->hsc->n_slots = n; ctx->hsc->next_uid = 0; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0; ctx->hsc->hole_lo = ctx->hsc->bhole_lo = 0;
     TRY(push_scal(ctx));
     LAUNCH(K_MISC, k_upload_book, nblk(n), TPB, ctx->posm.p, ctx->uid.p, ctx->slot_b.p, ctx->b_occ.p, ctx->sc, n, ctx->cap, uid ? 0 : 1, slot_b ? 0 : 1);
     TRY(member_snapshot(ctx));
@@ -794,7 +794,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   CKC(cudaMemcpyAsync(ctx->b_occ.p, bocc.data(), (size_t)ctx->cap * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
   ctx->hsc->glen = (int)gord.size(); ctx->hsc->ghead = 0; ctx->hsc->gtomb = 0; ctx->hsc->b_amax = b_amax;
-  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0;
+  ctx->hsc->n_slots = n; ctx->hsc->next_uid = mx + 1; ctx->hsc->listed = 0; ctx->hsc->rows_asym = 0; ctx->hsc->rev_valid = 0; ctx->hsc->need_rebuild = 0; ctx->hsc->rows_pending = 0; ctx->hsc->nat_sys = ctx->hsc->nat_ref = ctx->hsc->nat_gcmc = ctx->hsc->nlimbo = 0; ctx->hsc->hole_lo = ctx->hsc->bhole_lo = 0;
   TRY(push_scal(ctx));
   LAUNCH(K_MISC, k_count_members, nblk(n), TPB, ctx->posm.p, ctx->sc, n);
   TRY(member_snapshot(ctx));

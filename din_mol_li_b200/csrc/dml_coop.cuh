@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     if (!need) sc->lay_cur = lay_old ^ 1;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; sc->cols_used = sc->cols_tail0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; sc->cols_used = sc->cols_tail0; }
   }
   if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
     if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }

@@ -104,6 +104,7 @@ struct DevScal {
   long long overlap_passes;
   unsigned int ticket3;             // last-block election of k_pbc_disp
   unsigned int ticket4;             // last-block election of k_integrate
+  int hole_lo, bhole_lo;            // gcmc index reuse: no empty hs slot / free b index below these (reset when a rebuild frees the limbo slots)
 };
 
 enum { DML_E_OUT_OF_TESS = 1, DML_E_SUPERO_Z0 = 2, DML_E_ROW_OVERFLOW = 3, DML_E_CAPACITY = 4, DML_E_NO_PARTICLES = 5,

@@ -63,6 +63,31 @@ struct GcmcRng {
 
 __device__ __forceinline__ bool in_volume(const double4 &p, double z0, double zmax) { return !(p.z < z0 || p.z > zmax); }
 
+// Control-volume census (dana.F90:608-615) by the whole grid: gcc[c] = members of chunk c (1024 entries of the membership array)
+// inside [z0, zmax].  Inside k_gcmc the same loop is 98 dependent gather + barrier rounds of ONE block at 100 k members (~150 us of
+// the 426 us the kernel took); here it is one pass at full width.  k_gcmc adds the chunk counts up (and redoes the census itself
+// only when it had to compact the membership array first).
+__global__ void __launch_bounds__(256) k_gcmc_census(const double4 *__restrict__ posm, const int *__restrict__ gorder, int *__restrict__ gcc,
+                                                     const DevScal *__restrict__ sc) {
+  const int glen = sc->glen;
+  const double z0 = sc->z0, zmax = sc->zmax;
+  const int nchunk = (glen + GB - 1) / GB;
+  __shared__ int s_cnt[8];
+  for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    int in = 0;
+#pragma unroll
+    for (int k = 0; k < GB / 256; ++k) {
+      const int i = c * GB + k * 256 + threadIdx.x;
+      if (i < glen) { const int s = gorder[i]; if (s >= 0) in += in_volume(ld_rec(&posm[s]), z0, zmax) ? 1 : 0; }
+    }
+    in = __reduce_add_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = in;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_cnt[w]; gcc[c] = t; }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
   __shared__ int sh_scan[33];
   __shared__ int s_i[16];
@@ -77,7 +102,9 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
 
   // ---- compaction of the membership array when it carries many tombstones or is nearly full ----
   int glen = sc->glen;
+  bool compacted = false;
   if (sc->gtomb * 4 > glen || glen + A.nadj + 8 > A.gorder_cap) {
+    compacted = true;
     int *tmp = A.gorder + A.gorder_cap;                  // second half of the allocation is scratch
     int outn = 0;
     for (int base = 0; base < glen; base += GB) {
@@ -96,12 +123,23 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
   }
   // ---- control-volume census: n and the per-1024 chunk counts (dana.F90:608-615) ----
   int n = 0;
-  for (int base = 0, c = 0; base < glen; base += GB, ++c) {
-    int i = base + tid, in = 0;
-    if (i < glen) { int s = A.gorder[i]; if (s >= 0) in = in_volume(ld_rec(&A.posm[s]), z0, zmax) ? 1 : 0; }
-    int cnt = __syncthreads_count(in);
-    if (tid == 0) A.gcc[c] = cnt;
-    n += cnt;
+  if (compacted) {
+    for (int base = 0, c = 0; base < glen; base += GB, ++c) {
+      int i = base + tid, in = 0;
+      if (i < glen) { int s = A.gorder[i]; if (s >= 0) in = in_volume(ld_rec(&A.posm[s]), z0, zmax) ? 1 : 0; }
+      int cnt = __syncthreads_count(in);
+      if (tid == 0) A.gcc[c] = cnt;
+      n += cnt;
+    }
+  } else {                                               // chunk counts come from k_gcmc_census
+    const int nchunk0 = (glen + GB - 1) / GB;
+    int part = 0;
+    for (int c = tid; c < nchunk0; c += GB) part += A.gcc[c];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if ((tid & 31) == 0) sh_scan[tid >> 5] = part;
+    __syncthreads();
+    for (int w = 0; w < GB / 32; ++w) n += sh_scan[w];
+    __syncthreads();
   }
   if (tid == 0) A.gcc[(glen + GB - 1) / GB] = 0;
   int npend = 0;
@@ -164,15 +202,30 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
       __syncthreads();
       const int amax = sc->n_slots, nat_new = sc->nat_sys + 1, nlimbo = sc->nlimbo, b_amax = sc->b_amax;
       const bool hs_hole = amax >= nat_new + nlimbo, b_hole = b_amax >= nat_new;
+      // lowest empty index: four independent loads per thread and trip, the block leaves at the first trip that found one, and the
+      // search starts at the cursor below which nothing is free (a per-thread loop with a data-dependent exit ran ~100 dependent
+      // round trips per search at 100 k slots: most of the 426 us this kernel took)
       if (hs_hole) {
-        int best = 0x7fffffff;
-        for (int i = tid; i < amax && best == 0x7fffffff; i += GB) if (meta_of(ld_rec(&A.posm[i])) == 0) best = i;
-        if (best != 0x7fffffff) atomicMin(&s_i[3], best);
+        for (int base = sc->hole_lo; base < amax; base += 4 * GB) {
+          int best = 0x7fffffff;
+#pragma unroll
+          for (int k = 3; k >= 0; --k) { const int i = base + k * GB + tid; if (i < amax && meta_of(ld_rec(&A.posm[i])) == 0) best = i; }
+          if (best != 0x7fffffff) atomicMin(&s_i[3], best);
+          __syncthreads();
+          if (s_i[3] != 0x7fffffff) break;
+          __syncthreads();
+        }
       }
       if (b_hole) {
-        int best = 0x7fffffff;
-        for (int i = tid; i < b_amax && best == 0x7fffffff; i += GB) if (A.b_occ[i] == 0) best = i;
-        if (best != 0x7fffffff) atomicMin(&s_i[4], best);
+        for (int base = sc->bhole_lo; base < b_amax; base += 4 * GB) {
+          int best = 0x7fffffff;
+#pragma unroll
+          for (int k = 3; k >= 0; --k) { const int i = base + k * GB + tid; if (i < b_amax && A.b_occ[i] == 0) best = i; }
+          if (best != 0x7fffffff) atomicMin(&s_i[4], best);
+          __syncthreads();
+          if (s_i[4] != 0x7fffffff) break;
+          __syncthreads();
+        }
       }
       __syncthreads();
       if (tid == 0) {
@@ -181,8 +234,8 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
         if (ns >= A.cap || nb >= A.cap || ns == 0x7fffffff || nb == 0x7fffffff) { atomicCAS(&sc->err, 0, DML_E_CAPACITY); s_i[5] = -1; }
         else {
           s_i[5] = ns;
-          if (!hs_hole) sc->n_slots = amax + 1;
-          if (!b_hole) sc->b_amax = b_amax + 1;
+          if (!hs_hole) sc->n_slots = amax + 1; else sc->hole_lo = ns + 1;
+          if (!b_hole) sc->b_amax = b_amax + 1; else sc->bhole_lo = nb + 1;
           n = n + 1;
           // velocity from the Maxwell-Boltzmann distribution lands on the LAST atom of the list (dana.F90:665-668, Q6)
           int l = glen - 1;
@@ -208,19 +261,34 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           A.gorder[glen] = ns; A.gpos[ns] = glen; A.gcc[glen / GB] += 1;
           if ((glen + 1) % GB == 0) A.gcc[(glen + 1) / GB] = 0;
           A.pend[npend] = ns;
-          // -- ngroup_sort_atom (Neighbor.F90:271-318): own row (strict <, stencil x chain order) and append to the rows
-          //    of every ref atom within the list radius (<=) --
-          if (sc->listed) {
-            int base = sc->cols_used, cnt = 0;
-            bool ovf = false;
-            for (int nab = 0; nab < 27 && okc; ++nab) {
-              int nx = (c_map[nab][0] + rcx - 1 + g.nc[0]) % g.nc[0] + 1;
-              int ny = (c_map[nab][1] + rcy - 1 + g.nc[1]) % g.nc[1] + 1;
-              int nz = (c_map[nab][2] + rcz - 1 + g.nc[2]) % g.nc[2] + 1;
-              int nl = cell_lin(g, nx, ny, nz);
-              int cb = A.cell_start[nl], ce = A.cell_start[nl + 1];
-              // chain = atoms inserted in this call that fell into this cell (most recent first), then the sorted segment
-              for (int q = npend + (ce - cb) - 1; q >= 0; --q) {
+        }
+      }
+      __syncthreads();
+      // -- ngroup_sort_atom (Neighbor.F90:271-318): own row (strict <, stencil x chain order) and append to the rows of every ref
+      //    atom within the list radius (<=).  Warp 0, lane = stencil cell: every lane walks its own chain (atoms inserted in this
+      //    call that fell into the cell, most recent first, then the sorted segment), an exclusive prefix over the lanes gives the
+      //    cell's place in the new row; an atom sits in one cell only, so the appends to other rows never collide.  (One thread
+      //    doing the 27 cells in turn paid ~60 dependent round trips per accepted insertion.) --
+      if (s_i[5] >= 0 && tid < 32) {
+        const int ns = s_i[5];
+        if (sc->listed) {
+          const int base = sc->cols_used;
+          const int lane = tid;
+          int cb = 0, ce = 0, nl = -1;
+          if (lane < 27 && okc) {
+            int nx = (c_map[lane][0] + rcx - 1 + g.nc[0]) % g.nc[0] + 1;
+            int ny = (c_map[lane][1] + rcy - 1 + g.nc[1]) % g.nc[1] + 1;
+            int nz = (c_map[lane][2] + rcz - 1 + g.nc[2]) % g.nc[2] + 1;
+            nl = cell_lin(g, nx, ny, nz);
+            cb = A.cell_start[nl]; ce = A.cell_start[nl + 1];
+          }
+          const int npe = npend + 1;                        // pend[] already holds the new atom (skipped below)
+          int off = 0, total = 0;
+          bool ovf = false;
+          for (int pass = 0; pass < 2; ++pass) {
+            int cnt = 0;
+            if (nl >= 0) {
+              for (int q = npe + (ce - cb) - 1; q >= 0; --q) {
                 int s;
                 if (q >= ce - cb) {
                   s = A.pend[q - (ce - cb)];
@@ -235,25 +303,35 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
                 if (!(m & MF_TYPE)) continue;                       // removed from its chain (cgroup_unsort_atom)
                 double rd = dist2_idnint(g, p.x, p.y, p.z, rx, ry, rz);
                 if (rd < g.rc_list2) {
-                  if (base + cnt < A.cols_cap) { A.cols[base + cnt] = s; A.bq[base + cnt] = 0; } else ovf = true;
+                  if (pass == 1) { if (base + off + cnt < A.cols_cap) { A.cols[base + off + cnt] = s; A.bq[base + off + cnt] = 0; } else ovf = true; }
                   ++cnt;
                 }
-                if ((m & MF_REF) && !(rd > g.rc_list2)) {
+                if (pass == 1 && (m & MF_REF) && !(rd > g.rc_list2)) {
                   RowHead *h = &A.rh[s];
                   const int len = h->len;
                   if (len < h->cap) {
                     A.cols[h->start + len] = ns; h->len = len + 1;
                     if (len < 16) h->bq[len] = 0; else A.bq[h->start + len] = 0;   // appended entries carry no build distance: never skipped
                   }
-                  else { sc->row_overflow++; atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
+                  else { atomicAdd((unsigned long long *)&sc->row_overflow, 1ull); atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
                 }
               }
             }
-            if (ovf) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW);
-            rh_store(&A.rh[ns], make_uint4(0, 0, 0, 0), base, cnt, cnt + A.row_slack);   // zero build distances: nothing is ever skipped
-            sc->cols_used = base + cnt + A.row_slack;
-          } else A.rh[ns].len = 0;
-        }
+            if (pass == 0) {
+              int incl = cnt;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+              off = incl - cnt;
+              total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+          }
+          if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW);
+          __syncwarp();
+          if (lane == 0) {
+            rh_store(&A.rh[ns], make_uint4(0, 0, 0, 0), base, total, total + A.row_slack);   // zero build distances: nothing is ever skipped
+            sc->cols_used = base + total + A.row_slack;
+          }
+        } else if (tid == 0) A.rh[ns].len = 0;
       }
       __syncthreads();
       if (s_i[5] >= 0) { glen += 1; npend += 1; if (tid != 0) n = n + 1; }
@@ -301,6 +379,8 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
         A.gorder[A.gpos[s]] = -1; sc->gtomb++;
         A.rh[s].len = 0;
         A.b_occ[A.slot_b[s]] = 0;
+        if (A.slot_b[s] < sc->bhole_lo) sc->bhole_lo = A.slot_b[s];
+        if (!sc->listed && s < sc->hole_lo) sc->hole_lo = s;
         double4 p = ld_rec(&A.posm[s]);
         p.w = meta_as_double(sc->listed ? MF_LIMBO : 0);
         st_rec(&A.posm[s], p);
@@ -343,6 +423,7 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;
   A.nadj = nadj; A.cap = ctx->cap; A.listed = 1; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
+  LAUNCH(K_GCMC, k_gcmc_census, 148 * 4, 256, ctx->posm.p, ctx->gorder.p, ctx->gcc.p, ctx->sc);
   LAUNCH(K_GCMC, k_gcmc, 1, GB, A);
   ctx->n = std::min(ctx->cap, ctx->n + nadj);          // upper bound of hs%amax until the next read-back (empty slots are skipped)
   ctx->rp_nu = ctx->rp_ng = 0;

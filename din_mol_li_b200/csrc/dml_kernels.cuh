@@ -221,7 +221,7 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
     sc->need_rebuild = need;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     s_need_sh = need;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
   }
   // z-layer tables: after a rebuild both are zero (displacements restart); otherwise the one just filled becomes current
   // and the previous one is cleared for the next test_update

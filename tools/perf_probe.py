@@ -29,7 +29,8 @@ def probe(kind, n, variant, steps, out):
         os.environ[k] = v
     try:
         if (kind, n) not in _WL:
-            _WL[(kind, n)] = B.workload_brown(n, -104012) if kind == "brown" else B.workload_ermak(n, -104012, slab=(kind == "ermakslab"))
+            _WL[(kind, n)] = (B.workload_brown(n, -104012) if kind == "brown" else B.workload_gcmc(n, -104012) if kind == "gcmc" else
+                             B.workload_ermak(n, -104012, slab=(kind == "ermakslab")))
         w = _WL[(kind, n)]
         ctx = B.make_ctx(w, 0, 4242)
     finally:
@@ -79,7 +80,7 @@ def probe(kind, n, variant, steps, out):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("workloads", nargs="+", help="kind:n, kind in brown|ermak|ermakslab")
+    ap.add_argument("workloads", nargs="+", help="kind:n, kind in brown|gcmc|ermak|ermakslab")
     ap.add_argument("--variants", default="default")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "probe.jsonl"))
