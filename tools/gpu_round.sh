@@ -23,7 +23,7 @@ for w in $what; do
       echo "bench ref rc=$?"; cut -c1-300 $out/bench_ref_$tag.json ;;
     launches)
       timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches_$tag.csv \
-        python bench.py --steps 3 --warmup 3 --no-cpu --ermak-particles 0 --ensemble-replicas 0 > $out/launches_$tag.log 2>&1
+        python bench.py --steps 3 --warmup 3 --no-cpu --no-gcmc --ermak-particles 0 --ensemble-replicas 0 > $out/launches_$tag.log 2>&1
       echo "launches rc=$?"
       timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $out/launches_ermak1m_$tag.csv \
         python tools/perf_probe.py ermak:1000000 --steps 4 --out $out/probe_ncu_scratch.jsonl > $out/launches_ermak1m_$tag.log 2>&1
@@ -33,7 +33,7 @@ for w in $what; do
         python tools/perf_probe.py ermak:1000000 --steps 4 --out $out/probe_ncu_scratch.jsonl > $out/ncu_fuerza1m_$tag.log 2>&1
       echo "ncu fuerza rc=$?"
       timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_rows|k_ov_resolve|k_ov_detect|k_integrate|k_cell_order|k_test_update" -s 40 -c 12 -f \
-        -o $out/ncu_brown100k_$tag python bench.py --steps 3 --warmup 3 --no-cpu --ermak-particles 0 --ensemble-replicas 0 > $out/ncu_brown100k_$tag.log 2>&1
+        -o $out/ncu_brown100k_$tag python bench.py --steps 3 --warmup 3 --no-cpu --no-gcmc --ermak-particles 0 --ensemble-replicas 0 > $out/ncu_brown100k_$tag.log 2>&1
       echo "ncu brown rc=$?" ;;
     probe)
       timeout 900 python tools/perf_probe.py ${PROBE_WL:-brown:100000 ermak:1000000} --steps 30 --variants "${PROBE_VARIANTS:-default}" --out $out/probe_$tag.jsonl > $out/probe_$tag.log 2>&1
