@@ -58,7 +58,7 @@ struct dml_ctx {
   DBuf<double> vel, acel, pos_old, old_cg, ranv;
   DBuf<int> uid, slot_b;
   // cells
-  DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_cell, chain_pos;
+  DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
   DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
@@ -249,9 +249,9 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
   LAUNCH(K_BIN, k_bin, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->rh.p, ctx->halo_of.p, ctx->sc, ctx->geo, n, force);
   TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, true, 0, force));
   LAUNCH(K_SCATTER, k_scatter, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
-         ctx->sorted_slot.p, ctx->sc, n, force);
-  LAUNCH(K_CELL_ORDER, k_cell_order, std::min(nblk(nct, 128), 148 * 16), 128, ctx->posm.p, ctx->slot_b.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_slot.p,
-         ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_cell.p, ctx->sc, nct, force);
+         ctx->sorted_raw.p, ctx->sc, n, force);
+  LAUNCH(K_CELL_ORDER, k_cell_order, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->slot_b.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_raw.p,
+         ctx->sorted_slot.p, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_cell.p, ctx->sc, nct, force);
   return 0;
 }
 
@@ -281,7 +281,7 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0) {
   if (ctx->use_coop && n <= ctx->coop_tu_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
-    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
+    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_raw = ctx->sorted_raw.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
     A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
     A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
     A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
@@ -631,7 +631,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
   CKC(ctx->pos_old.ensure(c3, ctx->st)); CKC(ctx->old_cg.ensure(c3, ctx->st));
   CKC(ctx->ranv.ensure(c3, ctx->st)); CKC(ctx->uid.ensure(cap, ctx->st)); CKC(ctx->slot_b.ensure(cap, ctx->st));
-  CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
+  CKC(ctx->cell_of.ensure(cap, ctx->st)); CKC(ctx->sorted_slot.ensure(cap, ctx->st)); CKC(ctx->sorted_raw.ensure(cap, ctx->st)); CKC(ctx->chain_pos.ensure(cap, ctx->st));
   CKC(ctx->rh.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->rh.p, 0, (size_t)cap * sizeof(RowHead), ctx->st));
   CKC(ctx->cols.ensure((size_t)cap * (ROW_W + 32) + 4096, ctx->st));   // region A (ROW_W per slot) + tail
   CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
@@ -703,7 +703,7 @@ void dml_destroy(dml_ctx *ctx) {
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
-  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->chain_pos.release();
+  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->sorted_raw.release(); ctx->chain_pos.release();
   ctx->rh.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release(); ctx->ov_head.release(); ctx->ov_next.release();
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);

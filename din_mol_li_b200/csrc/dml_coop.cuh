@@ -71,7 +71,7 @@ __device__ void coop_scan(cg::grid_group &grid, int *__restrict__ in, int *__res
 }
 
 struct TUArgs {
-  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
+  double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_raw, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
   const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut, rmax_f, rmax_o;
   // neighbours of the call inside dml_step folded into the first pass over the slots: fuse bit 0 = the initialisation of the
   // overlap_moveback that follows (k_ov_init), bit 1 = the write-back of the overlap_moveback that came before (k_ov_apply)
@@ -142,10 +142,14 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   grid.sync();
   coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
   grid.sync();
-  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_slot, need, s);
+  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, need, s);
   grid.sync();
   if (gt == 0 && need) sc->rows_asym = sc->halo_flag ? 1 : 0;
-  for (int c = gt; c < A.nct; c += gsz) d_cell_order(A.posm, A.slot_b, A.cell_start, A.cell_cur, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, c);
+  {
+    const int nsorted = A.cell_start[A.nct];
+    for (int i = gt; i < nsorted; i += gsz)
+      d_cell_rank(A.posm, A.slot_b, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, i);
+  }
   if (!need || A.lazy) return;
   grid.sync();
   // phase 3: rows in one pass — update() + ngroup_cells, Neighbor.F90:608-633,465-548

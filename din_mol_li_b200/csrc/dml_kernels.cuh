@@ -327,32 +327,39 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
     d_scatter(posm, pos_old, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s);
 }
-// one thread per cell: insertion sort of the segment by descending slot_b, then gather the records
-__device__ __forceinline__ void d_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
-                                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
-                                             float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, int c) {
-  cell_cur[c] = 0;
-  int b = cell_start[c], e = cell_start[c + 1];
-  for (int i = b + 1; i < e; ++i) {
-    int s = sorted_slot[i], key = slot_b[s], j = i - 1;
-    while (j >= b) { int sj = sorted_slot[j]; if (slot_b[sj] >= key) break; sorted_slot[j + 1] = sj; --j; }
-    sorted_slot[j + 1] = s;
-  }
-  for (int i = b; i < e; ++i) {
-    const int sl = sorted_slot[i];
-    double4 p = ld_rec(&posm[sl]); st_rec(&sorted_posm[i], p);
-    // single-precision copy for the candidate scan of k_rows; w carries the slot so the fill pass needs no second lookup
-    sorted_posf[i] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(sl));
-    sorted_cell[i] = c;                                // cell of the i-th sorted particle (k_rows: no gather through cell_of[slot])
-  }
+// One thread per binned particle (raw = the scatter's output, in-cell order arbitrary): its place in the cell is the number of
+// cell mates with a larger b index (chains are visited in descending b index, Cells.F90:267-302), found with independent loads;
+// the thread then writes the slot, the record, its single-precision copy and the cell id at that place.  (One thread per CELL with
+// an insertion sort was a serial chain per dense cell — 28 atoms per cell over a metal slab — and a thread per empty cell in boxes
+// with more cells than particles: 1.15 M cells for 100 k particles at skin 2.)
+__device__ __forceinline__ void d_cell_rank(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_of,
+                                            const int *__restrict__ cell_start, int *__restrict__ cell_cur, const int *__restrict__ raw,
+                                            int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
+                                            float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, int i) {
+  const int sl = raw[i];
+  const int c = cell_of[sl];
+  const int b = cell_start[c], e = cell_start[c + 1];
+  const int key = slot_b[sl];
+  int rank = 0;
+  for (int j = b; j < e; ++j) rank += slot_b[raw[j]] > key ? 1 : 0;
+  if (rank == 0) cell_cur[c] = 0;                        // the scatter cursor of the cell is zero again between rebuilds
+  const int pos = b + rank;
+  const double4 p = ld_rec(&posm[sl]);
+  sorted_slot[pos] = sl;
+  st_rec(&sorted_posm[pos], p);
+  // single-precision copy for the candidate scan of k_rows; w carries the slot
+  sorted_posf[pos] = make_float4((float)p.x, (float)p.y, (float)p.z, __int_as_float(sl));
+  sorted_cell[pos] = c;                                  // cell of the sorted particle (k_rows: no gather through cell_of[slot])
 }
-__global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_start,
-                             int *__restrict__ cell_cur, int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
+__global__ void k_cell_order(const double4 *__restrict__ posm, const int *__restrict__ slot_b, const int *__restrict__ cell_of,
+                             const int *__restrict__ cell_start, int *__restrict__ cell_cur, const int *__restrict__ raw,
+                             int *__restrict__ sorted_slot, double4 *__restrict__ sorted_posm,
                              float4 *__restrict__ sorted_posf, int *__restrict__ sorted_cell, DevScal *__restrict__ sc, int ncell, int force) {
   REBUILD_GUARD(sc, force);
   if (blockIdx.x == 0 && threadIdx.x == 0 && ((volatile const DevScal *)sc)->need_rebuild) sc->rows_asym = sc->halo_flag ? 1 : 0;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x)
-    d_cell_order(posm, slot_b, cell_start, cell_cur, sorted_slot, sorted_posm, sorted_posf, sorted_cell, c);
+  const int nsorted = cell_start[ncell];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nsorted; i += gridDim.x * blockDim.x)
+    d_cell_rank(posm, slot_b, cell_of, cell_start, cell_cur, raw, sorted_slot, sorted_posm, sorted_posf, sorted_cell, i);
 }
 
 // ================================================================================================
