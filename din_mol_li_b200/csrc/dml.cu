@@ -58,6 +58,7 @@ struct dml_ctx {
   DBuf<double> vel, acel, pos_old, old_cg, ranv;
   DBuf<int> uid, slot_b;
   // cells
+  DBuf<int> b2slot;          // boxes without cell lists (ngroup_verlet): slot of every hs%b index
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
   DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
@@ -212,7 +213,15 @@ static void tessellate(dml_ctx *ctx) {
   int nc[3];
   for (int k = 0; k < 3; ++k) nc[k] = (int)(g.box[k] / rc);
   for (int k = 0; k < 3; ++k) g.nc[k] = nc[k];
-  if (nc[0] < 4 && nc[1] < 4 && nc[2] < 4) return;       // reference falls back to the O(N^2) list
+  if (nc[0] < 4 && nc[1] < 4 && nc[2] < 4) {             // no cells: the reference falls back to the O(N^2) list (ngroup_verlet)
+    // the z-layer displacement tables of the gather skip still want a layer thickness: one list radius
+    for (int k = 0; k < 3; ++k) { g.nc[k] = std::max(nc[k], 1); g.cell[k] = g.box[k] / (double)g.nc[k]; g.hd[k] = g.nc[k] + 2; }
+    g.inv_cell2 = 1.0 / g.cell[2];
+    ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
+    g.rows_fast = 0; g.lay_shift = 0; g.nlay = g.nc[2] + 2;
+    ctx->tessellated = false;
+    return;
+  }
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
   g.inv_cell2 = 1.0 / g.cell[2];
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
@@ -258,6 +267,11 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 // ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
+  if (!ctx->tessellated) {                                // ngroup_verlet, one warp per row
+    LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
+           ctx->sc, ctx->geo, n, ctx->row_slack);
+    return 0;
+  }
   int nw = std::min(nblk(n * std::max(ctx->geo.rows_fast, 1)), 148 * 8);   // grid-stride over particles: an idle (guarded) launch stays cheap
   LAUNCH(K_ROWS_FILL, k_rows, nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
          ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
@@ -270,8 +284,21 @@ static int enq_materialize_rows(dml_ctx *ctx) {
 static int enq_test_update(dml_ctx *ctx, int fuse = 0) {
   ctx->tu_fused = 0;
   tessellate(ctx);
-  if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction: the reference's O(N^2) ngroup_verlet path is not implemented on the device");
   int n = ctx->n, nct = ctx->nct;
+  if (!ctx->tessellated) {
+    // fewer than 4 cells on every axis: no cell lists (Cells.F90:231), rows by ngroup_verlet (Neighbor.F90:358-424)
+    if (ctx->cfg.reservoir == 3) FAIL("gcmc_run needs the cell lists: box smaller than 4 cells in every direction");
+    const int nbv = std::min(nblk(n), 148 * 6);
+    if (fuse & 2) LAUNCH(K_OV_APPLY, k_ov_apply, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->old_cg.p, ctx->ovst.p, ctx->sc, n);   // passes dml_step folds into the cooperative kernel
+    CKC(ctx->part.ensure((size_t)2 * nbv, ctx->st)); CKC(ctx->b2slot.ensure(ctx->cap, ctx->st));
+    LAUNCH(K_PBC_BIN, k_pbc_disp, nbv, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
+    CKC(cudaMemsetAsync(ctx->b2slot.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
+    LAUNCH(K_BIN, k_verlet_prepare, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->slot_b.p, ctx->b2slot.p, ctx->rh.p, ctx->halo_of.p, ctx->sc, n);
+    if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+    if (fuse & 1) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
+    ctx->binned = true;
+    return 0;
+  }
   if ((size_t)nct + 2 > ctx->cell_start.cap) {
     CKC(ctx->cell_cnt.ensure(nct + 1, ctx->st)); CKC(ctx->cell_start.ensure(nct + 2, ctx->st)); CKC(ctx->cell_cur.ensure(nct + 1, ctx->st));
     CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, ctx->cell_cnt.cap * sizeof(int), ctx->st));
@@ -703,7 +730,7 @@ void dml_destroy(dml_ctx *ctx) {
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
-  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->sorted_slot.release(); ctx->sorted_raw.release(); ctx->chain_pos.release();
+  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->b2slot.release(); ctx->sorted_slot.release(); ctx->sorted_raw.release(); ctx->chain_pos.release();
   ctx->rh.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release(); ctx->ov_head.release(); ctx->ov_next.release();
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
@@ -920,6 +947,7 @@ int dml_step(dml_ctx *ctx, int32_t nsteps) {
 
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) {
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
+  if (!ctx->tessellated) FAIL("dml_get_cells: the box has no cell lists (fewer than 4 cells on every axis, Cells.F90:231)");
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   TRY(enq_sort_cells(ctx, 1));
   CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));

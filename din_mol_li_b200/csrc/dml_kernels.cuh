@@ -868,6 +868,95 @@ __device__ __forceinline__ void d_rows_ml(const double4 *__restrict__ sorted_pos
   }
 }
 
+// ================================================================================================
+// K3b  Boxes with fewer than 4 cells on EVERY axis: the reference does not tessellate and builds the rows by the O(N^2) loop
+//      ngroup_verlet (Neighbor.F90:358-424): for every ref atom, candidates in ascending index of hs%b, vdistance, entry when
+//      rd <= (rcut+skin)^2 (inclusive here, strict in the cell walk).  Such a box holds a few hundred atoms at most.
+//      k_verlet_prepare is update() for this path (pos_old = pos, limbo slots freed, Neighbor.F90:608-633) plus the b-index -> slot
+//      table; k_rows_verlet builds one row per warp from the positions of the rebuild (pos_old), 32 candidates at a time.
+// ================================================================================================
+__global__ void __launch_bounds__(TPB) k_verlet_prepare(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ slot_b,
+                                                        int *__restrict__ b2slot, RowHead *__restrict__ rh, unsigned char *__restrict__ halo_of,
+                                                        DevScal *__restrict__ sc, int n) {
+  REBUILD_GUARD(sc, 0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { sc->rows_asym = 0; sc->halo_flag = 0; }
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    double4 p = ld_rec(&posm[s]);
+    const long long m = meta_of(p);
+    halo_of[s] = 0;
+    if (m & MF_TYPE) {
+      b2slot[slot_b[s]] = s;
+      pos_old[3 * s] = p.x; pos_old[3 * s + 1] = p.y; pos_old[3 * s + 2] = p.z;
+    } else {
+      if (m & MF_LIMBO) { p.w = meta_as_double(0); st_rec(&posm[s], p); }
+      rh[s].len = 0; rh[s].cap = 0;
+    }
+  }
+}
+__global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__ posm, const double *__restrict__ pos_old,
+                                                     const int *__restrict__ b2slot, RowHead *__restrict__ rh, int *__restrict__ cols,
+                                                     unsigned char *__restrict__ bq, DevScal *__restrict__ sc, Geo g, int n, int slack) {
+  if (!((volatile const DevScal *)sc)->rows_pending) return;
+  const unsigned int full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int b_amax = sc->b_amax;
+  for (int s = wid; s < n; s += nw) {
+    const long long m1 = meta_of(ld_rec_nc(&posm[s]));
+    if (!(m1 & MF_TYPE)) continue;
+    if (!(m1 & MF_REF)) { if (lane == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
+    const double px = pos_old[3 * s], py = pos_old[3 * s + 1], pz = pos_old[3 * s + 2];
+    int dst = s * ROW_W, lim = ROW_W, total = 0, cnt = 0;
+    uint4 hb = make_uint4(0, 0, 0, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      cnt = 0;
+      for (int j0 = 0; j0 < b_amax; j0 += 32) {
+        const int j = j0 + lane;
+        const int sj = j < b_amax ? b2slot[j] : -1;
+        bool hit = false; double rd = 0.0;
+        if (sj >= 0 && sj != s) {
+          rd = dist2_idnint(g, px, py, pz, pos_old[3 * sj], pos_old[3 * sj + 1], pos_old[3 * sj + 2]);   // vdistance(vd,ai,aj)
+          hit = !(rd > g.rc_list2);                          // "if (rd>rcut) cycle", Neighbor.F90:399
+        }
+        const unsigned int hm = __ballot_sync(full, hit);
+        if (pass == 1 && hit) {
+          const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
+          cols[dst + pos] = sj;
+          const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
+          if (pos < 16) {
+            const unsigned int sh = qb << (8 * (pos & 3));
+            if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else { if (pos < 12) hb.z |= sh; else hb.w |= sh; }
+          } else bq[dst + pos] = (unsigned char)qb;
+        }
+        cnt += __popc(hm);
+      }
+      if (pass == 0) {
+        total = cnt;
+        if (total + slack > ROW_W) {                        // long row: a segment of the tail region
+          const int need = total + slack;
+          int tb = 0;
+          if (lane == 0) tb = atomicAdd(&sc->cols_used, need);
+          tb = __shfl_sync(full, tb, 0);
+          if (tb + need > sc->cols_cap) { if (lane == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); total = -1; break; }
+          dst = tb; lim = need;
+        }
+      }
+    }
+    if (total < 0) { if (lane == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); continue; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      hb.x |= __shfl_xor_sync(full, hb.x, o); hb.y |= __shfl_xor_sync(full, hb.y, o);
+      hb.z |= __shfl_xor_sync(full, hb.z, o); hb.w |= __shfl_xor_sync(full, hb.w, o);
+    }
+    if (lane == 0) rh_store(&rh[s], hb, dst, total, lim);
+  }
+  __syncthreads();                                      // the last block to finish marks the rows as materialised
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&sc->ticket2, 1u) == gridDim.x - 1) { sc->ticket2 = 0; sc->rows_pending = 0; }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                               const int *__restrict__ sorted_slot,
                                               const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,

@@ -319,6 +319,33 @@ def test_step_with_folded_overlap_passes_bit_identical(name, nsteps, monkeypatch
     assert out[0][1:] == out[1][1:] and out[0][1] > 0
 
 
+@pytest.mark.parametrize("integrador,nsteps", [(1, 300), (0, 120)])
+def test_box_without_cell_lists_uses_verlet_rows(integrador, nsteps):
+    """A box with fewer than 4 cells on every axis is not tessellated (Cells.F90:231): the reference builds its rows with the
+    O(N^2) loop ngroup_verlet (Neighbor.F90:358-424: candidates in ascending hs%b index, inclusive <=).  Same rows at t = 0 and a
+    bit-identical replayed trajectory over several rebuilds."""
+    o = O.Oracle(idum=-77, xi=40.0, yi=40.0, z0=25.0, zmax=50.0, h=1e-2, nb_dcut=10.0, integrador=integrador, reservoir=1)
+    sc = o.scalars()
+    assert sc.tessellated == 0 and list(sc.ncells) == [3, 3, 3]
+    ctx = P.ctx_from_oracle(o)
+    ctx.test_update()
+    assert ctx.counters().tessellated == 0
+    P.compare_rows(o, ctx, what="verlet rows t=0")
+    ctx.close()
+    ls = P.Lockstep(o, strict=1)
+    nupd0 = o.scalars().nupd
+    for i in range(nsteps):
+        ls.step(check=True, tag="small box step %d" % (i + 1))
+        if i % 40 == 39:
+            P.compare_rows(o, ls.ctx, what="verlet rows after step %d" % (i + 1))
+    assert o.scalars().nupd > nupd0 + 2
+    # the production path (Philox, dml_step with its folded passes) runs on such a box too
+    ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=3)
+    ctx.step(50)
+    assert ctx.counters().nat_sys == o.scalars().nat_sys
+    ctx.close()
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
