@@ -157,18 +157,30 @@ def _deposited(z):
 def test_long_run_observables_statistical(name, nsteps, nseeds):
     """Production mode (Philox noise) against the oracle's own RNG: long-run observables agree within statistical error
     (north_star criterion 4).  Observables: deposited atoms (CG+F), particles in the system, mean height of the ions."""
+    from oracle import observables as OB
     dep_o, dep_g, n_o, n_g, zm_o, zm_g = [], [], [], [], [], []
+    prof_o, prof_g, gr_o, gr_g = [], [], [], []
+    NZ, NR, RMAX = 6, 8, 12.0
     for k in range(nseeds):
         d, o = case(name, idum=-104012 - 17 * k)
+        ztop = o.scalars().zmax * 1.1
+        box = list(o.scalars().box)
         ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=9000 + k)
         ctx.step(nsteps)
         c = ctx.counters()
         g = ctx.download(c.n_slots)
         alive = g["z"] > 0
         dep_g.append(_deposited(g["z"][alive])); n_g.append(int(alive.sum())); zm_g.append(g["pos"][alive & (g["z"] == 1), 2].mean())
+        # Li density profile and pair-distance histogram of everything, both computed on the device (dml_density_profile, dml_gr)
+        prof_g.append(ctx.density_profile(0.0, ztop, NZ, (1,)).astype(float))
+        h, nsel = ctx.gr(RMAX, NR, (1, 2, 3))
+        gr_g.append(h / float(nsel))
         o.step(nsteps)
         st = o.state()
         dep_o.append(_deposited(st["z"])); n_o.append(len(st["z"])); zm_o.append(st["pos"][st["z"] == 1, 2].mean())
+        prof_o.append(OB.density_profile(st["pos"][:, 2], st["z"], 0.0, ztop, NZ, (1,)).astype(float))
+        h, nsel = OB.gr(st["pos"], st["z"], box, (1, 1, 0), RMAX, NR, (1, 2, 3))
+        gr_o.append(h / float(nsel))
         ctx.close()
 
     def agree(a, b, what, floor):
@@ -180,6 +192,13 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
     agree(n_g, n_o, name + " particles", 1.0)
     agree(zm_g, zm_o, name + " mean ion height", 0.05)
     assert np.mean(dep_g) > 5          # the comparison is not vacuous
+    # north_star criterion 4 also names the Li density profile and g(r): bin by bin, same rule
+    pg, po, gg, go = np.array(prof_g), np.array(prof_o), np.array(gr_g), np.array(gr_o)
+    for b in range(NZ):
+        agree(pg[:, b], po[:, b], "%s Li density profile, z bin %d" % (name, b), 2.0)
+    for b in range(NR):
+        agree(gg[:, b], go[:, b], "%s pair-distance histogram per particle, r bin %d" % (name, b), 0.01)
+    assert pg.sum() > 100 and gg.sum() > 0.5
 
 
 def test_production_force_kernel_with_gather_skip_matches_reference_order():
