@@ -160,9 +160,11 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
     from oracle import observables as OB
     dep_o, dep_g, n_o, n_g, zm_o, zm_g = [], [], [], [], [], []
     prof_o, prof_g, gr_o, gr_g = [], [], [], []
+    acc_o, acc_g = [], []
     NZ, NR, RMAX = 6, 8, 12.0
     for k in range(nseeds):
         d, o = case(name, idum=-104012 - 17 * k)
+        uid0, nsys0 = int(o.state()["uid"].max()), o.scalars().nat_sys
         ztop = o.scalars().zmax * 1.1
         box = list(o.scalars().box)
         ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=9000 + k)
@@ -181,6 +183,11 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
         prof_o.append(OB.density_profile(st["pos"][:, 2], st["z"], 0.0, ztop, NZ, (1,)).astype(float))
         h, nsel = OB.gr(st["pos"], st["z"], box, (1, 1, 0), RMAX, NR, (1, 2, 3))
         gr_o.append(h / float(nsel))
+        # accepted insertions + deletions (GCMC acceptance ratio x nadj x nsteps): creation ranks only grow through insertions and
+        # atoms only leave sys through deletions, so both follow from the oracle's lists
+        created_o = int(st["uid"].max()) - uid0
+        acc_o.append(created_o + (created_o - (len(st["z"]) - nsys0)))
+        acc_g.append(int(c.gcmc_created + c.gcmc_destroyed))
         ctx.close()
 
     def agree(a, b, what, floor):
@@ -199,6 +206,9 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
     for b in range(NR):
         agree(gg[:, b], go[:, b], "%s pair-distance histogram per particle, r bin %d" % (name, b), 0.01)
     assert pg.sum() > 100 and gg.sum() > 0.5
+    if name == "gcmc":
+        agree(acc_g, acc_o, "gcmc accepted insertions + deletions", 4.0)
+        assert np.mean(acc_g) > 50
 
 
 def test_production_force_kernel_with_gather_skip_matches_reference_order():
