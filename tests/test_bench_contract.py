@@ -37,3 +37,31 @@ def test_algorithmic_bytes_table():
         assert B.algorithmic_bytes(k, N, R, E, nc) > 0
     assert B.algorithmic_bytes("fuerza", N, R, E, nc) == 32 * N + 8 * R + 4 * E + 32 * R
     assert B.algorithmic_bytes("no_such_kernel", N, R, E, nc) is None
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_bench_line_on_gpu_has_every_contract_key():
+    """The bench line of this framework (short run, extra sections off): ONE JSON line with the driver's keys, kernels counted,
+    roofline / e2e / clocks objects complete, e2e measured through host buffers (bytes > 0) and not a copy of the resident value."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "6", "--warmup", "3", "--no-cpu", "--no-gcmc", "--ermak-particles", "0",
+                        "--ensemble-replicas", "0", "--particles", "30000"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "particle_steps_per_s" and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["steps"] == 6 and d["vs_baseline"] is None
+    assert d["gpu_launches"] >= 6 * 5 and d["value"] > 1e6
+    rf = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in rf
+    assert rf["bound"] == "hbm" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-3
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert "workload" in d["config"] and "l2" in d["config"]
