@@ -281,7 +281,7 @@ static int enq_materialize_rows(dml_ctx *ctx) {
 // test_update (Neighbor.F90:668-713) enqueued without any host round trip: the rebuild decision is taken by
 // k_top2_final on the device and the rebuild kernels (update + ngroup_cells, Neighbor.F90:608-633,465-548) are
 // always launched but return immediately when no rebuild is due.
-static int enq_test_update(dml_ctx *ctx, int fuse = 0) {
+static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true) {
   ctx->tu_fused = 0;
   tessellate(ctx);
   int n = ctx->n, nct = ctx->nct;
@@ -304,7 +304,9 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0) {
     CKC(cudaMemsetAsync(ctx->cell_cnt.p, 0, ctx->cell_cnt.cap * sizeof(int), ctx->st));
     CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
   }
-  int force = ctx->cfg.reservoir == 3 ? 1 : 0;       // gcmc_run needs the cells of the current positions every step
+  // gcmc_run needs the cells of the current positions every step; inside dml_step only the test_update right in front of it has to
+  // provide them (the one in front of overlap_moveback sorts only when it rebuilds)
+  int force = (ctx->cfg.reservoir == 3 && cells_wanted) ? 1 : 0;
   if (ctx->use_coop && n <= ctx->coop_tu_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
@@ -566,7 +568,7 @@ static int enq_step(dml_ctx *ctx) {
       LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
   } else TRY(enq_integrate(ctx, false));
   const bool fz = tu_can_fuse(ctx) && ov_is_multi_launch(ctx);   // k_ov_init rides on the first test_update, k_ov_apply on the second
-  TRY(enq_test_update(ctx, fz ? 1 : 0));
+  TRY(enq_test_update(ctx, fz ? 1 : 0, false));
   TRY(enq_overlap(ctx, true, fz, fz));
   TRY(enq_test_update(ctx, fz ? 2 : 0));
   if (ctx->cfg.reservoir == 3) {

@@ -375,6 +375,27 @@ def test_box_without_cell_lists_uses_verlet_rows(integrador, nsteps):
     ctx.close()
 
 
+def test_gcmc_step_equals_call_site_sequence():
+    """dml_step on the grand-canonical case (whose first test_update skips the forced cell sort that only gcmc_run needs) against
+    the same loop body issued call site by call site (src/dana.F90:173-265), Philox noise: bit-identical state and counters."""
+    d, o = case("gcmc")
+    out = []
+    for fused in (True, False):
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=77)
+        if fused:
+            ctx.step(300)
+        else:
+            for i in range(300):
+                ctx.cbrownian_hs(); ctx.test_update(); ctx.overlap_moveback(); ctx.test_update(); ctx.msd_book(); ctx.promote()
+                ctx.gcmc_run(); ctx.calc_rho()
+        c = ctx.counters()
+        out.append((ctx.download(c.n_slots), (c.nupd_vlist, c.choques, c.gcmc_created, c.gcmc_destroyed, c.nat_sys, c.nat_ref, c.list_entries)))
+        ctx.close()
+    assert out[0][1] == out[1][1] and out[0][1][2] > 10 and out[0][1][3] > 10
+    for k in ("pos", "vel", "pos_old", "z", "flags", "uid", "slot_b"):
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+
+
 def test_slab_decomposition_two_gpus():
     """z-slab decomposition over NCCL (tests/slab_check.py under torchrun, 2 ranks): identical pair sets and forces within
     1e-12 of the single-GPU result, before and after a move + halo refresh.  Needs two GPUs on the box."""
