@@ -389,7 +389,7 @@ def test_gcmc_step_equals_call_site_sequence():
                 ctx.cbrownian_hs(); ctx.test_update(); ctx.overlap_moveback(); ctx.test_update(); ctx.msd_book(); ctx.promote()
                 ctx.gcmc_run(); ctx.calc_rho()
         c = ctx.counters()
-        out.append((ctx.download(c.n_slots), (c.nupd_vlist, c.choques, c.gcmc_created, c.gcmc_destroyed, c.nat_sys, c.nat_ref, c.list_entries)))
+        out.append((ctx.download(c.n_slots), (c.nupd_vlist, c.choques, c.gcmc_created, c.gcmc_destroyed, c.nat_sys, c.nat_ref, c.list_entries, c.nat_gcmc)))   # msd_t (log only) is an atomic sum: last-ulp noise
         ctx.close()
     assert out[0][1] == out[1][1] and out[0][1][2] > 10 and out[0][1][3] > 10
     for k in ("pos", "vel", "pos_old", "z", "flags", "uid", "slot_b"):
