@@ -78,6 +78,7 @@ struct dml_ctx {
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
   int tu_fused = 0;         // what the last test_update launch folded in (bit 0 k_ov_init, bit 1 k_ov_apply)
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
+  int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
@@ -196,6 +197,36 @@ static void set_box(dml_ctx *ctx, const double box[3]) {
     double rl = ctx->cfg.rcut + ctx->cfg.nb_dcut;
     ctx->geo.band2 = (float)(4.0 * (2.0 * 1.7321 * (rl + 1.0) * 3.0 * ulp + 1e-5 * rl * rl));
   }
+}
+
+// Keep the 32-byte particle records resident in the 126 MB L2 across the kernels of a step: every gather of the pair-force /
+// overlap / list kernels then hits L2 and HBM only sees the streaming arrays.  The window covers the slots in use
+// (plus head-room), not the capacity: a window larger than the persisting carve-out lowers the hit ratio of every record
+// (measured at 1 M particles: capacity 2.5 M slots -> pair force 41 -> 55 us, step 0.354 -> 0.428 ms).
+static void l2_window(dml_ctx *ctx, int nslots) {
+  if (ctx->no_l2_persist) return;
+  nslots = std::min(std::max(nslots, 1024), ctx->cap);
+  if (ctx->l2_max_persist < 0) {                         // device attributes are read once per context
+    int dev = 0, a = 0, b = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&a, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&b, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    ctx->l2_max_persist = a; ctx->l2_max_window = b;
+  }
+  if (ctx->l2_max_persist <= 0) return;
+  if (nslots <= ctx->l2_slots && nslots * 2 > ctx->l2_slots) return;      // the current window already fits
+  struct { size_t persistingL2CacheMaxSize, accessPolicyMaxWindowSize; } prop = {(size_t)ctx->l2_max_persist, (size_t)ctx->l2_max_window};
+  size_t bytes = (size_t)nslots * sizeof(double4);
+  size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+  attr.accessPolicyWindow.base_ptr = ctx->posm.p;
+  attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(ctx->st, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+  ctx->l2_slots = nslots;
 }
 
 // cgroup_tessellate — Cells.F90:180-265 (host side: it depends only on the box and rcut+nb_dcut)
@@ -508,6 +539,7 @@ static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
 static int finish(dml_ctx *ctx) {
   TRY(pull_scal(ctx));
   ctx->n = ctx->hsc->n_slots;
+  if (ctx->n > ctx->l2_slots) l2_window(ctx, ctx->n + ctx->n / 4);
   const size_t tail0 = (size_t)ctx->hsc->cols_tail0;
   size_t used = (size_t)std::max(ctx->hsc->cols_used, ctx->hsc->rev_used);
   if (used > tail0 && (used - tail0) * 2 > ctx->cols.cap - tail0) {          // half of the tail region is in use
@@ -647,6 +679,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
+  if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
   if (const char *e = getenv("DML_ROWS_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->rows_lanes = v; }
   if (const char *e = getenv("DML_FORCE_LEAN")) ctx->force_lean = atoi(e) != 0;
@@ -681,23 +714,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->rp_gauss.ensure((size_t)cap * 6, ctx->st)); CKC(ctx->rp_upbc.ensure(cap, ctx->st)); CKC(ctx->rp_uovl.ensure(cap, ctx->st));
   CKC(cudaMemsetAsync(ctx->posm.p, 0, (size_t)cap * sizeof(double4), ctx->st));
   CKC(cudaMemsetAsync(ctx->fe.p, 0, (size_t)cap * sizeof(double4), ctx->st));
-  {
-    // Keep the 32-byte particle records resident in the 126 MB L2 across the kernels of a step: every gather of the
-    // pair-force / overlap / list kernels then hits L2 and HBM only sees the streaming arrays.
-    cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev);
-    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("DML_NO_L2_PERSIST")) {
-      size_t want = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)cap * sizeof(double4));
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-      cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
-      attr.accessPolicyWindow.base_ptr = ctx->posm.p;
-      attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)cap * sizeof(double4), (size_t)prop.accessPolicyMaxWindowSize);
-      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      cudaStreamSetAttribute(ctx->st, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaGetLastError();
-    }
-  }
+  l2_window(ctx, cap);
   {
     int dev = 0, nsm = 0, coop = 0, b1 = 0, b2 = 0;
     cudaGetDevice(&dev);
@@ -782,6 +799,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
   if (!vel) CKC(cudaMemsetAsync(ctx->vel.p, 0, n3 * sizeof(double), ctx->st));
   if (!acel) CKC(cudaMemsetAsync(ctx->acel.p, 0, n3 * sizeof(double), ctx->st));
   ctx->n = n; ctx->binned = false;
+  l2_window(ctx, n + n / 4);
   if (ctx->cfg.reservoir != 3) {
     // No gcmc group to keep in list order: creation ranks, b indices, their occupancy and the two running maxima are filled in
     // on the device (k_upload_book), so the call is copies + three small kernels and one synchronisation.
