@@ -1,3 +1,5 @@
+"""tools/pcie_probe.py — pinned host <-> device copy rates of this box for the byte counts of bench.py's e2e leg (one copy against the
+number of separate arrays dml_upload / dml_download move): the floor the host-buffer path is compared with in DESIGN.md §6."""
 import torch, time
 n=109647
 for total,parts,name in ((18420696,1,"D2H one"),(18420696,11,"D2H 11 parts"),(14911992,1,"H2D one"),(14911992,9,"H2D 9 parts")):
