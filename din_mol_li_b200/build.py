@@ -7,14 +7,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdml.so")
 SRCS = ["dml.cu", "dana_host.cpp"]
-DEPS = ["dml.cu", "dml_coop.cuh", "dml_slab.cuh", os.path.join("..", "..", "tools", "dana_host.cpp"), "dana_host.cpp", os.path.join("..", "..", "include", "dml_host.h"), "dml_kernels.cuh", "dml_device.cuh", "dml_gcmc.cuh", os.path.join("..", "..", "include", "dml.h")]
+import glob
+DEPS = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.cpp")) +
+              glob.glob(os.path.join(HERE, "..", "include", "*.h")) + [os.path.join(HERE, "..", "tools", "dana_host.cpp")])
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ldl"]
 
 
 def build(force=False, verbose=False):
-    deps = [os.path.join(CSRC, d) for d in DEPS]
+    deps = DEPS
     if (not force) and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cmd = [NVCC] + FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SRCS]

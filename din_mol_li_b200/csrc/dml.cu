@@ -99,6 +99,7 @@ struct dml_ctx {
   DBuf<int> gorder, gpos, gcc, gpend, b_occ; int gorder_cap = 0;
   // replay
   DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
+  DBuf<int> rp_qstart, ov_draws;   // overlap_moveback replay queue: draws k = 0,1,.. of slot s read rp_uovl[rp_qstart[s] + k]
   // output reductions and observables (dml_observe.cuh)
   DBuf<double> obs_part, obs_out; DBuf<unsigned long long> obs_counts; DBuf<int> gr_cell_of, gr_cnt, gr_start; DBuf<double4> gr_sorted;
   unsigned int *obs_ticket = nullptr;
@@ -114,6 +115,8 @@ struct dml_ctx {
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } } while (0)
 #define FAIL(msg) do { ctx->err = (msg); return -1; } while (0)
 #define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+// every public entry point runs on the ctx's own device, whatever the calling thread's current device is
+#define ENTER(ctx) do { if (!(ctx)) return -1; cudaSetDevice((ctx)->cfg.device); } while (0)
 
 static int gcmc_run_impl(dml_ctx *ctx);
 static int enq_build_rev(dml_ctx *ctx);
@@ -467,6 +470,10 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
 static bool tu_can_fuse(const dml_ctx *ctx) { return ctx->use_coop && ctx->n <= ctx->coop_tu_max_n && !ctx->no_tu_fuse; }
 static bool ov_is_multi_launch(const dml_ctx *ctx) { return !(ctx->use_coop && ctx->n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0); }
 
+static OvRp ov_replay(const dml_ctx *ctx) {
+  OvRp r; r.vals = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; r.qstart = ctx->rp_qstart.p; r.draws = ctx->ov_draws.p;
+  return r;
+}
 static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false, bool defer_apply = false) {
   int n = ctx->n;
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
@@ -476,7 +483,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
     A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.ov_head = ctx->ov_head.p; A.ov_next = ctx->ov_next.p; A.uid = ctx->uid.p;
-    A.rp_uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
+    A.rp_uovl = ov_replay(ctx); A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
     A.n = n; A.guard_pass = ctx->ov_guard_pass;
     LAUNCH_COOP(K_OV_COOP, k_overlap_coop, ctx->coop_grid_ov, A);
     ctx->have_rp_ovl = false;
@@ -485,7 +492,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
   if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
          ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
-  const double *uovl = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr;
+  const OvRp uovl = ov_replay(ctx);
   if (ctx->cfg.prob >= 1.0) {
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
     LAUNCH(K_OV_PASS, k_ov_resolve, std::min(nblk(n, 4), 148 * 4), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
@@ -744,6 +751,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
 
 void dml_destroy(dml_ctx *ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->st);
   prof_collect(ctx);
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -766,7 +774,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
   ctx->wl.release(); if (ctx->wl_count) cudaFree(ctx->wl_count);
   ctx->snap_uid.release(); ctx->snap_mb.release(); ctx->mc_out.release(); ctx->mc_count.release();
-  ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
+  ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_qstart.release(); ctx->ov_draws.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
   if (ctx->hsc) cudaFreeHost(ctx->hsc);
@@ -783,7 +791,7 @@ static int member_snapshot(dml_ctx *ctx) {
 }
 
 int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, const double *acel, const double *pos_old,
-               const double *old_cg, const int32_t *z, const int32_t *flags, const int32_t *uid, const int32_t *slot_b) {
+               const double *old_cg, const int32_t *z, const int32_t *flags, const int32_t *uid, const int32_t *slot_b) { ENTER(ctx);
   TRY(ensure_particles(ctx, n));
   if (!pos || !z || !flags) FAIL("dml_upload: pos, z and flags are required");
   size_t n3 = (size_t)n * 3;
@@ -850,7 +858,7 @@ int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, co
 }
 
 int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel, double *force, double *epot, double *pos_old,
-                 double *old_cg, int32_t *z, int32_t *flags, int32_t *uid, int32_t *slot_b) {
+                 double *old_cg, int32_t *z, int32_t *flags, int32_t *uid, int32_t *slot_b) { ENTER(ctx);
   if (n > ctx->n) FAIL("dml_download: n exceeds the number of slots");
   size_t n3 = (size_t)n * 3;
   CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
@@ -874,7 +882,7 @@ int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel
   return 0;
 }
 
-int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s) {
+int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s) { ENTER(ctx);
   TRY(pull_scal(ctx));
   ctx->hsc->z0 = s->z0; ctx->hsc->z1 = s->z1; ctx->hsc->zmax = s->zmax; ctx->hsc->rho = s->rho; ctx->hsc->rho0 = s->rho0;
   TRY(push_scal(ctx));
@@ -883,14 +891,14 @@ int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s) {
   CKC(cudaStreamSynchronize(ctx->st));
   return 0;
 }
-int dml_get_scalars(dml_ctx *ctx, dml_scalars *s) {
+int dml_get_scalars(dml_ctx *ctx, dml_scalars *s) { ENTER(ctx);
   TRY(pull_scal(ctx));
   for (int k = 0; k < 3; ++k) s->box[k] = ctx->geo.box[k];
   s->z0 = ctx->hsc->z0; s->z1 = ctx->hsc->z1; s->zmax = ctx->hsc->zmax; s->rho = ctx->hsc->rho; s->rho0 = ctx->hsc->rho0;
   s->t = ctx->t; s->step = ctx->step;
   return 0;
 }
-int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
+int dml_get_counters(dml_ctx *ctx, dml_counters *c) { ENTER(ctx);
   TRY(pull_scal(ctx));
   memset(c, 0, sizeof *c);
   if (ctx->hsc->listed) {
@@ -909,55 +917,55 @@ int dml_get_counters(dml_ctx *ctx, dml_counters *c) {
   c->tessellated = ctx->tessellated; c->listed = h->listed; c->rows_asym = h->rows_asym;
   return 0;
 }
-int dml_reset_try_depo(dml_ctx *ctx) {
+int dml_reset_try_depo(dml_ctx *ctx) { ENTER(ctx);
   CKC(cudaMemsetAsync(&ctx->sc->try_, 0, sizeof(long long), ctx->st));
   CKC(cudaMemsetAsync(&ctx->sc->depo, 0, sizeof(long long), ctx->st));
   return 0;
 }
 
-int dml_test_update(dml_ctx *ctx) { TRY(enq_test_update(ctx)); return finish(ctx); }
-int dml_fuerza(dml_ctx *ctx) {
+int dml_test_update(dml_ctx *ctx) { ENTER(ctx); TRY(enq_test_update(ctx)); return finish(ctx); }
+int dml_fuerza(dml_ctx *ctx) { ENTER(ctx);
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("fuerza called without a neighbour list");
   TRY(enq_fuerza(ctx)); return finish(ctx);
 }
-int dml_ermak_a(dml_ctx *ctx) { TRY(enq_integrate(ctx, true)); return finish(ctx); }
-int dml_ermak_b(dml_ctx *ctx) {
+int dml_ermak_a(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, true)); return finish(ctx); }
+int dml_ermak_b(dml_ctx *ctx) { ENTER(ctx);
   LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
   return finish(ctx);
 }
-int dml_cbrownian_hs(dml_ctx *ctx) { TRY(enq_integrate(ctx, false)); return finish(ctx); }
-int dml_overlap_moveback(dml_ctx *ctx) {
+int dml_cbrownian_hs(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, false)); return finish(ctx); }
+int dml_overlap_moveback(dml_ctx *ctx) { ENTER(ctx);
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("overlap_moveback called without a neighbour list");
   TRY(enq_overlap(ctx)); return finish(ctx);
 }
-int dml_msd_book(dml_ctx *ctx) { LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc); return 0; }
-int dml_promote(dml_ctx *ctx) { TRY(enq_promote(ctx)); return finish(ctx); }
-int dml_gcmc_run(dml_ctx *ctx) { TRY(gcmc_run_impl(ctx)); return finish(ctx); }
-int dml_calc_rho(dml_ctx *ctx, double *rho) {
+int dml_msd_book(dml_ctx *ctx) { ENTER(ctx); LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc); return 0; }
+int dml_promote(dml_ctx *ctx) { ENTER(ctx); TRY(enq_promote(ctx)); return finish(ctx); }
+int dml_gcmc_run(dml_ctx *ctx) { ENTER(ctx); TRY(gcmc_run_impl(ctx)); return finish(ctx); }
+int dml_calc_rho(dml_ctx *ctx, double *rho) { ENTER(ctx);
   TRY(enq_calc_rho(ctx));
   TRY(finish(ctx));
   if (rho) *rho = ctx->hsc->rho;
   return 0;
 }
-int dml_maxz(dml_ctx *ctx, double *zmax) {
+int dml_maxz(dml_ctx *ctx, double *zmax) { ENTER(ctx);
   TRY(enq_maxz(ctx));
   TRY(finish(ctx));
   if (zmax) *zmax = ctx->hsc->zmax;
   return 0;
 }
-int dml_bloques(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia, int32_t *fired) {
+int dml_bloques(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia, int32_t *fired) { ENTER(ctx);
   TRY(do_bloques(ctx, nchunk, chunk_pos, chunk_pos_old, dist, rhomedia, fired));
   return finish(ctx);
 }
-int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia) {
+int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos, const double *chunk_pos_old, double dist, double rhomedia) { ENTER(ctx);
   ctx->ch_pos.assign(chunk_pos, chunk_pos + (size_t)nchunk * 3);
   ctx->ch_pos_old.assign(chunk_pos_old, chunk_pos_old + (size_t)nchunk * 3);
   ctx->ch_dist = dist; ctx->ch_rhomedia = rhomedia; ctx->have_chunk = true;
   return 0;
 }
-int dml_step(dml_ctx *ctx, int32_t nsteps) {
+int dml_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
   for (int i = 0; i < nsteps; ++i) {
     TRY(enq_step(ctx));
     if ((i & 15) == 15) TRY(finish(ctx));              // periodic error check / storage growth; no other host round trip
@@ -965,7 +973,7 @@ int dml_step(dml_ctx *ctx, int32_t nsteps) {
   return finish(ctx);
 }
 
-int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) {
+int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) { ENTER(ctx);
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
   if (!ctx->tessellated) FAIL("dml_get_cells: the box has no cell lists (fewer than 4 cells on every axis, Cells.F90:231)");
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
@@ -984,7 +992,7 @@ int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos
   return 0;
 }
 
-int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) {
+int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) { ENTER(ctx);
   if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("no neighbour list");
@@ -1000,7 +1008,7 @@ int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32
   }
   return rc;
 }
-int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn, const int32_t *rows) {
+int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn, const int32_t *rows) { ENTER(ctx);
   if (n > ctx->n) FAIL("dml_set_neighbors: n exceeds the number of slots");
   // same layout as the device build: a row that fits (with the gcmc slack) sits in its slot's ROW_W entries, longer ones in the tail
   const int tail0 = ctx->cap * ROW_W;
@@ -1029,17 +1037,41 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   return 0;
 }
 
-int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, const double *unif_pbc, const double *unif_ovl) {
+static int set_overlap_queue(dml_ctx *ctx, int n, const int *qstart, int nvals, const double *vals) {
+  CKC(ctx->rp_qstart.ensure((size_t)ctx->cap + 1, ctx->st)); CKC(ctx->ov_draws.ensure(ctx->cap, ctx->st));
+  CKC(ctx->rp_uovl.ensure((size_t)std::max(nvals, 1), ctx->st));
+  // slots beyond n (none exist yet) get empty queues
+  std::vector<int> qs((size_t)ctx->cap + 1, qstart[n]);
+  std::copy(qstart, qstart + n + 1, qs.begin());
+  CKC(cudaMemcpyAsync(ctx->rp_qstart.p, qs.data(), qs.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+  if (nvals) CKC(cudaMemcpyAsync(ctx->rp_uovl.p, vals, (size_t)nvals * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  CKC(cudaMemsetAsync(ctx->ov_draws.p, 0, (size_t)ctx->cap * sizeof(int), ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));                      // qs goes out of scope
+  ctx->have_rp_ovl = true;
+  return 0;
+}
+int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, const double *unif_pbc, const double *unif_ovl) { ENTER(ctx);
   if (n > ctx->cap) FAIL("replay arrays exceed capacity");
   if (gauss) CKC(cudaMemcpyAsync(ctx->rp_gauss.p, gauss, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   if (unif_pbc) CKC(cudaMemcpyAsync(ctx->rp_upbc.p, unif_pbc, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   else CKC(cudaMemsetAsync(ctx->rp_upbc.p, 0, (size_t)n * sizeof(double), ctx->st));
-  if (unif_ovl) { CKC(cudaMemcpyAsync(ctx->rp_uovl.p, unif_ovl, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->st)); ctx->have_rp_ovl = true; }
+  if (unif_ovl) {                                          // one value per slot: a queue of length 1 for every slot
+    std::vector<int> qs((size_t)n + 1);
+    for (int i = 0; i <= n; ++i) qs[i] = i;
+    TRY(set_overlap_queue(ctx, n, qs.data(), n, unif_ovl));
+  }
   CKC(cudaStreamSynchronize(ctx->st));
   ctx->have_rp = gauss != nullptr;
   return 0;
 }
-int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss) {
+int dml_set_replay_overlap(dml_ctx *ctx, int32_t n, const int32_t *qstart, int32_t nvals, const double *vals) {
+  ENTER(ctx);
+  if (n > ctx->cap || !qstart || nvals < 0 || (nvals > 0 && !vals)) FAIL("dml_set_replay_overlap: bad arguments");
+  TRY(set_overlap_queue(ctx, n, qstart, nvals, vals));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss) { ENTER(ctx);
   CKC(ctx->rp_gu.ensure((size_t)std::max(nu, 1), ctx->st)); CKC(ctx->rp_gg.ensure((size_t)std::max(ng, 1), ctx->st));
   if (nu) CKC(cudaMemcpyAsync(ctx->rp_gu.p, unif, (size_t)nu * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   if (ng) CKC(cudaMemcpyAsync(ctx->rp_gg.p, gauss, (size_t)ng * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
@@ -1059,7 +1091,7 @@ int dml_comm_unique_id(void *id128) {
   memcpy(id128, &id, sizeof id);
   return 0;
 }
-int dml_comm_init(dml_ctx *ctx, const void *id128, int32_t rank, int32_t nranks) {
+int dml_comm_init(dml_ctx *ctx, const void *id128, int32_t rank, int32_t nranks) { ENTER(ctx);
   NcclApi *N = nccl_api();
   if (!N) FAIL("libnccl.so.2 not found");
   ncclUniqueId id; memcpy(&id, id128, sizeof id);
@@ -1131,7 +1163,7 @@ static int slab_refresh_ghosts(dml_ctx *ctx) {
   ctx->n = n + ng;
   return 0;
 }
-int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) {
+int dml_slab_setup(dml_ctx *ctx, double zlo, double zhi) { ENTER(ctx);
   NcclApi *N = nccl_api();
   if (!ctx->comm || !N) FAIL("dml_slab_setup: call dml_comm_init first");
   TRY(finish(ctx));
@@ -1235,7 +1267,7 @@ static int slab_promote_rho(dml_ctx *ctx) {
   return 0;
 }
 // nsteps iterations of dana's loop body (dana.F90:173-265; Ermak integrator + piston) on the decomposed box
-int dml_slab_step(dml_ctx *ctx, int32_t nsteps) {
+int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
   if (!ctx->comm || !ctx->slab_ready) FAIL("dml_slab_step: call dml_comm_init and dml_slab_setup first");
   if (!ctx->cfg.integrador || ctx->cfg.reservoir != 1) FAIL("dml_slab_step: the decomposed box runs the Ermak integrator with the piston reservoir");
   for (int i = 0; i < nsteps; ++i) {
@@ -1257,11 +1289,11 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) {
   return finish(ctx);
 }
 // per-step refresh of the ghost positions from their owners (same lists as the last dml_slab_setup)
-int dml_slab_halo_exchange(dml_ctx *ctx) {
+int dml_slab_halo_exchange(dml_ctx *ctx) { ENTER(ctx);
   if (!ctx->comm) FAIL("dml_slab_halo_exchange: no communicator");
   return slab_exchange(ctx, false);
 }
-int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nsend_lo, int32_t *nsend_hi) {
+int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nsend_lo, int32_t *nsend_hi) { ENTER(ctx);
   if (n_owned) *n_owned = ctx->n_owned;
   if (n_ghost) *n_ghost = ctx->nrecv_lo + ctx->nrecv_hi;
   if (nsend_lo) *nsend_lo = ctx->nsend_lo;
@@ -1271,7 +1303,7 @@ int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nse
 
 
 // ---- output reductions and observables ---------------------------------------------------------------
-int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *temp, int32_t *n_mobile) {
+int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *temp, int32_t *n_mobile) { ENTER(ctx);
   const int n = ctx->n;
   const int nb = std::min(nblk(n, OBS_TPB), 148 * 4);
   CKC(ctx->obs_part.ensure((size_t)4 * 148 * 4, ctx->st)); CKC(ctx->obs_out.ensure(4, ctx->st));
@@ -1287,7 +1319,7 @@ int dml_salida_sums(dml_ctx *ctx, double *energia, double *energia_ref, double *
   return 0;
 }
 
-int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int32_t type_mask, int64_t *counts) {
+int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int32_t type_mask, int64_t *counts) { ENTER(ctx);
   if (nbins < 1 || nbins > OBS_MAX_BINS || !(zhi > zlo) || !counts) FAIL("dml_density_profile: need 1 <= nbins <= 8192, zhi > zlo and an output array");
   const int n = ctx->n;
   CKC(ctx->obs_counts.ensure(OBS_MAX_BINS, ctx->st));
@@ -1303,7 +1335,7 @@ int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int
   return 0;
 }
 
-int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t *counts, int32_t *n_selected) {
+int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t *counts, int32_t *n_selected) { ENTER(ctx);
   if (nbins < 1 || nbins > OBS_MAX_BINS || !(rmax > 0.0) || !counts) FAIL("dml_gr: need 1 <= nbins <= 8192, rmax > 0 and an output array");
   const int n = ctx->n;
   TRY(pull_scal(ctx));
@@ -1344,7 +1376,7 @@ int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t 
   return 0;
 }
 
-int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int32_t *kind, int32_t *uid_now, int32_t *z_now, int32_t *n_changes) {
+int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int32_t *kind, int32_t *uid_now, int32_t *z_now, int32_t *n_changes) { ENTER(ctx);
   if (!n_changes || max_changes < 0) FAIL("dml_membership_changes: n_changes is required");
   if (!ctx->have_snap) { TRY(member_snapshot(ctx)); *n_changes = 0; CKC(cudaStreamSynchronize(ctx->st)); return 0; }
   CKC(ctx->mc_out.ensure((size_t)std::max(max_changes, 1), ctx->st)); CKC(ctx->mc_count.ensure(1, ctx->st));
@@ -1370,13 +1402,13 @@ int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int
   return 0;
 }
 
-int dml_profile(dml_ctx *ctx, int32_t enable) {
+int dml_profile(dml_ctx *ctx, int32_t enable) { ENTER(ctx);
   prof_collect(ctx);
   ctx->profiling = enable != 0;
   if (enable) while (ctx->pool.size() < 8192) { ProfEv ev; cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.cls = 0; ctx->pool.push_back(ev); }
   return 0;
 }
-int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset) {
+int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset) { ENTER(ctx);
   prof_collect(ctx);
   double m = 0; int64_t l = 0;
   for (int i = 0; i < K_NKERN; ++i) if (cls == CLS_ALL || kern_cls[i] == cls) { m += ctx->prof_ms[i]; l += ctx->prof_n[i]; }
@@ -1385,7 +1417,7 @@ int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, in
   if (reset) for (int i = 0; i < 32; ++i) { ctx->prof_ms[i] = 0; ctx->prof_n[i] = 0; }
   return 0;
 }
-int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches) {
+int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches) { ENTER(ctx);
   prof_collect(ctx);
   if (kid < 0 || kid >= K_NKERN) return 1;
   if (name) *name = kern_name[kid];
@@ -1393,13 +1425,13 @@ int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms,
   if (launches) *launches = ctx->prof_n[kid];
   return 0;
 }
-int32_t dml_n_slots(dml_ctx *ctx) { return ctx->n; }
-int dml_set_strict_order(dml_ctx *ctx, int32_t on) {
+int32_t dml_n_slots(dml_ctx *ctx) { ENTER(ctx); return ctx->n; }
+int dml_set_strict_order(dml_ctx *ctx, int32_t on) { ENTER(ctx);
   ctx->cfg.strict_order = on ? 1 : 0;
   CKC(cudaMemsetAsync(&ctx->sc->rev_valid, 0, sizeof(int), ctx->st));   // the two kernels use differently scoped transposed rows
   return 0;
 }
-int64_t dml_launch_count(dml_ctx *ctx) { return ctx->launches; }
+int64_t dml_launch_count(dml_ctx *ctx) { ENTER(ctx); return ctx->launches; }
 void *dml_stream(dml_ctx *ctx) { return (void *)ctx->st; }
 
 } // extern "C"

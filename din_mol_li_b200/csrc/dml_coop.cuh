@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
 
 struct OVArgs {
   double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
-      *members, *roots, *ov_head, *ov_next; const int *uid; const double *rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass;
+      *members, *roots, *ov_head, *ov_next; const int *uid; OvRp rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass;
 };
 
 // overlap_moveback (dana.F90:849-943) in one launch (prob>=1)

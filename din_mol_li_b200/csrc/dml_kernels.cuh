@@ -1899,12 +1899,25 @@ __device__ __forceinline__ void ov_pos(const double4 *posm, const double *old_cg
 }
 // one reference pass (one recursion level) over the members [b,e) of one component; returns "again"
 struct OvAcc { long long tr, de, ch, ch3; };
+// Injected deposition uniforms of overlap_moveback (trace-replay parity mode): the k-th draw an atom makes inside one call reads
+// vals[qstart[slot] + k] (the reference draws a fresh ran(idum) at every retry of a failed deposition, dana.F90:898-911); the
+// per-slot draw counters are cleared by k_ov_init.  vals == nullptr: nothing injected (prob >= 1: the value never matters).
+struct OvRp { const double *vals; const int *qstart; int *draws; };
+__device__ __forceinline__ double ov_replay_draw(const OvRp &rp, int a1, bool lead, DevScal *sc, double prob) {
+  if (!rp.vals) return 0.0;
+  const int k = rp.draws[a1], b = rp.qstart[a1], cnt = rp.qstart[a1 + 1] - b;
+  __syncwarp(__activemask());
+  if (lead) rp.draws[a1] = k + 1;
+  if (k < cnt) return rp.vals[b + k];
+  if (prob < 1.0 && lead) atomicCAS(&sc->err, 0, DML_E_REPLAY_EXHAUSTED);
+  return 0.0;
+}
 __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                             const RowHead *__restrict__ rh,
                                             const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                             const unsigned int *__restrict__ lay,
                                             int *__restrict__ ovst, const int *__restrict__ members,
-                                            const int *__restrict__ uid, const double *__restrict__ rp_uovl, DevScal *__restrict__ sc,
+                                            const int *__restrict__ uid, const OvRp rp_uovl, DevScal *__restrict__ sc,
                                             const Geo &g, const Phys &ph, unsigned int step, int pass, int guard, double z0,
                                             int b, int e, OvAcc &acc) {
   bool again = false;
@@ -1934,7 +1947,7 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
       if (t2 == 2) {                                           // contact with metal: deposition attempt
         acc.tr++;
         double ne;
-        if (ph.rng_mode == 1) ne = rp_uovl ? rp_uovl[a1] : 0.0;
+        if (ph.rng_mode == 1) ne = ov_replay_draw(rp_uovl, a1, true, sc, ph.prob);
         else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
         if (ne < ph.prob) {
           acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
@@ -1973,7 +1986,7 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
                           const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                           const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                           const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
-                          const int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                          const int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                           DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sc->n_roots) return;
@@ -2007,7 +2020,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
                              const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                              const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
-                             int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                             int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
   const unsigned int FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -2118,7 +2131,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
           if (cgm) {                                                 // deposition attempt (uniform over the warp)
             acc.tr++;
             double ne;
-            if (ph.rng_mode == 1) ne = rp_uovl ? rp_uovl[a1] : 0.0;
+            if (ph.rng_mode == 1) ne = ov_replay_draw(rp_uovl, a1, lane == 0, sc, ph.prob);
             else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
             if (ne < ph.prob) {
               acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
@@ -2145,7 +2158,7 @@ __global__ void __launch_bounds__(128) k_ov_resolve(const double4 *__restrict__ 
                              const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                              const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
-                             int *__restrict__ members, const int *__restrict__ uid, const double *__restrict__ rp_uovl,
+                             int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
   p_ov_resolve(posm, old_cg, rh, cols, bq, lay, ovst, roots, ov_head, ov_next, members, uid, rp_uovl, sc, g, ph, step, guard_pass);
 }

@@ -49,7 +49,7 @@ SYMBOLS = [
     "dml_get_scalars", "dml_get_counters", "dml_reset_try_depo", "dml_test_update", "dml_fuerza", "dml_ermak_a",
     "dml_ermak_b", "dml_cbrownian_hs", "dml_overlap_moveback", "dml_msd_book", "dml_promote", "dml_gcmc_run",
     "dml_calc_rho", "dml_maxz", "dml_bloques", "dml_set_chunk_template", "dml_step", "dml_get_cells",
-    "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_gcmc", "dml_profile",
+    "dml_get_neighbors", "dml_set_neighbors", "dml_set_replay_integrator", "dml_set_replay_overlap", "dml_set_replay_gcmc", "dml_profile",
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
     "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
     "dml_salida_sums", "dml_density_profile", "dml_gr", "dml_membership_changes",
@@ -90,6 +90,7 @@ def lib():
         L.dml_set_neighbors.argtypes = [vp, i32, i32, vp, vp]
         L.dml_set_replay_integrator.argtypes = [vp, i32, vp, vp, vp]
         L.dml_set_replay_gcmc.argtypes = [vp, i32, vp, i32, vp]
+        L.dml_set_replay_overlap.argtypes = [vp, i32, vp, i32, vp]
         L.dml_profile.argtypes = [vp, i32]
         L.dml_profile_get.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(C.c_int64), i32]
         L.dml_profile_kernel.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(dbl), C.POINTER(C.c_int64)]
@@ -393,6 +394,11 @@ class Ctx:
         g, u, o = _f64(gauss), _f64(unif_pbc), _f64(unif_ovl)
         n = [a.shape[0] for a in (g, u, o) if a is not None][0]
         self._chk(lib().dml_set_replay_integrator(self.h, n, _p(g), _p(u), _p(o)))
+
+    def set_replay_overlap(self, qstart, vals):
+        """Per-slot queues of the deposition uniforms overlap_moveback draws (k-th draw of slot s = vals[qstart[s] + k])."""
+        q, v = _i32(qstart), _f64(vals)
+        self._chk(lib().dml_set_replay_overlap(self.h, q.shape[0] - 1, _p(q), v.shape[0], _p(v)))
 
     def set_replay_gcmc(self, unif, gauss):
         u, g = _f64(unif), _f64(gauss)

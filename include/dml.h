@@ -10,7 +10,8 @@
  *   - return 0 = ok, <0 = error; dml_last_error(ctx) gives the message.  Never exits the process.
  *     The Fortran shim maps rc/=0 onto `call werr(msg,.true.)` (src/Errors.f90:59-87).
  *   - plain pointers and sizes only; caller owns host arrays, ctx owns device memory and one stream.
- *   - not re-entrant per ctx (one host thread per ctx); any number of ctxs per process; no globals.
+ *   - not re-entrant per ctx (one host thread per ctx); any number of ctxs per process; no globals.  Every entry point
+ *     selects the ctx's own device (cudaSetDevice) first, so ctxs on different GPUs can be driven from any host thread.
  *   - particle arrays are indexed by "slot" = index in the reference's hs%a(:) minus 1
  *     (src/Neighbor.F90:32, src/Groups.F90:179-219).  z[slot]==0 marks an empty slot.
  *   - there is NO CPU fallback: every call needs a CUDA device.
@@ -144,6 +145,10 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
  * Brownian uses the first 3), unif_pbc: [n] uniform drawn by atom_pbc, unif_ovl: [n] uniform drawn by the
  * first CG contact of the slot in overlap_moveback.  Valid for the next integrator/overlap call. */
 int dml_set_replay_integrator(dml_ctx *ctx, int32_t n, const double *gauss, const double *unif_pbc, const double *unif_ovl);
+/* Deposition uniforms of the next dml_overlap_moveback as per-slot queues: the k-th draw of slot s inside the call (the reference
+ * draws a fresh ran(idum) at every retry of a failed deposition, src/dana.F90:898-911) reads vals[qstart[s] + k]; qstart has n+1
+ * entries.  With prob < 1 an exhausted queue is an error; with prob >= 1 the value never matters. */
+int dml_set_replay_overlap(dml_ctx *ctx, int32_t n, const int32_t *qstart, int32_t nvals, const double *vals);
 /* uniforms / gaussians consumed by the next dml_gcmc_run in order */
 int dml_set_replay_gcmc(dml_ctx *ctx, int32_t nu, const double *unif, int32_t ng, const double *gauss);
 

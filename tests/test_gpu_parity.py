@@ -62,6 +62,29 @@ def test_lockstep_replay_bit_exact(name, nsteps):
         ls.step(check=True, tag="%s step %d" % (name, i + 1))
 
 
+@pytest.mark.parametrize("name,nsteps,over", [
+    ("ermak", 400, dict(prob=0.5)), ("brown", 60, dict(prob=0.5)), ("brown", 60, dict(dif_sei=50.0)),
+    ("brown", 120, dict(prob=0.3, dif_sei=20.0)), ("gcmc", 200, dict(prob=0.5, dif_sei=50.0))])
+@pytest.mark.parametrize("coop", [1, 0])
+def test_lockstep_replay_reference_branches(name, nsteps, over, coop, monkeypatch):
+    """Branches of the reference that none of its three fixtures takes (all have prob = 1.0 and dif_sei = dif_sc): a deposition
+    attempt that fails with probability 1 - prob (src/dana.F90:898-911 in overlap_moveback, 1236-1240 in atom_pbc: the atom goes back
+    to old_cg, skip = .false., and draws again at its next visit) and the slower diffusion below z = 80 (src/dana.F90:817-821).
+    Lock-step against the oracle with its random numbers injected (per-slot queues for the repeated draws), both launch forms."""
+    if not coop:
+        monkeypatch.setenv("DML_NO_COOP", "1")
+    d, o = case(name, nwr=10 ** 9, **over)               # salida() never runs: try / depo accumulate over the whole test
+    if name == "ermak":
+        o.step(150)                                       # deposits exist: contacts with metal happen
+    ls = P.Lockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
+    t0, d0 = o.scalars().try_, o.scalars().depo
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s %s step %d" % (name, over, i + 1))
+    sc = o.scalars()
+    if "prob" in over:
+        assert sc.try_ - t0 > (sc.depo - d0) >= 0 and sc.try_ - t0 >= 3, "no failed deposition attempt happened: the test is vacuous"
+
+
 @pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40), ("gcmc", 150)])
 def test_lockstep_replay_multi_launch_path(name, nsteps, monkeypatch):
     """Same lock-step comparison with the persistent cooperative kernels switched off: the one-launch-per-phase path that
@@ -423,3 +446,68 @@ def test_slab_step_two_gpus():
                         "--master-port", "29619", os.path.join(root, "tests", "slab_step_check.py")], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") == 2
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Parity at the sizes bench.py runs (BASELINE configs 2-4), production launch configuration: no DML_* overrides, row order
+# (strict_order = 0), n > 65 536 so overlap_moveback takes k_ov_detect / k_ov_link / k_ov_resolve, 400-1000 A boxes (wider
+# fp32 prefilter band and build-distance quantisation), the z-layer tables and the persisting-L2 window live.
+# ------------------------------------------------------------------------------------------------------------------------
+def _bench():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    return bench
+
+
+def _oracle_of(w, mnb=10000, **over):
+    kw = dict(idum=w["seed"], prob=1.0, h=w["h"], nst=10 ** 9, nwr=10 ** 9, xi=w["xi"], yi=w["yi"], dist=w["dist"], z0=w["z0"], zmax=w["zmax"],
+              dif_sc=250.0, dif_sei=250.0, nb_dcut=w["nb_dcut"], integrador=w["integrador"], reservoir=w["reservoir"], chunk_xyz=w["chunk"],
+              init_xyz=w["pos"], init_z=w.get("z"), mnb=mnb, act=w.get("act", 0.0), nadj=w.get("nadj", 0), ov_guard_pass=64)
+    kw.update(over)
+    return O.Oracle(**kw)
+
+
+@pytest.mark.parametrize("which,nsteps", [("brown", 8), ("gcmc", 6)])
+def test_lockstep_at_bench_size_100k(which, nsteps):
+    """BASELINE configs 2 and 3 exactly as bench.py builds them (100 k particles): rows at t = 0 and a lock-step replay against the
+    oracle, every state array bit-for-bit after every call site, rows compared after every gcmc_run."""
+    B = _bench()
+    w = B.workload_brown(100000, -104012) if which == "brown" else B.workload_gcmc(100000, -104012)
+    O.set_threads(len(os.sched_getaffinity(0)))
+    o = _oracle_of(w)
+    assert o.scalars().nat_sys > 99000
+    ls = P.Lockstep(o, strict=0, chunk_xyz=w["chunk"], capacity=int(o.scalars().nat_sys * 1.3) + 8192, fresh=True)
+    ch0 = o.scalars().choques
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s 100k step %d" % (which, i + 1))
+    assert o.scalars().choques - ch0 > 100                  # hard-sphere move-backs happened: the overlap resolver was exercised
+    if which == "brown":
+        assert o.scalars().nat_sys > w["pos"].shape[0]      # the chunk reservoir added a block
+    else:
+        c = ls.ctx.counters()
+        assert c.gcmc_created + c.gcmc_destroyed > 10
+    P.compare_rows(o, ls.ctx, what=which + " 100k rows at the end")
+
+
+@pytest.mark.parametrize("slab", [False, True])
+def test_rows_and_forces_at_1m(slab):
+    """BASELINE config 4's box on one GPU (1 M particles, Ermak + piston; slab=True adds the two-layer CG electrode: rows of 60-90
+    entries built by whole warps): neighbour rows bit-exact at t = 0, then replayed steps with the production pair-force kernel
+    within 1e-12 of the oracle's forces and energies and every other array bit-for-bit."""
+    B = _bench()
+    w = B.workload_ermak(1000000, -104012, slab=slab)
+    O.set_threads(len(os.sched_getaffinity(0)))
+    o = _oracle_of(w, mnb=256)
+    n = o.scalars().nat_sys
+    assert n > 990000
+    ls = P.Lockstep(o, strict=0, capacity=n + 65536, fresh=True)          # compares the rows at t = 0
+    ne = ls.ctx.counters().list_entries
+    assert ne > 4 * n
+    nsteps = 4 if not slab else 2
+    for i in range(nsteps):
+        ls.step(check=True, tag="1M%s step %d" % (" + CG slab" if slab else "", i + 1))
+    st = o.state()
+    ref = (st["flags"] & 1) > 0
+    assert (np.abs(st["force"][ref]).sum(axis=1) > 0).sum() > 20          # the force comparison is not vacuous
