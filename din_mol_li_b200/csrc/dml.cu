@@ -61,7 +61,7 @@ struct dml_ctx {
   DBuf<int> b2slot;          // boxes without cell lists (ngroup_verlet): slot of every hs%b index
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
-  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, qmin, fnz; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -70,9 +70,7 @@ struct dml_ctx {
   DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
   DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
-  int rows_lanes = 1;       // DML_ROWS_LANES: lanes per particle in the fast row build (1, 2 or 4)
-  bool rows_legacy = false; // DML_ROWS_LEGACY=1: 27-cell ordered walk for every row (the fast walk needs >= 3 cells per axis)
-  bool lazy_rows = false;   // build the rows of a rebuild only when something reads them (Brownian mode: half are never read)
+  bool rows_legacy = false; // DML_ROWS_LEGACY=1: 27-cell ordered walk of one thread for every row (the staged walk needs >= 3 cells per axis)
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
@@ -80,15 +78,8 @@ struct dml_ctx {
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
-  int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 3, 4, 5)
-  bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel (measured: the fused
-                             // kernel takes exactly the sum of the two, 77 us vs 38 + 39 us at 1 M, so the default keeps them apart)
-  int force_pf = 0, force_pf_ahead = 148 * TPB, force_ppt = 1;   // DML_FORCE_PF / DML_FORCE_PPT: see k_fuerza_sub, k_fuerza_ppt
-  bool force_lean = false;    // DML_FORCE_LEAN=1: two-pass pair force (lean streaming pass + worklist pass), see k_fuerza_lean
-  DBuf<int> wl; int *wl_count = nullptr;
-  bool force_wq = false;      // DML_FORCE_WQ=1: warp-queue pair-force kernel (k_fuerza_wq)
-  bool force_batch = false;   // DML_FORCE_BATCH=1: batched index/record requests in the production pair-force kernel
-  int force_lanes = 1;      // lanes per particle in the production pair-force kernel (DML_FORCE_LANES overrides)
+  int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 4, 6, 8)
+  bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
   DBuf<int> scan_sums; DBuf<unsigned long long> scan_state; unsigned int *scan_tickets = nullptr; unsigned int scan_epoch = 0;
   DBuf<int> rev_cnt;
@@ -121,6 +112,7 @@ struct dml_ctx {
 static int gcmc_run_impl(dml_ctx *ctx);
 static int enq_build_rev(dml_ctx *ctx);
 static int enq_sort_cells(dml_ctx *ctx, int force);
+static int enq_materialize_rows(dml_ctx *ctx);
 static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
 
@@ -195,7 +187,7 @@ static void set_box(dml_ctx *ctx, const double box[3]) {
   {
     // fp32 error band of k_rows: coordinates up to L (+ one list radius outside the box) carry ulp(L)/2 each, the image shift
     // another ulp; |d(d^2)| <= 2*sqrt(3)*rc*err + rounding of the products.  A factor 4 of slack on top.
-    double L = std::max(std::max(box[0], box[1]), box[2]) * 1.5 + 64.0;
+    double L = std::max(std::max(box[0], box[1]), box[2]) * 2.5 + 64.0;   // k_rows folds the image shift into the particle's coordinate: |p + box| < 2 box
     double ulp = std::ldexp(1.0, (int)std::ceil(std::log2(L)) - 23);
     double rl = ctx->cfg.rcut + ctx->cfg.nb_dcut;
     ctx->geo.band2 = (float)(4.0 * (2.0 * 1.7321 * (rl + 1.0) * 3.0 * ulp + 1e-5 * rl * rl));
@@ -259,7 +251,7 @@ static void tessellate(dml_ctx *ctx) {
   for (int k = 0; k < 3; ++k) { g.cell[k] = g.box[k] / (double)nc[k]; g.hd[k] = nc[k] + 2; }
   g.inv_cell2 = 1.0 / g.cell[2];
   ctx->nct = g.hd[0] * g.hd[1] * g.hd[2];
-  g.rows_fast = (nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3 && ctx->cap < (1 << 26) && !ctx->rows_legacy) ? ctx->rows_lanes : 0;
+  g.rows_fast = (nc[0] >= 3 && nc[1] >= 3 && nc[2] >= 3 && !ctx->rows_legacy) ? 1 : 0;
   g.lay_shift = 0; while (((g.nc[2] + 2) >> g.lay_shift) + 1 > LAY_MAX) g.lay_shift++;
   g.nlay = ((g.nc[2] + 1) >> g.lay_shift) + 1;
   ctx->tessellated = true;
@@ -298,17 +290,20 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
   return 0;
 }
 
-// ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending
+// ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending.
+// Rows are always built on demand (the first consumer after a rebuild): in Brownian mode the list rebuilt by the second
+// test_update of a step is superseded by the next step's rebuild before anything reads it.
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
   if (!ctx->tessellated) {                                // ngroup_verlet, one warp per row
-    LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
+    LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->bq.p,
            ctx->sc, ctx->geo, n, ctx->row_slack);
     return 0;
   }
-  int nw = std::min(nblk(n * std::max(ctx->geo.rows_fast, 1)), 148 * 8);   // grid-stride over particles: an idle (guarded) launch stays cheap
-  LAUNCH(K_ROWS_FILL, k_rows, nw, TPB, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
-         ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  prof_begin(ctx, K_ROWS_FILL);
+  k_rows<<<nblk(n, RB), RB, ROWS_SMEM, ctx->st>>>(ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
+                                                  ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  prof_end(ctx);
   return 0;
 }
 
@@ -328,7 +323,6 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true)
     LAUNCH(K_PBC_BIN, k_pbc_disp, nbv, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
     CKC(cudaMemsetAsync(ctx->b2slot.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
     LAUNCH(K_BIN, k_verlet_prepare, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->slot_b.p, ctx->b2slot.p, ctx->rh.p, ctx->halo_of.p, ctx->sc, n);
-    if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
     if (fuse & 1) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
     ctx->binned = true;
     return 0;
@@ -341,12 +335,14 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true)
   // gcmc_run needs the cells of the current positions every step; inside dml_step only the test_update right in front of it has to
   // provide them (the one in front of overlap_moveback sorts only when it rebuilds)
   int force = (ctx->cfg.reservoir == 3 && cells_wanted) ? 1 : 0;
+  // a forced sort without a rebuild replaces the snapshot that pending rows would be built from: build them first (no-op otherwise)
+  if (force) TRY(enq_materialize_rows(ctx));
   if (ctx->use_coop && n <= ctx->coop_tu_max_n) {
     TUArgs A;
     A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
     A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_raw = ctx->sorted_raw.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
     A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
-    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = ctx->lazy_rows ? 1 : 0;
+    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = 1;
     A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
     A.fuse = ctx->no_tu_fuse ? 0 : fuse; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p; A.ov_head = ctx->ov_head.p;
     A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p;
@@ -359,7 +355,6 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true)
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
   LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
   TRY(enq_sort_cells(ctx, force));
-  if (!ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
   ctx->binned = true;
   return 0;
 }
@@ -370,10 +365,10 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
   if (ermak)
     LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n, ctx->lay.p, ctx->cfg.rcut);
   else
     LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n, ctx->lay.p, ctx->cfg.rcut);
   ctx->have_rp = false;
   return 0;
 }
@@ -385,7 +380,7 @@ static int enq_build_rev(dml_ctx *ctx) {
     RevArgs A;
     A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.posm = ctx->posm.p; A.rev_start = ctx->rev_start.p; A.rev_len = ctx->rev_len.p; A.rev_cnt = ctx->rev_cnt.p;
     A.rev_cols = ctx->rev_cols.p; A.bq = ctx->bq.p; A.rev_bq = ctx->rev_bq.p; A.halo_of = ctx->halo_of.p; A.halo_only = ctx->cfg.strict_order ? 0 : 1;
-    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.n = n;
+    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.n = n; A.qmin = ctx->qmin.p;
     LAUNCH_COOP(K_REV, k_rev_coop, ctx->coop_grid_rev, A);
     return 0;
   }
@@ -393,7 +388,7 @@ static int enq_build_rev(dml_ctx *ctx) {
          ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
   LAUNCH(K_REV, k_rev_fill, std::min(nblk(n), 148 * 8), TPB, ctx->rh.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
-         ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
+         ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n, ctx->qmin.p);
   LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
   return 0;
 }
@@ -402,66 +397,26 @@ static int enq_qtab(dml_ctx *ctx) {
   LAUNCH(K_MISC, k_qtab, 1, 256, ctx->lay.p, ctx->sc, ctx->geo, ctx->ph.r0_max, ctx->cfg.rcut);
   return 0;
 }
-// fused = called from the step sequence, where the integrator / test_update that ran just before refreshed the skip tables
+// fused = called from the step sequence, right after the integrator whose last block refreshed the skip tables (d_qtab);
+// a stand-alone call (and the slab step, whose halo refresh adds the ghosts' moves) refreshes them with k_qtab first
 static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
-  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
-  // fused: called from the step sequence — the production kernel also applies ermak_b (see k_fuerza_sub<.., FUSEB>)
+  TRY(enq_materialize_rows(ctx));
   TRY(enq_build_rev(ctx));                              // guarded on the device: no-ops unless rows are asymmetric and the transposed rows stale
-  if (ctx->cfg.strict_order)
+  if (ctx->cfg.strict_order) {
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
-           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n);
-  else
-  {
-#define FSUB(L, B, F) LAUNCH(K_FUERZA, (k_fuerza_sub<L, B, F>), nblk(n * L), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B))
-#define FPPT(P, B) LAUNCH(K_FUERZA, (k_fuerza_ppt<P, B>), nblk(n, TPB * P), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->force_pf)
-#define FWQ(B) LAUNCH(K_FUERZA, (k_fuerza_wq<B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n)
-    if (ctx->force_lean && ctx->force_lanes == 1) {
-      const bool fb = fused && ctx->fuse_ermak_b;
-      if (!ctx->wl_count) { CKC(cudaMalloc(&ctx->wl_count, 2 * sizeof(int))); CKC(cudaMemsetAsync(ctx->wl_count, 0, 2 * sizeof(int), ctx->st)); }
-      CKC(ctx->wl.ensure((size_t)ctx->cap + 32, ctx->st));
-      const int gw = 148 * 6;
-#define FLEAN(F) do { \
-      LAUNCH(K_FUERZA, (k_fuerza_lean<F>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->rev_len.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-             ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->wl.p, ctx->wl_count); \
-      LAUNCH(K_FUERZA, (k_fuerza_work<F, 4>), gw, TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, \
-             ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->wl.p, ctx->wl_count, \
-             (unsigned int *)(ctx->wl_count + 1)); } while (0)
-      if (fb) FLEAN(true); else FLEAN(false);
-#undef FLEAN
-    }
-    else if (ctx->force_wq && ctx->force_lanes == 1 && ctx->force_ppt == 1 && !ctx->force_batch && !(fused && ctx->fuse_ermak_b)) {
-      if (ctx->force_minb == 5) FWQ(5); else if (ctx->force_minb == 3) FWQ(3); else if (ctx->force_minb >= 6) FWQ(6); else FWQ(4);
-    }
-    else if (ctx->force_ppt == 2 && !(fused && ctx->fuse_ermak_b)) { if (ctx->force_minb >= 4) FPPT(2, 4); else if (ctx->force_minb == 3) FPPT(2, 3); else FPPT(2, 2); }
-    else if (ctx->force_ppt == 4 && !(fused && ctx->fuse_ermak_b)) { if (ctx->force_minb >= 3) FPPT(4, 3); else FPPT(4, 2); }
-    else if (ctx->force_batch && ctx->force_lanes == 1 && !(fused && ctx->fuse_ermak_b) && ctx->force_minb <= 5) {
-#define FSUBB(B) LAUNCH(K_FUERZA, (k_fuerza_sub<1, B, false, TPB, true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B))
-      if (ctx->force_minb == 5) FSUBB(5); else if (ctx->force_minb == 3) FSUBB(3); else if (ctx->force_minb == 2) FSUBB(2); else FSUBB(4);
-#undef FSUBB
-    }
-    else if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 4) FSUB(1, 4, true); else FSUB(1, 3, true); }
-    else if (ctx->force_lanes == 1 && ctx->force_minb >= 9) {      // 128-thread blocks: register budgets between the 256-thread steps
-#define FSUB128(B) LAUNCH(K_FUERZA, (k_fuerza_sub<1, B, false, 128>), nblk(n, 128), 128, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
-                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->force_pf, ctx->force_pf_ahead * (B) / 2)
-      if (ctx->force_minb == 9) FSUB128(9); else if (ctx->force_minb == 10) FSUB128(10); else FSUB128(11);
-#undef FSUB128
-    }
-    else switch (ctx->force_lanes) {
-      case 1: if (ctx->force_minb == 5) FSUB(1, 5, false); else if (ctx->force_minb == 3) FSUB(1, 3, false); else if (ctx->force_minb == 2) FSUB(1, 2, false); else FSUB(1, 4, false); break;
-      case 2: FSUB(2, 5, false); break; case 4: FSUB(4, 5, false); break; default: FSUB(8, 5, false); break;
-    }
-#undef FSUB
-#undef FPPT
-#undef FWQ
+           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->fnz.p);
+    return 0;
   }
+  if (!fused) TRY(enq_qtab(ctx));
+#define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->rev_start.p, \
+                       ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p)
+  if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 6) FSUB(true, 6); else FSUB(true, 4); }
+  else if (ctx->force_minb >= 8) FSUB(false, 8);
+  else if (ctx->force_minb >= 6) FSUB(false, 6);
+  else FSUB(false, 4);
+#undef FSUB
   return 0;
 }
 
@@ -476,12 +431,12 @@ static OvRp ov_replay(const dml_ctx *ctx) {
 }
 static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false, bool defer_apply = false) {
   int n = ctx->n;
-  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  TRY(enq_materialize_rows(ctx));
   if (!fused) TRY(enq_qtab(ctx));
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
-    A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.qmin = ctx->qmin.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.ov_head = ctx->ov_head.p; A.ov_next = ctx->ov_next.p; A.uid = ctx->uid.p;
     A.rp_uovl = ov_replay(ctx); A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
     A.n = n; A.guard_pass = ctx->ov_guard_pass;
@@ -491,7 +446,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
   }
   if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
-         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
+         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n, ctx->qmin.p);
   const OvRp uovl = ov_replay(ctx);
   if (ctx->cfg.prob >= 1.0) {
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
@@ -604,7 +559,7 @@ static int enq_step(dml_ctx *ctx) {
   if (ctx->cfg.integrador) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
     if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
-      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n);
+      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n, ctx->fnz.p);
   } else TRY(enq_integrate(ctx, false));
   const bool fz = tu_can_fuse(ctx) && ov_is_multi_launch(ctx);   // k_ov_init rides on the first test_update, k_ov_apply on the second
   TRY(enq_test_update(ctx, fz ? 1 : 0, false));
@@ -680,21 +635,13 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
-  ctx->lazy_rows = !cfg->integrador && cfg->reservoir != 3 && !getenv("DML_EAGER_ROWS");
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
-  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 11) ctx->force_minb = v; }
+  if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 8) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
   if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
-  if (const char *e = getenv("DML_ROWS_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->rows_lanes = v; }
-  if (const char *e = getenv("DML_FORCE_LEAN")) ctx->force_lean = atoi(e) != 0;
-  if (const char *e = getenv("DML_FORCE_WQ")) ctx->force_wq = atoi(e) != 0;
-  if (const char *e = getenv("DML_FORCE_BATCH")) ctx->force_batch = atoi(e) != 0;
-  if (const char *e = getenv("DML_FORCE_PF")) ctx->force_pf = atoi(e) & 31;
-  if (const char *e = getenv("DML_FORCE_PPT")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ctx->force_ppt = v; }
-  if (const char *e = getenv("DML_FORCE_LANES")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) ctx->force_lanes = v; if (v != 1) ctx->fuse_ermak_b = false; }
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
@@ -708,6 +655,9 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
   CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
+  CKC(ctx->qmin.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->qmin.p, 0, cap, ctx->st));      // 0 = never skip the row
+  CKC(ctx->fnz.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->fnz.p, 0, cap, ctx->st));
+  CKC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM));
   CKC(ctx->lay.ensure(3 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0xff, 3 * LAY_MAX * sizeof(unsigned int), ctx->st));   // 2 displacement tables + the skip tables (k_qtab)
   CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
   CKC(ctx->rev_start.ensure(cap + 1, ctx->st)); CKC(ctx->rev_len.ensure(cap, ctx->st)); CKC(ctx->rev_cnt.ensure(cap, ctx->st));
@@ -729,7 +679,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_overlap_coop, TPB, 0);
-    ctx->coop_grid_tu = nsm * b1; ctx->coop_grid_ov = nsm * b2;
+    ctx->coop_grid_tu = nsm * std::min(b1, 4); ctx->coop_grid_ov = nsm * b2;   // a larger grid only makes the grid-wide barriers slower
     { int b3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_rev_coop, TPB, 0); ctx->coop_grid_rev = getenv("DML_NO_REV_COOP") ? 0 : nsm * std::min(b3, 4); }
     if (const char *e = getenv("DML_COOP_TU_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b1) ctx->coop_grid_tu = nsm * v; }   // blocks per SM of k_test_update_coop
     if (const char *e = getenv("DML_COOP_OV_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b2) ctx->coop_grid_ov = nsm * v; }
@@ -766,13 +716,12 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
   ctx->mig_ri.release(); ctx->cnt_own.release(); ctx->cnt_all.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
   ctx->top2_own.release(); ctx->top2_all.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->sorted_cell.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->qmin.release(); ctx->fnz.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
   ctx->obs_part.release(); ctx->obs_out.release(); ctx->obs_counts.release(); ctx->gr_cell_of.release(); ctx->gr_cnt.release(); ctx->gr_start.release();
   ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
-  ctx->wl.release(); if (ctx->wl_count) cudaFree(ctx->wl_count);
   ctx->snap_uid.release(); ctx->snap_mb.release(); ctx->mc_out.release(); ctx->mc_count.release();
   ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_qstart.release(); ctx->ov_draws.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
@@ -902,7 +851,7 @@ int dml_get_counters(dml_ctx *ctx, dml_counters *c) { ENTER(ctx);
   TRY(pull_scal(ctx));
   memset(c, 0, sizeof *c);
   if (ctx->hsc->listed) {
-    if (ctx->lazy_rows) { TRY(enq_materialize_rows(ctx)); }
+    TRY(enq_materialize_rows(ctx));
     CKC(cudaMemsetAsync(&ctx->sc->list_entries, 0, sizeof(long long), ctx->st));
     LAUNCH(K_MISC, k_sum_rowlen, 64, TPB, ctx->rh.p, ctx->n, &ctx->sc->list_entries);
     TRY(pull_scal(ctx));
@@ -931,7 +880,7 @@ int dml_fuerza(dml_ctx *ctx) { ENTER(ctx);
 }
 int dml_ermak_a(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, true)); return finish(ctx); }
 int dml_ermak_b(dml_ctx *ctx) { ENTER(ctx);
-  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
+  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
   return finish(ctx);
 }
 int dml_cbrownian_hs(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, false)); return finish(ctx); }
@@ -976,7 +925,7 @@ int dml_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) { ENTER(ctx);
   if (!ctx->binned) FAIL("dml_get_cells: call dml_test_update first");
   if (!ctx->tessellated) FAIL("dml_get_cells: the box has no cell lists (fewer than 4 cells on every axis, Cells.F90:231)");
-  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  TRY(enq_materialize_rows(ctx));
   TRY(enq_sort_cells(ctx, 1));
   CKC(cudaMemsetAsync(ctx->chain_pos.p, 0xff, (size_t)ctx->cap * sizeof(int), ctx->st));
   LAUNCH(K_MISC, k_chain_pos, nblk(ctx->nct, 128), 128, ctx->cell_start.p, ctx->sorted_slot.p, ctx->chain_pos.p, ctx->nct);
@@ -993,7 +942,7 @@ int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos
 }
 
 int dml_get_neighbors(dml_ctx *ctx, int32_t n, int32_t width, int32_t *nn, int32_t *rows) { ENTER(ctx);
-  if (ctx->lazy_rows) TRY(enq_materialize_rows(ctx));
+  TRY(enq_materialize_rows(ctx));
   TRY(pull_scal(ctx));
   if (!ctx->hsc->listed) FAIL("no neighbour list");
   std::vector<RowHead> rh(n);
@@ -1025,6 +974,7 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   std::vector<int> cols(off, -1);
   for (int i = 0; i < n; ++i) for (int m = 0; m < nn[i]; ++m) cols[(size_t)rh[i].start + m] = rows[(size_t)i * width + m];
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));   // caller's rows carry no build distances: never skip
+  CKC(cudaMemsetAsync(ctx->qmin.p, 0, ctx->qmin.cap, ctx->st));
   CKC(cudaMemcpyAsync(ctx->rh.p, rh.data(), ctx->n * sizeof(RowHead), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));
@@ -1277,7 +1227,7 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
     TRY(slab_exchange(ctx, false, true));                 // ghosts at their new positions; their moves enter the skip bound
     TRY(enq_fuerza(ctx, true));
     if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
-      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n);
+      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
     TRY(slab_test_update(ctx));
     TRY(enq_overlap(ctx, true));
     TRY(slab_exchange(ctx, false, true));

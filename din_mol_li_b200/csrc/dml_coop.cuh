@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     if (!need) sc->lay_cur = lay_old ^ 1;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = A.lazy ? 1 : 0; sc->cols_used = sc->cols_tail0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
   }
   if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
     if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }
@@ -150,14 +150,11 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     for (int i = gt; i < nsorted; i += gsz)
       d_cell_rank(A.posm, A.slot_b, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, i);
   }
-  if (!need || A.lazy) return;
-  grid.sync();
-  // phase 3: rows in one pass — update() + ngroup_cells, Neighbor.F90:608-633,465-548
-  d_rows(A.sorted_posm, A.sorted_posf, A.sorted_slot, A.sorted_cell, A.cell_start, A.rh, A.cols, A.bq, sc, A.g, A.nct, A.slack);
+  // the rows themselves (ngroup_cells, Neighbor.F90:465-548) are built from this snapshot by k_rows when a consumer first needs them
 }
 
 struct OVArgs {
-  double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
+  double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned char *qmin; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
       *members, *roots, *ov_head, *ov_next; const int *uid; OvRp rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass;
 };
 
@@ -166,7 +163,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
   p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.ov_head, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
+  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n, A.qmin);
   grid.sync();
   p_ov_link(A.parent, A.ovst, A.ov_head, A.ov_next, A.roots, A.sc, A.n);
   grid.sync();
@@ -181,7 +178,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
 // here an idle call is one launch whose blocks return on the guard, which nobody rewrites before the last phase.
 struct RevArgs {
   const RowHead *rh; const int *cols; const double4 *posm; int *rev_start, *rev_len, *rev_cnt, *rev_cols;
-  const unsigned char *bq; unsigned char *rev_bq; const unsigned char *halo_of; int halo_only; int *sums; DevScal *sc; int n;
+  const unsigned char *bq; unsigned char *rev_bq; const unsigned char *halo_of; int halo_only; int *sums; DevScal *sc; int n; unsigned char *qmin;
 };
 __global__ void __launch_bounds__(TPB) k_rev_coop(RevArgs A) {
   REV_GUARD(A.sc);
@@ -190,7 +187,7 @@ __global__ void __launch_bounds__(TPB) k_rev_coop(RevArgs A) {
   grid.sync();
   coop_scan<true>(grid, A.rev_cnt, A.rev_start, A.n, A.sums, &A.sc->rev_used);
   grid.sync();
-  p_rev_fill(A.rh, A.cols, A.posm, A.rev_start, A.rev_len, A.rev_cols, A.bq, A.rev_bq, A.halo_of, A.halo_only, A.sc, A.n);
+  p_rev_fill(A.rh, A.cols, A.posm, A.rev_start, A.rev_len, A.rev_cols, A.bq, A.rev_bq, A.halo_of, A.halo_only, A.sc, A.n, A.qmin);
   if (blockIdx.x == 0 && threadIdx.x == 0) A.sc->rev_valid = 1;   // every block read the guard before the first grid.sync
 }
 

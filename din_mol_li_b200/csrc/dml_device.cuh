@@ -66,6 +66,20 @@ __device__ __forceinline__ int rh_byte(const uint4 &h, int jj) {
   return (int)((w >> (8 * (jj & 3))) & 255u);
 }
 
+// smallest byte of a 16-byte head restricted to its first len entries (255 for an empty row): the row's nearest build distance
+__device__ __forceinline__ int head_min(const uint4 &h, int len) {
+  const unsigned int w[4] = {h.x, h.y, h.z, h.w};
+  unsigned int m = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = len - 4 * i;                                          // valid bytes of this word
+    const unsigned int fill = k >= 4 ? 0u : (k <= 0 ? 0xffffffffu : (0xffffffffu << (8 * k)));
+    m = __vminu4(m, w[i] | fill);
+  }
+  m = __vminu4(m, m >> 16); m = __vminu4(m, m >> 8);
+  return (int)(m & 255u);
+}
+
 // ---- device-resident scalars (one struct in global memory; the host mirrors it on demand) --------------
 struct DevScal {
   double z0, z1, zmax, rho, rho0;
@@ -175,13 +189,25 @@ struct Philox {
     uint64_t b = ((uint64_t)c[2 * i] << 32) | c[2 * i + 1];
     return ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
   }
-  // two independent standard normals (Box–Muller, fp64; a single-precision log/sincos variant was measured: the integrator
-  // kernel is bound by its memory streams, not by these instructions, so there was nothing to gain)
+  // two independent standard normals in fp64 (gcmc_run's velocity draw: three per accepted insertion)
   __device__ __forceinline__ void gauss2(double &g0, double &g1) const {
     double u = u01(0), v = u01(1);
     double r = sqrt(-2.0 * log(u));
     double s, c_; sincospi(2.0 * v, &s, &c_);
     g0 = r * c_; g1 = r * s;
+  }
+  // Four independent standard normals from the four 32-bit words (Box-Muller in single precision, results widened to fp64).
+  // The reference's own gasdev works at this resolution (its radius, logarithm and factor are real(sp): logf and a float sqrt,
+  // dana.F90:1406-1428).  The fp64 form (log + sincospi in double, one Philox block per pair) made the Ermak half-step
+  // instruction-bound: 33 M warp instructions per million particles, 69 us where its 164 bytes per particle stream in ~30 us.
+  __device__ __forceinline__ void gauss4f(double &g0, double &g1, double &g2, double &g3) const {
+    const float k = 2.3283064365386963e-10f;                 // 2^-32
+    const float u0 = __fmaf_rn(__uint2float_rz(c[0]), k, 1.1641532182693481e-10f), v0 = __uint2float_rz(c[1]) * k;   // u in (0,1], v in [0,1)
+    const float u1 = __fmaf_rn(__uint2float_rz(c[2]), k, 1.1641532182693481e-10f), v1 = __uint2float_rz(c[3]) * k;
+    const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u1));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * v0, &s0, &c0); sincospif(2.0f * v1, &s1, &c1);
+    g0 = (double)(r0 * c0); g1 = (double)(r0 * s0); g2 = (double)(r1 * c1); g3 = (double)(r1 * s1);
   }
 };
 

@@ -13,10 +13,10 @@
 namespace dml {
 
 struct GcmcArgs {
-  double4 *posm; double4 *fe; double *vel, *acel, *pos_old, *old_cg;
+  double4 *posm; double4 *fe; unsigned char *fnz; double *vel, *acel, *pos_old, *old_cg;
   int *uid, *slot_b, *b_occ;
   const int *cell_of_unused; const int *cell_start; const int *sorted_slot; const double4 *sorted_posm;
-  RowHead *rh; int *cols; unsigned char *bq; int cols_cap;
+  RowHead *rh; int *cols; unsigned char *bq; unsigned char *qmin; int cols_cap;
   int *gorder, *gpos, *gcc; int gorder_cap;
   int *pend;                       // slots inserted during this call, in insertion order
   const double *rp_u, *rp_g; int rp_nu, rp_ng;
@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
             A.old_cg[3 * ns + k] = 1e8;
           }
           st_rec(&A.fe[ns], ld_rec(&A.fe[tmpl]));             // force and epot of the template (atom_asign)
+          A.fnz[ns] = 1;
           A.pos_old[3 * ns] = rx; A.pos_old[3 * ns + 1] = ry; A.pos_old[3 * ns + 2] = rz;
           for (int k = 0; k < 3; ++k) A.vel[3 * last + k] = beta * rng.gauss();
           double4 pn = {rx, ry, rz, meta_as_double(with_disp((long long)zt | MF_REF | MF_GCMC, DISP_INF))};
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
                   if (len < h->cap) {
                     A.cols[h->start + len] = ns; h->len = len + 1;
                     if (len < 16) h->bq[len] = 0; else A.bq[h->start + len] = 0;   // appended entries carry no build distance: never skipped
+                    A.qmin[s] = 0;
                   }
                   else { atomicAdd((unsigned long long *)&sc->row_overflow, 1ull); atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
                 }
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           __syncwarp();
           if (lane == 0) {
             rh_store(&A.rh[ns], make_uint4(0, 0, 0, 0), base, total, total + A.row_slack);   // zero build distances: nothing is ever skipped
+            A.qmin[ns] = 0;
             sc->cols_used = base + total + A.row_slack;
           }
         } else if (tid == 0) A.rh[ns].len = 0;
@@ -415,14 +418,15 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   CKC(ctx->gpend.ensure((size_t)nadj + 8, ctx->st));
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && ctx->rp_nu == 0 && nadj > 0) FAIL("replay mode: call dml_set_replay_gcmc before gcmc_run");
   GcmcArgs A;
-  A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.fe = ctx->fe.p;
+  A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.fe = ctx->fe.p; A.fnz = ctx->fnz.p;
   A.pos_old = ctx->pos_old.p; A.old_cg = ctx->old_cg.p; A.uid = ctx->uid.p; A.slot_b = ctx->slot_b.p; A.b_occ = ctx->b_occ.p;
   A.cell_of_unused = nullptr; A.cell_start = ctx->cell_start.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
-  A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.cols_cap = (int)ctx->cols.cap;
+  A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.qmin = ctx->qmin.p; A.cols_cap = (int)ctx->cols.cap;
   A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;
   A.nadj = nadj; A.cap = ctx->cap; A.listed = 1; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
+  TRY(enq_materialize_rows(ctx));                       // the incremental list upkeep of an accepted attempt edits the rows in place
   LAUNCH(K_GCMC, k_gcmc_census, 148 * 4, 256, ctx->posm.p, ctx->gorder.p, ctx->gcc.p, ctx->sc);
   LAUNCH(K_GCMC, k_gcmc, 1, GB, A);
   ctx->n = std::min(ctx->cap, ctx->n + nadj);          // upper bound of hs%amax until the next read-back (empty slots are skipped)

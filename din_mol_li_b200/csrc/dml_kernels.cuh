@@ -467,7 +467,7 @@ __device__ __forceinline__ int nab_of(int dx, int dy, int dz) {
 // dependent instructions per row: measured 326 us instead of 163 us of test_update per step on the 1 M box with the CG slab.
 __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                                const int *__restrict__ sorted_slot, const int *__restrict__ sorted_cell,
-                                               const int *__restrict__ cell_start, RowHead *__restrict__ rh,
+                                               const int *__restrict__ cell_start, RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
                                                int *__restrict__ cols, unsigned char *__restrict__ bq,
                                                DevScal *__restrict__ sc, const Geo &g, int slack, int t) {
   const unsigned int full = 0xffffffffu;
@@ -504,7 +504,7 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
       if (lane == 0) tb = atomicAdd(&sc->cols_used, need);
       tb = __shfl_sync(full, tb, 0);
       if (tb + need > sc->cols_cap) {
-        if (lane == 0) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); }
+        if (lane == 0) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); qmin[s] = 0; }
         return;
       }
     }
@@ -520,7 +520,7 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
   }
   __syncwarp();
   // settle: the reference's exact test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515), ordered compaction in place
-  int cnt = 0;
+  int cnt = 0, qm = 255;
   uint4 hb = make_uint4(0, 0, 0, 0);
   for (int i0 = 0; i0 < npark; i0 += 32) {
     const int i = i0 + lane;
@@ -536,6 +536,7 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
     if (hit) {
       const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
       cols[tb + pos] = slot;
+      qm = min(qm, (int)qb);
       if (pos < 16) {
         const unsigned int sh = qb << (8 * (pos & 3));
         if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else { if (pos < 12) hb.z |= sh; else hb.w |= sh; }
@@ -548,324 +549,8 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
     hb.x |= __shfl_xor_sync(full, hb.x, o); hb.y |= __shfl_xor_sync(full, hb.y, o);
     hb.z |= __shfl_xor_sync(full, hb.z, o); hb.w |= __shfl_xor_sync(full, hb.w, o);
   }
-  if (lane == 0) rh_store(&rh[s], hb, tb, cnt, npark + slack);
-}
-
-// One thread per cell-sorted ref particle.
-//  fast path (every axis has >= 3 cells): ncu on the 27-cell walk showed 53 % of the kernel's instructions in the "next stencil
-//    cell" step, executed 105 times per warp with 8 lanes active.  The three x-neighbours of a stencil row are contiguous in the
-//    cell-sorted arrays, so the walk visits 9 segments (plus the periodic wrap cell at the box edge) instead of 27 cells, in
-//    single precision, parking candidates below the upper edge of the fp32 error band in shared memory.  The parked ones get
-//    the reference's exact fp64 test and are inserted by key = (stencil position, sorted index) — the reference's row order
-//    (stencil order x chain order, Neighbor.F90:497-540) — into the at most ROW_W entries of the row.
-//  long rows (next to dense metal; more than ROW_W parked) and boxes with fewer than 3 cells on an axis (where the reference
-//    visits a cell twice) take the ordered 27-cell walk, the former into a segment of the tail region.
-constexpr int KEY_SHIFT = 26, KEY_MASK = (1 << KEY_SHIFT) - 1;
-// build-distance bytes of the row being settled live in the thread's own words of the segment table (free once the walk is over)
-#define SQB(i) (reinterpret_cast<unsigned char *>(&s_seg[(i) >> 2][tid])[(i) & 3])
-template <int L>
-__device__ __forceinline__ void d_rows_ml(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
-                                          const int *__restrict__ sorted_slot,
-                                          const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                          RowHead *__restrict__ rh,
-                                          int *__restrict__ cols, unsigned char *__restrict__ bq,
-                                          DevScal *__restrict__ sc, const Geo &g, int ncell, int slack,
-                                          int (*s_key)[TPB], int (*s_seg)[TPB]);
-__device__ __forceinline__ void d_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
-                                       const int *__restrict__ sorted_slot,
-                                       const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                       RowHead *__restrict__ rh,
-                                       int *__restrict__ cols, unsigned char *__restrict__ bq,
-                                       DevScal *__restrict__ sc, const Geo &g, int ncell, int slack) {
-  __shared__ int s_key[ROW_W][TPB];
-  __shared__ int s_seg[18][TPB];
-  const int tid = threadIdx.x;
-  if (g.rows_fast == 2) { d_rows_ml<2>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack, s_key, s_seg); return; }
-  if (g.rows_fast == 4) { d_rows_ml<4>(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack, s_key, s_seg); return; }
-  const int nsorted = cell_start[ncell];              // number of binned particles
-  const int gsz = gridDim.x * blockDim.x;
-  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
-  const float rc2hi = (float)g.rc_list2 + g.band2;
-  const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;     // below this the fp32 distance is inside the list radius for sure
-  const float bqs = __double2float_rd(g.bq_scale * 0.999999);
-  __shared__ int s_long[TPB];
-  __shared__ int s_nlong;
-  for (int tbase = blockIdx.x * blockDim.x; tbase < nsorted; tbase += gsz) {   // block-uniform trip count: the long rows of a trip are built by whole warps below
-    if (tid == 0) s_nlong = 0;
-    __syncthreads();
-    const int t = tbase + tid;
-    if (t < nsorted) {
-    const double4 p = ld_rec_nc(&sorted_posm[t]);
-    const int s = sorted_slot[t];
-    if (!(meta_of(p) & MF_REF)) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0);   // rows exist only for ref atoms
-    else {
-    const int lin = sorted_cell[t];
-    const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-    int npark = 0;
-    bool done = false;
-    if (g.rows_fast) {
-      const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
-      // cell_pbc wraps the centre like any other cell (a particle binned in a halo cell looks around the wrapped cell)
-      const int ecx = (cx - 1 < 0 ? cx - 1 + g.nc[0] : (cx - 1 >= g.nc[0] ? cx - 1 - g.nc[0] : cx - 1)) + 1;
-      const int ecy = (cy - 1 < 0 ? cy - 1 + g.nc[1] : (cy - 1 >= g.nc[1] ? cy - 1 - g.nc[1] : cy - 1)) + 1;
-      const int ecz = (cz - 1 < 0 ? cz - 1 + g.nc[2] : (cz - 1 >= g.nc[2] ? cz - 1 - g.nc[2] : cz - 1)) + 1;
-      const bool edge = ecx == 1 || ecx == g.nc[0];
-      const int xa = max(ecx - 1, 1), xb = min(ecx + 1, g.nc[0]), xw = ecx == 1 ? g.nc[0] : 1;
-      int rowy[3], rowz[3];                               // wrapped neighbour rows, as offsets into cell_start
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        int ny = ecy - 2 + d, nz = ecz - 2 + d;
-        ny = (ny < 0 ? ny + g.nc[1] : (ny >= g.nc[1] ? ny - g.nc[1] : ny)) + 1;
-        nz = (nz < 0 ? nz + g.nc[2] : (nz >= g.nc[2] ? nz - g.nc[2] : nz)) + 1;
-        rowy[d] = g.hd[0] * ny; rowz[d] = g.hd[0] * g.hd[1] * nz;
-      }
-      const float bxf = g.pbc[0] ? (float)g.box[0] : 0.0f, byf = g.pbc[1] ? (float)g.box[1] : 0.0f;
-      const float sy0 = ecy - 2 < 0 ? -byf : 0.0f, sy2 = ecy >= g.nc[1] ? byf : 0.0f;
-      for (int round = 0; round < (edge ? 2 : 1); ++round) {   // round 1: the periodic wrap cell of a particle at the box edge
-        // the nine segment ranges are requested together (18 loads in flight) and kept in shared memory: the walk below then
-        // advances with two shared-memory reads instead of recomputing a wrapped cell index
-        const int x0 = round ? xw : xa, x1 = (round ? xw : xb) + 1;
-#pragma unroll
-        for (int idx = 0; idx < 9; ++idx) {
-          const int row = rowy[idx % 3] + rowz[idx / 3];
-          s_seg[2 * idx][tid] = __ldg(&cell_start[row + x0]); s_seg[2 * idx + 1][tid] = __ldg(&cell_start[row + x1]);
-        }
-        // minimum image without branches: all candidates of a segment sit in the same periodic image relative to the particle
-        // (the x-neighbours of round 0 are inside the box, the wrap cell of round 1 one box length away; a stencil row that
-        // wrapped in y is one box length away in y), so the shift is a per-segment constant.  It is the operation the branchy
-        // form applies whenever the pair can be inside the list radius (cells are at least one list radius wide).
-        const float sx = round ? (ecx == 1 ? -bxf : bxf) : 0.0f;
-        int seg = 0, u = s_seg[0][tid], e = s_seg[1][tid];
-        float sy = sy0;                                     // segments 0,3,6 look at row ecy-1, 1,4,7 at ecy, 2,5,8 at ecy+1
-        for (;;) {
-          while (u == e) {
-            if (++seg == 9) break;
-            u = s_seg[2 * seg][tid]; e = s_seg[2 * seg + 1][tid];
-            const int dy = seg - 3 * (seg / 3);
-            sy = dy == 0 ? sy0 : (dy == 1 ? 0.0f : sy2);
-          }
-          if (seg == 9) break;
-          if (u != t) {
-            const float4 q = __ldg(&sorted_posf[u]);
-            const float vx = (q.x - pxf) + sx, vy = (q.y - pyf) + sy, vz = q.z - pzf;
-            const float d2 = vx * vx + vy * vy + vz * vz;
-            if (d2 <= rc2hi) {
-              // parked word: sorted index | segment << 26 | round << 30 | "inside the list radius for sure" << 31
-              if (npark < ROW_W) s_key[npark][tid] = u | (seg << KEY_SHIFT) | (round << 30) | (d2 < rc2lo ? (int)0x80000000 : 0);
-              ++npark;
-            }
-          }
-          ++u;
-        }
-      }
-      if (npark + slack <= ROW_W) {
-        // ---- settle: exact test only inside the fp32 error band, key, insertion in row order ----
-        int cnt = 0;
-        for (int i = 0; i < npark; ++i) {
-          const int wd = s_key[i][tid];
-          const int uq = wd & KEY_MASK, sg = (wd >> KEY_SHIFT) & 15;
-          const float4 q = __ldg(&sorted_posf[uq]);
-          float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
-          if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
-          if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
-          const float d2 = vx * vx + vy * vy + vz * vz;
-          bool hit = wd < 0;
-          if (!hit) {                                      // the reference's test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515)
-            const double4 qd = ld_rec_nc(&sorted_posm[uq]);
-            hit = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z) < g.rc_list2;
-          }
-          if (hit) {
-            const int dzs = sg / 3, dys = sg - 3 * dzs;    // 0..2
-            int ddx;
-            if (wd & (1 << 30)) ddx = ecx == 1 ? -1 : 1;
-            else {
-              const int row = rowy[0] * (dys == 0) + rowy[1] * (dys == 1) + rowy[2] * (dys == 2) + rowz[0] * (dzs == 0) + rowz[1] * (dzs == 1) + rowz[2] * (dzs == 2);
-              ddx = uq >= __ldg(&cell_start[row + ecx + 1]) ? 1 : (uq >= __ldg(&cell_start[row + ecx]) ? 0 : -1);
-            }
-            const int key = (nab_of(ddx, dys - 1, dzs - 1) << KEY_SHIFT) | uq;
-            // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
-            const unsigned char qb = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
-            int j = cnt;
-            while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; SQB(j) = SQB(j - 1); --j; }
-            s_key[j][tid] = key; SQB(j) = qb; ++cnt;
-          }
-        }
-        const int dst = s * ROW_W;
-        uint4 hb = make_uint4(0, 0, 0, 0);
-        for (int i = 0; i < cnt; ++i) {
-          cols[dst + i] = sorted_slot[s_key[i][tid] & KEY_MASK];
-          const unsigned int sh = (unsigned int)SQB(i) << (8 * (i & 3));
-          if (i < 8) { if (i < 4) hb.x |= sh; else hb.y |= sh; } else if (i < 16) { if (i < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + i] = SQB(i);
-        }
-        for (int i = cnt; i < ((cnt + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
-        rh_store(&rh[s], hb, dst, cnt, ROW_W);              // one full-sector store per row
-        done = true;
-      }
-    } else {
-      const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, s * ROW_W, ROW_W, true);
-      npark = o.npark;
-      if (npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); done = true; }
-    }
-    if (!done) s_long[atomicAdd(&s_nlong, 1)] = t;        // long row (next to dense metal): built by a warp, see rows_long_warp
-    }
-    }
-    __syncthreads();
-    const int nlong = s_nlong;
-    for (int i = tid >> 5; i < nlong; i += TPB / 32)
-      rows_long_warp(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, slack, s_long[i]);
-    __syncthreads();
-  }
-}
-// L lanes per particle (L = 2 or 4, all in one warp): a 100 k box gives one thread per particle only 5 warps per scheduler and the
-// kernel is a chain of dependent L1/L2 round trips, so the nine (or eighteen) segments of a particle are dealt out to L lanes.
-// Every lane walks and settles its own segments into its own shared-memory column exactly like the single-lane path; the row
-// position of a hit is its position in the lane's sorted column plus the number of smaller keys in the other lanes' columns.
-template <int L>
-__device__ __forceinline__ void d_rows_ml(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
-                                          const int *__restrict__ sorted_slot,
-                                          const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                          RowHead *__restrict__ rh,
-                                          int *__restrict__ cols, unsigned char *__restrict__ bq,
-                                          DevScal *__restrict__ sc, const Geo &g, int ncell, int slack,
-                                          int (*s_key)[TPB], int (*s_seg)[TPB]) {
-  const int tid = threadIdx.x, lane = tid & 31, sub = tid & (L - 1);
-  const unsigned int gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (lane & ~(L - 1));
-  const int nsorted = cell_start[ncell];
-  const int gsz = (gridDim.x * blockDim.x) / L;
-  const float hbx = g.pbc[0] ? 0.5f * (float)g.box[0] : 3.0e38f, hby = g.pbc[1] ? 0.5f * (float)g.box[1] : 3.0e38f;
-  const float rc2hi = (float)g.rc_list2 + g.band2;
-  const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;
-  const float bqs = __double2float_rd(g.bq_scale * 0.999999);
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / L; t < nsorted; t += gsz) {
-    const double4 p = ld_rec_nc(&sorted_posm[t]);
-    const int s = sorted_slot[t];
-    if (!(meta_of(p) & MF_REF)) { if (sub == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }
-    const int lin = sorted_cell[t];
-    const int cx = lin % g.hd[0], r = lin / g.hd[0], cy = r % g.hd[1], cz = r / g.hd[1];
-    const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
-    const int ecx = (cx - 1 < 0 ? cx - 1 + g.nc[0] : (cx - 1 >= g.nc[0] ? cx - 1 - g.nc[0] : cx - 1)) + 1;
-    const int ecy = (cy - 1 < 0 ? cy - 1 + g.nc[1] : (cy - 1 >= g.nc[1] ? cy - 1 - g.nc[1] : cy - 1)) + 1;
-    const int ecz = (cz - 1 < 0 ? cz - 1 + g.nc[2] : (cz - 1 >= g.nc[2] ? cz - 1 - g.nc[2] : cz - 1)) + 1;
-    const bool edge = ecx == 1 || ecx == g.nc[0];
-    const int xa = max(ecx - 1, 1), xb = min(ecx + 1, g.nc[0]), xw = ecx == 1 ? g.nc[0] : 1;
-    int ry0, ry1, ry2, rz0, rz1, rz2;
-    {
-      int a = ecy - 2, b = ecy - 1, c = ecy, d = ecz - 2, e = ecz - 1, f = ecz;
-      a = (a < 0 ? a + g.nc[1] : a) + 1; b += 1; c = (c >= g.nc[1] ? c - g.nc[1] : c) + 1;
-      d = (d < 0 ? d + g.nc[2] : d) + 1; e += 1; f = (f >= g.nc[2] ? f - g.nc[2] : f) + 1;
-      ry0 = g.hd[0] * a; ry1 = g.hd[0] * b; ry2 = g.hd[0] * c;
-      const int hz = g.hd[0] * g.hd[1];
-      rz0 = hz * d; rz1 = hz * e; rz2 = hz * f;
-    }
-    // own segments: v = sub, sub+L, ... over the 9 (edge: 18) virtual segments; v >= 9 is the wrap cell of stencil row v-9
-    const int nv = edge ? 18 : 9;
-    int nown = 0;
-    for (int v = sub; v < nv; v += L, ++nown) {
-      const int rnd = v >= 9 ? 1 : 0, idx = v - 9 * rnd, dz = idx / 3, dy = idx - 3 * dz;
-      const int row = (dy == 0 ? ry0 : (dy == 1 ? ry1 : ry2)) + (dz == 0 ? rz0 : (dz == 1 ? rz1 : rz2));
-      s_seg[2 * nown][tid] = __ldg(&cell_start[row + (rnd ? xw : xa)]);
-      s_seg[2 * nown + 1][tid] = __ldg(&cell_start[row + (rnd ? xw : xb) + 1]);
-    }
-    int npark = 0;
-    if (nown > 0) {
-      int j = 0, u = s_seg[0][tid], e = s_seg[1][tid];
-      for (;;) {
-        while (u == e) { if (++j == nown) break; u = s_seg[2 * j][tid]; e = s_seg[2 * j + 1][tid]; }
-        if (j == nown) break;
-        if (u != t) {
-          const float4 q = __ldg(&sorted_posf[u]);
-          float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
-          if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
-          if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
-          const float d2 = vx * vx + vy * vy + vz * vz;
-          if (d2 <= rc2hi) {
-            const int v = sub + j * L, rnd = v >= 9 ? 1 : 0;
-            if (npark < ROW_W) s_key[npark][tid] = u | ((v - 9 * rnd) << KEY_SHIFT) | (rnd << 30) | (d2 < rc2lo ? (int)0x80000000 : 0);
-            ++npark;
-          }
-        }
-        ++u;
-      }
-    }
-    int ntot = npark;
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) ntot += __shfl_xor_sync(gmask, ntot, o);
-    if (ntot + slack <= ROW_W) {
-      // ---- settle own column ----
-      int cnt = 0;
-      for (int i = 0; i < npark; ++i) {
-        const int wd = s_key[i][tid];
-        const int uq = wd & KEY_MASK, sg = (wd >> KEY_SHIFT) & 15;
-        const float4 q = __ldg(&sorted_posf[uq]);
-        float vx = q.x - pxf, vy = q.y - pyf, vz = q.z - pzf;
-        if (vx > hbx) vx -= 2.0f * hbx; else if (vx < -hbx) vx += 2.0f * hbx;
-        if (vy > hby) vy -= 2.0f * hby; else if (vy < -hby) vy += 2.0f * hby;
-        const float d2 = vx * vx + vy * vy + vz * vz;
-        bool hit = wd < 0;
-        if (!hit) {
-          const double4 qd = ld_rec_nc(&sorted_posm[uq]);
-          hit = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z) < g.rc_list2;
-        }
-        if (hit) {
-          const int dzs = sg / 3, dys = sg - 3 * dzs;
-          int ddx;
-          if (wd & (1 << 30)) ddx = ecx == 1 ? -1 : 1;
-          else {
-            const int row = (dys == 0 ? ry0 : (dys == 1 ? ry1 : ry2)) + (dzs == 0 ? rz0 : (dzs == 1 ? rz1 : rz2));
-            ddx = uq >= __ldg(&cell_start[row + ecx + 1]) ? 1 : (uq >= __ldg(&cell_start[row + ecx]) ? 0 : -1);
-          }
-          const int key = (nab_of(ddx, dys - 1, dzs - 1) << KEY_SHIFT) | uq;
-          const unsigned char qb = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
-          int j = cnt;
-          while (j > 0 && s_key[j - 1][tid] > key) { s_key[j][tid] = s_key[j - 1][tid]; SQB(j) = SQB(j - 1); --j; }
-          s_key[j][tid] = key; SQB(j) = qb; ++cnt;
-        }
-      }
-      __syncwarp(gmask);
-      // ---- merge by rank: position = own index + smaller keys in the other lanes' columns ----
-      int cnts[L];
-#pragma unroll
-      for (int o = 0; o < L; ++o) cnts[o] = __shfl_sync(gmask, cnt, (lane & ~(L - 1)) + o);
-      int total = 0;
-#pragma unroll
-      for (int o = 0; o < L; ++o) total += cnts[o];
-      const int dst = s * ROW_W, tbase = tid & ~(L - 1);
-      uint4 hb = make_uint4(0, 0, 0, 0);
-      for (int i = 0; i < cnt; ++i) {
-        const int key = s_key[i][tid];
-        int rank = i;
-#pragma unroll
-        for (int o = 0; o < L; ++o) {
-          if (o == sub) continue;
-          for (int m = 0; m < cnts[o]; ++m) rank += s_key[m][tbase + o] < key ? 1 : 0;
-        }
-        cols[dst + rank] = sorted_slot[key & KEY_MASK];
-        const unsigned int sh = (unsigned int)SQB(i) << (8 * (rank & 3));
-        if (rank < 8) { if (rank < 4) hb.x |= sh; else hb.y |= sh; } else if (rank < 16) { if (rank < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + rank] = SQB(i);
-      }
-#pragma unroll
-      for (int o = 1; o < L; o <<= 1) {
-        hb.x |= __shfl_xor_sync(gmask, hb.x, o); hb.y |= __shfl_xor_sync(gmask, hb.y, o);
-        hb.z |= __shfl_xor_sync(gmask, hb.z, o); hb.w |= __shfl_xor_sync(gmask, hb.w, o);
-      }
-      if (sub == 0) {
-        for (int i = total; i < ((total + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
-        rh_store(&rh[s], hb, dst, total, ROW_W);
-      }
-      __syncwarp(gmask);                                  // the columns are reused by the next particle of the group
-      continue;
-    }
-    // long row: ordered 27-cell walk by the first lane into a segment of the tail region (see d_rows)
-    if (sub == 0) {
-      const int need = ntot + slack;
-      const int tb = atomicAdd(&sc->cols_used, need);
-      if (tb + need > sc->cols_cap) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); }
-      else {
-        const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, tb, need, false);
-        rh_store(&rh[s], o.hb, tb, o.cnt, need);
-      }
-    }
-  }
+  qm = __reduce_min_sync(full, qm);
+  if (lane == 0) { rh_store(&rh[s], hb, tb, cnt, npark + slack); qmin[s] = (unsigned char)qm; }
 }
 
 // ================================================================================================
@@ -894,8 +579,8 @@ __global__ void __launch_bounds__(TPB) k_verlet_prepare(double4 *__restrict__ po
   }
 }
 __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__ posm, const double *__restrict__ pos_old,
-                                                     const int *__restrict__ b2slot, RowHead *__restrict__ rh, int *__restrict__ cols,
-                                                     unsigned char *__restrict__ bq, DevScal *__restrict__ sc, Geo g, int n, int slack) {
+                                                     const int *__restrict__ b2slot, RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
+                                                     int *__restrict__ cols, unsigned char *__restrict__ bq, DevScal *__restrict__ sc, Geo g, int n, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
   const unsigned int full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -904,6 +589,7 @@ __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__
   for (int s = wid; s < n; s += nw) {
     const long long m1 = meta_of(ld_rec_nc(&posm[s]));
     if (!(m1 & MF_TYPE)) continue;
+    if (lane == 0) qmin[s] = 0;                          // O(N^2) rows of a tiny box: no gather skipping
     if (!(m1 & MF_REF)) { if (lane == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
     const double px = pos_old[3 * s], py = pos_old[3 * s + 1], pz = pos_old[3 * s + 2];
     int dst = s * ROW_W, lim = ROW_W, total = 0, cnt = 0;
@@ -957,14 +643,255 @@ __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__
   }
 }
 
-__global__ void __launch_bounds__(TPB) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
-                                              const int *__restrict__ sorted_slot,
-                                              const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                              RowHead *__restrict__ rh,
-                                              int *__restrict__ cols, unsigned char *__restrict__ bq,
-                                              DevScal *__restrict__ sc, Geo g, int ncell, int slack) {
+// ---- asynchronous bulk copies global -> shared (cp.async.bulk, completion on an mbarrier; SASS: UBLKCP / SYNCS) ----------------
+__device__ __forceinline__ unsigned int smem_u32(const void *p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 16-byte aligned source / destination, size a multiple of 16 bytes
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, unsigned int bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+  unsigned int ok = 0;
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ================================================================================================
+// k_rows — ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild, one thread per sorted ref particle,
+// one block per RB consecutive sorted particles.
+//  staging  The RB particles of a block sit in consecutive cells c0..c1 of the (halo-inclusive) linear cell order, so for each of
+//           the nine (dy,dz) stencil rows the cells c0-1+shift .. c1+1+shift hold every candidate of every particle of the block
+//           that does not come through a periodic wrap, and they are ONE contiguous range of the cell-sorted arrays.  The nine
+//           ranges of the single-precision copy (16 B per candidate) are brought into shared memory by nine bulk copies
+//           (cp.async.bulk + mbarrier: the one tile-movement kernel of the path), capped at WCAP candidates each; candidates
+//           outside the staged ranges (periodic wrap cells, ranges beyond the cap next to dense metal) are read from global memory
+//           through the same generic pointer.
+//  walk     per stencil row the x-neighbours cx-1..cx+1 are one contiguous run of candidates (the wrap cell of a particle at the
+//           periodic x edge is a second, short run): nine runs of ~4 candidates instead of 27 cells of ~1.4, each with a warp-uniform
+//           trip count (redux max).  Candidates are screened in fp32 (one load, three subtractions, three fused multiply-adds, one
+//           compare) with a rigorous error band; only the ones inside the band (~0.5 %) get the reference's fp64 test (vdistance,
+//           Groups.F90:995-1016; strict <, Neighbor.F90:515).  The minimum image is a per-run constant folded into the particle's
+//           coordinate: all candidates of a cell sit in the same periodic image relative to the particle, and it is the operation
+//           the branchy form applies whenever the pair can be inside the list radius (cells are at least one list radius wide, at
+//           least three per axis).
+//  order    a hit knows its stencil position nab (Cells.F90:28-36) and its rank among the hits of that cell (cells are scanned in
+//           chain order = ascending sorted index); 27 byte counters per thread in shared memory, one prefix pass in map order, and
+//           every hit lands at prefix[nab] + rank: the reference's row order (stencil order x chain order) without sorting.
+//  rows     written as the slot's own ROW_W entries + one 32-byte RowHead + the qmin byte.  Rows that do not fit (next to dense
+//           metal) are rebuilt by whole warps (rows_long_warp); particles binned in an x/y halo cell and boxes with fewer than 3
+//           cells on an axis (where the reference visits a cell twice) take the ordered walk of one thread (rows_ordered_into).
+//  history  round 1 gathered every candidate through L1/L2 per thread and ordered the hits by key insertion: 57 us at 110 k
+//           particles (24.8 M warp instructions, IPC 0.5); a 27-cell walk in map order over the staged windows needed no ordering
+//           but 21.3 M instructions (69 us: 27 x (two dependent cell_start loads + a loop of ~4.6 trips with 45 % of the lanes idle)).
+// ================================================================================================
+constexpr int RB = 256;          // sorted particles per block
+constexpr int WCAP = 384;        // staged candidates per stencil row
+constexpr size_t ROWS_OFF_HIT = (size_t)9 * WCAP * sizeof(float4);
+constexpr size_t ROWS_OFF_META = ROWS_OFF_HIT + (size_t)ROW_W * RB * sizeof(int);
+constexpr size_t ROWS_OFF_QB = ROWS_OFF_META + (size_t)ROW_W * RB * sizeof(unsigned short);
+constexpr size_t ROWS_OFF_CNT = ROWS_OFF_QB + (size_t)ROW_W * RB;
+constexpr size_t ROWS_OFF_LONG = ROWS_OFF_CNT + (size_t)28 * RB;
+constexpr size_t ROWS_SMEM = ROWS_OFF_LONG + (size_t)RB * sizeof(int);
+
+__device__ __forceinline__ int row_qmin(const uint4 &hb, int cnt, const unsigned char *__restrict__ bq, int dst) {
+  int m = head_min(hb, cnt);
+  for (int i = 16; i < cnt; ++i) m = min(m, (int)bq[dst + i]);
+  return m;
+}
+
+__global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
+                                               const int *__restrict__ sorted_slot,
+                                               const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
+                                               RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
+                                               int *__restrict__ cols, unsigned char *__restrict__ bq,
+                                               DevScal *__restrict__ sc, const __grid_constant__ Geo g, int ncell, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
-  d_rows(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, ncell, slack);
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  float4 *s_win = reinterpret_cast<float4 *>(rows_smem);                                              // [9][WCAP]
+  int (*s_hit)[RB] = reinterpret_cast<int (*)[RB]>(rows_smem + ROWS_OFF_HIT);                         // slot of parked hit i
+  unsigned short (*s_meta)[RB] = reinterpret_cast<unsigned short (*)[RB]>(rows_smem + ROWS_OFF_META);  // nab | rank in its cell << 5
+  unsigned char (*s_qb)[RB] = reinterpret_cast<unsigned char (*)[RB]>(rows_smem + ROWS_OFF_QB);        // build-distance byte
+  unsigned char (*s_cnt)[RB] = reinterpret_cast<unsigned char (*)[RB]>(rows_smem + ROWS_OFF_CNT);      // [27] hits per stencil cell, then their prefix
+  int *s_long = reinterpret_cast<int *>(rows_smem + ROWS_OFF_LONG);
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_wlo[9], s_whi[9];
+  __shared__ int s_nlong;
+  const unsigned int full = 0xffffffffu;
+  const int tid = threadIdx.x;
+  const int nsorted = __ldg(&cell_start[ncell]);        // number of binned particles
+  const int t0 = blockIdx.x * RB;
+  if (t0 < nsorted) {                                   // block-uniform
+    const int tl = min(t0 + RB, nsorted) - 1;
+    if (tid < 9) {
+      int lo = 0, hi = 0;
+      if (g.rows_fast) {
+        const int c0 = __ldg(&sorted_cell[t0]), c1 = __ldg(&sorted_cell[tl]);
+        const int sh = (tid % 3 - 1) * g.hd[0] + (tid / 3 - 1) * g.hd[0] * g.hd[1];
+        const int ca = min(max(c0 - 1 + sh, 0), ncell), cb = min(max(c1 + 2 + sh, 0), ncell);
+        if (ca < cb) { lo = __ldg(&cell_start[ca]); hi = min(__ldg(&cell_start[cb]), lo + WCAP); }
+      }
+      s_wlo[tid] = lo; s_whi[tid] = hi;
+    }
+    if (tid == 0) { s_nlong = 0; mbar_init(&s_bar, 1); }
+    {                                                    // hit counters of the block: 28 * RB bytes
+      unsigned int *z = reinterpret_cast<unsigned int *>(rows_smem + ROWS_OFF_CNT);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) z[i * RB + tid] = 0u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int bytes = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) bytes += (unsigned int)(s_whi[k] - s_wlo[k]) * (unsigned int)sizeof(float4);
+      mbar_expect_tx(&s_bar, bytes);
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (s_whi[k] > s_wlo[k]) bulk_g2s(s_win + k * WCAP, sorted_posf + s_wlo[k], (unsigned int)(s_whi[k] - s_wlo[k]) * (unsigned int)sizeof(float4), &s_bar);
+    }
+    // ---- own particle (while the copies are in flight) ----
+    const int t = t0 + tid;
+    int mode = 0;                                       // 0 nothing to build, 1 staged walk, 2 ordered walk of one thread
+    double4 p = make_double4(0, 0, 0, 0);
+    int s = 0, cx = 1, cy = 1, cz = 1;
+    if (t < nsorted) {
+      p = ld_rec_nc(&sorted_posm[t]);
+      s = __ldg(&sorted_slot[t]);
+      if (!(meta_of(p) & MF_REF)) { rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); qmin[s] = 255; }   // rows exist only for ref atoms
+      else {
+        const int lin = __ldg(&sorted_cell[t]);
+        cx = lin % g.hd[0]; const int r = lin / g.hd[0]; cy = r % g.hd[1]; cz = r / g.hd[1];
+        mode = (g.rows_fast && cx >= 1 && cx <= g.nc[0] && cy >= 1 && cy <= g.nc[1]) ? 1 : 2;
+      }
+    }
+    const float pxf = (float)p.x, pyf = (float)p.y, pzf = (float)p.z;
+    const float bxf = g.pbc[0] ? (float)g.box[0] : 0.0f, byf = g.pbc[1] ? (float)g.box[1] : 0.0f;
+    // wrapped neighbour rows (cell_pbc wraps every axis, z included, Cells.F90:387-391) as offsets into cell_start; the image
+    // shift of a wrapped y row is folded into the particle's y
+    int ly0, ly1, ly2, lz0, lz1, lz2;
+    float py0 = pyf, py2 = pyf;
+    {
+      const int ecz = (cz - 1 < 0 ? cz - 1 + g.nc[2] : (cz - 1 >= g.nc[2] ? cz - 1 - g.nc[2] : cz - 1)) + 1;   // a centre in the z halo is wrapped like any other cell
+      int a = cy - 1, c = cy + 1;
+      if (a < 1) { a += g.nc[1]; py0 = pyf + byf; }        // candidates of the wrapped row sit one box length up: vy = q.y - (py + by)
+      if (c > g.nc[1]) { c -= g.nc[1]; py2 = pyf - byf; }
+      ly0 = a * g.hd[0]; ly1 = cy * g.hd[0]; ly2 = c * g.hd[0];
+      int d = ecz - 1, f = ecz + 1;
+      if (d < 1) d += g.nc[2];
+      if (f > g.nc[2]) f -= g.nc[2];
+      const int hz = g.hd[0] * g.hd[1];
+      lz0 = d * hz; lz1 = ecz * hz; lz2 = f * hz;
+    }
+    const int xa = max(cx - 1, 1), xb = min(cx + 1, g.nc[0]);
+    const int xw = mode == 1 ? (cx == 1 ? g.nc[0] : (cx == g.nc[0] ? 1 : 0)) : 0;     // periodic wrap cell of a particle at the x edge
+    const float pxw = cx == 1 ? pxf + bxf : pxf - bxf;
+    const int dxw = cx == 1 ? -1 : 1;
+    const float rc2hi = (float)g.rc_list2 + g.band2;
+    const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;     // below this the fp32 distance is inside the list radius for sure
+    const float bqs = __double2float_rd(g.bq_scale * 0.999999);
+    int npark = 0;
+    // one candidate: fp32 screen, exact test inside the band, stencil position and rank, park
+#define ROWS_CAND(U, Q, PX, PY, DXV, DYC, DZC) do {                                                                         \
+      const float vx_ = (Q).x - (PX), vy_ = (Q).y - (PY), vz_ = (Q).z - pzf;                                                 \
+      const float d2_ = __fmaf_rn(vx_, vx_, __fmaf_rn(vy_, vy_, vz_ * vz_));                                                 \
+      if (d2_ <= rc2hi && (U) != t) {                                                                                        \
+        bool hit_ = d2_ < rc2lo;                                                                                             \
+        if (!hit_) {                                   /* the reference's test (vdistance, Groups.F90:995-1016; strict <) */  \
+          const double4 qd_ = ld_rec_nc(&sorted_posm[(U)]);                                                                  \
+          hit_ = dist2_idnint(g, qd_.x, qd_.y, qd_.z, p.x, p.y, p.z) < g.rc_list2;                                           \
+        }                                                                                                                    \
+        if (hit_) {                                                                                                          \
+          const int nab_ = nab_of((DXV), (DYC), (DZC));                                                                      \
+          const int c_ = s_cnt[nab_][tid];                                                                                   \
+          s_cnt[nab_][tid] = (unsigned char)(c_ + 1);                                                                        \
+          if (npark < ROW_W) {                                                                                               \
+            s_hit[npark][tid] = __float_as_int((Q).w);         /* w carries the slot */                                     \
+            s_meta[npark][tid] = (unsigned short)(nab_ | (c_ << 5));                                                         \
+            /* lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers) */ \
+            s_qb[npark][tid] = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2_ - g.band2, 0.0f)), bqs));         \
+          }                                                                                                                  \
+          ++npark;                                                                                                           \
+        }                                                                                                                    \
+      }                                                                                                                      \
+    } while (0)
+    mbar_wait(&s_bar, 0u);
+    if (__any_sync(full, mode == 1)) {
+      const bool anyw = __any_sync(full, xw != 0);
+#pragma unroll
+      for (int seg = 0; seg < 9; ++seg) {
+        const int dy = seg % 3 - 1, dz = seg / 3 - 1;
+        const int row = (dy < 0 ? ly0 : (dy == 0 ? ly1 : ly2)) + (dz < 0 ? lz0 : (dz == 0 ? lz1 : lz2));
+        const float pys = dy < 0 ? py0 : (dy == 0 ? pyf : py2);
+        int u0 = 0, b1 = 0, b2 = 0, n = 0, uw = 0, nw = 0;
+        if (mode == 1) {
+          u0 = __ldg(&cell_start[row + xa]); b1 = __ldg(&cell_start[row + cx]); b2 = __ldg(&cell_start[row + cx + 1]);
+          n = __ldg(&cell_start[row + xb + 1]) - u0;
+          if (xw) { uw = __ldg(&cell_start[row + xw]); nw = __ldg(&cell_start[row + xw + 1]) - uw; }
+        }
+        const int wlo = s_wlo[seg], whi = s_whi[seg];
+        {
+          const float4 *cp = (u0 >= wlo && u0 + n <= whi) ? (s_win + seg * WCAP + (u0 - wlo)) : (sorted_posf + u0);
+          const int nmax = __reduce_max_sync(full, n);
+          for (int i = 0; i < nmax; ++i) {
+            if (i < n) {
+              const float4 q = cp[i];
+              const int u = u0 + i;
+              ROWS_CAND(u, q, pxf, pys, (u >= b1 ? 1 : 0) + (u >= b2 ? 1 : 0) - 1, dy, dz);
+            }
+          }
+        }
+        if (anyw) {                                       // wrap cell of the particles at the periodic x edge
+          const float4 *cp = (uw >= wlo && uw + nw <= whi) ? (s_win + seg * WCAP + (uw - wlo)) : (sorted_posf + uw);
+          const int nmax = __reduce_max_sync(full, nw);
+          for (int i = 0; i < nmax; ++i) {
+            if (i < nw) {
+              const float4 q = cp[i];
+              ROWS_CAND(uw + i, q, pxw, pys, dxw, dy, dz);
+            }
+          }
+        }
+      }
+    }
+#undef ROWS_CAND
+    if (mode == 1) {
+      if (npark + slack <= ROW_W) {
+        // prefix of the per-cell hit counts in map order, then every hit goes to prefix[nab] + rank
+        int run = 0;
+#pragma unroll
+        for (int nab = 0; nab < 27; ++nab) { const int c = s_cnt[nab][tid]; s_cnt[nab][tid] = (unsigned char)run; run += c; }
+        const int dst = s * ROW_W;
+        uint4 hb = make_uint4(0, 0, 0, 0);
+        int qm = 255;
+        for (int i = 0; i < npark; ++i) {
+          const int mt = s_meta[i][tid];
+          const int pos = (int)s_cnt[mt & 31][tid] + (mt >> 5);
+          const unsigned int qb = s_qb[i][tid];
+          cols[dst + pos] = s_hit[i][tid];
+          qm = min(qm, (int)qb);
+          const unsigned int sh = qb << (8 * (pos & 3));
+          if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else if (pos < 16) { if (pos < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + pos] = (unsigned char)qb;
+        }
+        for (int i = npark; i < ((npark + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
+        rh_store(&rh[s], hb, dst, npark, ROW_W);             // one full-sector store per row
+        qmin[s] = (unsigned char)qm;
+      } else s_long[atomicAdd(&s_nlong, 1)] = t;             // long row (next to dense metal): built by a warp below
+    } else if (mode == 2) {
+      const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, s * ROW_W, ROW_W, true);
+      if (o.npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); qmin[s] = (unsigned char)row_qmin(o.hb, o.cnt, bq, s * ROW_W); }
+      else s_long[atomicAdd(&s_nlong, 1)] = t;
+    }
+    __syncthreads();
+    const int nlong = s_nlong;
+    for (int i = tid >> 5; i < nlong; i += RB / 32)
+      rows_long_warp(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, qmin, cols, bq, sc, g, slack, s_long[i]);
+  }
   __syncthreads();                                      // the last block to finish marks the rows as materialised
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1036,7 +963,7 @@ __global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restric
 __device__ __forceinline__ void p_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
-                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n, unsigned char *__restrict__ qmin) {
   const bool light = halo_only && sc->rows_asym == 1;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     if (light && !halo_of[s]) continue;
@@ -1048,15 +975,16 @@ __device__ __forceinline__ void p_rev_fill(const RowHead *__restrict__ rh, const
       int j = cols[m.x + jj];
       int w = rev_start[j] + atomicAdd(&rev_len[j], 1);
       rev_cols[w] = s; rev_bq[w] = (unsigned char)(jj < 16 ? rh_byte(h, jj) : (int)bq[m.x + jj]);
+      qmin[j] = 0;                                        // j is visited from a transposed row: its own row's nearest distance no longer bounds its partners
     }
   }
 }
 __global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
-                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n, unsigned char *__restrict__ qmin) {
   REV_GUARD(sc);
-  p_rev_fill(rh, cols, posm, rev_start, rev_len, rev_cols, bq, rev_bq, halo_of, halo_only, sc, n);
+  p_rev_fill(rh, cols, posm, rev_start, rev_len, rev_cols, bq, rev_bq, halo_of, halo_only, sc, n, qmin);
 }
 __global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
@@ -1066,7 +994,7 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
                                                 const int *__restrict__ rev_start, const int *__restrict__ rev_len,
                                                 const int *__restrict__ rev_cols, const DevScal *__restrict__ sc,
                                                 const int *__restrict__ uid, double4 *__restrict__ fe,
-                                                Geo g, Phys ph, int n) {
+                                                Geo g, Phys ph, int n, unsigned char *__restrict__ fnz) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   double4 p1 = ld_rec_nc(&posm[s]);
@@ -1172,12 +1100,11 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
     }
   }
   st_rec(&fe[s], make_double4(fx, fy, fz, ep));        // force(3) + epot in one 256-bit store
+  fnz[s] = (fx != 0.0 || fy != 0.0 || fz != 0.0 || ep != 0.0) ? 1 : 0;   // see k_fuerza_sub
 }
 
-// Production variant of the pair force: LANES lanes per ref particle share its row (n̄n ≈ 6 in solution), so the
-// index loads and record gathers of one particle are in flight together; partial sums are combined with shuffles
-// (no atomics).  Same terms as k_fuerza<false>; only the summation order differs (1e-12 budget of the north star).
-// the rarely taken heavy part (pair inside the cut-off) lives out of line so the gather loop stays lean in registers
+// Production pair force (row order instead of the reference's global visiting order: same terms, 1e-12 budget of the north star).
+// the rarely taken heavy part (pair inside the cut-off) lives out of line so the streaming path stays lean in registers
 __device__ __noinline__ double4 lj_terms(double vx, double vy, double vz, double dr2, double eps, double r0p6) {
   double dr = sqrt(dr2);
   double b = r0p6;
@@ -1206,9 +1133,9 @@ __device__ __forceinline__ unsigned int need16(const uint4 &h, int len, int qmax
   }
   return len >= 16 ? need : (need & ((1u << len) - 1u));
 }
-// Pair term of the production kernels once the partner's record is here: cheap cut-off tests first, heavy math out of line.
+// Pair term of the production kernel once the partner's record is here: cheap cut-off tests first, heavy math out of line.
 // pass 0 = own row, pass 1 = transposed row (reverse visits come from row owners only).
-struct FAcc { double fx, fy, fz, ep; bool hit; };
+struct FAcc { double fx, fy, fz, ep; };
 __device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const double4 &p1, int k3, const double4 &p2,
                                             int pass, int asym, bool i_halo, FAcc &a) {
   double vx = p1.x - p2.x, vy = p1.y - p2.y, vz = p1.z - p2.z;
@@ -1225,363 +1152,106 @@ __device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const 
   const double4 t = lj_terms(vx, vy, vz, dr2, ph.eps[km], ph.r0p6[km]);
   // weight 2 = own visit + the reverse visit by j, when j is a row owner that sees i (exact doubling, one rounding per add)
   const double w = (pass == 0 && (m2 & MF_ANYREF) && (asym == 0 || (asym == 1 && !i_halo))) ? 2.0 : 1.0;
-  a.fx += w * t.x; a.fy += w * t.y; a.fz += w * t.z; a.ep += w * t.w; a.hit = true;
+  a.fx += w * t.x; a.fy += w * t.y; a.fz += w * t.z; a.ep += w * t.w;
 }
 // Gather skip: an entry whose build-time distance D satisfies D - S > r0_max cannot be inside any cut-off, S being a
 // bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
 // around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
-// integrator moved since.  qmax is the largest quantised D that still has to be looked at.
-// FUSEB: the thread that holds the finished force of a particle also does its ermak_b update (dana.F90:1031-1052) — same
-// arithmetic as k_ermak_b, one pass less over records and forces; vel/acel/ranv are requested with the first round trip.
-// Row walk of one ref particle whose record, row head and skip bound are already in registers (shared by the kernels below).
-template <int LANES, bool BATCH = false, bool SKIPHEAD = false>
-__device__ __forceinline__ void fuerza_row(const double4 *__restrict__ posm, const int *__restrict__ cols, const int *__restrict__ rev_start,
-                                           const int *__restrict__ rev_len, const int *__restrict__ rev_cols,
-                                           const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-                                           const Geo &g, const Phys &ph, const double4 &p1, int k3, int s, int sub, int rs0, int rl0,
-                                           const uint4 &h16, int qmax, int asym, bool i_halo, FAcc &a) {
+// integrator moved since.  qmax is the largest quantised D that still has to be looked at (d_qtab tabulates it per z-layer).
+// Row walk of one ref particle whose record and skip bound are in registers: own row, then (asymmetric rows) the transposed one.
+__device__ __noinline__ void fuerza_row(const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const int *__restrict__ cols,
+                                        const int *__restrict__ rev_start, const int *__restrict__ rev_len, const int *__restrict__ rev_cols,
+                                        const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
+                                        const Geo &g, const Phys &ph, const double4 &p1, int k3, int s,
+                                        int qmax, int asym, bool i_halo, FAcc &a) {
+  const int4 rm = rh_meta(&rh[s]);
+  const uint4 h16 = rh_bq16(&rh[s]);
   const int npass = asym ? 2 : 1;
   for (int pass = 0; pass < npass; ++pass) {
-    const int off = pass == 0 ? rs0 : rev_start[s];
+    const int off = pass == 0 ? rm.x : rev_start[s];
     const int *lst = (pass == 0 ? cols : rev_cols) + off;
     const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
-    const int len = pass == 0 ? rl0 : rev_len[s];
-    int jstart = sub;
-    if (LANES == 1 && pass == 0) {                     // head: the skip decision of the first sixteen entries is already here
-      unsigned int need = SKIPHEAD ? 0u : need16(h16, len, qmax);
-      if (BATCH && need && (off & 3) == 0) {
-        // The block lives as long as its slowest thread, and a thread that needs K entries used to pay 2K dependent round
-        // trips (index, record, index, record, ...).  Here the indices of entries 0-7 come back together (two 16-byte loads,
-        // one sector) and the records are requested two at a time: 1 + ceil(K/2) round trips.
-        const int4 *l4 = reinterpret_cast<const int4 *>(lst);
-        const int4 ca = (need & 0x0fu) ? __ldg(l4) : make_int4(0, 0, 0, 0);
-        const int4 cb = (need & 0xf0u) ? __ldg(l4 + 1) : make_int4(0, 0, 0, 0);
-        unsigned int lo = need & 0xffu;
-        need &= ~0xffu;
-        while (lo) {
-          const int q0 = __ffs(lo) - 1; lo &= lo - 1;
-          const bool two = lo != 0u;
-          const int q1 = two ? __ffs(lo) - 1 : q0; lo &= lo - 1;
-          const int4 s0 = q0 < 4 ? ca : cb, s1 = q1 < 4 ? ca : cb;
-          const int j0 = (q0 & 2) ? ((q0 & 1) ? s0.w : s0.z) : ((q0 & 1) ? s0.y : s0.x);
-          const int j1 = (q1 & 2) ? ((q1 & 1) ? s1.w : s1.z) : ((q1 & 1) ? s1.y : s1.x);
-          const double4 r0 = ld_rec_nc(&posm[j0]);
-          const double4 r1 = ld_rec_nc(&posm[j1]);
-          fuerza_pair(g, ph, p1, k3, r0, 0, asym, i_halo, a);
-          if (two) fuerza_pair(g, ph, p1, k3, r1, 0, asym, i_halo, a);
-        }
-      }
+    const int len = pass == 0 ? rm.y : rev_len[s];
+    int jstart = 0;
+    if (pass == 0) {                                   // head: the skip decision of the first sixteen entries is already here
+      unsigned int need = need16(h16, len, qmax);
       while (need) {
         const int q = __ffs(need) - 1; need &= need - 1;
         fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[q])]), 0, asym, i_halo, a);
       }
       jstart = 16;
     }
-    for (int j0 = jstart; j0 < len; j0 += 8 * LANES) {
+    for (int j0 = jstart; j0 < len; j0 += 8) {
       unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int jj = j0 + q * LANES;
-        int b = 1000;
-        if (jj < len) b = (pass == 0 && jj < 16) ? rh_byte(h16, jj) : (int)__ldg(&lq[jj]);
+        const int jj = j0 + q;
+        const int b = jj < len ? (int)__ldg(&lq[jj]) : 1000;
         need |= (b <= qmax ? 1u : 0u) << q;
       }
       while (need) {
         const int q = __ffs(need) - 1; need &= need - 1;
-        fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[j0 + q * LANES])]), pass, asym, i_halo, a);
-      }
-    }
-  }
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// pf: L2 prefetch switches (DML_FORCE_PF).  The kernel is bound by memory latency, not bandwidth (ncu: long-scoreboard stalls,
-// 3 TB/s of DRAM traffic): bit 0 asks L2 for the record and row head of the particle that the thread taking this block's place
-// will own (slot + pf_ahead, pf_ahead = threads resident on the device), bit 1 for the first sector of this particle's own row
-// in region A (its address depends on the slot alone) while record and head are still on their way.
-template <int LANES, int MINB, bool FUSEB, int BS = TPB, bool BATCH = false>
-__global__ void __launch_bounds__(BS, MINB) k_fuerza_sub(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
-    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n,
-    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, int pf, int pf_ahead) {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = gt / LANES, sub = gt % LANES;
-  bool act = s < n;
-  // everything addressed by the slot alone is requested together (one memory round trip, two sectors): the particle
-  // record and the row head (where the row lives, its length, its first sixteen build distances)
-  double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
-  const int rs0 = rm.x, rl0 = rm.y;
-  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
-  if (pf && sub == 0) {
-    if ((pf & 2) && act) prefetch_l2(&cols[(size_t)s * ROW_W]);
-    if ((pf & 1) && s + pf_ahead < n) { prefetch_l2(&posm[s + pf_ahead]); prefetch_l2(&rh[s + pf_ahead]); }
-    if ((pf & 4) && s + pf_ahead < n) prefetch_l2(&cols[(size_t)(s + pf_ahead) * ROW_W]);
-  }
-  double bv[3] = {0.0, 0.0, 0.0}, ba[3] = {0.0, 0.0, 0.0}, br[3] = {0.0, 0.0, 0.0};
-  if (FUSEB && act) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { bv[k] = vel[3 * s + k]; ba[k] = acel[3 * s + k]; br[k] = __ldg(&ranv[3 * s + k]); }
-  }
-  const long long m1 = meta_of(p1);
-  act = act && (m1 & MF_REF);
-  FAcc a = {0.0, 0.0, 0.0, 0.0, false};
-  if (act) {
-    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
-    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
-    const bool i_halo = asym == 1 && halo_of[s] != 0;
-    // pf bits 3,4: diagnostics for tools/perf_probe.py only (wrong forces): 8 = rows taken as empty, 16 = no skip bound (look at all)
-    const int qmax = (pf & 16) ? 255 : skip_qmax(g, sc, lay, p1.z, ph.r0_max);
-    fuerza_row<LANES, BATCH>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, sub, rs0, (pf & 8) ? 0 : rl0, h16, qmax, asym, i_halo, a);
-  }
-  if (LANES > 1) {
-    if (__any_sync(0xffffffffu, a.hit)) {
-#pragma unroll
-      for (int o = LANES / 2; o > 0; o >>= 1) {
-        a.fx += __shfl_xor_sync(0xffffffffu, a.fx, o); a.fy += __shfl_xor_sync(0xffffffffu, a.fy, o);
-        a.fz += __shfl_xor_sync(0xffffffffu, a.fz, o); a.ep += __shfl_xor_sync(0xffffffffu, a.ep, o);
-      }
-    }
-  }
-  if (act && sub == 0) {
-    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
-    if (FUSEB) {
-      const int zt = (int)(m1 & MF_TYPE);
-      if (zt != 2) {
-        const double mass = ph.mass[zt - 1];
-        const double fv[3] = {a.fx, a.fy, a.fz};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          vel[3 * s + k] = ph.cc0 * bv[k] + ph.cc1mcc2 * ba[k] + ph.cc2 * fv[k] / mass + br[k];
-          acel[3 * s + k] = fv[k] / mass;
-        }
+        fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[j0 + q])]), pass, asym, i_halo, a);
       }
     }
   }
 }
 
-// Warp-queue form of the production kernel (DML_FORCE_WQ, default on).  ncu on the thread-per-particle kernel: a warp makes
-// 1.7 trips through the gather loop with 5 lanes active, every trip two dependent memory round trips (index, record) of about
-// a microsecond each under load, so a warp lives 4.5 round trips of which only the first streams.  Here the needed head
-// entries of the 32 particles of a warp (about 9) are renumbered 0..T-1 by a prefix sum over the lanes and handed out one per
-// lane: all indices travel together, then all records.  A lane that finds its pair inside the cut-off parks the term in shared
-// memory (ordered by entry number, i.e. by owner and row position); the owners then add their terms in row order, so the result
-// is bit-identical to the thread-per-particle kernel.  More than WQ_HITS terms in one warp (next to dense metal): the warp falls
-// back to the serial walk.  Entries beyond the row head and transposed rows keep the serial walk.
-constexpr int WQ_HITS = 32;
-template <int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_fuerza_wq(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
-    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n) {
-  __shared__ double4 s_hit[TPB / 32][WQ_HITS];
-  __shared__ unsigned char s_own[TPB / 32][WQ_HITS];
-  const unsigned int full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  bool act = s < n;
-  const double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
-  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
-  const long long m1 = meta_of(p1);
-  act = act && (m1 & MF_REF);
-  const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
-  int pk = 0, qmax = 0;
-  unsigned int need = 0u;
-  if (act) {
-    pk = ((int)(m1 & MF_TYPE) - 1) * 3;                // k3 in bits 0-3, i_halo in bit 4
-    if (asym == 1 && halo_of[s] != 0) pk |= 16;
-    qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
-    need = need16(h16, rm.y, qmax);
-  }
-  const int cnt = __popc(need);
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if (lane >= o) incl += y; }
-  const int base = incl - cnt;
-  const int T = __shfl_sync(full, incl, 31);
-  FAcc a = {0.0, 0.0, 0.0, 0.0, false};
-  int nh = 0;
-  bool overflow = false;
-  for (int e0 = 0; e0 < T; e0 += 32) {                 // warp-uniform
-    const int e = e0 + lane;
-    const bool on = e < T;
-    int owner = 0;                                     // last lane whose first entry number is <= e
-#pragma unroll
-    for (int st = 16; st > 0; st >>= 1) {
-      const int cand = owner + st;
-      const int b = __shfl_sync(full, base, cand & 31);
-      if (b <= e) owner = cand;
-    }
-    unsigned int nm = __shfl_sync(full, need, owner);
-    const int kth = e - __shfl_sync(full, base, owner);
-    const double ox = __shfl_sync(full, p1.x, owner), oy = __shfl_sync(full, p1.y, owner), oz = __shfl_sync(full, p1.z, owner);
-    const int ors = __shfl_sync(full, rm.x, owner), opk = __shfl_sync(full, pk, owner);
-    FAcc t = {0.0, 0.0, 0.0, 0.0, false};
-    if (on) {
-      for (int i = 0; i < kth; ++i) nm &= nm - 1;      // kth-th needed entry of the owner (kth < 16, usually 0 or 1)
-      const int q = __ffs(nm) - 1;
-      const int j = __ldg(&cols[ors + q]);
-      fuerza_pair(g, ph, make_double4(ox, oy, oz, 0.0), opk & 15, ld_rec_nc(&posm[j]), 0, asym, (opk & 16) != 0, t);
-    }
-    const unsigned int hm = __ballot_sync(full, t.hit);
-    if (hm) {
-      if (nh + __popc(hm) > WQ_HITS) { overflow = true; break; }
-      if (t.hit) {
-        const int pos = nh + __popc(hm & ((1u << lane) - 1u));
-        s_hit[w][pos] = make_double4(t.fx, t.fy, t.fz, t.ep); s_own[w][pos] = (unsigned char)owner;
-      }
-      nh += __popc(hm);
-    }
-  }
-  __syncwarp();
-  if (!overflow) {
-    for (int h = 0; h < nh; ++h) {
-      if ((int)s_own[w][h] == lane) { const double4 c = s_hit[w][h]; a.fx += c.x; a.fy += c.y; a.fz += c.z; a.ep += c.w; a.hit = true; }
-    }
-  }
-  if (act) {
-    const int k3 = pk & 15; const bool i_halo = (pk & 16) != 0;
-    if (overflow) fuerza_row<1, false, false>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
-    else if (rm.y > 16 || asym) fuerza_row<1, false, true>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
-    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
-  }
-}
-
-// Two-pass form of the production pair force (DML_FORCE_LEAN).  The probes of DESIGN.md §6 split the one-kernel form into ~27 us of
-// streaming at half occupancy (the gather code costs 64 registers) and ~13 us of dependent gathers.  Here the first pass only
-// streams: record + row head in, skip decision, and for a particle none of whose entries can be inside a cut-off (most of them) the
-// zero force out — with FUSEB also its ermak_b update (dana.F90:1031-1052), the arithmetic of k_ermak_b with force 0 — while the
-// others go to a worklist (warp-aggregated append).  The second pass runs the usual row walk for the worklist only.  Same terms in
-// the same order as k_fuerza_sub, hence bit-identical.
-template <bool FUSEB>
-__global__ void __launch_bounds__(TPB) k_fuerza_lean(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const int *__restrict__ rev_len,
-    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n,
-    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv,
-    int *__restrict__ wl, int *__restrict__ wl_count) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  bool act = s < n;
-  const double4 p1 = act ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-  const int4 rm = act ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
-  const uint4 h16 = act ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
-  const long long m1 = meta_of(p1);
-  act = act && (m1 & MF_REF);
-  bool work = false;
-  if (act) {
-    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
-    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
-    work = need16(h16, rm.y, qmax) != 0u || rm.y > 16;   // entries beyond the head carry their bytes elsewhere: second pass
-    if (asym == 2) work = true;
-    else if (asym == 1 && (halo_of[s] != 0 || rev_len[s] != 0)) work = true;
-  }
-  const unsigned int wm = __ballot_sync(0xffffffffu, work);
-  if (wm) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(wl_count, __popc(wm));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (work) wl[base + __popc(wm & ((1u << lane) - 1u))] = s;
-  }
-  if (act && !work) {
-    st_rec(&fe[s], make_double4(0.0, 0.0, 0.0, 0.0));
-    if (FUSEB) {
-      const int zt = (int)(m1 & MF_TYPE);
-      if (zt != 2) {
-        const double mass = ph.mass[zt - 1];
-        const double fz = 0.0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double bv = vel[3 * s + k], ba = acel[3 * s + k], br = __ldg(&ranv[3 * s + k]);
-          vel[3 * s + k] = ph.cc0 * bv + ph.cc1mcc2 * ba + ph.cc2 * fz / mass + br;
-          acel[3 * s + k] = fz / mass;
-        }
-      }
-    }
-  }
-}
+// One thread per slot.  The streaming part of a particle is its 32-byte record, ONE byte (qmin: the nearest build-time distance
+// of its row, written by the list build) and the 32-byte force/energy it writes: in solution two particles out of three have
+// nothing within reach since the rows were built (qmin above the skip bound of their z-layer, read from a shared-memory copy of
+// the 1 KB table d_qtab keeps) and never touch their row head, row or any partner.  The others take the row walk out of line.
+// Round-1 kernel for comparison: record + 32-byte head for every slot and the bound evaluated per particle (5 table loads + fp64
+// arithmetic): 41 us at 1 M, of which 27 us streaming at 64 registers.
+// FUSEB: the thread that holds the finished force also does the particle's ermak_b update (dana.F90:1031-1052), same arithmetic
+// as k_ermak_b.
 template <bool FUSEB, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_fuerza_work(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
+__global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const unsigned char *__restrict__ qmin,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph,
-    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv,
-    const int *__restrict__ wl, int *__restrict__ wl_count, unsigned int *__restrict__ ticket) {
-  const int nw = *((volatile int *)wl_count);
-  const int asym = __ldg(&sc->rows_asym);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) {
-    const int s = wl[i];
-    const double4 p1 = ld_rec_nc(&posm[s]);
-    const int4 rm = rh_meta(&rh[s]);
-    const uint4 h16 = rh_bq16(&rh[s]);
-    const long long m1 = meta_of(p1);
+    const DevScal *__restrict__ sc, double4 *__restrict__ fe, const __grid_constant__ Geo g, const __grid_constant__ Phys ph, int n,
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, unsigned char *__restrict__ fnz) {
+  __shared__ unsigned int s_qt[LAY_MAX / 4];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = s < n;
+  // everything addressed by the slot alone is requested together
+  const double4 p1 = in ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
+  const int qm = in ? (int)__ldg(&qmin[s]) : 255;
+  const int was_nz = in ? (int)fnz[s] : 0;
+  {
+    const unsigned int *qt = lay + 2 * LAY_MAX;                     // table 0 of d_qtab: bound for the largest cut-off of the pair table
+    for (int i = threadIdx.x; i < (g.nlay + 3) / 4; i += blockDim.x) s_qt[i] = __ldg(&qt[i]);
+  }
+  __syncthreads();
+  const long long m1 = meta_of(p1);
+  if (!in || !(m1 & MF_REF)) return;
+  FAcc a = {0.0, 0.0, 0.0, 0.0};
+  const int qmax = (int)reinterpret_cast<const unsigned char *>(s_qt)[layer_of(g, p1.z)];
+  if (qm <= qmax) {
+    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
     const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
     const bool i_halo = asym == 1 && halo_of[s] != 0;
-    const int qmax = skip_qmax(g, sc, lay, p1.z, ph.r0_max);
-    FAcc a = {0.0, 0.0, 0.0, 0.0, false};
-    fuerza_row<1, false, false>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, 0, rm.x, rm.y, h16, qmax, asym, i_halo, a);
-    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
-    if (FUSEB) {
-      const int zt = (int)(m1 & MF_TYPE);
-      if (zt != 2) {
-        const double mass = ph.mass[zt - 1];
-        const double fv[3] = {a.fx, a.fy, a.fz};
+    fuerza_row(posm, rh, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, qmax, asym, i_halo, a);
+  }
+  // fnz[s] == 0 guarantees that fe[s] already holds zeros: a particle with nothing inside its cut-offs (nearly all of them in
+  // solution) then writes nothing at all
+  const int nz = (a.fx != 0.0 || a.fy != 0.0 || a.fz != 0.0 || a.ep != 0.0) ? 1 : 0;
+  if (nz | was_nz) st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
+  if (nz != was_nz) fnz[s] = (unsigned char)nz;
+  if (FUSEB) {
+    const int zt = (int)(m1 & MF_TYPE);
+    if (zt != 2) {
+      const double mass = ph.mass[zt - 1];
+      const double fv[3] = {a.fx, a.fy, a.fz};
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double bv = vel[3 * s + k], ba = acel[3 * s + k], br = __ldg(&ranv[3 * s + k]);
-          vel[3 * s + k] = ph.cc0 * bv + ph.cc1mcc2 * ba + ph.cc2 * fv[k] / mass + br;
-          acel[3 * s + k] = fv[k] / mass;
-        }
+      for (int k = 0; k < 3; ++k) {
+        const double v = vel[3 * s + k], ac = acel[3 * s + k];
+        vel[3 * s + k] = ph.cc0 * v + ph.cc1mcc2 * ac + ph.cc2 * fv[k] / mass + __ldg(&ranv[3 * s + k]);
+        acel[3 * s + k] = fv[k] / mass;
       }
     }
-  }
-  __syncthreads();                                       // the last block to finish empties the worklist for the next call
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; *wl_count = 0; }
-  }
-}
-
-// PPT particles per thread (slots s, s + blockDim, ...): the records and row heads of all of them are requested before the
-// first one is worked on, so a thread keeps PPT x 64 bytes in flight during the streaming part instead of 64 (DML_FORCE_PPT).
-template <int PPT, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_fuerza_ppt(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
-    const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
-    const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-    const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
-    const DevScal *__restrict__ sc, double4 *__restrict__ fe, Geo g, Phys ph, int n, int pf) {
-  const int s0 = blockIdx.x * (blockDim.x * PPT) + threadIdx.x;
-  double4 p[PPT]; int4 rm[PPT]; uint4 h[PPT];
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int s = s0 + k * blockDim.x;
-    const bool in = s < n;
-    p[k] = in ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-    rm[k] = in ? rh_meta(&rh[s]) : make_int4(0, 0, 0, 0);
-    h[k] = in ? rh_bq16(&rh[s]) : make_uint4(0, 0, 0, 0);
-    if ((pf & 2) && in) prefetch_l2(&cols[(size_t)s * ROW_W]);
-  }
-  const int asym = __ldg(&sc->rows_asym);
-#pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const int s = s0 + k * blockDim.x;
-    const long long m1 = meta_of(p[k]);
-    if (s >= n || !(m1 & MF_REF)) continue;
-    FAcc a = {0.0, 0.0, 0.0, 0.0, false};
-    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
-    const bool i_halo = asym == 1 && halo_of[s] != 0;
-    const int qmax = skip_qmax(g, sc, lay, p[k].z, ph.r0_max);
-    fuerza_row<1>(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p[k], k3, s, 0, rm[k].x, rm[k].y, h[k], qmax, asym, i_halo, a);
-    st_rec(&fe[s], make_double4(a.fx, a.fy, a.fz, a.ep));
   }
 }
 
@@ -1640,7 +1310,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
                                                    double *__restrict__ pos_old, double *__restrict__ old_cg, double *__restrict__ ranv,
                                                    const int *__restrict__ uid, const double *__restrict__ rp_gauss,
                                                    const double *__restrict__ rp_upbc, DevScal *__restrict__ sc, Geo g, Phys ph,
-                                                   unsigned int step, int n) {
+                                                   unsigned int step, int n, unsigned int *__restrict__ lay, double rmax_o) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   BlockAcc acc = {0, 0, 0.0, 0.0, 0.0f};
   if (s < n) {
@@ -1657,8 +1327,9 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
         for (int i = 0; i < (ERMAK ? 6 : 3); ++i) gs[i] = rp_gauss[6 * s + i];
       } else {
         Philox r; unsigned int id = (unsigned int)uid[s];
-#pragma unroll
-        for (int i = 0; i < (ERMAK ? 3 : 2); ++i) { r.run(ph.seed, id, step, RS_INTEG0 + i, 0u); r.gauss2(gs[2 * i], gs[2 * i + 1]); }
+        double sp0, sp1;
+        r.run(ph.seed, id, step, RS_INTEG0, 0u); r.gauss4f(gs[0], gs[1], gs[2], gs[3]);
+        if (ERMAK) { r.run(ph.seed, id, step, RS_INTEG1, 0u); r.gauss4f(gs[4], gs[5], sp0, sp1); }
       }
       if (ERMAK) {
         double a[3] = {acel[3 * s], acel[3 * s + 1], acel[3 * s + 2]};
@@ -1701,19 +1372,31 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
     }
   }
   block_flush(acc, sc);
+  // The last block to finish refreshes the per-layer skip tables (d_qtab) with this call's largest move: the pair force that
+  // follows an Ermak half-step reads its bound from there (one byte per particle instead of the formula).
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&sc->ticket4, 1u) == gridDim.x - 1) ? 1 : 0; }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) sc->ticket4 = 0u;
+  __threadfence();
+  d_qtab(lay, sc, g, ph.r0_max, rmax_o);
 }
 
 // ermak_b — dana.F90:1031-1052
 __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
-                                                 const double4 *__restrict__ fe, const double *__restrict__ ranv, Phys ph, int n) {
+                                                 const double4 *__restrict__ fe, const double *__restrict__ ranv, Phys ph, int n,
+                                                 const unsigned char *__restrict__ fnz) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   long long m = meta_of(ld_rec_nc(&posm[s]));
+  const int nz = (int)__ldg(&fnz[s]);
   if (!(m & MF_REF)) return;
   int zt = (int)(m & MF_TYPE);
   if (zt == 2) return;
   double mass = ph.mass[zt - 1];
-  const double4 f4 = ld_rec_nc(&fe[s]);
+  const double4 f4 = nz ? ld_rec_nc(&fe[s]) : make_double4(0.0, 0.0, 0.0, 0.0);     // fnz == 0: fe[s] holds zeros (k_fuerza_sub)
   const double fv[3] = {f4.x, f4.y, f4.z};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -1767,19 +1450,21 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) {
+                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ qmin) {
   const int s_end = n;
   const double rcut = sqrt(g.rcut2);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
     // one round trip for everything addressed by the slot alone
     const double4 p1 = ld_rec_nc(&posm[s]);
-    const int4 rm = rh_meta(&rh[s]);
-    const int b = rm.x, len = rm.y;
-    const uint4 h16 = rh_bq16(&rh[s]);
+    const int qm = (int)__ldg(&qmin[s]);
     const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
     const float d1 = disp_of(m1);
     const int qmax = skip_qtab(g, lay, p1.z, 1);          // same build-distance skip as the pair force (covers new and old positions)
+    if (qm > qmax) continue;                              // nothing of this row can be within rcut in any new/old combination
+    const int4 rm = rh_meta(&rh[s]);
+    const int b = rm.x, len = rm.y;
+    const uint4 h16 = rh_bq16(&rh[s]);
     bool inv = false, have_o1 = false;
     double o1[3] = {0.0, 0.0, 0.0};
     for (int j0 = 0; j0 < len; j0 += 16) {
@@ -1823,7 +1508,7 @@ __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ p
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
+                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ qmin) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n, qmin); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;

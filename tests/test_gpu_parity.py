@@ -282,12 +282,12 @@ def test_fused_ermak_b_is_bit_identical(monkeypatch):
     assert np.abs(out[0]["vel"]).sum() > 0
 
 
-@pytest.mark.parametrize("env", ["DML_FORCE_WQ=1", "DML_FORCE_BATCH=1", "DML_FORCE_PPT=2", "DML_FORCE_PF=3", "DML_FORCE_WQ=1,DML_FORCE_MINB=3",
-                                 "DML_FORCE_LEAN=1", "DML_FORCE_LEAN=1,DML_FUSE_ERMAK_B=1", "DML_FORCE_LEAN=0"])
-def test_pair_force_kernel_variants_bit_identical(env, monkeypatch):
-    """The alternative schedules of the production pair-force kernel (warp queue, batched requests, two particles per thread,
-    L2 prefetch) add the same terms in the same order as the default one: a Philox run of tests/ermak (deposit grows, so
-    cut-off hits, CG partners and long rows occur) must end bit-identical in every array."""
+@pytest.mark.parametrize("env", ["DML_FORCE_MINB=4", "DML_FORCE_MINB=8", "DML_ROWS_LEGACY=1", "DML_NO_COOP=1"])
+def test_kernel_launch_variants_bit_identical(env, monkeypatch):
+    """Regression test, device against device (the oracle comparisons are the lock-step tests): other register budgets of the
+    production pair-force kernel, the one-thread ordered row walk instead of the staged one, and the multi-launch forms of
+    test_update / overlap_moveback give the bit-identical Philox trajectory of tests/ermak (deposit grows, so cut-off hits, CG
+    partners and long rows occur)."""
     d, o = case("ermak")
     out = []
     for variant in ("", env):
