@@ -74,7 +74,9 @@ struct dml_ctx {
   int coop_max_n = 65536;   // persistent cooperative kernels pay off while launch latency dominates (overlap_moveback)
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
-  int tu_fused = 0;         // what the last test_update launch folded in (bit 0 k_ov_init, bit 1 k_ov_apply)
+  int tu_fused = 0;         // what the last test_update launch folded in (bit 0 k_ov_init, bit 1 k_ov_apply, bit 2 the tail of the step)
+  bool sort_maybe_pending = false;   // a deferring test_update was enqueued since the last cell sort (k_sort_catchup is launched on demand)
+  DBuf<double4> snap;       // positions of a rebuild whose cell sort was deferred
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
@@ -113,6 +115,7 @@ static int gcmc_run_impl(dml_ctx *ctx);
 static int enq_build_rev(dml_ctx *ctx);
 static int enq_sort_cells(dml_ctx *ctx, int force);
 static int enq_materialize_rows(dml_ctx *ctx);
+static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force);
 static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
 
@@ -295,6 +298,12 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 // test_update of a step is superseded by the next step's rebuild before anything reads it.
 static int enq_materialize_rows(dml_ctx *ctx) {
   int n = ctx->n, nct = ctx->nct;
+  if (ctx->sort_maybe_pending && ctx->tessellated) {      // the cell sort a deferring test_update left behind (no-op unless pending)
+    TUArgs A;
+    fill_tu_args(ctx, A, 0);
+    LAUNCH_COOP(K_TU_COOP, k_sort_catchup, ctx->coop_grid_tu, A);
+    ctx->sort_maybe_pending = false;
+  }
   if (!ctx->tessellated) {                                // ngroup_verlet, one warp per row
     LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->bq.p,
            ctx->sc, ctx->geo, n, ctx->row_slack);
@@ -310,7 +319,21 @@ static int enq_materialize_rows(dml_ctx *ctx) {
 // test_update (Neighbor.F90:668-713) enqueued without any host round trip: the rebuild decision is taken by
 // k_top2_final on the device and the rebuild kernels (update + ngroup_cells, Neighbor.F90:608-633,465-548) are
 // always launched but return immediately when no rebuild is due.
-static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true) {
+static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force) {
+  int n = ctx->n, nct = ctx->nct;
+  A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
+  A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_raw = ctx->sorted_raw.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
+  A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
+  A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = 1;
+  A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
+  A.fuse = 0; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p; A.ov_head = ctx->ov_head.p;
+  A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p;
+  A.area = ctx->geo.box[0] * ctx->geo.box[1]; A.h_over_tau = ctx->cfg.h / ctx->cfg.tau; A.use_z1 = ctx->cfg.reservoir == 2 ? 1 : 0; A.piston = ctx->cfg.reservoir == 1 ? 1 : 0;
+  A.defer = 0; A.snap = ctx->snap.p;
+}
+// fuse: see TUArgs (bits 0-1 overlap_moveback's first / last pass, bit 2 the tail of the loop body); defer: leave the cell sort of a
+// rebuild to whoever needs the cells first
+static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true, bool defer = false) {
   ctx->tu_fused = 0;
   tessellate(ctx);
   int n = ctx->n, nct = ctx->nct;
@@ -339,13 +362,11 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true)
   if (force) TRY(enq_materialize_rows(ctx));
   if (ctx->use_coop && n <= ctx->coop_tu_max_n) {
     TUArgs A;
-    A.posm = ctx->posm.p; A.pos_old = ctx->pos_old.p; A.part = ctx->part.p; A.cell_of = ctx->cell_of.p; A.cell_cnt = ctx->cell_cnt.p;
-    A.cell_start = ctx->cell_start.p; A.cell_cur = ctx->cell_cur.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_raw = ctx->sorted_raw.p; A.sorted_cell = ctx->sorted_cell.p; A.sorted_posm = ctx->sorted_posm.p; A.sorted_posf = ctx->sorted_posf.p;
-    A.slot_b = ctx->slot_b.p; A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.halo_of = ctx->halo_of.p; A.lay = ctx->lay.p;
-    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.g = ctx->geo; A.n = n; A.nct = nct; A.force_sort = force; A.slack = ctx->row_slack; A.lazy = 1;
-    A.nb_dcut = ctx->cfg.nb_dcut; A.rmax_f = ctx->ph.r0_max; A.rmax_o = ctx->cfg.rcut;
-    A.fuse = ctx->no_tu_fuse ? 0 : fuse; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p; A.ov_head = ctx->ov_head.p;
-    A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p;
+    fill_tu_args(ctx, A, force);
+    A.fuse = ctx->no_tu_fuse ? 0 : fuse;
+    A.defer = (defer && !force) ? 1 : 0;
+    if (A.defer) { CKC(ctx->snap.ensure(ctx->cap, ctx->st)); A.snap = ctx->snap.p; ctx->sort_maybe_pending = true; }
+    else ctx->sort_maybe_pending = false;                 // a sorting call catches up with (or supersedes) a deferred sort
     ctx->tu_fused = A.fuse;
     LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
     ctx->binned = true;
@@ -365,10 +386,10 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
   if (ermak)
     LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n, ctx->lay.p, ctx->cfg.rcut);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
   else
     LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n, ctx->lay.p, ctx->cfg.rcut);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
   ctx->have_rp = false;
   return 0;
 }
@@ -397,8 +418,7 @@ static int enq_qtab(dml_ctx *ctx) {
   LAUNCH(K_MISC, k_qtab, 1, 256, ctx->lay.p, ctx->sc, ctx->geo, ctx->ph.r0_max, ctx->cfg.rcut);
   return 0;
 }
-// fused = called from the step sequence, right after the integrator whose last block refreshed the skip tables (d_qtab);
-// a stand-alone call (and the slab step, whose halo refresh adds the ghosts' moves) refreshes them with k_qtab first
+// fused = called from the step sequence: the production kernel may also apply ermak_b (k_fuerza_sub<true, ..>)
 static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
   TRY(enq_materialize_rows(ctx));
@@ -408,7 +428,6 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->fnz.p);
     return 0;
   }
-  if (!fused) TRY(enq_qtab(ctx));
 #define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
                        ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p)
@@ -564,13 +583,17 @@ static int enq_step(dml_ctx *ctx) {
   const bool fz = tu_can_fuse(ctx) && ov_is_multi_launch(ctx);   // k_ov_init rides on the first test_update, k_ov_apply on the second
   TRY(enq_test_update(ctx, fz ? 1 : 0, false));
   TRY(enq_overlap(ctx, true, fz, fz));
-  TRY(enq_test_update(ctx, fz ? 2 : 0));
+  // the second test_update also carries the tail of the loop body (msd bookkeeping, promotion, calc_rho, maxz) when it runs as
+  // one cooperative launch, and in Brownian mode leaves the cell sort of its rebuild to whoever needs it (nobody, usually: Q11)
+  const bool tail = ctx->cfg.reservoir != 3 && ctx->tessellated && ctx->use_coop && n <= ctx->coop_tu_max_n && !ctx->no_tu_fuse;
+  TRY(enq_test_update(ctx, (fz ? 2 : 0) | (tail ? 4 : 0), true, tail && !ctx->cfg.integrador));
+  const bool tail_done = (ctx->tu_fused & 4) != 0;
   if (ctx->cfg.reservoir == 3) {
     LAUNCH(K_MISC, k_msd_book, 1, 1, ctx->sc);
     TRY(enq_promote(ctx));
     TRY(gcmc_run_impl(ctx));
     TRY(enq_calc_rho(ctx));
-  } else {
+  } else if (!tail_done) {
     LAUNCH(K_PROMOTE, k_promote_rho, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, n);
   }
   if (ctx->cfg.reservoir == 2) {
@@ -580,7 +603,7 @@ static int enq_step(dml_ctx *ctx) {
     TRY(do_bloques(ctx, nch, ctx->ch_pos.data(), ctx->ch_pos_old.data(), ctx->ch_dist, ctx->ch_rhomedia, &fired));
     if (fired) for (int i = 0; i < nch; ++i) { ctx->ch_pos[3 * i + 2] += ctx->ch_dist; ctx->ch_pos_old[3 * i + 2] += ctx->ch_dist; }
   }
-  if (ctx->cfg.reservoir == 1) TRY(enq_maxz(ctx));
+  if (ctx->cfg.reservoir == 1 && !tail_done) TRY(enq_maxz(ctx));
   ctx->t = ctx->t + ctx->cfg.h;
   return 0;
 }
@@ -707,7 +730,7 @@ void dml_destroy(dml_ctx *ctx) {
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
   ctx->pos_old.release(); ctx->old_cg.release(); ctx->ranv.release(); ctx->uid.release(); ctx->slot_b.release();
-  ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->b2slot.release(); ctx->sorted_slot.release(); ctx->sorted_raw.release(); ctx->chain_pos.release();
+  ctx->snap.release(); ctx->cell_of.release(); ctx->cell_cnt.release(); ctx->cell_start.release(); ctx->cell_cur.release(); ctx->b2slot.release(); ctx->sorted_slot.release(); ctx->sorted_raw.release(); ctx->chain_pos.release();
   ctx->rh.release(); ctx->cols.release(); ctx->scan_sums.release(); ctx->part.release();
   ctx->parent.release(); ctx->ovst.release(); ctx->comp_cnt.release(); ctx->comp_off.release(); ctx->members.release(); ctx->roots.release(); ctx->ov_head.release(); ctx->ov_next.release();
   if (ctx->comm && nccl_api() && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);

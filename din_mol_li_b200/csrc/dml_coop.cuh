@@ -74,9 +74,40 @@ struct TUArgs {
   double4 *posm; double *pos_old; double *part; int *cell_of, *cell_cnt, *cell_start, *cell_cur, *sorted_slot, *sorted_raw, *sorted_cell; double4 *sorted_posm; float4 *sorted_posf;
   const int *slot_b; RowHead *rh; int *cols; unsigned char *bq, *halo_of; unsigned int *lay; int *sums; DevScal *sc; Geo g; int n, nct, force_sort, slack, lazy; double nb_dcut, rmax_f, rmax_o;
   // neighbours of the call inside dml_step folded into the first pass over the slots: fuse bit 0 = the initialisation of the
-  // overlap_moveback that follows (k_ov_init), bit 1 = the write-back of the overlap_moveback that came before (k_ov_apply)
+  // overlap_moveback that follows (k_ov_init), bit 1 = the write-back of the overlap_moveback that came before (k_ov_apply),
+  // bit 2 = the tail of the loop body: msd bookkeeping + F -> CG promotion (dana.F90:201-202,228-236) + calc_rho (521-549) and,
+  // with the piston, maxz (776-794) after the rebuild decision
   int fuse; int *parent, *ovst, *comp_cnt, *ov_head; double *vel, *acel; const double *old_cg;
+  double area, h_over_tau; int use_z1, piston;
+  // defer = 1: a rebuild snapshots the positions (snap) and leaves the cell sort to whoever needs the cells first (sc->sort_pending):
+  // the list rebuilt by the second test_update of a Brownian step is superseded by the next step's rebuild before anything reads it
+  int defer; double4 *snap;
 };
+
+// cgroup_sort (Cells.F90:267-302) by the whole grid: bin -> scan -> scatter -> order inside every cell; three grid-wide barriers.
+// rebuild: the sort belongs to a list rebuild (halo flags, row heads of empty slots); snapshot: also update()'s pos_old = pos.
+__device__ __forceinline__ void coop_sort_cells(cg::grid_group &grid, const TUArgs &A, const double4 *src, bool rebuild, bool snapshot) {
+  const int gsz = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
+  DevScal *sc = A.sc;
+  for (int s = gt; s < A.n; s += gsz) d_bin(src, A.cell_of, A.cell_cnt, A.rh, A.halo_of, sc, A.g, rebuild, s);
+  grid.sync();
+  coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
+  grid.sync();
+  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, src, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, snapshot, s);
+  grid.sync();
+  if (gt == 0 && rebuild) { sc->rows_asym = sc->halo_flag ? 1 : 0; sc->sort_pending = 0; }
+  const int nsorted = A.cell_start[A.nct];
+  for (int i = gt; i < nsorted; i += gsz)
+    d_cell_rank(src, A.slot_b, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, i);
+}
+// the cell sort a deferred rebuild left behind, for a consumer that needs the cells before the next test_update
+__global__ void __launch_bounds__(TPB) k_sort_catchup(TUArgs A) {
+  if (!((volatile const DevScal *)A.sc)->sort_pending) return;
+  cg::grid_group grid = cg::this_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.sc->halo_flag = 0;
+  grid.sync();
+  coop_sort_cells(grid, A, A.snap, true, false);
+}
 
 // test_update (Neighbor.F90:668-713) in one launch
 __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
@@ -86,11 +117,17 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   // phase 0: do_pbc + per-block top-2 squared displacement
   if (gt == 0) sc->halo_flag = 0;
   __shared__ unsigned int s_lay[LAY_MAX];
+  __shared__ int s_red[34];
   for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) s_lay[i] = 0u;
   __syncthreads();
   const int lay_old = sc->lay_cur;
   const int was_listed = sc->listed;                             // read before the first grid.sync: block 0 rewrites it right after
+  const int pending_in = sc->sort_pending;
+  const int par = sc->tu_par;
+  const bool tail = (A.fuse & 4) != 0;
+  const double z0 = sc->z0, zl = A.use_z1 ? sc->z1 : sc->zmax;
   double a1 = -1.0, a2 = -1.0;
+  int c_rho = 0, c_dref = 0;
   if (gt == 0 && (A.fuse & 2)) {                                 // k_ov_apply's bookkeeping (dana.F90:939-941)
     if (sc->ch_later > sc->choques2) sc->choques2 = sc->ch_later;
     sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
@@ -106,11 +143,25 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     }
     if (rd >= 0.0) lay_note(s_lay, A.g, A.posm[s].z, rd);
     top2_merge(a1, a2, rd, -1.0);
+    if (tail) {                                                  // promotion loop + census of calc_rho (same pass as k_promote_rho)
+      double4 p = ld_rec(&A.posm[s]);
+      long long m = meta_of(p);
+      if ((m & MF_REF) && (m & MF_TYPE) == 3) {
+        c_dref++;
+        m = (m & ~(MF_TYPE | MF_REF | MF_GCMC)) | 2;
+        p.w = meta_as_double(m); st_rec(&A.posm[s], p);
+      }
+      if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c_rho++;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&A.lay[(lay_old ^ 1) * LAY_MAX + i], s_lay[i]);
   block_top2(a1, a2);
   if (threadIdx.x == 0) { A.part[2 * blockIdx.x] = a1; A.part[2 * blockIdx.x + 1] = a2; }
+  if (tail) {                                                    // one pair of atomics per block
+    c_rho = block_sum_int(c_rho, s_red); c_dref = block_sum_int(c_dref, s_red);
+    if (threadIdx.x == 0) { if (c_rho) atomicAdd(&sc->rho_cnt2[par], c_rho); if (c_dref) atomicAdd(&sc->dref_cnt2[par], c_dref); }
+  }
   grid.sync();
   // phase 1: every block reduces the partials to the same decision (top-2 merging is order independent)
   a1 = 1e-16; a2 = 1e-16;                                        // Neighbor.F90:643-644
@@ -123,34 +174,71 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   }
   __syncthreads();
   const bool need = s_need != 0;
+  // fused tail: rho of this step (every thread computes it from the finished census), then the piston
+  double lohi = 0.0;
+  if (tail) {
+    const int gct = *((volatile int *)&sc->rho_cnt2[par]);
+    const double rho = gct / (A.area * (zl - z0));               // box(1)*box(2)*(z-z0), dana.F90:521-549
+    if (A.piston) lohi = A.h_over_tau * ((sc->rho0 - rho) / rho);  // maxz, dana.F90:776-794
+    if (gt == 0) {
+      const int dr = *((volatile int *)&sc->dref_cnt2[par]);
+      sc->msd_t = sc->msd_t / sc->nat_ref;                       // dana.F90:201-202 (before the promotion loop)
+      sc->msd_max = fmax(sc->msd_max, sc->msd_t);
+      sc->nat_ref -= dr;
+      sc->rho = rho;
+      sc->tu_par = par ^ 1; sc->rho_cnt2[par ^ 1] = 0; sc->dref_cnt2[par ^ 1] = 0;
+    }
+  }
   if (gt == 0) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
     if (!need) sc->lay_cur = lay_old ^ 1;
     if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
+    if (tail && A.piston) {                                      // k_maxz's scalar part; the skip tables of this call are not read again inside dml_step
+      sc->maxz_disp += fabs(lohi) * fmax(sc->zmax - z0, 0.0) * 1.01;
+      sc->maxz_fac += fabs(lohi) * 1.01;
+      sc->zmax = sc->zmax - lohi * (sc->zmax - z0);
+    }
   }
   if (blockIdx.x == 0) {                                         // z-layer tables (see k_top2_final)
     if (need) { for (int i = threadIdx.x; i < 2 * LAY_MAX; i += blockDim.x) A.lay[i] = 0u; }
     else { for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) A.lay[lay_old * LAY_MAX + i] = 0u; }
     __threadfence();
     __syncthreads();
-    d_qtab(A.lay, sc, A.g, A.rmax_f, A.rmax_o);                  // skip tables for the consumers that follow
+    if (!tail) d_qtab(A.lay, sc, A.g, A.rmax_f, A.rmax_o);       // skip tables for the consumers that follow (none after the tail of a step)
+    else { __syncthreads(); if (threadIdx.x == 0) sc->step_disp_bits = 0u; }   // end of the step: the next integrator call records its own largest move
   }
-  if (!(need || A.force_sort)) return;
-  // phase 2: binning
-  for (int s = gt; s < A.n; s += gsz) d_bin(A.posm, A.cell_of, A.cell_cnt, A.rh, A.halo_of, sc, A.g, need, s);
-  grid.sync();
-  coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
-  grid.sync();
-  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, need, s);
-  grid.sync();
-  if (gt == 0 && need) sc->rows_asym = sc->halo_flag ? 1 : 0;
-  {
-    const int nsorted = A.cell_start[A.nct];
-    for (int i = gt; i < nsorted; i += gsz)
-      d_cell_rank(A.posm, A.slot_b, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, A.sorted_slot, A.sorted_posm, A.sorted_posf, A.sorted_cell, i);
+  const bool defer = A.defer && !A.force_sort;
+  const bool do_sort = !defer && (need || pending_in || A.force_sort);
+  if (need && defer) {
+    // update() without the cell sort: pos_old = pos (Neighbor.F90:620-624), igroup_clean (Groups.F90:1036-1053), snapshot for the deferred sort
+    for (int s = gt; s < A.n; s += gsz) {
+      double4 p = ld_rec(&A.posm[s]);
+      const long long m = meta_of(p);
+      if (m & MF_TYPE) { A.pos_old[3 * s] = p.x; A.pos_old[3 * s + 1] = p.y; A.pos_old[3 * s + 2] = p.z; }
+      else if (m & MF_LIMBO) { p.w = meta_as_double(0); st_rec(&A.posm[s], p); }
+      st_rec(&A.snap[s], p);
+    }
+    if (gt == 0) sc->sort_pending = 1;
   }
+  if (tail && A.piston && !(do_sort)) {                          // maxz on the particles (after the snapshot; a sorting call does it at its end)
+    for (int s = gt; s < A.n; s += gsz) {
+      double4 p = ld_rec(&A.posm[s]);
+      if ((meta_of(p) & MF_TYPE) && p.z > z0) { p.z = p.z - lohi * (p.z - z0); st_rec(&A.posm[s], p); }
+    }
+  }
+  if (!do_sort) return;
+  // phase 2: cells.  Source of the positions: the snapshot of a deferred rebuild that is being caught up with, else the records.
+  const bool from_snap = !need && pending_in;
+  coop_sort_cells(grid, A, from_snap ? A.snap : A.posm, need || pending_in, need);
   // the rows themselves (ngroup_cells, Neighbor.F90:465-548) are built from this snapshot by k_rows when a consumer first needs them
+  if (tail && A.piston) {                                        // maxz on the particles, after everything that needed the positions of the rebuild
+    grid.sync();
+    for (int s = gt; s < A.n; s += gsz) {
+      double4 p = ld_rec(&A.posm[s]);
+      if ((meta_of(p) & MF_TYPE) && p.z > z0) { p.z = p.z - lohi * (p.z - z0); st_rec(&A.posm[s], p); }
+    }
+  }
 }
 
 struct OVArgs {

@@ -172,6 +172,19 @@ __device__ __forceinline__ int skip_qtab(const Geo &g, const unsigned int *__res
   const unsigned char *qt = reinterpret_cast<const unsigned char *>(lay + 2 * LAY_MAX) + which * LAY_MAX;
   return (int)__ldg(&qt[layer_of(g, z)]);
 }
+// One entry of the tables: the bound of layer l uses the top of the layer where the per-particle formula used z.
+__device__ __forceinline__ int qtab_entry(const unsigned int *lt, const Geo &g, int l, double thick, double maxz_fac, double z0, double zmax,
+                                          double dsum, double sdisp, double rmax) {
+  unsigned int mx = 0u;
+#pragma unroll
+  for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldcg(&lt[q])); }
+  double ztop = thick * (double)(l + 1);             // every particle of layer l sits below ...
+  if (l == g.nlay - 1) ztop = fmax(ztop, zmax);      // ... except in the last one, which also takes what is above the box (up to the ceiling)
+  const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
+  const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
+  if (since > g.cell[2]) return 255;                 // particles may have changed layer: no skipping
+  return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
+}
 // Executed by one block.  sc is read around L1 (the block may hold a stale line of it from earlier in its kernel).
 __device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const DevScal *sc, const Geo &g, double rmax_f, double rmax_o) {
   volatile const DevScal *v = sc;
@@ -181,19 +194,8 @@ __device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const Dev
   const double maxz_fac = v->maxz_fac, z0 = v->z0, zmax = v->zmax, dsum = v->dsum_tu;
   const double sdisp = (double)__int_as_float((int)v->step_disp_bits);
   for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
-    unsigned int mx = 0u;
-#pragma unroll
-    for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldcg(&lt[q])); }
-    double ztop = thick * (double)(l + 1);             // every particle of layer l sits below ...
-    if (l == g.nlay - 1) ztop = fmax(ztop, zmax);      // ... except in the last one, which also takes what is above the box (up to the ceiling)
-    const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
-    const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
-    int qf = 255, qo = 255;
-    if (!(since > g.cell[2])) {                        // else particles may have changed layer: no skipping
-      qf = (int)fmin(255.0, ceil((rmax_f * 1.000001 + S) * g.bq_scale) + 1.0);
-      qo = (int)fmin(255.0, ceil((rmax_o * 1.000001 + S) * g.bq_scale) + 1.0);
-    }
-    qt[l] = (unsigned char)qf; qt[LAY_MAX + l] = (unsigned char)qo;
+    qt[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_f);
+    qt[LAY_MAX + l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_o);
   }
 }
 __global__ void k_qtab(unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, double rmax_f, double rmax_o) { d_qtab(lay, sc, g, rmax_f, rmax_o); }
@@ -308,10 +310,11 @@ __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, i
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
     d_bin(posm, cell_of, cell_cnt, rh, halo_of, sc, g, rebuild, s);
 }
-__device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
+// src: where the binned positions came from (the records, or the snapshot of a deferred rebuild: dml_coop.cuh)
+__device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const double4 *src, const int *__restrict__ cell_of,
                                           const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
                                           bool snapshot, int s) {
-  double4 p = ld_rec(&posm[s]);
+  double4 p = ld_rec(&src[s]);
   long long m = meta_of(p);
   if (m & MF_TYPE) {
     int lin = cell_of[s];
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, dou
   REBUILD_GUARD(sc, force);
   const bool snapshot = ((volatile const DevScal *)sc)->need_rebuild != 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
-    d_scatter(posm, pos_old, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s);
+    d_scatter(posm, pos_old, posm, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s);
 }
 // One thread per binned particle (raw = the scatter's output, in-cell order arbitrary): its place in the cell is the number of
 // cell mates with a larger b index (chains are visited in descending b index, Cells.F90:267-302), found with independent loads;
@@ -724,8 +727,10 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_wlo[9], s_whi[9];
   __shared__ int s_nlong;
+  __shared__ unsigned char s_nab[27];                   // stencil position of (run, x-neighbour): inverse of the map, Cells.F90:28-36
   const unsigned int full = 0xffffffffu;
   const int tid = threadIdx.x;
+  if (tid < 27) s_nab[tid] = (unsigned char)nab_of(tid % 3 - 1, (tid / 3) % 3 - 1, tid / 9 - 1);   // index = run * 3 + x-neighbour
   const int nsorted = __ldg(&cell_start[ncell]);        // number of binned particles
   const int t0 = blockIdx.x * RB;
   if (t0 < nsorted) {                                   // block-uniform
@@ -797,28 +802,16 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
     const float rc2lo = __double2float_rd(g.rc_list2) - g.band2;     // below this the fp32 distance is inside the list radius for sure
     const float bqs = __double2float_rd(g.bq_scale * 0.999999);
     int npark = 0;
-    // one candidate: fp32 screen, exact test inside the band, stencil position and rank, park
-#define ROWS_CAND(U, Q, PX, PY, DXV, DYC, DZC) do {                                                                         \
+    // One candidate inside the loops: the fp32 screen and nothing else.  A candidate below the upper edge of the error band is
+    // parked as one word (sorted index | run << 24 | x-neighbour << 28 | "inside the list radius for sure" << 30); everything a hit
+    // needs beyond that (exact test, stencil position, rank, build-distance byte) is done afterwards with all lanes busy: inlined
+    // here it ran in nearly every iteration for the two or three lanes that had a hit (20 M warp instructions, 4 of them useful).
+#define ROWS_CAND(U, Q, PX, PY, DXV, SEG) do {                                                                               \
       const float vx_ = (Q).x - (PX), vy_ = (Q).y - (PY), vz_ = (Q).z - pzf;                                                 \
       const float d2_ = __fmaf_rn(vx_, vx_, __fmaf_rn(vy_, vy_, vz_ * vz_));                                                 \
-      if (d2_ <= rc2hi && (U) != t) {                                                                                        \
-        bool hit_ = d2_ < rc2lo;                                                                                             \
-        if (!hit_) {                                   /* the reference's test (vdistance, Groups.F90:995-1016; strict <) */  \
-          const double4 qd_ = ld_rec_nc(&sorted_posm[(U)]);                                                                  \
-          hit_ = dist2_idnint(g, qd_.x, qd_.y, qd_.z, p.x, p.y, p.z) < g.rc_list2;                                           \
-        }                                                                                                                    \
-        if (hit_) {                                                                                                          \
-          const int nab_ = nab_of((DXV), (DYC), (DZC));                                                                      \
-          const int c_ = s_cnt[nab_][tid];                                                                                   \
-          s_cnt[nab_][tid] = (unsigned char)(c_ + 1);                                                                        \
-          if (npark < ROW_W) {                                                                                               \
-            s_hit[npark][tid] = __float_as_int((Q).w);         /* w carries the slot */                                     \
-            s_meta[npark][tid] = (unsigned short)(nab_ | (c_ << 5));                                                         \
-            /* lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers) */ \
-            s_qb[npark][tid] = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2_ - g.band2, 0.0f)), bqs));         \
-          }                                                                                                                  \
-          ++npark;                                                                                                           \
-        }                                                                                                                    \
+      if (d2_ <= rc2hi && ((SEG) != 4 || (U) != t)) {          /* the particle itself sits in the centre run */             \
+        if (npark < ROW_W) s_hit[npark][tid] = (U) | ((SEG) << 24) | ((DXV) << 28) | (d2_ < rc2lo ? (1 << 30) : 0);         \
+        ++npark;                                                                                                             \
       }                                                                                                                      \
     } while (0)
     mbar_wait(&s_bar, 0u);
@@ -839,12 +832,13 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
         {
           const float4 *cp = (u0 >= wlo && u0 + n <= whi) ? (s_win + seg * WCAP + (u0 - wlo)) : (sorted_posf + u0);
           const int nmax = __reduce_max_sync(full, n);
-          for (int i = 0; i < nmax; ++i) {
-            if (i < n) {
-              const float4 q = cp[i];
-              const int u = u0 + i;
-              ROWS_CAND(u, q, pxf, pys, (u >= b1 ? 1 : 0) + (u >= b2 ? 1 : 0) - 1, dy, dz);
-            }
+          for (int i = 0; i < nmax; i += 4) {              // four independent candidates per trip
+            float4 q[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (i + e < n) q[e] = cp[i + e];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (i + e < n) { const int u = u0 + i + e; ROWS_CAND(u, q[e], pxf, pys, (u >= b1 ? 1 : 0) + (u >= b2 ? 1 : 0), seg); }
           }
         }
         if (anyw) {                                       // wrap cell of the particles at the periodic x edge
@@ -853,13 +847,50 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
           for (int i = 0; i < nmax; ++i) {
             if (i < nw) {
               const float4 q = cp[i];
-              ROWS_CAND(uw + i, q, pxw, pys, dxw, dy, dz);
+              ROWS_CAND(uw + i, q, pxw, pys, dxw + 1, seg);
             }
           }
         }
       }
     }
 #undef ROWS_CAND
+    // ---- settle the parked candidates: exact test inside the band, stencil position, rank among the hits of its cell ----
+    if (mode == 1 && npark + slack > ROW_W) mode = 3;      // cannot fit the slot's own storage whatever the exact tests say: long row
+    {
+      const int np = mode == 1 ? npark : 0;
+      const int npmax = __reduce_max_sync(full, np);
+      int nh = 0;
+      for (int i = 0; i < npmax; ++i) {
+        if (i < np) {
+          const int wd = s_hit[i][tid];
+          const int u = wd & 0xffffff, seg = (wd >> 24) & 15, dxv = (wd >> 28) & 3;
+          const int wlo = s_wlo[seg];
+          const float4 q = (u >= wlo && u < s_whi[seg]) ? s_win[seg * WCAP + (u - wlo)] : __ldg(&sorted_posf[u]);
+          bool hit = (wd >> 30) & 1;
+          if (!hit) {                                      // the reference's test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515)
+            const double4 qd = ld_rec_nc(&sorted_posm[u]);
+            hit = dist2_idnint(g, qd.x, qd.y, qd.z, p.x, p.y, p.z) < g.rc_list2;
+          }
+          if (hit) {
+            const int dz3 = seg / 3, dy3 = seg - 3 * dz3;
+            // the run's image (wrap cell: one box length in x; wrapped y row: one box length in y) for the build-distance byte
+            const float pxs = (dxv - 1 == dxw && xw) ? pxw : pxf;
+            const float pys = dy3 == 0 ? py0 : (dy3 == 1 ? pyf : py2);
+            const float vx = q.x - pxs, vy = q.y - pys, vz = q.z - pzf;
+            const float d2 = __fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz));
+            const int nab = s_nab[seg * 3 + dxv];
+            const int c = s_cnt[nab][tid];
+            s_cnt[nab][tid] = (unsigned char)(c + 1);
+            s_hit[nh][tid] = __float_as_int(q.w);           // w carries the slot (nh <= i: compaction in place)
+            s_meta[nh][tid] = (unsigned short)(nab | (c << 5));
+            // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
+            s_qb[nh][tid] = (unsigned char)min(255, (int)__fmul_rd(__fsqrt_rd(fmaxf(d2 - g.band2, 0.0f)), bqs));
+            ++nh;
+          }
+        }
+      }
+      npark = mode == 1 ? nh : npark;
+    }
     if (mode == 1) {
       if (npark + slack <= ROW_W) {
         // prefix of the per-cell hit counts in map order, then every hit goes to prefix[nab] + rank
@@ -882,7 +913,8 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
         rh_store(&rh[s], hb, dst, npark, ROW_W);             // one full-sector store per row
         qmin[s] = (unsigned char)qm;
       } else s_long[atomicAdd(&s_nlong, 1)] = t;             // long row (next to dense metal): built by a warp below
-    } else if (mode == 2) {
+    } else if (mode == 3) s_long[atomicAdd(&s_nlong, 1)] = t;
+    else if (mode == 2) {
       const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, s * ROW_W, ROW_W, true);
       if (o.npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); qmin[s] = (unsigned char)row_qmin(o.hb, o.cnt, bq, s * ROW_W); }
       else s_long[atomicAdd(&s_nlong, 1)] = t;
@@ -1221,8 +1253,14 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   const int qm = in ? (int)__ldg(&qmin[s]) : 255;
   const int was_nz = in ? (int)fnz[s] : 0;
   {
-    const unsigned int *qt = lay + 2 * LAY_MAX;                     // table 0 of d_qtab: bound for the largest cut-off of the pair table
-    for (int i = threadIdx.x; i < (g.nlay + 3) / 4; i += blockDim.x) s_qt[i] = __ldg(&qt[i]);
+    // skip bound per z-layer for the largest cut-off of the pair table, from the displacement table of the last test_update and what
+    // the integrator / maxz moved since (same formula as d_qtab; every block tabulates it for itself while its records travel)
+    unsigned char *q8 = reinterpret_cast<unsigned char *>(s_qt);
+    const unsigned int *lt = lay + __ldg(&sc->lay_cur) * LAY_MAX;
+    const double thick = g.cell[2] * (double)(1 << g.lay_shift);
+    const double maxz_fac = __ldg(&sc->maxz_fac), z0 = __ldg(&sc->z0), zmax = __ldg(&sc->zmax), dsum = __ldg(&sc->dsum_tu);
+    const double sdisp = (double)__int_as_float((int)__ldg(&sc->step_disp_bits));
+    for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) q8[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, ph.r0_max);
   }
   __syncthreads();
   const long long m1 = meta_of(p1);
@@ -1260,6 +1298,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
 // ================================================================================================
 struct BlockAcc { long long tr, de; double msd, mv; float dmax; };
 
+// One set of atomics per BLOCK: a per-warp flush put 60 k atomics per call on two addresses at 1 M particles.
 __device__ __forceinline__ void block_flush(BlockAcc a, DevScal *sc) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1267,7 +1306,14 @@ __device__ __forceinline__ void block_flush(BlockAcc a, DevScal *sc) {
     a.msd += __shfl_xor_sync(0xffffffffu, a.msd, o); a.mv = fmax(a.mv, __shfl_xor_sync(0xffffffffu, a.mv, o));
     a.dmax = fmaxf(a.dmax, __shfl_xor_sync(0xffffffffu, a.dmax, o));
   }
-  if ((threadIdx.x & 31) == 0) {
+  __shared__ long long s_tr[32], s_de[32];
+  __shared__ double s_msd[32], s_mv[32];
+  __shared__ float s_dm[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { s_tr[w] = a.tr; s_de[w] = a.de; s_msd[w] = a.msd; s_mv[w] = a.mv; s_dm[w] = a.dmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < nw; ++i) { a.tr += s_tr[i]; a.de += s_de[i]; a.msd += s_msd[i]; a.mv = fmax(a.mv, s_mv[i]); a.dmax = fmaxf(a.dmax, s_dm[i]); }
     if (a.tr) atomicAdd((unsigned long long *)&sc->try_, (unsigned long long)a.tr);
     if (a.de) atomicAdd((unsigned long long *)&sc->depo, (unsigned long long)a.de);
     if (a.msd != 0.0) atomicAdd(&sc->msd_t, a.msd);
@@ -1310,15 +1356,21 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
                                                    double *__restrict__ pos_old, double *__restrict__ old_cg, double *__restrict__ ranv,
                                                    const int *__restrict__ uid, const double *__restrict__ rp_gauss,
                                                    const double *__restrict__ rp_upbc, DevScal *__restrict__ sc, Geo g, Phys ph,
-                                                   unsigned int step, int n, unsigned int *__restrict__ lay, double rmax_o) {
+                                                   unsigned int step, int n) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   BlockAcc acc = {0, 0, 0.0, 0.0, 0.0f};
   if (s < n) {
+    // everything addressed by the slot alone is requested together: one memory round trip in front of the arithmetic
     double4 p = ld_rec(&posm[s]);
+    double v[3] = {0.0, 0.0, 0.0}, a[3] = {0.0, 0.0, 0.0};
+    if (ERMAK) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { v[j] = vel[3 * s + j]; a[j] = acel[3 * s + j]; }
+    }
+    const unsigned int id = (unsigned int)uid[s];
     long long m = meta_of(p);
     if (m & MF_REF) {
       double q[3] = {p.x, p.y, p.z}, og[3] = {p.x, p.y, p.z};
-      double v[3] = {vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]};
       old_cg[3 * s] = og[0]; old_cg[3 * s + 1] = og[1]; old_cg[3 * s + 2] = og[2];
       int zt = (int)(m & MF_TYPE);
       double gs[6];
@@ -1326,13 +1378,12 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
 #pragma unroll
         for (int i = 0; i < (ERMAK ? 6 : 3); ++i) gs[i] = rp_gauss[6 * s + i];
       } else {
-        Philox r; unsigned int id = (unsigned int)uid[s];
+        Philox r;
         double sp0, sp1;
         r.run(ph.seed, id, step, RS_INTEG0, 0u); r.gauss4f(gs[0], gs[1], gs[2], gs[3]);
         if (ERMAK) { r.run(ph.seed, id, step, RS_INTEG1, 0u); r.gauss4f(gs[4], gs[5], sp0, sp1); }
       }
       if (ERMAK) {
-        double a[3] = {acel[3 * s], acel[3 * s + 1], acel[3 * s + 2]};
         double sm = ph.sqrt_mass[zt - 1];
         double A = ph.skt / sm * ph.sdr, B = ph.skt / sm * ph.sdv;
 #pragma unroll
@@ -1352,7 +1403,7 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
         }
       }
       double zmax = sc->zmax;
-      RngSrc rs = {ph.rng_mode, ph.seed, (unsigned int)uid[s], step, rp_upbc, s};
+      RngSrc rs = {ph.rng_mode, ph.seed, id, step, rp_upbc, s};
       bool wrote_v = !ERMAK;                               // the Brownian step always rewrites vel
       bool depos = atom_pbc_dev(g, ph, zmax, q, pos_old + 3 * (size_t)s, og, v, m, rs, acc, wrote_v);
       if (!depos) {
@@ -1372,16 +1423,6 @@ __global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, d
     }
   }
   block_flush(acc, sc);
-  // The last block to finish refreshes the per-layer skip tables (d_qtab) with this call's largest move: the pair force that
-  // follows an Ermak half-step reads its bound from there (one byte per particle instead of the formula).
-  __shared__ int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(&sc->ticket4, 1u) == gridDim.x - 1) ? 1 : 0; }
-  __syncthreads();
-  if (!s_last) return;
-  if (threadIdx.x == 0) sc->ticket4 = 0u;
-  __threadfence();
-  d_qtab(lay, sc, g, ph.r0_max, rmax_o);
 }
 
 // ermak_b — dana.F90:1031-1052

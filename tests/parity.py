@@ -236,3 +236,43 @@ class Lockstep:
         a = (so.nupd - self.nupd0, so.nat_sys, so.nat_ref)
         b = (cg.nupd_vlist, cg.nat_sys, cg.nat_ref)
         assert a == b, tag + " counters oracle %s vs device %s" % (a, b)
+
+
+class FusedLockstep:
+    """dml_step(1) — the fused loop body the bench runs (test_update carrying overlap_moveback's first / last pass and the tail of
+    the step, deferred cell sorts, lazily built rows) — against the oracle's own step, the device fed with the random numbers the
+    oracle consumed in that step (trace-replay), every state array compared bit-for-bit at the end of each step."""
+
+    def __init__(self, o, strict=1, chunk_xyz=None, capacity=None):
+        self.o = o
+        self.rtol = 0.0 if strict else 1e-12
+        self.ctx = ctx_from_oracle(o, rng_mode=dml.RNG_REPLAY, strict=strict, capacity=capacity)
+        self.ctx.test_update()                              # the oracle has not moved since its last list build: same rows
+        compare_rows(o, self.ctx, what="rows at start")
+        if o.params.reservoir == 2:
+            ch = ChunkTemplate(chunk_xyz, o.scalars().zmax, o.params.dist + 3.2)
+            self.ctx.set_chunk_template(ch.pos, ch.pos_old, ch.dist, RHOMEDIA)
+        self.nupd0 = o.scalars().nupd - self.ctx.counters().nupd_vlist
+        o.trace_enable(True)
+
+    def step(self, check=True, tag=""):
+        o, ctx = self.o, self.ctx
+        p = o.params
+        amax = o.scalars().hs_amax
+        u2s = uid_to_slot(o)
+        o.trace_clear()
+        o.step(1)
+        gauss, upbc, uovl, gu, gg = replay_from_trace(o, u2s, amax, 6 if p.integrador else 3)
+        ctx.set_replay_integrator(gauss, upbc, None)
+        ctx.set_replay_overlap(*uovl)
+        if p.reservoir == 3:
+            ctx.set_replay_gcmc(gu, gg)
+        ctx.step(1)
+        if check:
+            fields = ("pos", "vel", "acel", "pos_old", "z", "flags", "uid", "slot_b") if p.reservoir == 3 else ("pos", "vel", "acel", "pos_old", "old_cg", "z", "flags")
+            compare_state(o, ctx, fields=fields, force=bool(p.integrador), rtol=self.rtol, what=tag)
+            so, sg, cg = o.scalars(), ctx.scalars(), ctx.counters()
+            assert (so.rho, so.zmax, so.z0) == (sg.rho, sg.zmax, sg.z0), tag + " scalars oracle %s vs device %s" % ((so.rho, so.zmax, so.z0), (sg.rho, sg.zmax, sg.z0))
+            a = (so.nupd - self.nupd0, so.nat_sys, so.nat_ref, so.choques)
+            b = (cg.nupd_vlist, cg.nat_sys, cg.nat_ref, cg.choques)
+            assert a == b, tag + " counters oracle %s vs device %s" % (a, b)

@@ -85,6 +85,25 @@ def test_lockstep_replay_reference_branches(name, nsteps, over, coop, monkeypatc
         assert sc.try_ - t0 > (sc.depo - d0) >= 0 and sc.try_ - t0 >= 3, "no failed deposition attempt happened: the test is vacuous"
 
 
+@pytest.mark.parametrize("name,nsteps", [("ermak", 300), ("brown", 120), ("gcmc", 300)])
+@pytest.mark.parametrize("coop", [1, 0])
+def test_fused_step_replay_bit_exact(name, nsteps, coop, monkeypatch):
+    """dml_step itself (not the call-site API) against the oracle: the fused loop body the bench runs — test_update launches that
+    carry overlap_moveback's first / last pass and the tail of the step (msd, promotion, calc_rho, maxz), the deferred cell sort of
+    a Brownian step's second rebuild, rows built on demand — must leave every array bit-identical to the oracle's after every step
+    when it consumes the oracle's random numbers.  coop=0: the one-launch-per-phase forms."""
+    if not coop:
+        monkeypatch.setenv("DML_NO_COOP", "1")
+    else:
+        monkeypatch.setenv("DML_COOP_MAX_N", "100")          # multi-launch overlap_moveback between one-launch test_updates,
+        monkeypatch.setenv("DML_COOP_TU_MAX_N", "4194304")   # i.e. the combination boxes above 65 536 slots (bench.py's) take
+    d, o = case(name, nwr=10 ** 9)
+    ls = P.FusedLockstep(o, strict=1, chunk_xyz=d.get("chunk_xyz"))
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s fused step %d" % (name, i + 1))
+    assert o.scalars().nupd > 3
+
+
 @pytest.mark.parametrize("name,nsteps", [("ermak", 60), ("brown", 40), ("gcmc", 150)])
 def test_lockstep_replay_multi_launch_path(name, nsteps, monkeypatch):
     """Same lock-step comparison with the persistent cooperative kernels switched off: the one-launch-per-phase path that
@@ -176,22 +195,36 @@ def _deposited(z):
     return int((z >= 2).sum())
 
 
-@pytest.mark.parametrize("name,nsteps,nseeds", [("ermak", 2000, 5), ("gcmc", 1500, 5)])
+@pytest.mark.parametrize("name,nsteps,nseeds", [("ermak", 2000, 8), ("gcmc", 1500, 8)])
 def test_long_run_observables_statistical(name, nsteps, nseeds):
     """Production mode (Philox noise) against the oracle's own RNG: long-run observables agree within statistical error
-    (north_star criterion 4).  Observables: deposited atoms (CG+F), particles in the system, mean height of the ions."""
+    (north_star criterion 4).  Observables: deposited atoms (CG+F), particles in the system, mean height of the ions, the Li
+    density profile, the pair-distance histogram and (gcmc) the accepted insertions + deletions.
+    A run may end in the reference's own abort `supero z0` (src/dana.F90:907): maxz never updates box(3), so ions pushed above it
+    sit in halo cells that no stencil visits (SURVEY.md Q-list, Cells.F90:248), pass through each other and blow up when they
+    come back; such a draw is replaced by the next seed on either side (at most two per side)."""
     from oracle import observables as OB
     dep_o, dep_g, n_o, n_g, zm_o, zm_g = [], [], [], [], [], []
     prof_o, prof_g, gr_o, gr_g = [], [], [], []
     acc_o, acc_g = [], []
     NZ, NR, RMAX = 6, 8, 12.0
-    for k in range(nseeds):
+    k, aborted = -1, 0
+    while len(dep_g) < nseeds:
+        k += 1
         d, o = case(name, idum=-104012 - 17 * k)
         uid0, nsys0 = int(o.state()["uid"].max()), o.scalars().nat_sys
         ztop = o.scalars().zmax * 1.1
         box = list(o.scalars().box)
         ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=9000 + k)
-        ctx.step(nsteps)
+        try:
+            ctx.step(nsteps)
+            o.step(nsteps)
+        except (dml.DmlError, RuntimeError) as e:
+            assert "supero z0" in str(e), e
+            aborted += 1
+            assert aborted <= 4
+            ctx.close()
+            continue
         c = ctx.counters()
         g = ctx.download(c.n_slots)
         alive = g["z"] > 0
@@ -200,7 +233,6 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
         prof_g.append(ctx.density_profile(0.0, ztop, NZ, (1,)).astype(float))
         h, nsel = ctx.gr(RMAX, NR, (1, 2, 3))
         gr_g.append(h / float(nsel))
-        o.step(nsteps)
         st = o.state()
         dep_o.append(_deposited(st["z"])); n_o.append(len(st["z"])); zm_o.append(st["pos"][st["z"] == 1, 2].mean())
         prof_o.append(OB.density_profile(st["pos"][:, 2], st["z"], 0.0, ztop, NZ, (1,)).astype(float))
@@ -216,7 +248,7 @@ def test_long_run_observables_statistical(name, nsteps, nseeds):
     def agree(a, b, what, floor):
         a, b = np.array(a, float), np.array(b, float)
         se = np.sqrt((a.var(ddof=1) + b.var(ddof=1)) / len(a)) + floor
-        assert abs(a.mean() - b.mean()) <= 4.5 * se, "%s: device %s vs oracle %s (se %.3g)" % (what, a, b, se)
+        assert abs(a.mean() - b.mean()) <= 4.0 * se, "%s: device %s vs oracle %s (se %.3g)" % (what, a, b, se)
 
     agree(dep_g, dep_o, name + " deposited atoms", 1.0)
     agree(n_g, n_o, name + " particles", 1.0)
@@ -489,6 +521,30 @@ def test_lockstep_at_bench_size_100k(which, nsteps):
         c = ls.ctx.counters()
         assert c.gcmc_created + c.gcmc_destroyed > 10
     P.compare_rows(o, ls.ctx, what=which + " 100k rows at the end")
+
+
+@pytest.mark.parametrize("which,nsteps", [("brown", 6), ("gcmc", 4)])
+def test_fused_step_at_bench_size_100k(which, nsteps):
+    """The same 100 k workloads through dml_step (what bench.py times), production launch configuration, against the oracle's step."""
+    B = _bench()
+    w = B.workload_brown(100000, -104012) if which == "brown" else B.workload_gcmc(100000, -104012)
+    O.set_threads(len(os.sched_getaffinity(0)))
+    o = _oracle_of(w)
+    ls = P.FusedLockstep(o, strict=0, chunk_xyz=w["chunk"], capacity=int(o.scalars().nat_sys * 1.3) + 8192)
+    for i in range(nsteps):
+        ls.step(check=True, tag="%s 100k fused step %d" % (which, i + 1))
+    P.compare_rows(o, ls.ctx, what=which + " 100k rows at the end")
+
+
+def test_fused_step_at_1m():
+    """BASELINE config 4's box on one GPU through dml_step: Ermak + piston, 1 M particles, production pair force (1e-12)."""
+    B = _bench()
+    w = B.workload_ermak(1000000, -104012)
+    O.set_threads(len(os.sched_getaffinity(0)))
+    o = _oracle_of(w, mnb=256)
+    ls = P.FusedLockstep(o, strict=0, capacity=o.scalars().nat_sys + 65536)
+    for i in range(3):
+        ls.step(check=True, tag="1M fused step %d" % (i + 1))
 
 
 @pytest.mark.parametrize("slab", [False, True])

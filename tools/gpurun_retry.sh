@@ -1,0 +1,11 @@
+#!/bin/bash
+# tools/gpurun_retry.sh <timeout> <command...> — gpurun with retries while the pod answers "busy" (exit code 3 / transient)
+t=$1; shift
+for i in 1 2 3 4 5 6 7 8 9 10; do
+  /usr/local/graft/bin/gpurun --timeout $t -- "$@" > /tmp/gpurun_last.log 2>&1
+  rc=$?
+  if grep -q "status=transient" /tmp/gpurun_last.log || [ $rc -eq 3 ]; then sleep 90; continue; fi
+  break
+done
+cat /tmp/gpurun_last.log
+exit $rc

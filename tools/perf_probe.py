@@ -70,6 +70,19 @@ def probe(kind, n, variant, steps, out):
            "min_ms": round(min(per), 4), "max_ms": round(max(per), 4), "psteps_per_s": c.nat_sys / (step_ms * 1e-3),
            "nupd": int(c.nupd_vlist), "list_entries": int(c.list_entries),
            "kernels_us_per_step": {k: [round(v[0] / steps * 1e3, 1), round(v[1] / steps, 2)] for k, v in kern.items() if v[1]}}
+    if kind.startswith("ermak"):
+        # pair force alone on a FIXED state (same rows, same skip bound from call to call): comparable across kernel variants
+        ctx.profile(True)
+        ctx.profile_get(dml.CLS_ALL, reset=True)
+        nf = 20
+        for _ in range(nf):
+            with torch.cuda.stream(ext):
+                flush.zero_()
+            ctx.fuerza()
+        torch.cuda.synchronize()
+        kf = ctx.profile_kernels()
+        ctx.profile(False)
+        rec["fuerza_fixed_state_us"] = round(kf["fuerza"][0] / kf["fuerza"][1] * 1e3, 2)
     print(json.dumps(rec), flush=True)
     out.write(json.dumps(rec) + "\n")
     out.flush()
