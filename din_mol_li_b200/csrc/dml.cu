@@ -61,7 +61,7 @@ struct dml_ctx {
   DBuf<int> b2slot;          // boxes without cell lists (ngroup_verlet): slot of every hs%b index
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
-  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, qmin, fnz; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, fnz; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -305,13 +305,13 @@ static int enq_materialize_rows(dml_ctx *ctx) {
     ctx->sort_maybe_pending = false;
   }
   if (!ctx->tessellated) {                                // ngroup_verlet, one warp per row
-    LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->bq.p,
+    LAUNCH(K_ROWS_FILL, k_rows_verlet, std::min(nblk(n * 32), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->b2slot.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
            ctx->sc, ctx->geo, n, ctx->row_slack);
     return 0;
   }
   prof_begin(ctx, K_ROWS_FILL);
-  k_rows<<<nblk(n, RB), RB, ROWS_SMEM, ctx->st>>>(ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
-                                                  ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
+  k_rows<<<std::min(nblk(n, RB), 148 * 2), RB, ROWS_SMEM, ctx->st>>>(ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
+                                                  ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   prof_end(ctx);
   return 0;
 }
@@ -401,7 +401,7 @@ static int enq_build_rev(dml_ctx *ctx) {
     RevArgs A;
     A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.posm = ctx->posm.p; A.rev_start = ctx->rev_start.p; A.rev_len = ctx->rev_len.p; A.rev_cnt = ctx->rev_cnt.p;
     A.rev_cols = ctx->rev_cols.p; A.bq = ctx->bq.p; A.rev_bq = ctx->rev_bq.p; A.halo_of = ctx->halo_of.p; A.halo_only = ctx->cfg.strict_order ? 0 : 1;
-    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.n = n; A.qmin = ctx->qmin.p;
+    A.sums = ctx->coop_sums.p; A.sc = ctx->sc; A.n = n;
     LAUNCH_COOP(K_REV, k_rev_coop, ctx->coop_grid_rev, A);
     return 0;
   }
@@ -409,7 +409,7 @@ static int enq_build_rev(dml_ctx *ctx) {
          ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   TRY(scan_excl(ctx, ctx->rev_cnt.p, ctx->rev_start.p, n, &ctx->sc->rev_used, true, 1, 0));
   LAUNCH(K_REV, k_rev_fill, std::min(nblk(n), 148 * 8), TPB, ctx->rh.p, ctx->cols.p, ctx->posm.p, ctx->rev_start.p, ctx->rev_len.p,
-         ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n, ctx->qmin.p);
+         ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->cfg.strict_order ? 0 : 1, ctx->sc, n);
   LAUNCH(K_REV, k_rev_done, 1, 1, ctx->sc);
   return 0;
 }
@@ -428,7 +428,7 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
            ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->fnz.p);
     return 0;
   }
-#define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->qmin.p, ctx->cols.p, ctx->rev_start.p, \
+#define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
                        ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p)
   if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 6) FSUB(true, 6); else FSUB(true, 4); }
@@ -455,7 +455,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
   if (ctx->use_coop && n <= ctx->coop_max_n && ctx->cfg.prob >= 1.0) {
     OVArgs A;
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
-    A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.qmin = ctx->qmin.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
+    A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.ov_head = ctx->ov_head.p; A.ov_next = ctx->ov_next.p; A.uid = ctx->uid.p;
     A.rp_uovl = ov_replay(ctx); A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
     A.n = n; A.guard_pass = ctx->ov_guard_pass;
@@ -465,7 +465,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
   }
   if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
   LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
-         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n, ctx->qmin.p);
+         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
   const OvRp uovl = ov_replay(ctx);
   if (ctx->cfg.prob >= 1.0) {
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
@@ -678,7 +678,6 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));
   CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
-  CKC(ctx->qmin.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->qmin.p, 0, cap, ctx->st));      // 0 = never skip the row
   CKC(ctx->fnz.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->fnz.p, 0, cap, ctx->st));
   CKC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM));
   CKC(ctx->lay.ensure(3 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0xff, 3 * LAY_MAX * sizeof(unsigned int), ctx->st));   // 2 displacement tables + the skip tables (k_qtab)
@@ -739,7 +738,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
   ctx->mig_ri.release(); ctx->cnt_own.release(); ctx->cnt_all.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
   ctx->top2_own.release(); ctx->top2_all.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->qmin.release(); ctx->fnz.release(); ctx->sorted_cell.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -985,19 +984,20 @@ int dml_set_neighbors(dml_ctx *ctx, int32_t n, int32_t width, const int32_t *nn,
   // same layout as the device build: a row that fits (with the gcmc slack) sits in its slot's ROW_W entries, longer ones in the tail
   const int tail0 = ctx->cap * ROW_W;
   std::vector<RowHead> rh(ctx->n);
-  memset(rh.data(), 0, rh.size() * sizeof(RowHead));        // zero build distances: never skip
+  memset(rh.data(), 0, rh.size() * sizeof(RowHead));        // zero build distances, q5 = 0 (no near list): every entry is looked at
+  for (auto &h : rh) { for (int k = 0; k < 4; ++k) { h.near[k] = -1; h.nbq[k] = 255; } }
   size_t off = (size_t)tail0;
   for (int i = 0; i < n; ++i) {
-    rh[i].len = nn[i];
+    if (nn[i] < 0 || nn[i] + ctx->row_slack > 65535) FAIL("dml_set_neighbors: row length out of range");
+    rh[i].len = (unsigned short)nn[i];
     if (nn[i] + ctx->row_slack <= ROW_W) { rh[i].start = i * ROW_W; rh[i].cap = ROW_W; }
-    else { rh[i].start = (int)off; rh[i].cap = nn[i] + ctx->row_slack; off += (size_t)rh[i].cap; }
+    else { rh[i].start = (int)off; rh[i].cap = (unsigned short)(nn[i] + ctx->row_slack); off += (size_t)rh[i].cap; }
   }
   CKC(ctx->cols.ensure(off + 4096, ctx->st, true)); CKC(ctx->rev_cols.ensure(ctx->cols.cap, ctx->st));
   CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st));
   std::vector<int> cols(off, -1);
   for (int i = 0; i < n; ++i) for (int m = 0; m < nn[i]; ++m) cols[(size_t)rh[i].start + m] = rows[(size_t)i * width + m];
   CKC(cudaMemsetAsync(ctx->bq.p, 0, ctx->bq.cap, ctx->st));   // caller's rows carry no build distances: never skip
-  CKC(cudaMemsetAsync(ctx->qmin.p, 0, ctx->qmin.cap, ctx->st));
   CKC(cudaMemcpyAsync(ctx->rh.p, rh.data(), ctx->n * sizeof(RowHead), cudaMemcpyHostToDevice, ctx->st));
   CKC(cudaMemcpyAsync(ctx->cols.p, cols.data(), off * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
   TRY(pull_scal(ctx));

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
 }
 
 struct OVArgs {
-  double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned char *qmin; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
+  double4 *posm; double *vel, *acel; const double *old_cg; const RowHead *rh; const int *cols; const unsigned char *bq; const unsigned int *lay; int *parent, *ovst, *comp_cnt, *comp_off,
       *members, *roots, *ov_head, *ov_next; const int *uid; OvRp rp_uovl; DevScal *sc; Geo g; Phys ph; unsigned int step; int n, guard_pass;
 };
 
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
   p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.ov_head, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n, A.qmin);
+  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
   grid.sync();
   p_ov_link(A.parent, A.ovst, A.ov_head, A.ov_next, A.roots, A.sc, A.n);
   grid.sync();
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
 // here an idle call is one launch whose blocks return on the guard, which nobody rewrites before the last phase.
 struct RevArgs {
   const RowHead *rh; const int *cols; const double4 *posm; int *rev_start, *rev_len, *rev_cnt, *rev_cols;
-  const unsigned char *bq; unsigned char *rev_bq; const unsigned char *halo_of; int halo_only; int *sums; DevScal *sc; int n; unsigned char *qmin;
+  const unsigned char *bq; unsigned char *rev_bq; const unsigned char *halo_of; int halo_only; int *sums; DevScal *sc; int n;
 };
 __global__ void __launch_bounds__(TPB) k_rev_coop(RevArgs A) {
   REV_GUARD(A.sc);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TPB) k_rev_coop(RevArgs A) {
   grid.sync();
   coop_scan<true>(grid, A.rev_cnt, A.rev_start, A.n, A.sums, &A.sc->rev_used);
   grid.sync();
-  p_rev_fill(A.rh, A.cols, A.posm, A.rev_start, A.rev_len, A.rev_cols, A.bq, A.rev_bq, A.halo_of, A.halo_only, A.sc, A.n, A.qmin);
+  p_rev_fill(A.rh, A.cols, A.posm, A.rev_start, A.rev_len, A.rev_cols, A.bq, A.rev_bq, A.halo_of, A.halo_only, A.sc, A.n);
   if (blockIdx.x == 0 && threadIdx.x == 0) A.sc->rev_valid = 1;   // every block read the guard before the first grid.sync
 }
 

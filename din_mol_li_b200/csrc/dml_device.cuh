@@ -44,40 +44,65 @@ __device__ __forceinline__ void st_rec(double4 *p, const double4 &r) {
 }
 
 // ---- row head: one 32-byte sector per slot ---------------------------------------------------------------------
-// Everything a consumer needs before it touches a row, fetched with the particle record in ONE memory round trip and written
-// by the list build as ONE full-sector store (three scattered 4-byte arrays cost three read-modify-write sectors per row):
-// the first 16 quantised build distances of the row (see k_rows / skip_qmax) and where the row lives.
+// Everything a consumer needs before it touches a row, fetched together with the particle record in ONE memory round trip and
+// written by the list build as ONE full-sector store: where the row lives, and the NEAR LIST — the (up to) four entries of the row
+// with the smallest quantised build-time distance (see k_rows), as slot ids in row order, plus the fifth-smallest distance.
+// A consumer that has to look at every entry with build distance <= qmax (pair force, overlap detection: see skip_qmax) finds
+// all of them in the near list whenever q5 > qmax — in solution that is nearly always — and goes from the head straight to the
+// partners' records; round 1 kept sixteen distance bytes here and paid a third dependent round trip for the indices.
 struct __align__(32) RowHead {
-  unsigned char bq[16];
-  int start;      // first entry in cols[] (slot*ROW_W, or a segment of the tail region for long rows)
-  int len;        // nn(i)   (Neighbor.F90:45)
-  int cap;        // entries that fit at start (gcmc appends, Neighbor.F90:295-314)
-  int pad;
+  int near[4];            // -1 = none
+  unsigned char nbq[4];   // quantised build distances of near[]; 255 = none
+  int start;              // first entry in cols[] / bq[] (slot*ROW_W, or a segment of the tail region for long rows)
+  unsigned short len;     // nn(i)   (Neighbor.F90:45)
+  unsigned short cap;     // entries that fit at start (gcmc appends, Neighbor.F90:295-314)
+  unsigned char q5;       // fifth-smallest build distance of the row (255 = fewer than five entries; 0 = near list not maintained)
+  unsigned char pad[3];
 };
-__device__ __forceinline__ uint4 rh_bq16(const RowHead *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
-__device__ __forceinline__ int4 rh_meta(const RowHead *p) { return __ldg(reinterpret_cast<const int4 *>(p) + 1); }   // {start, len, cap, pad}
-__device__ __forceinline__ void rh_store(RowHead *p, const uint4 &b, int start, int len, int cap) {
-  reinterpret_cast<uint4 *>(p)[0] = b;
-  reinterpret_cast<int4 *>(p)[1] = make_int4(start, len, cap, 0);
+struct RowMeta { unsigned int nbq; int start, len, cap, q5; };
+__device__ __forceinline__ int4 rh_near(const RowHead *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ RowMeta rh_meta(const RowHead *p) {
+  const int4 v = __ldg(reinterpret_cast<const int4 *>(p) + 1);
+  RowMeta m; m.nbq = (unsigned int)v.x; m.start = v.y; m.len = v.z & 0xffff; m.cap = (v.z >> 16) & 0xffff; m.q5 = v.w & 255;
+  return m;
 }
-// build-distance byte of entry jj of a row: the head holds the first 16, the tail array the rest (indexed like cols[])
-__device__ __forceinline__ int rh_byte(const uint4 &h, int jj) {
-  const unsigned int w = jj < 8 ? (jj < 4 ? h.x : h.y) : (jj < 12 ? h.z : h.w);
-  return (int)((w >> (8 * (jj & 3))) & 255u);
+__device__ __forceinline__ void rh_store(RowHead *p, const int4 &nr, unsigned int nbq, int start, int len, int cap, int q5) {
+  reinterpret_cast<int4 *>(p)[0] = nr;
+  reinterpret_cast<int4 *>(p)[1] = make_int4((int)nbq, start, (len & 0xffff) | (min(cap, 65535) << 16), q5 & 255);
 }
-
-// smallest byte of a 16-byte head restricted to its first len entries (255 for an empty row): the row's nearest build distance
-__device__ __forceinline__ int head_min(const uint4 &h, int len) {
-  const unsigned int w[4] = {h.x, h.y, h.z, h.w};
-  unsigned int m = 0xffffffffu;
+// a row without a near list (empty, or one whose every entry has to be looked at): q5 = 255 means "nothing beyond the near list"
+__device__ __forceinline__ void rh_store_plain(RowHead *p, int start, int len, int cap, int q5) {
+  rh_store(p, make_int4(-1, -1, -1, -1), 0xffffffffu, start, len, cap, q5);
+}
+// The five smallest keys (build distance << 16 | row position) of a row, ascending: a compare-exchange chain in registers.
+struct Near5 { unsigned int k[5]; };
+__device__ __forceinline__ void near5_init(Near5 &n) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) n.k[i] = 0xffffffffu;
+}
+__device__ __forceinline__ void near5_add(Near5 &n, unsigned int key) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { const unsigned int lo = min(n.k[i], key); key = max(n.k[i], key); n.k[i] = lo; }
+}
+// head of a finished row from its five smallest keys: the four nearest in ROW order.  Key layout: distance << 16 | position
+// (NEAR_POS_BITS wide) [| index into the caller's own table of slot ids]; slot_of(key) returns the slot id of the entry.
+template <int POS_SHIFT, typename SlotOf>
+__device__ __forceinline__ void rh_store_near(RowHead *p, const Near5 &n, int start, int len, int cap, SlotOf slot_of) {
+  unsigned int e[4];                                     // low 16 key bits << 8 | distance: sorting orders by row position
+#pragma unroll
+  for (int i = 0; i < 4; ++i) e[i] = n.k[i] == 0xffffffffu ? 0xffffffffu : (((n.k[i] & 0xffffu) << 8) | (n.k[i] >> 16));
+#define CE_(a, b) { const unsigned int lo_ = min(e[a], e[b]), hi_ = max(e[a], e[b]); e[a] = lo_; e[b] = hi_; }
+  CE_(0, 1) CE_(2, 3) CE_(0, 2) CE_(1, 3) CE_(1, 2)
+#undef CE_
+  int nr[4]; unsigned int nb = 0u;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int k = len - 4 * i;                                          // valid bytes of this word
-    const unsigned int fill = k >= 4 ? 0u : (k <= 0 ? 0xffffffffu : (0xffffffffu << (8 * k)));
-    m = __vminu4(m, w[i] | fill);
+    const bool on = e[i] != 0xffffffffu;
+    nr[i] = on ? slot_of((int)(e[i] >> 8)) : -1;
+    nb |= (on ? (e[i] & 255u) : 255u) << (8 * i);
   }
-  m = __vminu4(m, m >> 16); m = __vminu4(m, m >> 8);
-  return (int)(m & 255u);
+  const int q5 = n.k[4] == 0xffffffffu ? 255 : (int)(n.k[4] >> 16);
+  rh_store(p, make_int4(nr[0], nr[1], nr[2], nr[3]), nb, start, len, cap, q5);
 }
 
 // ---- device-resident scalars (one struct in global memory; the host mirrors it on demand) --------------

@@ -16,7 +16,7 @@ struct GcmcArgs {
   double4 *posm; double4 *fe; unsigned char *fnz; double *vel, *acel, *pos_old, *old_cg;
   int *uid, *slot_b, *b_occ;
   const int *cell_of_unused; const int *cell_start; const int *sorted_slot; const double4 *sorted_posm;
-  RowHead *rh; int *cols; unsigned char *bq; unsigned char *qmin; int cols_cap;
+  RowHead *rh; int *cols; unsigned char *bq; int cols_cap;
   int *gorder, *gpos, *gcc; int gorder_cap;
   int *pend;                       // slots inserted during this call, in insertion order
   const double *rp_u, *rp_g; int rp_nu, rp_ng;
@@ -312,8 +312,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
                   const int len = h->len;
                   if (len < h->cap) {
                     A.cols[h->start + len] = ns; h->len = len + 1;
-                    if (len < 16) h->bq[len] = 0; else A.bq[h->start + len] = 0;   // appended entries carry no build distance: never skipped
-                    A.qmin[s] = 0;
+                    A.bq[h->start + len] = 0; h->q5 = 0;   // appended entries carry no build distance: never skipped, and the near list of the head is no longer complete
                   }
                   else { atomicAdd((unsigned long long *)&sc->row_overflow, 1ull); atomicCAS(&sc->err, 0, DML_E_ROW_OVERFLOW); }
                 }
@@ -330,11 +329,10 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
           if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW);
           __syncwarp();
           if (lane == 0) {
-            rh_store(&A.rh[ns], make_uint4(0, 0, 0, 0), base, total, total + A.row_slack);   // zero build distances: nothing is ever skipped
-            A.qmin[ns] = 0;
+            rh_store_plain(&A.rh[ns], base, total, total + A.row_slack, 0);   // zero build distances, no near list: nothing is ever skipped
             sc->cols_used = base + total + A.row_slack;
           }
-        } else if (tid == 0) A.rh[ns].len = 0;
+        } else if (tid == 0) rh_store_plain(&A.rh[ns], ns * ROW_W, 0, 0, 255);
       }
       __syncthreads();
       if (s_i[5] >= 0) { glen += 1; npend += 1; if (tid != 0) n = n + 1; }
@@ -380,7 +378,7 @@ __global__ void __launch_bounds__(GB) k_gcmc(GcmcArgs A) {
         n = n - 1;
         A.gcc[A.gpos[s] / GB] -= 1;
         A.gorder[A.gpos[s]] = -1; sc->gtomb++;
-        A.rh[s].len = 0;
+        rh_store_plain(&A.rh[s], s * ROW_W, 0, 0, 255);
         A.b_occ[A.slot_b[s]] = 0;
         if (A.slot_b[s] < sc->bhole_lo) sc->bhole_lo = A.slot_b[s];
         if (!sc->listed && s < sc->hole_lo) sc->hole_lo = s;
@@ -421,7 +419,7 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.fe = ctx->fe.p; A.fnz = ctx->fnz.p;
   A.pos_old = ctx->pos_old.p; A.old_cg = ctx->old_cg.p; A.uid = ctx->uid.p; A.slot_b = ctx->slot_b.p; A.b_occ = ctx->b_occ.p;
   A.cell_of_unused = nullptr; A.cell_start = ctx->cell_start.p; A.sorted_slot = ctx->sorted_slot.p; A.sorted_posm = ctx->sorted_posm.p;
-  A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.qmin = ctx->qmin.p; A.cols_cap = (int)ctx->cols.cap;
+  A.rh = ctx->rh.p; A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.cols_cap = (int)ctx->cols.cap;
   A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;

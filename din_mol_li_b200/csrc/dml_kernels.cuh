@@ -6,6 +6,7 @@
 namespace dml {
 
 constexpr int TPB = 256;
+constexpr int ROW_W = 24;   // Poisson(5.8) neighbours in solution: P(n > 16) = 1.2e-4 left a dozen rows per 100 k particles on the serial ordered walk (a 28 us tail of the 70 us kernel, ncu: SMs active 57 % of the time); P(n > 24) = 3e-9
 
 // Guard used by every kernel of the rebuild sequence: they are always launched (no host round trip) and return
 // immediately unless test_update decided to rebuild (or the caller forces the cell sort, e.g. for gcmc).
@@ -299,7 +300,7 @@ __device__ __forceinline__ void d_bin(const double4 *__restrict__ posm, int *__r
     } else { cell_of[s] = -1; atomicCAS(&sc->err, 0, DML_E_OUT_OF_TESS); }
   } else {
     cell_of[s] = -1;
-    if (rebuild) { rh[s].len = 0; rh[s].cap = 0; halo_of[s] = 0; }
+    if (rebuild) { rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255); halo_of[s] = 0; }
   }
 }
 __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, int *__restrict__ cell_of, int *__restrict__ cell_cnt,
@@ -375,7 +376,6 @@ __global__ void k_cell_order(const double4 *__restrict__ posm, const int *__rest
 // get a segment of the tail region [cols_tail0, cols_cap) by an atomic bump and are written by a second walk of the same
 // thread.  Where the row lives, its length and its first 16 build distances are the slot's RowHead (dml_device.cuh); the
 // build distances of entries 16.. of a long row are in bq[], indexed like cols[].
-constexpr int ROW_W = 24;   // Poisson(5.8) neighbours in solution: P(n > 16) = 1.2e-4 left a dozen rows per 100 k particles on the serial ordered walk (a 28 us tail of the 70 us kernel, ncu: SMs active 57 % of the time); P(n > 24) = 3e-9
 
 // One thread per cell-sorted ref particle, two dense loops and no per-thread arrays (a queue or a table of cell ranges in local
 // memory costs more L2/DRAM traffic than the whole list):
@@ -389,7 +389,7 @@ constexpr int ROW_W = 24;   // Poisson(5.8) neighbours in solution: P(n > 16) = 
 // in nearly every iteration with ~5 lanes active.
 // Ordered walk + settle of one particle into cols[dst .. dst+lim): the reference's enumeration (27 stencil cells in map order x
 // chain order).  Returns the number of parked candidates; cnt / hb describe the finished row when npark <= lim.
-struct RowOut { int npark, cnt; uint4 hb; };
+struct RowOut { int npark, cnt; Near5 n5; };
 __device__ __forceinline__ RowOut rows_ordered_into(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                                     const int *__restrict__ sorted_slot, const int *__restrict__ cell_start,
                                                     int *__restrict__ cols, unsigned char *__restrict__ bq, const Geo &g,
@@ -421,7 +421,7 @@ __device__ __forceinline__ RowOut rows_ordered_into(const double4 *__restrict__ 
     ++u;
   }
   // ---- settle: the reference's exact fp64 test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515) ----
-  RowOut o; o.npark = npark; o.cnt = 0; o.hb = make_uint4(0, 0, 0, 0);
+  RowOut o; o.npark = npark; o.cnt = 0; near5_init(o.n5);
   const int nset = min(npark, lim);
   for (int i = 0; i < nset; ++i) {
     const int uq = cols[dst + i];
@@ -432,10 +432,8 @@ __device__ __forceinline__ RowOut rows_ordered_into(const double4 *__restrict__ 
       cols[dst + cnt] = sorted_slot[uq];               // cnt <= i: compaction in place
       // lower bound of the build-time distance in 1/255 of the list radius (feeds the gather skip of the consumers)
       const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
-      if (cnt < 16) {
-        const unsigned int sh = qb << (8 * (cnt & 3));
-        if (cnt < 8) { if (cnt < 4) o.hb.x |= sh; else o.hb.y |= sh; } else { if (cnt < 12) o.hb.z |= sh; else o.hb.w |= sh; }
-      } else bq[dst + cnt] = (unsigned char)qb;
+      bq[dst + cnt] = (unsigned char)qb;
+      near5_add(o.n5, (qb << 16) | (unsigned int)min(cnt, 65535));
       o.cnt = cnt + 1;
     }
   }
@@ -470,7 +468,7 @@ __device__ __forceinline__ int nab_of(int dx, int dy, int dz) {
 // dependent instructions per row: measured 326 us instead of 163 us of test_update per step on the 1 M box with the CG slab.
 __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                                const int *__restrict__ sorted_slot, const int *__restrict__ sorted_cell,
-                                               const int *__restrict__ cell_start, RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
+                                               const int *__restrict__ cell_start, RowHead *__restrict__ rh,
                                                int *__restrict__ cols, unsigned char *__restrict__ bq,
                                                DevScal *__restrict__ sc, const Geo &g, int slack, int t) {
   const unsigned int full = 0xffffffffu;
@@ -507,7 +505,7 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
       if (lane == 0) tb = atomicAdd(&sc->cols_used, need);
       tb = __shfl_sync(full, tb, 0);
       if (tb + need > sc->cols_cap) {
-        if (lane == 0) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); qmin[s] = 0; }
+        if (lane == 0) { atomicCAS(&sc->err, 0, DML_E_COLS_OVERFLOW); rh_store_plain(&rh[s], s * ROW_W, 0, ROW_W, 255); }
         return;
       }
     }
@@ -523,8 +521,7 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
   }
   __syncwarp();
   // settle: the reference's exact test (vdistance, Groups.F90:995-1016; strict <, Neighbor.F90:515), ordered compaction in place
-  int cnt = 0, qm = 255;
-  uint4 hb = make_uint4(0, 0, 0, 0);
+  int cnt = 0;
   for (int i0 = 0; i0 < npark; i0 += 32) {
     const int i = i0 + lane;
     bool hit = false; int slot = -1; unsigned int qb = 0u;
@@ -539,21 +536,25 @@ __device__ __forceinline__ void rows_long_warp(const double4 *__restrict__ sorte
     if (hit) {
       const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
       cols[tb + pos] = slot;
-      qm = min(qm, (int)qb);
-      if (pos < 16) {
-        const unsigned int sh = qb << (8 * (pos & 3));
-        if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else { if (pos < 12) hb.z |= sh; else hb.w |= sh; }
-      } else bq[tb + pos] = (unsigned char)qb;
+      bq[tb + pos] = (unsigned char)qb;
     }
     cnt += __popc(hm);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    hb.x |= __shfl_xor_sync(full, hb.x, o); hb.y |= __shfl_xor_sync(full, hb.y, o);
-    hb.z |= __shfl_xor_sync(full, hb.z, o); hb.w |= __shfl_xor_sync(full, hb.w, o);
+  __syncwarp();
+  // near list: the five smallest (distance, position) keys of the finished row, one warp-wide minimum per round
+  Near5 n5; near5_init(n5);
+  unsigned int last = 0u;
+  for (int r5 = 0; r5 < 5; ++r5) {
+    unsigned int best = 0xffffffffu;
+    for (int i = lane; i < cnt; i += 32) {
+      const unsigned int key = ((unsigned int)bq[tb + i] << 16) | (unsigned int)min(i, 65535);
+      if ((r5 == 0 || key > last) && key < best) best = key;
+    }
+    best = __reduce_min_sync(full, best);
+    if (best == 0xffffffffu) break;
+    n5.k[r5] = best; last = best;
   }
-  qm = __reduce_min_sync(full, qm);
-  if (lane == 0) { rh_store(&rh[s], hb, tb, cnt, npark + slack); qmin[s] = (unsigned char)qm; }
+  if (lane == 0) rh_store_near<0>(&rh[s], n5, tb, cnt, npark + slack, [&](int pos) { return cols[tb + pos]; });
 }
 
 // ================================================================================================
@@ -577,12 +578,12 @@ __global__ void __launch_bounds__(TPB) k_verlet_prepare(double4 *__restrict__ po
       pos_old[3 * s] = p.x; pos_old[3 * s + 1] = p.y; pos_old[3 * s + 2] = p.z;
     } else {
       if (m & MF_LIMBO) { p.w = meta_as_double(0); st_rec(&posm[s], p); }
-      rh[s].len = 0; rh[s].cap = 0;
+      rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255);
     }
   }
 }
 __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__ posm, const double *__restrict__ pos_old,
-                                                     const int *__restrict__ b2slot, RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
+                                                     const int *__restrict__ b2slot, RowHead *__restrict__ rh,
                                                      int *__restrict__ cols, unsigned char *__restrict__ bq, DevScal *__restrict__ sc, Geo g, int n, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
   const unsigned int full = 0xffffffffu;
@@ -592,11 +593,9 @@ __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__
   for (int s = wid; s < n; s += nw) {
     const long long m1 = meta_of(ld_rec_nc(&posm[s]));
     if (!(m1 & MF_TYPE)) continue;
-    if (lane == 0) qmin[s] = 0;                          // O(N^2) rows of a tiny box: no gather skipping
-    if (!(m1 & MF_REF)) { if (lane == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); continue; }   // rows exist only for ref atoms
+    if (!(m1 & MF_REF)) { if (lane == 0) rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255); continue; }   // rows exist only for ref atoms
     const double px = pos_old[3 * s], py = pos_old[3 * s + 1], pz = pos_old[3 * s + 2];
     int dst = s * ROW_W, lim = ROW_W, total = 0, cnt = 0;
-    uint4 hb = make_uint4(0, 0, 0, 0);
     for (int pass = 0; pass < 2; ++pass) {
       cnt = 0;
       for (int j0 = 0; j0 < b_amax; j0 += 32) {
@@ -611,11 +610,7 @@ __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__
         if (pass == 1 && hit) {
           const int pos = cnt + __popc(hm & ((1u << lane) - 1u));
           cols[dst + pos] = sj;
-          const unsigned int qb = (unsigned int)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
-          if (pos < 16) {
-            const unsigned int sh = qb << (8 * (pos & 3));
-            if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else { if (pos < 12) hb.z |= sh; else hb.w |= sh; }
-          } else bq[dst + pos] = (unsigned char)qb;
+          bq[dst + pos] = (unsigned char)min(255, (int)(sqrt(rd) * g.bq_scale * 0.999999999));
         }
         cnt += __popc(hm);
       }
@@ -631,13 +626,8 @@ __global__ void __launch_bounds__(TPB) k_rows_verlet(const double4 *__restrict__
         }
       }
     }
-    if (total < 0) { if (lane == 0) rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, ROW_W); continue; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      hb.x |= __shfl_xor_sync(full, hb.x, o); hb.y |= __shfl_xor_sync(full, hb.y, o);
-      hb.z |= __shfl_xor_sync(full, hb.z, o); hb.w |= __shfl_xor_sync(full, hb.w, o);
-    }
-    if (lane == 0) rh_store(&rh[s], hb, dst, total, lim);
+    if (total < 0) { if (lane == 0) rh_store_plain(&rh[s], s * ROW_W, 0, ROW_W, 255); continue; }
+    if (lane == 0) rh_store_plain(&rh[s], dst, total, lim, 0);   // O(N^2) rows of a tiny box: no near list, every entry is looked at
   }
   __syncthreads();                                      // the last block to finish marks the rows as materialised
   if (threadIdx.x == 0) {
@@ -704,16 +694,10 @@ constexpr size_t ROWS_OFF_CNT = ROWS_OFF_QB + (size_t)ROW_W * RB;
 constexpr size_t ROWS_OFF_LONG = ROWS_OFF_CNT + (size_t)28 * RB;
 constexpr size_t ROWS_SMEM = ROWS_OFF_LONG + (size_t)RB * sizeof(int);
 
-__device__ __forceinline__ int row_qmin(const uint4 &hb, int cnt, const unsigned char *__restrict__ bq, int dst) {
-  int m = head_min(hb, cnt);
-  for (int i = 16; i < cnt; ++i) m = min(m, (int)bq[dst + i]);
-  return m;
-}
-
 __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sorted_posm, const float4 *__restrict__ sorted_posf,
                                                const int *__restrict__ sorted_slot,
                                                const int *__restrict__ sorted_cell, const int *__restrict__ cell_start,
-                                               RowHead *__restrict__ rh, unsigned char *__restrict__ qmin,
+                                               RowHead *__restrict__ rh,
                                                int *__restrict__ cols, unsigned char *__restrict__ bq,
                                                DevScal *__restrict__ sc, const __grid_constant__ Geo g, int ncell, int slack) {
   if (!((volatile const DevScal *)sc)->rows_pending) return;
@@ -732,8 +716,12 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
   const int tid = threadIdx.x;
   if (tid < 27) s_nab[tid] = (unsigned char)nab_of(tid % 3 - 1, (tid / 3) % 3 - 1, tid / 9 - 1);   // index = run * 3 + x-neighbour
   const int nsorted = __ldg(&cell_start[ncell]);        // number of binned particles
-  const int t0 = blockIdx.x * RB;
-  if (t0 < nsorted) {                                   // block-uniform
+  if (tid == 0) mbar_init(&s_bar, 1);
+  unsigned int phase = 0u;
+  // persistent grid (two blocks per SM), batch-stride: a launch that finds nothing pending costs one wave of empty blocks (a grid
+  // of one block per batch paid 12 us per idle launch at 1 M particles for 13 waves of 106 KB shared-memory allocations)
+  for (int t0 = blockIdx.x * RB; t0 < nsorted; t0 += gridDim.x * RB, phase ^= 1u) {
+    __syncthreads();                                    // previous batch done with the windows, the hit tables and s_nlong
     const int tl = min(t0 + RB, nsorted) - 1;
     if (tid < 9) {
       int lo = 0, hi = 0;
@@ -745,7 +733,7 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
       }
       s_wlo[tid] = lo; s_whi[tid] = hi;
     }
-    if (tid == 0) { s_nlong = 0; mbar_init(&s_bar, 1); }
+    if (tid == 0) s_nlong = 0;
     {                                                    // hit counters of the block: 28 * RB bytes
       unsigned int *z = reinterpret_cast<unsigned int *>(rows_smem + ROWS_OFF_CNT);
 #pragma unroll
@@ -769,7 +757,7 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
     if (t < nsorted) {
       p = ld_rec_nc(&sorted_posm[t]);
       s = __ldg(&sorted_slot[t]);
-      if (!(meta_of(p) & MF_REF)) { rh_store(&rh[s], make_uint4(0, 0, 0, 0), s * ROW_W, 0, 0); qmin[s] = 255; }   // rows exist only for ref atoms
+      if (!(meta_of(p) & MF_REF)) rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255);   // rows exist only for ref atoms
       else {
         const int lin = __ldg(&sorted_cell[t]);
         cx = lin % g.hd[0]; const int r = lin / g.hd[0]; cy = r % g.hd[1]; cz = r / g.hd[1];
@@ -814,7 +802,20 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
         ++npark;                                                                                                             \
       }                                                                                                                      \
     } while (0)
-    mbar_wait(&s_bar, 0u);
+    // the bounds of the nine runs are requested together, before the wait for the staged windows (36 independent loads in flight
+    // instead of nine dependent batches: with 5 A cells at skin 2 the cell table is 4.6 MB and every batch is an L2 round trip)
+    int ru0[9], rb1[9], rb2[9], rn[9];
+#pragma unroll
+    for (int seg = 0; seg < 9; ++seg) {
+      const int dy = seg % 3 - 1, dz = seg / 3 - 1;
+      const int row = (dy < 0 ? ly0 : (dy == 0 ? ly1 : ly2)) + (dz < 0 ? lz0 : (dz == 0 ? lz1 : lz2));
+      ru0[seg] = rb1[seg] = rb2[seg] = rn[seg] = 0;
+      if (mode == 1) {
+        ru0[seg] = __ldg(&cell_start[row + xa]); rb1[seg] = __ldg(&cell_start[row + cx]); rb2[seg] = __ldg(&cell_start[row + cx + 1]);
+        rn[seg] = __ldg(&cell_start[row + xb + 1]);
+      }
+    }
+    mbar_wait(&s_bar, phase);
     if (__any_sync(full, mode == 1)) {
       const bool anyw = __any_sync(full, xw != 0);
 #pragma unroll
@@ -822,12 +823,9 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
         const int dy = seg % 3 - 1, dz = seg / 3 - 1;
         const int row = (dy < 0 ? ly0 : (dy == 0 ? ly1 : ly2)) + (dz < 0 ? lz0 : (dz == 0 ? lz1 : lz2));
         const float pys = dy < 0 ? py0 : (dy == 0 ? pyf : py2);
-        int u0 = 0, b1 = 0, b2 = 0, n = 0, uw = 0, nw = 0;
-        if (mode == 1) {
-          u0 = __ldg(&cell_start[row + xa]); b1 = __ldg(&cell_start[row + cx]); b2 = __ldg(&cell_start[row + cx + 1]);
-          n = __ldg(&cell_start[row + xb + 1]) - u0;
-          if (xw) { uw = __ldg(&cell_start[row + xw]); nw = __ldg(&cell_start[row + xw + 1]) - uw; }
-        }
+        const int u0 = ru0[seg], b1 = rb1[seg], b2 = rb2[seg], n = rn[seg] - ru0[seg];
+        int uw = 0, nw = 0;
+        if (xw) { uw = __ldg(&cell_start[row + xw]); nw = __ldg(&cell_start[row + xw + 1]) - uw; }
         const int wlo = s_wlo[seg], whi = s_whi[seg];
         {
           const float4 *cp = (u0 >= wlo && u0 + n <= whi) ? (s_win + seg * WCAP + (u0 - wlo)) : (sorted_posf + u0);
@@ -898,31 +896,28 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
 #pragma unroll
         for (int nab = 0; nab < 27; ++nab) { const int c = s_cnt[nab][tid]; s_cnt[nab][tid] = (unsigned char)run; run += c; }
         const int dst = s * ROW_W;
-        uint4 hb = make_uint4(0, 0, 0, 0);
-        int qm = 255;
+        Near5 n5; near5_init(n5);
         for (int i = 0; i < npark; ++i) {
           const int mt = s_meta[i][tid];
           const int pos = (int)s_cnt[mt & 31][tid] + (mt >> 5);
           const unsigned int qb = s_qb[i][tid];
           cols[dst + pos] = s_hit[i][tid];
-          qm = min(qm, (int)qb);
-          const unsigned int sh = qb << (8 * (pos & 3));
-          if (pos < 8) { if (pos < 4) hb.x |= sh; else hb.y |= sh; } else if (pos < 16) { if (pos < 12) hb.z |= sh; else hb.w |= sh; } else bq[dst + pos] = (unsigned char)qb;
+          bq[dst + pos] = (unsigned char)qb;
+          near5_add(n5, (qb << 16) | ((unsigned int)pos << 8) | (unsigned int)i);   // position orders the near list, i finds the slot again
         }
         for (int i = npark; i < ((npark + 7) & ~7); ++i) cols[dst + i] = -1;   // leave no partly written sector behind
-        rh_store(&rh[s], hb, dst, npark, ROW_W);             // one full-sector store per row
-        qmin[s] = (unsigned char)qm;
+        rh_store_near<8>(&rh[s], n5, dst, npark, ROW_W, [&](int k16) { return s_hit[k16 & 255][tid]; });  // one full-sector store per row
       } else s_long[atomicAdd(&s_nlong, 1)] = t;             // long row (next to dense metal): built by a warp below
     } else if (mode == 3) s_long[atomicAdd(&s_nlong, 1)] = t;
     else if (mode == 2) {
       const RowOut o = rows_ordered_into(sorted_posm, sorted_posf, sorted_slot, cell_start, cols, bq, g, p, t, cx, cy, cz, s * ROW_W, ROW_W, true);
-      if (o.npark + slack <= ROW_W) { rh_store(&rh[s], o.hb, s * ROW_W, o.cnt, ROW_W); qmin[s] = (unsigned char)row_qmin(o.hb, o.cnt, bq, s * ROW_W); }
+      if (o.npark + slack <= ROW_W) rh_store_near<0>(&rh[s], o.n5, s * ROW_W, o.cnt, ROW_W, [&](int pos) { return cols[s * ROW_W + pos]; });
       else s_long[atomicAdd(&s_nlong, 1)] = t;
     }
     __syncthreads();
     const int nlong = s_nlong;
     for (int i = tid >> 5; i < nlong; i += RB / 32)
-      rows_long_warp(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, qmin, cols, bq, sc, g, slack, s_long[i]);
+      rows_long_warp(sorted_posm, sorted_posf, sorted_slot, sorted_cell, cell_start, rh, cols, bq, sc, g, slack, s_long[i]);
   }
   __syncthreads();                                      // the last block to finish marks the rows as materialised
   if (threadIdx.x == 0) {
@@ -982,8 +977,8 @@ __device__ __forceinline__ void p_rev_count(const RowHead *__restrict__ rh, cons
     rev_len[s] = 0;                                     // becomes the fill cursor of k_rev_fill
     if (light && !halo_of[s]) continue;                 // light mode: only rows of halo-cell particles are transposed
     if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) continue;
-    const int4 m = rh_meta(&rh[s]);
-    for (int jj = 0; jj < m.y; ++jj) atomicAdd(&rev_cnt[cols[m.x + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
+    const RowMeta m = rh_meta(&rh[s]);
+    for (int jj = 0; jj < m.len; ++jj) atomicAdd(&rev_cnt[cols[m.start + jj]], 1);   // rev_cnt is all zero between builds (the scan clears it)
   }
 }
 __global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restrict__ cols,
@@ -995,28 +990,26 @@ __global__ void k_rev_count(const RowHead *__restrict__ rh, const int *__restric
 __device__ __forceinline__ void p_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
-                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n, unsigned char *__restrict__ qmin) {
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   const bool light = halo_only && sc->rows_asym == 1;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     if (light && !halo_of[s]) continue;
     if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) continue;
-    const int4 m = rh_meta(&rh[s]);
-    const uint4 h = rh_bq16(&rh[s]);
+    const RowMeta m = rh_meta(&rh[s]);
     // the scan cleared rev_len; it is rebuilt here as the fill cursor and ends as the row length
-    for (int jj = 0; jj < m.y; ++jj) {
-      int j = cols[m.x + jj];
+    for (int jj = 0; jj < m.len; ++jj) {
+      int j = cols[m.start + jj];
       int w = rev_start[j] + atomicAdd(&rev_len[j], 1);
-      rev_cols[w] = s; rev_bq[w] = (unsigned char)(jj < 16 ? rh_byte(h, jj) : (int)bq[m.x + jj]);
-      qmin[j] = 0;                                        // j is visited from a transposed row: its own row's nearest distance no longer bounds its partners
+      rev_cols[w] = s; rev_bq[w] = bq[m.start + jj];
     }
   }
 }
 __global__ void k_rev_fill(const RowHead *__restrict__ rh, const int *__restrict__ cols,
                            const double4 *__restrict__ posm, const int *__restrict__ rev_start, int *__restrict__ rev_len,
                            int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, unsigned char *__restrict__ rev_bq,
-                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n, unsigned char *__restrict__ qmin) {
+                           const unsigned char *__restrict__ halo_of, int halo_only, const DevScal *__restrict__ sc, int n) {
   REV_GUARD(sc);
-  p_rev_fill(rh, cols, posm, rev_start, rev_len, rev_cols, bq, rev_bq, halo_of, halo_only, sc, n, qmin);
+  p_rev_fill(rh, cols, posm, rev_start, rev_len, rev_cols, bq, rev_bq, halo_of, halo_only, sc, n);
 }
 __global__ void k_rev_done(DevScal *sc) { if (sc->rows_asym && !sc->rev_valid) sc->rev_valid = 1; }
 // Reverse-visit candidates of atom s: with symmetric rows they are the ref entries of its own row, otherwise rev(s).
@@ -1034,8 +1027,8 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
   if (!(m1 & MF_REF)) return;
   int k = (int)(m1 & MF_TYPE);
   const int asym = sc->rows_asym;
-  const int4 rm = rh_meta(&rh[s]);
-  int b = rm.x, len = rm.y;
+  const RowMeta rm = rh_meta(&rh[s]);
+  int b = rm.start, len = rm.len;
   const int *rv = asym ? rev_cols + rev_start[s] : cols + b;
   int rvlen = asym ? rev_len[s] : len;
   double fx = 0.0, fy = 0.0, fz = 0.0, ep = 0.0;
@@ -1151,20 +1144,6 @@ __device__ __noinline__ double4 lj_terms(double vx, double vy, double vz, double
   r.w = aux * .5;
   return r;
 }
-// ---- build-distance heads -------------------------------------------------------------------------------------------
-// need16(): bit q set <=> entry q (< len, < 16) of the row has a quantised build distance <= qmax, i.e. has to be looked at.
-// Byte-wise SIMD compares on the four words of the 16-byte head; the 4 compare bytes of a word are squeezed to a nibble.
-__device__ __forceinline__ unsigned int need16(const uint4 &h, int len, int qmax) {
-  const unsigned int q4 = (unsigned int)qmax * 0x01010101u;
-  const unsigned int w[4] = {h.x, h.y, h.z, h.w};
-  unsigned int need = 0u;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const unsigned int m = __vcmpleu4(w[i], q4) & 0x01010101u;         // 1 per byte whose value is <= qmax
-    need |= (((m * 0x01020408u) >> 24) & 0xfu) << (4 * i);
-  }
-  return len >= 16 ? need : (need & ((1u << len) - 1u));
-}
 // Pair term of the production kernel once the partner's record is here: cheap cut-off tests first, heavy math out of line.
 // pass 0 = own row, pass 1 = transposed row (reverse visits come from row owners only).
 struct FAcc { double fx, fy, fz, ep; };
@@ -1190,30 +1169,20 @@ __device__ __forceinline__ void fuerza_pair(const Geo &g, const Phys &ph, const 
 // bound of |move of i| + |move of j| since the rows were built: the largest displacement recorded for the z-layers
 // around i at the last test_update (or the global top-2 sum if smaller), plus what maxz (z-dependent) and the
 // integrator moved since.  qmax is the largest quantised D that still has to be looked at (d_qtab tabulates it per z-layer).
-// Row walk of one ref particle whose record and skip bound are in registers: own row, then (asymmetric rows) the transposed one.
-__device__ __noinline__ void fuerza_row(const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const int *__restrict__ cols,
+// Full row walk of one ref particle (taken when the near list of its head does not hold every entry that has to be looked at, or
+// when rows are asymmetric): own row, then the transposed one; eight build-distance bytes per trip.
+__device__ __noinline__ void fuerza_row(const double4 *__restrict__ posm, const int *__restrict__ cols,
                                         const int *__restrict__ rev_start, const int *__restrict__ rev_len, const int *__restrict__ rev_cols,
                                         const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
-                                        const Geo &g, const Phys &ph, const double4 &p1, int k3, int s,
+                                        const Geo &g, const Phys &ph, const double4 &p1, int k3, int s, int start, int len0,
                                         int qmax, int asym, bool i_halo, FAcc &a) {
-  const int4 rm = rh_meta(&rh[s]);
-  const uint4 h16 = rh_bq16(&rh[s]);
   const int npass = asym ? 2 : 1;
   for (int pass = 0; pass < npass; ++pass) {
-    const int off = pass == 0 ? rm.x : rev_start[s];
+    const int off = pass == 0 ? start : rev_start[s];
     const int *lst = (pass == 0 ? cols : rev_cols) + off;
     const unsigned char *lq = (pass == 0 ? bq : rev_bq) + off;
-    const int len = pass == 0 ? rm.y : rev_len[s];
-    int jstart = 0;
-    if (pass == 0) {                                   // head: the skip decision of the first sixteen entries is already here
-      unsigned int need = need16(h16, len, qmax);
-      while (need) {
-        const int q = __ffs(need) - 1; need &= need - 1;
-        fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[__ldg(&lst[q])]), 0, asym, i_halo, a);
-      }
-      jstart = 16;
-    }
-    for (int j0 = jstart; j0 < len; j0 += 8) {
+    const int len = pass == 0 ? len0 : rev_len[s];
+    for (int j0 = 0; j0 < len; j0 += 8) {
       unsigned int need = 0u;                                      // eight build-distance bytes per trip, loads back to back
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -1229,17 +1198,21 @@ __device__ __noinline__ void fuerza_row(const double4 *__restrict__ posm, const 
   }
 }
 
-// One thread per slot.  The streaming part of a particle is its 32-byte record, ONE byte (qmin: the nearest build-time distance
-// of its row, written by the list build) and the 32-byte force/energy it writes: in solution two particles out of three have
-// nothing within reach since the rows were built (qmin above the skip bound of their z-layer, read from a shared-memory copy of
-// the 1 KB table d_qtab keeps) and never touch their row head, row or any partner.  The others take the row walk out of line.
-// Round-1 kernel for comparison: record + 32-byte head for every slot and the bound evaluated per particle (5 table loads + fp64
-// arithmetic): 41 us at 1 M, of which 27 us streaming at 64 registers.
+// One thread per slot; two dependent memory round trips for nearly every particle of a solution:
+//  1. the record, the 32-byte row head (near list: the four nearest entries of the row as slot ids with their build distances, and
+//     the fifth-nearest distance) and the "force is non-zero" byte, all addressed by the slot alone;
+//  2. the records of the near-list partners whose build distance is within the skip bound of the particle's z-layer (the bound is
+//     tabulated per layer by every block for itself while round trip 1 is in flight).
+// Only when the fifth-nearest entry is within the bound too (dense neighbourhoods, long after a rebuild) or the rows are asymmetric
+// does the thread walk the row itself (index and distance-byte loads: a third dependent round trip, out of line).  The terms are
+// added in row order on both paths.  A particle with nothing inside its cut-offs whose stored force is already zero writes nothing.
+// Round 1: record + head with sixteen distance bytes, then indices, then partners (41 us at 1 M particles); an intermediate form
+// that skipped the head behind a one-byte "nearest distance" array moved fewer bytes and was slower (a fourth dependent trip).
 // FUSEB: the thread that holds the finished force also does the particle's ermak_b update (dana.F90:1031-1052), same arithmetic
 // as k_ermak_b.
 template <bool FUSEB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
-    const double4 *__restrict__ posm, const RowHead *__restrict__ rh, const unsigned char *__restrict__ qmin,
+    const double4 *__restrict__ posm, const RowHead *__restrict__ rh,
     const int *__restrict__ cols, const int *__restrict__ rev_start, const int *__restrict__ rev_len,
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
@@ -1250,28 +1223,47 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   const bool in = s < n;
   // everything addressed by the slot alone is requested together
   const double4 p1 = in ? ld_rec_nc(&posm[s]) : make_double4(0, 0, 0, 0);
-  const int qm = in ? (int)__ldg(&qmin[s]) : 255;
+  const int4 nr = in ? rh_near(&rh[s]) : make_int4(-1, -1, -1, -1);
+  RowMeta rm; rm.nbq = 0xffffffffu; rm.start = 0; rm.len = 0; rm.cap = 0; rm.q5 = 255;
+  if (in) rm = rh_meta(&rh[s]);
   const int was_nz = in ? (int)fnz[s] : 0;
   {
     // skip bound per z-layer for the largest cut-off of the pair table, from the displacement table of the last test_update and what
     // the integrator / maxz moved since (same formula as d_qtab; every block tabulates it for itself while its records travel)
+    // (both displacement tables are requested before lay_cur is known: one round trip, in parallel with the record's)
     unsigned char *q8 = reinterpret_cast<unsigned char *>(s_qt);
-    const unsigned int *lt = lay + __ldg(&sc->lay_cur) * LAY_MAX;
     const double thick = g.cell[2] * (double)(1 << g.lay_shift);
-    const double maxz_fac = __ldg(&sc->maxz_fac), z0 = __ldg(&sc->z0), zmax = __ldg(&sc->zmax), dsum = __ldg(&sc->dsum_tu);
-    const double sdisp = (double)__int_as_float((int)__ldg(&sc->step_disp_bits));
-    for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) q8[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, ph.r0_max);
+    for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
+      unsigned int m0 = 0u, m1_ = 0u;
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) { const int q = l + d; if (q >= 0 && q < g.nlay) { m0 = max(m0, __ldg(&lay[q])); m1_ = max(m1_, __ldg(&lay[LAY_MAX + q])); } }
+      const unsigned int mx = __ldg(&sc->lay_cur) ? m1_ : m0;
+      const double maxz_fac = __ldg(&sc->maxz_fac), z0 = __ldg(&sc->z0), zmax = __ldg(&sc->zmax), dsum = __ldg(&sc->dsum_tu);
+      const double sdisp = (double)__int_as_float((int)__ldg(&sc->step_disp_bits));
+      double ztop = thick * (double)(l + 1);
+      if (l == g.nlay - 1) ztop = fmax(ztop, zmax);
+      const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
+      const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
+      q8[l] = (unsigned char)((since > g.cell[2]) ? 255 : (int)fmin(255.0, ceil((ph.r0_max * 1.000001 + S) * g.bq_scale) + 1.0));
+    }
   }
   __syncthreads();
   const long long m1 = meta_of(p1);
   if (!in || !(m1 & MF_REF)) return;
   FAcc a = {0.0, 0.0, 0.0, 0.0};
   const int qmax = (int)reinterpret_cast<const unsigned char *>(s_qt)[layer_of(g, p1.z)];
-  if (qm <= qmax) {
-    const int asym = __ldg(&sc->rows_asym);              // 0 symmetric, 1 halo-only, 2 general
-    const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+  const int asym = __ldg(&sc->rows_asym);                // 0 symmetric, 1 halo-only, 2 general
+  const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
+  if (asym == 0 && rm.q5 > qmax) {
+    // every entry that has to be looked at is in the near list (row order)
+    // (usually none or one of them is within the bound: no need to keep four partner records in flight)
+    const int nrs[4] = {nr.x, nr.y, nr.z, nr.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[nrs[k]]), 0, 0, false, a);
+  } else {
     const bool i_halo = asym == 1 && halo_of[s] != 0;
-    fuerza_row(posm, rh, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, qmax, asym, i_halo, a);
+    fuerza_row(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, rm.start, rm.len, qmax, asym, i_halo, a);
   }
   // fnz[s] == 0 guarantees that fe[s] already holds zeros: a particle with nothing inside its cut-offs (nearly all of them in
   // solution) then writes nothing at all
@@ -1491,55 +1483,58 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ qmin) {
+                                                   DevScal *__restrict__ sc, Geo g, int n) {
   const int s_end = n;
   const double rcut = sqrt(g.rcut2);
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
     // one round trip for everything addressed by the slot alone
     const double4 p1 = ld_rec_nc(&posm[s]);
-    const int qm = (int)__ldg(&qmin[s]);
+    const int4 nr = rh_near(&rh[s]);
+    const RowMeta rm = rh_meta(&rh[s]);
     const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
     const float d1 = disp_of(m1);
     const int qmax = skip_qtab(g, lay, p1.z, 1);          // same build-distance skip as the pair force (covers new and old positions)
-    if (qm > qmax) continue;                              // nothing of this row can be within rcut in any new/old combination
-    const int4 rm = rh_meta(&rh[s]);
-    const int b = rm.x, len = rm.y;
-    const uint4 h16 = rh_bq16(&rh[s]);
+    const int b = rm.start, len = rm.len;
     bool inv = false, have_o1 = false;
     double o1[3] = {0.0, 0.0, 0.0};
-    for (int j0 = 0; j0 < len; j0 += 16) {
-      unsigned int need;
-      if (j0 == 0) need = need16(h16, len, qmax);
-      else {
-        need = 0u;
+    // one entry of the row: conflict-graph edge when any new/old combination of the pair can be within rcut
+    auto look = [&](int j) {
+      const double4 p2 = ld_rec_nc(&posm[j]);
+      const long long m2 = meta_of(p2);
+      if (!(m2 & MF_TYPE)) return;
+      // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
+      // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
+      const double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
+      {
+        // (slab mode: a ghost that is mobile on its owner, MF_GREF, carries an infinite bound and its old_cg was saved
+        //  when the step started, so it joins the conflict graph like a ref atom)
+        const double thr = (rcut + (double)d1 + ((m2 & MF_ANYREF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
+        if (rd_nn > thr * thr) return;
+      }
+      if (!have_o1) { o1[0] = old_cg[3 * s]; o1[1] = old_cg[3 * s + 1]; o1[2] = old_cg[3 * s + 2]; have_o1 = true; }
+      bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
+      if (m2 & MF_ANYREF) {
+        const double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
+        hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
+              dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
+        if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
+      }
+      inv = inv || hit;
+    };
+    if (rm.q5 > qmax) {                                   // every entry that has to be looked at is in the near list of the head
+      const int nrs[4] = {nr.x, nr.y, nr.z, nr.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if ((int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) look(nrs[k]);
+    } else {
+      for (int j0 = 0; j0 < len; j0 += 16) {
+        unsigned int need = 0u;
 #pragma unroll
         for (int q = 0; q < 16; ++q) { const int jj = j0 + q; const int bb = jj < len ? (int)__ldg(&bq[b + jj]) : 1000; need |= (bb <= qmax ? 1u : 0u) << q; }
-      }
-      while (need) {
-        const int q = __ffs(need) - 1; need &= need - 1u;
-        const int j = __ldg(&cols[b + j0 + q]);
-        const double4 p2 = ld_rec_nc(&posm[j]);
-        const long long m2 = meta_of(p2);
-        if (!(m2 & MF_TYPE)) continue;
-        // Exact-safe prefilter: by the triangle inequality no new/old combination can be within rcut when the current
-        // separation exceeds rcut + |move of i| + |move of j| (bounds carried in the records, tiny relative margin).
-        const double rd_nn = dist2_idnint(g, p1.x, p1.y, p1.z, p2.x, p2.y, p2.z);
-        {
-          // (slab mode: a ghost that is mobile on its owner, MF_GREF, carries an infinite bound and its old_cg was saved
-          //  when the step started, so it joins the conflict graph like a ref atom)
-          const double thr = (rcut + (double)d1 + ((m2 & MF_ANYREF) ? (double)disp_of(m2) : 0.0)) * 1.000001;
-          if (rd_nn > thr * thr) continue;
+        while (need) {
+          const int q = __ffs(need) - 1; need &= need - 1u;
+          look(__ldg(&cols[b + j0 + q]));
         }
-        if (!have_o1) { o1[0] = old_cg[3 * s]; o1[1] = old_cg[3 * s + 1]; o1[2] = old_cg[3 * s + 2]; have_o1 = true; }
-        bool hit = rd_nn <= g.rcut2 || dist2_idnint(g, o1[0], o1[1], o1[2], p2.x, p2.y, p2.z) <= g.rcut2;
-        if (m2 & MF_ANYREF) {
-          const double o2[3] = {old_cg[3 * j], old_cg[3 * j + 1], old_cg[3 * j + 2]};
-          hit = hit || dist2_idnint(g, p1.x, p1.y, p1.z, o2[0], o2[1], o2[2]) <= g.rcut2 ||
-                dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) <= g.rcut2;
-          if (hit) { uf_unite(parent, s, j); atomicOr(&ovst[j], OV_INVOLVED); }
-        }
-        inv = inv || hit;
       }
     }
     if (inv) atomicOr(&ovst[s], OV_INVOLVED);
@@ -1549,7 +1544,7 @@ __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ p
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ qmin) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n, qmin); }
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
@@ -1655,14 +1650,13 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
     if (!((st1 >> OV_TSHIFT) & 3)) continue;
     st1 |= OV_SKIP;
     double q1[3]; ov_pos(posm, old_cg, a1, st1, q1);
-    const int4 rm = rh_meta(&rh[a1]);
-    const uint4 h16 = rh_bq16(&rh[a1]);
-    const int rb = rm.x, rl = rm.y;
+    const RowMeta rm = rh_meta(&rh[a1]);
+    const int rb = rm.start, rl = rm.len;
     // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
     // new/old combination, so skipping it here changes nothing and saves the dependent gathers of the replay
     const int qmax = skip_qtab(g, lay, ld_rec_nc(&posm[a1]).z, 1);
     for (int jj = 0; jj < rl; ++jj) {
-      if ((jj < 16 ? rh_byte(h16, jj) : (int)__ldg(&bq[rb + jj])) > qmax) continue;
+      if ((int)__ldg(&bq[rb + jj]) > qmax) continue;
       int a2 = cols[rb + jj];
       int st2 = ((volatile int *)ovst)[a2];
       int t2 = (st2 >> OV_TSHIFT) & 3;
@@ -1821,9 +1815,8 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
           __syncwarp();
           continue;
         }
-        const int4 rm = rh_meta(&rh[a1]);
-        const uint4 h16 = rh_bq16(&rh[a1]);
-        const int rb = rm.x, rl = rm.y;
+        const RowMeta rm = rh_meta(&rh[a1]);
+        const int rb = rm.start, rl = rm.len;
         // the build-distance skip of k_ov_detect (same bound, same record): an entry it skipped cannot be within rcut in any
         // new/old combination, so skipping it here changes nothing
         const int qmax = skip_qtab(g, lay, rec1.z, 1);
@@ -1833,7 +1826,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
           bool in = false;
           int a2 = -1, st2 = 0, t2 = 0;
           double q2[3] = {0.0, 0.0, 0.0};
-          if (jj < rl && (jj < 16 ? rh_byte(h16, jj) : (int)__ldg(&bq[rb + jj])) <= qmax) {
+          if (jj < rl && (int)__ldg(&bq[rb + jj]) <= qmax) {
             a2 = __ldg(&cols[rb + jj]);
             st2 = vst[a2];
             t2 = (st2 >> OV_TSHIFT) & 3;                            // 0 = limbo (dana.F90:881-883)

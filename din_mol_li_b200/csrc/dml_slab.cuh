@@ -124,7 +124,7 @@ __global__ void k_slab_mig_pack(double4 *__restrict__ posm, const double *__rest
   for (int k = 0; k < 3; ++k) { o[4 + k] = vel[3 * s + k]; o[7 + k] = acel[3 * s + k]; o[10 + k] = old_cg[3 * s + k]; }
   out_i[i] = uid[s];
   st_rec(&posm[s], make_double4(0.0, 0.0, 0.0, meta_as_double(0)));
-  rh[s].len = 0; rh[s].cap = 0;
+  rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255);
 }
 __global__ void k_slab_holes(const double4 *__restrict__ posm, int *__restrict__ holes, int *__restrict__ counts, int n_owned) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +147,7 @@ __global__ void k_slab_mig_unpack(double4 *__restrict__ posm, double *__restrict
   for (int k = 0; k < 3; ++k) { vel[3 * s + k] = o[4 + k]; acel[3 * s + k] = o[7 + k]; old_cg[3 * s + k] = o[10 + k]; pos_old[3 * s + k] = o[k]; }
   uid[s] = in_i[i]; slot_b[s] = s; halo_of[s] = 0;
   st_rec(&fe[s], make_double4(0.0, 0.0, 0.0, 0.0));
-  rh[s].len = 0; rh[s].cap = 0;
+  rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255);
 }
 // fresh ghosts: pos_old = old_cg = pos, no velocity, no row
 __global__ void k_slab_ghost_init(const double4 *__restrict__ posm, double *__restrict__ pos_old, double *__restrict__ old_cg,
@@ -158,7 +158,7 @@ __global__ void k_slab_ghost_init(const double4 *__restrict__ posm, double *__re
   const double4 p = ld_rec_nc(&posm[s]);
   const double q[3] = {p.x, p.y, p.z};
   for (int k = 0; k < 3; ++k) { pos_old[3 * s + k] = q[k]; old_cg[3 * s + k] = q[k]; vel[3 * s + k] = 0.0; acel[3 * s + k] = 0.0; }
-  rh[s].len = 0; rh[s].cap = 0;
+  rh_store_plain(&rh[s], s * ROW_W, 0, 0, 255);
 }
 // previous positions of the ghosts = where they are when the step starts (their owners' old_cg of this step)
 __global__ void k_slab_ghost_save(const double4 *__restrict__ posm, double *__restrict__ old_cg, int first, int cnt) {
