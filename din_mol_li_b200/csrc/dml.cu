@@ -50,7 +50,7 @@ struct dml_ctx {
   int64_t nupd = 0, step = 0, choques2 = 0, overlap_passes = 0;
   double t = 0.0;
   int64_t launches = 0;
-  bool profiling = false; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
+  bool profiling = false; int prof_only = -1; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
   double prof_ms[32] = {0}; int64_t prof_n[32] = {0};
   // particle state
   DBuf<float4> sorted_posf;                            // single-precision copy of the cell-sorted records (k_rows prefilter)
@@ -75,6 +75,11 @@ struct dml_ctx {
   int coop_tu_max_n = 4194304;  // test_update is a chain of short data-dependent phases, most of them idle when no rebuild is due: the
                                 // one-launch form wins at every size measured (100 k: 0.312 -> 0.300 ms/step, 1 M: 0.449 -> 0.405 ms/step)
   int tu_fused = 0;         // what the last test_update launch folded in (bit 0 k_ov_init, bit 1 k_ov_apply, bit 2 the tail of the step)
+  // CUDA graph of part a of the loop body (enq_step_a): every launch is unconditional with device-side guards, so the captured
+  // sequence stays valid until the slot count or the geometry changes; replaying it removes the ~6 us host / front-end gap in front
+  // of each of the ~11 launches of a step
+  cudaGraphExec_t step_graph = nullptr; int sg_n = -1, sg_nct = -1; Geo sg_geo; int64_t sg_launches = 0; bool use_graph = true;
+  bool step_tail_done = false;       // enq_step_a folded the tail of the step into the second test_update
   bool sort_maybe_pending = false;   // a deferring test_update was enqueued since the last cell sort (k_sort_catchup is launched on demand)
   DBuf<double4> snap;       // positions of a rebuild whose cell sort was deferred
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
@@ -133,7 +138,7 @@ static const int kern_cls[K_NKERN] = {CLS_LIST, CLS_BIN, CLS_BIN, CLS_LIST, CLS_
 
 static void prof_begin(dml_ctx *ctx, int cls) {
   ctx->launches++;
-  if (!ctx->profiling) return;
+  if (!ctx->profiling || (ctx->prof_only >= 0 && ctx->prof_only != cls)) return;
   ProfEv ev;
   if (!ctx->pool.empty()) { ev = ctx->pool.back(); ctx->pool.pop_back(); }
   else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
@@ -141,7 +146,7 @@ static void prof_begin(dml_ctx *ctx, int cls) {
   cudaEventRecord(ev.a, ctx->st);
   ctx->evs.push_back(ev);
 }
-static void prof_end(dml_ctx *ctx) { if (ctx->profiling) cudaEventRecord(ctx->evs.back().b, ctx->st); }
+static void prof_end(dml_ctx *ctx, int cls) { if (ctx->profiling && !(ctx->prof_only >= 0 && ctx->prof_only != cls)) cudaEventRecord(ctx->evs.back().b, ctx->st); }
 static void prof_collect(dml_ctx *ctx) {
   if (ctx->evs.empty()) return;
   cudaStreamSynchronize(ctx->st);
@@ -152,10 +157,10 @@ static void prof_collect(dml_ctx *ctx) {
   }
   ctx->evs.clear();
 }
-#define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx); } while (0)
+#define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx, cls); } while (0)
 
 #define LAUNCH_COOP(kid, kern, grid, argstruct) do { prof_begin(ctx, kid); void *a_[] = {(void *)&(argstruct)}; \
-  cudaError_t e_ = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TPB), a_, 0, ctx->st); prof_end(ctx); \
+  cudaError_t e_ = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TPB), a_, 0, ctx->st); prof_end(ctx, kid); \
   if (e_ != cudaSuccess) { ctx->err = std::string("cooperative launch of " #kern ": ") + cudaGetErrorString(e_); return -1; } } while (0)
 
 static inline int nblk(int n, int b = TPB) { return std::max(1, (n + b - 1) / b); }
@@ -312,7 +317,7 @@ static int enq_materialize_rows(dml_ctx *ctx) {
   prof_begin(ctx, K_ROWS_FILL);
   k_rows<<<std::min(nblk(n, RB), 148 * 2), RB, ROWS_SMEM, ctx->st>>>(ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
                                                   ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
-  prof_end(ctx);
+  prof_end(ctx, K_ROWS_FILL);
   return 0;
 }
 
@@ -384,12 +389,13 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
   int n = ctx->n;
   ctx->step++;
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
+  LAUNCH(K_MISC, k_tick, 1, 1, ctx->sc);                  // the Philox step word lives on the device (DevScal::istep)
   if (ermak)
     LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
   else
     LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, (unsigned int)ctx->step, n);
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
   ctx->have_rp = false;
   return 0;
 }
@@ -457,7 +463,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
     A.posm = ctx->posm.p; A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p; A.rh = ctx->rh.p;
     A.cols = ctx->cols.p; A.bq = ctx->bq.p; A.lay = ctx->lay.p; A.parent = ctx->parent.p; A.ovst = ctx->ovst.p; A.comp_cnt = ctx->comp_cnt.p;
     A.comp_off = ctx->comp_off.p; A.members = ctx->members.p; A.roots = ctx->roots.p; A.ov_head = ctx->ov_head.p; A.ov_next = ctx->ov_next.p; A.uid = ctx->uid.p;
-    A.rp_uovl = ov_replay(ctx); A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = (unsigned int)ctx->step;
+    A.rp_uovl = ov_replay(ctx); A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.step = STEP_FROM_DEVICE;
     A.n = n; A.guard_pass = ctx->ov_guard_pass;
     LAUNCH_COOP(K_OV_COOP, k_overlap_coop, ctx->coop_grid_ov, A);
     ctx->have_rp_ovl = false;
@@ -471,7 +477,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
     LAUNCH(K_OV_PASS, k_ov_resolve, std::min(nblk(n, 4), 148 * 4), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
            ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->ov_head.p, ctx->ov_next.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
-           (unsigned int)ctx->step, ctx->ov_guard_pass);
+           STEP_FROM_DEVICE, ctx->ov_guard_pass);
   } else {
     LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
     LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
@@ -486,7 +492,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
         CKC(cudaMemsetAsync(&ctx->sc->again, 0, sizeof(int), ctx->st));
         LAUNCH(K_OV_PASS, k_ov_pass, nblk(nroots, 64), 64, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p,
                ctx->bq.p, ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
-               (unsigned int)ctx->step, pass, (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
+               STEP_FROM_DEVICE, pass, (ctx->ov_guard_pass > 0 && pass >= ctx->ov_guard_pass) ? 1 : 0);
         TRY(pull_scal(ctx));
         if (!ctx->hsc->again) { CKC(cudaMemsetAsync(&ctx->sc->any_active, 0, sizeof(int), ctx->st)); ctx->hsc->any_active = pass + 1;
                                 CKC(cudaMemcpyAsync(&ctx->sc->any_active, &ctx->hsc->any_active, sizeof(int), cudaMemcpyHostToDevice, ctx->st)); break; }
@@ -529,6 +535,7 @@ static int finish(dml_ctx *ctx) {
     CKC(ctx->bq.ensure(ctx->cols.cap, ctx->st, true)); CKC(ctx->rev_bq.ensure(ctx->cols.cap, ctx->st, false));
     ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
     ctx->hsc->rev_valid = 0;
+    ctx->sg_n = -1;                                         // the captured step holds the old pointers
     TRY(push_scal(ctx));
     CKC(cudaStreamSynchronize(ctx->st));
   }
@@ -572,8 +579,9 @@ static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double
   return enq_test_update(ctx);
 }
 
-// one iteration of dana's loop body (dana.F90:173-265), enqueue only (reservoir 2 reads rho once per step)
-static int enq_step(dml_ctx *ctx) {
+// one iteration of dana's loop body (dana.F90:173-265), enqueue only.  Part a: everything up to calc_rho (no host round trip);
+// part b: the reservoirs that need the host (reservoir 2 reads rho once per step) and the end of the step.
+static int enq_step_a(dml_ctx *ctx) {
   int n = ctx->n;
   if (ctx->cfg.integrador) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
@@ -596,6 +604,11 @@ static int enq_step(dml_ctx *ctx) {
   } else if (!tail_done) {
     LAUNCH(K_PROMOTE, k_promote_rho, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1], ctx->cfg.reservoir == 2 ? 1 : 0, n);
   }
+  ctx->step_tail_done = tail_done;
+  return 0;
+}
+static int enq_step_b(dml_ctx *ctx) {
+  const bool tail_done = ctx->step_tail_done;
   if (ctx->cfg.reservoir == 2) {
     if (!ctx->have_chunk) FAIL("reservoir 2: call dml_set_chunk_template before dml_step");
     int fired = 0;
@@ -607,6 +620,36 @@ static int enq_step(dml_ctx *ctx) {
   ctx->t = ctx->t + ctx->cfg.h;
   return 0;
 }
+static bool graph_ok(const dml_ctx *ctx) {
+  return ctx->use_graph && !ctx->profiling && ctx->ph.rng_mode == DML_RNG_PHILOX && ctx->cfg.prob >= 1.0 && ctx->cfg.reservoir != 3 &&
+         ctx->tessellated && ctx->use_coop && ctx->n <= ctx->coop_tu_max_n;
+}
+// part a of one step: replay of the captured graph when there is a valid one, capture + launch otherwise
+static int launch_step_a(dml_ctx *ctx) {
+  if (!graph_ok(ctx)) return enq_step_a(ctx);
+  if ((size_t)ctx->nct + 2 > ctx->cell_start.cap) return enq_step_a(ctx);   // (re)allocation of the cell tables happens outside a capture
+  if (!ctx->cfg.integrador) CKC(ctx->snap.ensure(ctx->cap, ctx->st));
+  if (!ctx->step_graph || ctx->sg_n != ctx->n || ctx->sg_nct != ctx->nct || memcmp(&ctx->sg_geo, &ctx->geo, sizeof(Geo)) != 0) {
+    if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
+    const int64_t step0 = ctx->step, l0 = ctx->launches;
+    cudaGraph_t g = nullptr;
+    CKC(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+    const int rc = enq_step_a(ctx);
+    cudaError_t e = cudaStreamEndCapture(ctx->st, &g);
+    ctx->sg_launches = ctx->launches - l0;
+    ctx->step = step0; ctx->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess || !g) { cudaGetLastError(); ctx->use_graph = false; return enq_step_a(ctx); }   // capture not possible here: plain launches from now on
+    e = cudaGraphInstantiate(&ctx->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); ctx->step_graph = nullptr; ctx->use_graph = false; return enq_step_a(ctx); }
+    ctx->sg_n = ctx->n; ctx->sg_nct = ctx->nct; ctx->sg_geo = ctx->geo;
+  }
+  ctx->step++; ctx->launches += ctx->sg_launches;
+  CKC(cudaGraphLaunch(ctx->step_graph, ctx->st));
+  return 0;
+}
+static int enq_step(dml_ctx *ctx) { TRY(launch_step_a(ctx)); return enq_step_b(ctx); }
 
 #include "dml_gcmc.cuh"
 
@@ -665,6 +708,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
   if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
+  if (getenv("DML_NO_GRAPH")) ctx->use_graph = false;
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
   CKC(ctx->vel.ensure(c3, ctx->st)); CKC(ctx->acel.ensure(c3, ctx->st)); CKC(ctx->fe.ensure(cap, ctx->st));
@@ -725,6 +769,7 @@ void dml_destroy(dml_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->st);
+  if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
   prof_collect(ctx);
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
@@ -856,6 +901,7 @@ int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel
 int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s) { ENTER(ctx);
   TRY(pull_scal(ctx));
   ctx->hsc->z0 = s->z0; ctx->hsc->z1 = s->z1; ctx->hsc->zmax = s->zmax; ctx->hsc->rho = s->rho; ctx->hsc->rho0 = s->rho0;
+  ctx->hsc->istep = (unsigned int)s->step;
   TRY(push_scal(ctx));
   set_box(ctx, s->box);
   ctx->t = s->t; ctx->step = s->step;
@@ -942,6 +988,51 @@ int dml_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
     if ((i & 15) == 15) TRY(finish(ctx));              // periodic error check / storage growth; no other host round trip
   }
   return finish(ctx);
+}
+
+// Ensemble of independent replicas on one GPU (BASELINE config 5): every ctx has its own stream, so enqueueing the
+// same step of all replicas from ONE host thread lets their (latency-bound, machine-underfilling) kernels overlap on the device.
+// Part a of every replica is enqueued before the first part b (the only host round trip: reservoir 2 reads rho) is waited for.
+int dml_ensemble_step(dml_ctx **ctxs, int32_t nctx, int32_t nsteps) {
+  if (!ctxs || nctx <= 0) return -1;
+  for (int i = 0; i < nsteps; ++i) {
+    for (int r = 0; r < nctx; ++r) { dml_ctx *ctx = ctxs[r]; ENTER(ctx); TRY(launch_step_a(ctx)); }
+    for (int r = 0; r < nctx; ++r) { dml_ctx *ctx = ctxs[r]; ENTER(ctx); TRY(enq_step_b(ctx)); if ((i & 15) == 15) TRY(finish(ctx)); }
+  }
+  for (int r = 0; r < nctx; ++r) { dml_ctx *ctx = ctxs[r]; ENTER(ctx); TRY(finish(ctx)); }
+  return 0;
+}
+// a replica of an ensemble leaves room for the others: one block per SM for the cooperative kernels (a grid that fills the
+// machine cannot overlap with another replica's; measured with 4 x 200 k boxes: 7.5e8 -> 9.6e8 particle-steps/s)
+int dml_set_ensemble_member(dml_ctx *ctx, int32_t on) { ENTER(ctx);
+  int dev = 0, nsm = 0;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  int b1 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
+  ctx->coop_grid_tu = nsm * (on ? 1 : std::min(b1, 4));
+  return 0;
+}
+
+// Host-buffer path of a host that keeps the frame (what salida() reads: positions and element, src/dana.F90:1151-1157): new
+// positions in, frame out; membership, velocities and the neighbour structures stay resident.
+int dml_upload_positions(dml_ctx *ctx, int32_t n, const double *pos, const double *pos_old) { ENTER(ctx);
+  if (n != ctx->n) FAIL("dml_upload_positions: n must be the current number of slots (use dml_upload for structural changes)");
+  if (!pos) FAIL("dml_upload_positions: pos is required");
+  const size_t n3 = (size_t)n * 3;
+  CKC(ctx->stage_d.ensure(n3, ctx->st));
+  CKC(cudaMemcpyAsync(ctx->stage_d.p, pos, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  if (pos_old) CKC(cudaMemcpyAsync(ctx->pos_old.p, pos_old, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+  LAUNCH(K_PACK, k_repos, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, n);
+  return 0;                                               // stream-ordered: the next call on this ctx sees the new positions
+}
+int dml_download_frame(dml_ctx *ctx, int32_t n, double *pos, int32_t *z) { ENTER(ctx);
+  if (n > ctx->n) FAIL("dml_download_frame: n exceeds the number of slots");
+  const size_t n3 = (size_t)n * 3;
+  CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
+  LAUNCH(K_PACK, k_unpack, nblk(n), TPB, ctx->posm.p, pos ? ctx->stage_d.p : nullptr, z ? ctx->stage_i.p : nullptr, (int *)nullptr, n);
+  if (pos) CKC(cudaMemcpyAsync(pos, ctx->stage_d.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  if (z) CKC(cudaMemcpyAsync(z, ctx->stage_i.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
 }
 
 int dml_get_cells(dml_ctx *ctx, int32_t n, int32_t *cell_xyz, int32_t *chain_pos) { ENTER(ctx);
@@ -1301,7 +1392,7 @@ int dml_density_profile(dml_ctx *ctx, double zlo, double zhi, int32_t nbins, int
   prof_begin(ctx, K_MISC);
   k_density_profile<<<std::min(nblk(n, OBS_TPB), 148 * 2), OBS_TPB, (size_t)nbins * sizeof(unsigned int), ctx->st>>>(ctx->posm.p, n, zlo, dz, nbins, type_mask,
                                                                                                                   ctx->obs_counts.p);
-  prof_end(ctx);
+  prof_end(ctx, K_MISC);
   CKC(cudaMemcpyAsync(counts, ctx->obs_counts.p, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaStreamSynchronize(ctx->st));
   CKC(cudaGetLastError());
@@ -1340,7 +1431,7 @@ int dml_gr(dml_ctx *ctx, double rmax, int32_t nbins, int32_t type_mask, int64_t 
     prof_begin(ctx, K_MISC);
     k_gr_pairs<<<nblk(hsel, OBS_TPB), OBS_TPB, (size_t)nbins * sizeof(unsigned int), ctx->st>>>(ctx->gr_sorted.p, hsel, ctx->gr_start.p, gg, ctx->geo,
                                                                                               rmax * rmax, dr_bin, nbins, ctx->obs_counts.p);
-    prof_end(ctx);
+    prof_end(ctx, K_MISC);
   }
   CKC(cudaMemcpyAsync(counts, ctx->obs_counts.p, (size_t)nbins * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
   CKC(cudaStreamSynchronize(ctx->st));
@@ -1378,6 +1469,7 @@ int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int
 int dml_profile(dml_ctx *ctx, int32_t enable) { ENTER(ctx);
   prof_collect(ctx);
   ctx->profiling = enable != 0;
+  ctx->prof_only = enable >= 2 ? enable - 2 : -1;          // enable = 2 + kernel id: events around that kernel only (undisturbed pipeline)
   if (enable) while (ctx->pool.size() < 8192) { ProfEv ev; cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.cls = 0; ctx->pool.push_back(ev); }
   return 0;
 }

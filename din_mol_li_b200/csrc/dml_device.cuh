@@ -143,6 +143,8 @@ struct DevScal {
   long long overlap_passes;
   unsigned int ticket3;             // last-block election of k_pbc_disp
   unsigned int ticket4;             // last-block election of k_integrate
+  unsigned int istep;               // integrator calls so far: the step word of the Philox counters (kernels read it here so that a captured
+                                    // CUDA graph of the loop body stays valid from step to step)
   int sort_pending;                 // a rebuild snapshotted the positions but the cell sort was left to whoever needs it first (dml_coop.cuh)
   int tu_par, rho_cnt2[2], dref_cnt2[2];   // census / promotion counters of the fused step tail, double-buffered by call parity
   int hole_lo, bhole_lo;            // gcmc index reuse: no empty hs slot / free b index below these (reset when a rebuild frees the limbo slots)

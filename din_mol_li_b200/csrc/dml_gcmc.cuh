@@ -53,11 +53,11 @@ struct GcmcRng {
   const GcmcArgs *A; int iu, ig, ctr;
   __device__ double unif() {
     if (A->ph.rng_mode == 1) { if (iu >= A->rp_nu) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.5; } return A->rp_u[iu++]; }
-    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step, RS_GCMC, 0u); return r.u01(0);
+    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step == STEP_FROM_DEVICE ? A->sc->istep : A->step, RS_GCMC, 0u); return r.u01(0);
   }
   __device__ double gauss() {
     if (A->ph.rng_mode == 1) { if (ig >= A->rp_ng) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.0; } return A->rp_g[ig++]; }
-    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step, RS_GCMC, 1u); double a, b; r.gauss2(a, b); return a;
+    Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step == STEP_FROM_DEVICE ? A->sc->istep : A->step, RS_GCMC, 1u); double a, b; r.gauss2(a, b); return a;
   }
 };
 
@@ -423,7 +423,7 @@ static int gcmc_run_impl(dml_ctx *ctx) {
   A.gorder = ctx->gorder.p; A.gpos = ctx->gpos.p; A.gcc = ctx->gcc.p; A.gorder_cap = ctx->gorder_cap;
   A.pend = ctx->gpend.p; A.rp_u = ctx->rp_gu.p; A.rp_g = ctx->rp_gg.p; A.rp_nu = ctx->rp_nu; A.rp_ng = ctx->rp_ng;
   A.sc = ctx->sc; A.g = ctx->geo; A.ph = ctx->ph; A.act = ctx->cfg.act; A.beta_kT = ctx->cfg.kB_ui_gcmc * ctx->cfg.Tsist;
-  A.nadj = nadj; A.cap = ctx->cap; A.listed = 1; A.row_slack = ctx->row_slack; A.step = (unsigned int)ctx->step;
+  A.nadj = nadj; A.cap = ctx->cap; A.listed = 1; A.row_slack = ctx->row_slack; A.step = STEP_FROM_DEVICE;
   TRY(enq_materialize_rows(ctx));                       // the incremental list upkeep of an accepted attempt edits the rows in place
   LAUNCH(K_GCMC, k_gcmc_census, 148 * 4, 256, ctx->posm.p, ctx->gorder.p, ctx->gcc.p, ctx->sc);
   LAUNCH(K_GCMC, k_gcmc, 1, GB, A);

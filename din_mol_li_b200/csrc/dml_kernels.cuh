@@ -6,6 +6,9 @@
 namespace dml {
 
 constexpr int TPB = 256;
+constexpr unsigned int STEP_FROM_DEVICE = 0xffffffffu;   // kernels given this step word read DevScal::istep
+// one integrator call = one tick of the Philox step word (dml_step enqueues it in front of the integrator)
+__global__ void k_tick(DevScal *sc) { sc->istep = sc->istep + 1u; }
 constexpr int ROW_W = 24;   // Poisson(5.8) neighbours in solution: P(n > 16) = 1.2e-4 left a dozen rows per 100 k particles on the serial ordered walk (a 28 us tail of the 70 us kernel, ncu: SMs active 57 % of the time); P(n > 24) = 3e-9
 
 // Guard used by every kernel of the rebuild sequence: they are always launched (no host round trip) and return
@@ -1344,11 +1347,12 @@ __device__ __forceinline__ bool atom_pbc_dev(const Geo &g, const Phys &ph, doubl
 }
 
 template <bool ERMAK>
-__global__ void __launch_bounds__(TPB) k_integrate(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acel,
+__global__ void __launch_bounds__(TPB, 4) k_integrate(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acel,
                                                    double *__restrict__ pos_old, double *__restrict__ old_cg, double *__restrict__ ranv,
                                                    const int *__restrict__ uid, const double *__restrict__ rp_gauss,
                                                    const double *__restrict__ rp_upbc, DevScal *__restrict__ sc, Geo g, Phys ph,
                                                    unsigned int step, int n) {
+  if (step == STEP_FROM_DEVICE) step = sc->istep;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   BlockAcc acc = {0, 0, 0.0, 0.0, 0.0f};
   if (s < n) {
@@ -1708,6 +1712,7 @@ __global__ void k_ov_pass(const double4 *__restrict__ posm, const double *__rest
                           const int *__restrict__ roots, const int *__restrict__ comp_cnt, const int *__restrict__ comp_off,
                           const int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                           DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int pass, int guard) {
+  if (step == STEP_FROM_DEVICE) step = sc->istep;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sc->n_roots) return;
   int root = roots[r], b = comp_off[root], e = b + comp_cnt[root];
@@ -1742,6 +1747,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
                              const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
                              int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
+  if (step == STEP_FROM_DEVICE) step = sc->istep;
   const unsigned int FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -2009,6 +2015,16 @@ __global__ void k_pack(double4 *__restrict__ posm, const double *__restrict__ po
   if (f & 8) m = MF_LIMBO;
   else if (zz >= 1 && zz <= 3) m = with_disp(zz | ((f & 1) ? MF_REF : 0) | ((f & 2) ? MF_GCMC : 0) | ((f & 4) ? MF_SKIP : 0), DISP_INF);
   double4 p = {pos[3 * s], pos[3 * s + 1], pos[3 * s + 2], meta_as_double(m)};
+  st_rec(&posm[s], p);
+}
+// new coordinates for the same atoms (dml_upload_positions): element, membership and flags stay; the displacement bound is unknown
+__global__ void k_repos(double4 *__restrict__ posm, const double *__restrict__ pos, int n) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double4 p = ld_rec(&posm[s]);
+  const long long m = meta_of(p);
+  if (!(m & MF_TYPE)) return;
+  p.x = pos[3 * s]; p.y = pos[3 * s + 1]; p.z = pos[3 * s + 2]; p.w = meta_as_double(with_disp(m, DISP_INF));
   st_rec(&posm[s], p);
 }
 __global__ void k_unpack(const double4 *__restrict__ posm, double *__restrict__ pos, int *__restrict__ z, int *__restrict__ flags, int n) {

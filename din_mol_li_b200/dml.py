@@ -53,6 +53,7 @@ SYMBOLS = [
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
     "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
     "dml_salida_sums", "dml_density_profile", "dml_gr", "dml_membership_changes",
+    "dml_ensemble_step", "dml_set_ensemble_member", "dml_upload_positions", "dml_download_frame",
 ]
 
 _lib = None
@@ -107,6 +108,10 @@ def lib():
         L.dml_density_profile.argtypes = [vp, dbl, dbl, i32, i32, vp]
         L.dml_gr.argtypes = [vp, dbl, i32, i32, vp, C.POINTER(i32)]
         L.dml_membership_changes.argtypes = [vp, i32, vp, vp, vp, vp, C.POINTER(i32)]
+        L.dml_ensemble_step.argtypes = [C.POINTER(vp), i32, i32]
+        L.dml_set_ensemble_member.argtypes = [vp, i32]
+        L.dml_upload_positions.argtypes = [vp, i32, vp, vp]
+        L.dml_download_frame.argtypes = [vp, i32, vp, vp]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -218,6 +223,15 @@ def make_config(box, h, nb_dcut, z0, zmax, integrador, reservoir, capacity, prob
 
 class DmlError(RuntimeError):
     pass
+
+
+def ensemble_step(ctxs, nsteps=1):
+    """dml_ensemble_step: nsteps of every replica, enqueued by this one host thread on the replicas' own streams."""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = lib().dml_ensemble_step(arr, len(ctxs), nsteps)
+    if rc != 0:
+        msgs = [lib().dml_last_error(c.h).decode() for c in ctxs]
+        raise DmlError("dml_ensemble_step failed: " + "; ".join(m for m in msgs if m))
 
 
 class Ctx:
@@ -337,6 +351,20 @@ class Ctx:
     def step(self, n=1):
         self._chk(lib().dml_step(self.h, n))
 
+    def upload_positions(self, pos, pos_old=None):
+        pos, po = _f64(pos), _f64(pos_old)
+        self._keep = (pos, po)                                # the copy is stream-ordered: keep the arrays alive
+        self._chk(lib().dml_upload_positions(self.h, pos.shape[0], _p(pos), _p(po)))
+
+    def download_frame(self, n=None):
+        n = self.n_slots() if n is None else n
+        pos, z = np.empty((n, 3)), np.empty(n, np.int32)
+        self._chk(lib().dml_download_frame(self.h, n, _p(pos), _p(z)))
+        return pos, z
+
+    def set_ensemble_member(self, on=True):
+        self._chk(lib().dml_set_ensemble_member(self.h, 1 if on else 0))
+
     # --- output reductions and observables (salida/kion sums, rho(z), g(r)) ---
     def salida_sums(self):
         """energia (sum of epot over sys, dana.F90:1160), energia over hs%ref only, temp (kion, dana.F90:1342-1376), j."""
@@ -406,6 +434,12 @@ class Ctx:
 
     def profile(self, on=True):
         self._chk(lib().dml_profile(self.h, 1 if on else 0))
+
+    def profile_only(self, kernel_name):
+        """CUDA events around the launches of ONE kernel (by its dml_profile_kernel name): the rest of the pipeline runs undisturbed."""
+        names = list(self.profile_kernels().keys())
+        self._chk(lib().dml_profile(self.h, 2 + names.index(kernel_name)))
+        self.profile_get(CLS_ALL, reset=True)
 
     def profile_get(self, cls, reset=False):
         ms = C.c_double()

@@ -114,6 +114,16 @@ int dml_set_chunk_template(dml_ctx *ctx, int32_t nchunk, const double *chunk_pos
 /* nsteps full loop iterations (src/dana.F90:173-265 minus salida/timer) without returning to the caller
  * between call sites (reservoir 2 uses the template given to dml_set_chunk_template). */
 int dml_step(dml_ctx *ctx, int32_t nsteps);
+/* The same for an ensemble of independent replicas on one GPU (BASELINE config 5): one host thread enqueues the
+ * step of every replica on its own stream so their kernels overlap; no data-path communication.  dml_set_ensemble_member sizes
+ * the cooperative kernels of a ctx so that the replicas can overlap (call it once per member before the loop). */
+int dml_ensemble_step(dml_ctx **ctxs, int32_t nctx, int32_t nsteps);
+int dml_set_ensemble_member(dml_ctx *ctx, int32_t on);
+/* Frame path of a host that only follows the coordinates (what salida() reads, src/dana.F90:1151-1157): new positions of the same
+ * atoms in (membership, velocities, lists stay resident; n must equal the current slot count; the copy is stream-ordered),
+ * positions + element out (synchronous). */
+int dml_upload_positions(dml_ctx *ctx, int32_t n, const double *pos, const double *pos_old);
+int dml_download_frame(dml_ctx *ctx, int32_t n, double *pos, int32_t *z);
 
 /* Output path on the device: what salida() needs without downloading the frame.
  * dml_salida_sums: energia = sum of epot over sys (src/dana.F90:1155-1163), temp = kion(sys) (src/dana.F90:1342-1376:
@@ -167,7 +177,7 @@ int dml_slab_info(dml_ctx *ctx, int32_t *n_owned, int32_t *n_ghost, int32_t *nse
 
 /* Timing helper for bench.py: device-side duration (ms) of the kernels of the named class accumulated since
  * the last call with reset!=0.  cls: 0 pair force, 1 list build, 2 integrator, 3 overlap, 4 all. */
-int dml_profile(dml_ctx *ctx, int32_t enable);
+int dml_profile(dml_ctx *ctx, int32_t enable);   /* 0 off, 1 every kernel, 2+kid only kernel kid (dml_profile_kernel order) */
 int dml_profile_get(dml_ctx *ctx, int32_t cls, double *ms, int64_t *launches, int32_t reset);
 /* per-kernel timing: kid = 0,1,2,... until the call returns 1; name points to a static string */
 int dml_profile_kernel(dml_ctx *ctx, int32_t kid, const char **name, double *ms, int64_t *launches);

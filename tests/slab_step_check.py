@@ -27,10 +27,10 @@ def make_cfg(box, cap, dev):
                            rng_mode=dml.RNG_PHILOX, seed=99, strict_order=0, device=dev)
 
 
-def main():
-    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+def check(rank, world, lr, nsteps=NSTEPS):
+    """The comparison itself, on an initialised process group (bench.py's slab section calls it too and puts the verdict in its JSON).
+    Returns a dict with ok (all ranks) and the figures printed below."""
+    NSTEPS = nsteps
     box = [200.0, 200.0, 400.0]
     pos0, _ = dml.host_pos_inic(-104012, box[0], box[1], box[2])
     n = len(pos0)
@@ -115,8 +115,18 @@ def main():
     dist.all_reduce(t)
     slab.close()
     dist.barrier()
+    return {"ok": t.item() == 0, "ranks": world, "steps": NSTEPS, "particles": int(ntot), "partition_exact": bool(part_ok and inside),
+            "rebuilds_slab_vs_single": [int(c.nupd_vlist), int(fc.nupd_vlist)], "fraction_of_particles_within_1e-6_of_single_gpu": frac,
+            "deposited_slab_vs_single": [int(ndep), int(dep_ref)], "zmax_slab_vs_single": [ss.zmax, fs.zmax], "migrated": int(migrated)}
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    r = check(rank, world, lr)
     dist.destroy_process_group()
-    sys.exit(0 if t.item() == 0 else 1)
+    sys.exit(0 if r["ok"] else 1)
 
 
 if __name__ == "__main__":

@@ -40,14 +40,13 @@ def probe(kind, n, variant, steps, out):
             else:
                 os.environ[k] = v
     ext = torch.cuda.ExternalStream(dml.lib().dml_stream(ctx.h), device=0)
-    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    flush = B.L2Flush(ext)
     for _ in range(6):
         ctx.step(1)
     torch.cuda.synchronize()
     evs = []
     for _ in range(steps):
-        with torch.cuda.stream(ext):
-            flush.zero_()
+        flush()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(ext)
         ctx.step(1)
@@ -59,8 +58,7 @@ def probe(kind, n, variant, steps, out):
     ctx.profile(True)
     ctx.profile_get(dml.CLS_ALL, reset=True)
     for _ in range(steps):
-        with torch.cuda.stream(ext):
-            flush.zero_()
+        flush()
         ctx.step(1)
     torch.cuda.synchronize()
     kern = ctx.profile_kernels()
@@ -76,8 +74,7 @@ def probe(kind, n, variant, steps, out):
         ctx.profile_get(dml.CLS_ALL, reset=True)
         nf = 20
         for _ in range(nf):
-            with torch.cuda.stream(ext):
-                flush.zero_()
+            flush()
             ctx.fuerza()
         torch.cuda.synchronize()
         kf = ctx.profile_kernels()
