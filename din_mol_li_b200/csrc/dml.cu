@@ -1,6 +1,7 @@
 // dml.cu — C-ABI entry points of libdml.so (declared in include/dml.h) and the host orchestration of
 // the kernels in dml_kernels.cuh.  No CPU fallback: every entry point needs a CUDA device.
 #include "../../include/dml.h"
+#include "../../include/dml_host.h"
 #include "dml_kernels.cuh"
 #include "dml_coop.cuh"
 #include "dml_slab.cuh"
@@ -78,6 +79,7 @@ struct dml_ctx {
   // CUDA graph of part a of the loop body (enq_step_a): every launch is unconditional with device-side guards, so the captured
   // sequence stays valid until the slot count or the geometry changes; replaying it removes the ~6 us host / front-end gap in front
   // of each of the ~11 launches of a step
+  std::vector<ProfEv> sg_evs; bool sg_ran = false;   // event pairs recorded inside the captured step (dml_profile(2 + kid)) and whether it ran since they were read
   cudaGraphExec_t step_graph = nullptr; int sg_n = -1, sg_nct = -1; Geo sg_geo; int64_t sg_launches = 0; bool use_graph = true;
   bool step_tail_done = false;       // enq_step_a folded the tail of the step into the second test_update
   bool sort_maybe_pending = false;   // a deferring test_update was enqueued since the last cell sort (k_sort_catchup is launched on demand)
@@ -97,6 +99,7 @@ struct dml_ctx {
   DBuf<int> gorder, gpos, gcc, gpend, b_occ; int gorder_cap = 0;
   // replay
   DBuf<double> rp_gauss, rp_upbc, rp_uovl, rp_gu, rp_gg; bool have_rp = false, have_rp_ovl = false; int rp_nu = 0, rp_ng = 0;
+  DBuf<int> ord;            // DML_RNG_REFERENCE: slot of every creation rank (hs%ref in list order)
   DBuf<int> rp_qstart, ov_draws;   // overlap_moveback replay queue: draws k = 0,1,.. of slot s read rp_uovl[rp_qstart[s] + k]
   // output reductions and observables (dml_observe.cuh)
   DBuf<double> obs_part, obs_out; DBuf<unsigned long long> obs_counts; DBuf<int> gr_cell_of, gr_cnt, gr_start; DBuf<double4> gr_sorted;
@@ -390,12 +393,17 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
   ctx->step++;
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
   LAUNCH(K_MISC, k_tick, 1, 1, ctx->sc);                  // the Philox step word lives on the device (DevScal::istep)
-  if (ermak)
-    LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
-  else
-    LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
-           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
+  if (ctx->ph.rng_mode == DML_RNG_REFERENCE) {
+    // the reference's sequential stream: one thread walks hs%ref in creation-rank order (k_integrate_seq)
+    TRY(pull_scal(ctx));
+    const int nord = std::max(ctx->hsc->next_uid, 1);
+    CKC(ctx->ord.ensure((size_t)nord + 64, ctx->st));
+    CKC(cudaMemsetAsync(ctx->ord.p, 0xff, (size_t)nord * sizeof(int), ctx->st));
+    LAUNCH(K_MISC, k_ord_scatter, nblk(n), TPB, ctx->posm.p, ctx->uid.p, ctx->ord.p, n, nord);
+    if (ermak) LAUNCH(K_INTEGRATE, (k_integrate_seq<true>), 1, 32, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p, ctx->ord.p, nord, ctx->sc, ctx->geo, ctx->ph);
+    else LAUNCH(K_INTEGRATE, (k_integrate_seq<false>), 1, 32, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p, ctx->ord.p, nord, ctx->sc, ctx->geo, ctx->ph);
+    return 0;
+  }
   ctx->have_rp = false;
   return 0;
 }
@@ -454,7 +462,15 @@ static OvRp ov_replay(const dml_ctx *ctx) {
   OvRp r; r.vals = ctx->have_rp_ovl ? ctx->rp_uovl.p : nullptr; r.qstart = ctx->rp_qstart.p; r.draws = ctx->ov_draws.p;
   return r;
 }
+static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer_apply);
 static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false, bool defer_apply = false) {
+  if (ctx->ph.rng_mode != DML_RNG_REFERENCE) return enq_overlap_impl(ctx, fused, init_done, defer_apply);
+  LAUNCH(K_MISC, k_rng_mark, 1, 1, ctx->sc);              // the reference draws one uniform per deposition attempt (dana.F90:898): consumed afterwards
+  TRY(enq_overlap_impl(ctx, fused, init_done, defer_apply));
+  LAUNCH(K_MISC, k_rng_advance, 1, 1, ctx->sc);
+  return 0;
+}
+static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer_apply) {
   int n = ctx->n;
   TRY(enq_materialize_rows(ctx));
   if (!fused) TRY(enq_qtab(ctx));
@@ -525,6 +541,10 @@ static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
 // errors, and grow the neighbour storage while there is still head-room.
 static int finish(dml_ctx *ctx) {
   TRY(pull_scal(ctx));
+  if (ctx->sg_ran && !ctx->sg_evs.empty()) {              // kernels timed inside the captured step (the stream is idle here)
+    for (auto &ev : ctx->sg_evs) { float ms = 0; if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { ctx->prof_ms[ev.cls] += ms; ctx->prof_n[ev.cls]++; } }
+  }
+  ctx->sg_ran = false;
   ctx->n = ctx->hsc->n_slots;
   if (ctx->n > ctx->l2_slots) l2_window(ctx, ctx->n + ctx->n / 4);
   const size_t tail0 = (size_t)ctx->hsc->cols_tail0;
@@ -621,7 +641,7 @@ static int enq_step_b(dml_ctx *ctx) {
   return 0;
 }
 static bool graph_ok(const dml_ctx *ctx) {
-  return ctx->use_graph && !ctx->profiling && ctx->ph.rng_mode == DML_RNG_PHILOX && ctx->cfg.prob >= 1.0 && ctx->cfg.reservoir != 3 &&
+  return ctx->use_graph && (!ctx->profiling || ctx->prof_only >= 0) && ctx->ph.rng_mode == DML_RNG_PHILOX && ctx->cfg.prob >= 1.0 && ctx->cfg.reservoir != 3 &&
          ctx->tessellated && ctx->use_coop && ctx->n <= ctx->coop_tu_max_n;
 }
 // part a of one step: replay of the captured graph when there is a valid one, capture + launch otherwise
@@ -632,12 +652,16 @@ static int launch_step_a(dml_ctx *ctx) {
   if (!ctx->step_graph || ctx->sg_n != ctx->n || ctx->sg_nct != ctx->nct || memcmp(&ctx->sg_geo, &ctx->geo, sizeof(Geo)) != 0) {
     if (ctx->step_graph) { cudaGraphExecDestroy(ctx->step_graph); ctx->step_graph = nullptr; }
     const int64_t step0 = ctx->step, l0 = ctx->launches;
+    prof_collect(ctx);                                      // events of plain launches so far
+    for (auto &ev : ctx->sg_evs) ctx->pool.push_back(ev);
+    ctx->sg_evs.clear();
     cudaGraph_t g = nullptr;
     CKC(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
     const int rc = enq_step_a(ctx);
     cudaError_t e = cudaStreamEndCapture(ctx->st, &g);
     ctx->sg_launches = ctx->launches - l0;
     ctx->step = step0; ctx->launches = l0;
+    ctx->sg_evs.swap(ctx->evs);                             // event-record nodes of the graph: read after every replay (finish)
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess || !g) { cudaGetLastError(); ctx->use_graph = false; return enq_step_a(ctx); }   // capture not possible here: plain launches from now on
     e = cudaGraphInstantiate(&ctx->step_graph, g, 0);
@@ -647,6 +671,7 @@ static int launch_step_a(dml_ctx *ctx) {
   }
   ctx->step++; ctx->launches += ctx->sg_launches;
   CKC(cudaGraphLaunch(ctx->step_graph, ctx->st));
+  ctx->sg_ran = true;
   return 0;
 }
 static int enq_step(dml_ctx *ctx) { TRY(launch_step_a(ctx)); return enq_step_b(ctx); }
@@ -700,6 +725,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ph.fac_sc = std::sqrt(2.0 * cfg->dif_sc * cfg->h); ph.fac_sei = std::sqrt(2.0 * cfg->dif_sei * cfg->h);
   ph.integrador = cfg->integrador; ph.piston = cfg->reservoir == 1; ph.chunks = cfg->reservoir == 2;
   ph.rng_mode = cfg->rng_mode; ph.seed = cfg->seed;
+  if (cfg->rng_mode == DML_RNG_REFERENCE && cfg->prob < 1.0)
+    FAIL("DML_RNG_REFERENCE needs prob = 1: the order of the deposition draws of overlap_moveback is only reproduced in number");
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
@@ -790,7 +817,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->obs_part.release(); ctx->obs_out.release(); ctx->obs_counts.release(); ctx->gr_cell_of.release(); ctx->gr_cnt.release(); ctx->gr_start.release();
   ctx->gr_sorted.release(); if (ctx->obs_ticket) cudaFree(ctx->obs_ticket);
   ctx->snap_uid.release(); ctx->snap_mb.release(); ctx->mc_out.release(); ctx->mc_count.release();
-  ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_qstart.release(); ctx->ov_draws.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
+  ctx->rp_gauss.release(); ctx->rp_upbc.release(); ctx->rp_uovl.release(); ctx->rp_qstart.release(); ctx->ov_draws.release(); ctx->ord.release(); ctx->rp_gu.release(); ctx->rp_gg.release();
   ctx->stage_d.release(); ctx->stage_f.release(); ctx->stage_i.release();
   if (ctx->sc) cudaFree(ctx->sc);
   if (ctx->hsc) cudaFreeHost(ctx->hsc);
@@ -913,6 +940,18 @@ int dml_get_scalars(dml_ctx *ctx, dml_scalars *s) { ENTER(ctx);
   for (int k = 0; k < 3; ++k) s->box[k] = ctx->geo.box[k];
   s->z0 = ctx->hsc->z0; s->z1 = ctx->hsc->z1; s->zmax = ctx->hsc->zmax; s->rho = ctx->hsc->rho; s->rho0 = ctx->hsc->rho0;
   s->t = ctx->t; s->step = ctx->step;
+  return 0;
+}
+int dml_set_rng_state(dml_ctx *ctx, const dmlh_rng *r) { ENTER(ctx);
+  TRY(pull_scal(ctx));
+  ctx->hsc->rr.idum = r->idum; ctx->hsc->rr.ix = r->ix; ctx->hsc->rr.iy = r->iy; ctx->hsc->rr.stored = r->stored; ctx->hsc->rr.g = r->g; ctx->hsc->rr.calls = r->calls;
+  TRY(push_scal(ctx));
+  CKC(cudaStreamSynchronize(ctx->st));
+  return 0;
+}
+int dml_get_rng_state(dml_ctx *ctx, dmlh_rng *r) { ENTER(ctx);
+  TRY(pull_scal(ctx));
+  r->idum = ctx->hsc->rr.idum; r->ix = ctx->hsc->rr.ix; r->iy = ctx->hsc->rr.iy; r->stored = ctx->hsc->rr.stored; r->g = ctx->hsc->rr.g; r->calls = ctx->hsc->rr.calls;
   return 0;
 }
 int dml_get_counters(dml_ctx *ctx, dml_counters *c) { ENTER(ctx);
@@ -1468,6 +1507,7 @@ int dml_membership_changes(dml_ctx *ctx, int32_t max_changes, int32_t *slot, int
 
 int dml_profile(dml_ctx *ctx, int32_t enable) { ENTER(ctx);
   prof_collect(ctx);
+  ctx->sg_n = -1;                                         // the captured step is re-recorded with / without event nodes
   ctx->profiling = enable != 0;
   ctx->prof_only = enable >= 2 ? enable - 2 : -1;          // enable = 2 + kernel id: events around that kernel only (undisturbed pipeline)
   if (enable) while (ctx->pool.size() < 8192) { ProfEv ev; cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.cls = 0; ctx->pool.push_back(ev); }

@@ -105,6 +105,67 @@ __device__ __forceinline__ void rh_store_near(RowHead *p, const Near5 &n, int st
   rh_store(p, make_int4(nr[0], nr[1], nr[2], nr[3]), nb, start, len, cap, q5);
 }
 
+// ---- the reference's own generator on the device (DML_RNG_REFERENCE) --------------------------------------------------------
+// ran (src/dana.F90:1407-1428): Park-Miller with Schrage's trick combined with a 13/17/5 xorshift; gasdev (1379-1404): Marsaglia's
+// polar method whose squared radius, logarithm and factor are real(sp).  The logarithm is glibc's logf, restated here (its table
+// and polynomial are public: sysdeps/ieee754/flt-32/e_logf.c, logf_data.c of glibc 2.28+): 16-entry table, degree-3 polynomial in
+// double, one rounding to float.  tests/ checks the restatement against the host libm over every float in (0, 1].
+// One stream, one spare deviate, shared by every caller in call order: all draws are made by ONE thread.
+struct RefRng { int idum, ix, iy, stored; double g; unsigned long long calls; };
+__device__ __forceinline__ float ref_logf(float x) {
+  const double T[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},
+    {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5},
+    {0x1p+0, 0x0p+0}, {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5}, {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3}, {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3}, {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},
+    {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+  const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2, Ln2 = 0x1.62e42fefa39efp-1;
+  const unsigned int ix = (unsigned int)__float_as_int(x);          // callers pass 0 < x < 1 (normal numbers)
+  if (ix == 0x3f800000u) return 0.0f;
+  const unsigned int tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u);
+  const int k = (int)tmp >> 23;
+  const unsigned int iz = ix - (tmp & 0xff800000u);
+  const double z = (double)__int_as_float((int)iz);
+  const double r = z * T[i][0] - 1.0;
+  const double y0 = T[i][1] + (double)k * Ln2;
+  const double r2 = r * r;
+  double y = A1 * r + A2;
+  y = A0 * r2 + y;
+  y = y * r2 + (y0 + r);
+  return (float)y;
+}
+__device__ __forceinline__ double ref_ran(RefRng *r) {
+  const double am = 0x1.fffffep-1 / 2147483647.0;                   // nearest(1.0,-1.0)/real(im,dp)
+  r->calls++;
+  if (r->idum <= 0 || r->iy < 0) {
+    const int a = abs(r->idum);
+    r->iy = (888889999 ^ a) | 1;
+    r->ix = 777755555 ^ a;
+    r->idum = a + 1;
+  }
+  unsigned int x = (unsigned int)r->ix;
+  x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+  r->ix = (int)x;
+  const int k = r->iy / 127773;
+  r->iy = 16807 * (r->iy - k * 127773) - 2836 * k;
+  if (r->iy < 0) r->iy += 2147483647;
+  return am * (double)((2147483647 & (r->ix ^ r->iy)) | 1);
+}
+__device__ __forceinline__ double ref_gasdev(RefRng *r) {
+  if (r->stored) { r->stored = 0; return r->g; }
+  double a, b; float s;
+  do {
+    a = 2.0 * ref_ran(r) - 1.0;
+    b = 2.0 * ref_ran(r) - 1.0;
+    s = (float)(a * a + b * b);
+  } while (!((double)s > 0.0 && (double)s < 1.0));
+  const float f = (float)sqrt(-2.0 * (double)ref_logf(s) / (double)s);
+  r->g = b * (double)f; r->stored = 1;
+  return a * (double)f;
+}
+
 // ---- device-resident scalars (one struct in global memory; the host mirrors it on demand) --------------
 struct DevScal {
   double z0, z1, zmax, rho, rho0;
@@ -143,6 +204,7 @@ struct DevScal {
   long long overlap_passes;
   unsigned int ticket3;             // last-block election of k_pbc_disp
   unsigned int ticket4;             // last-block election of k_integrate
+  RefRng rr; long long rr_mark;     // DML_RNG_REFERENCE: the reference's generator state; try_ when the running overlap_moveback started
   unsigned int istep;               // integrator calls so far: the step word of the Philox counters (kernels read it here so that a captured
                                     // CUDA graph of the loop body stays valid from step to step)
   int sort_pending;                 // a rebuild snapshotted the positions but the cell sort was left to whoever needs it first (dml_coop.cuh)

@@ -53,10 +53,12 @@ struct GcmcRng {
   const GcmcArgs *A; int iu, ig, ctr;
   __device__ double unif() {
     if (A->ph.rng_mode == 1) { if (iu >= A->rp_nu) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.5; } return A->rp_u[iu++]; }
+    if (A->ph.rng_mode == 2) return ref_ran(&A->sc->rr);
     Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step == STEP_FROM_DEVICE ? A->sc->istep : A->step, RS_GCMC, 0u); return r.u01(0);
   }
   __device__ double gauss() {
     if (A->ph.rng_mode == 1) { if (ig >= A->rp_ng) { atomicCAS(&A->sc->err, 0, DML_E_REPLAY_EXHAUSTED); return 0.0; } return A->rp_g[ig++]; }
+    if (A->ph.rng_mode == 2) return ref_gasdev(&A->sc->rr);
     Philox r; r.run(A->ph.seed, (unsigned int)(ctr++), A->step == STEP_FROM_DEVICE ? A->sc->istep : A->step, RS_GCMC, 1u); double a, b; r.gauss2(a, b); return a;
   }
 };

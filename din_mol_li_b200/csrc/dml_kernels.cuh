@@ -1318,7 +1318,7 @@ __device__ __forceinline__ void block_flush(BlockAcc a, DevScal *sc) {
 }
 
 // atom_pbc — dana.F90:1187-1250.  Returns depos.  The deposition uniform is drawn only when z<=0.
-struct RngSrc { int mode; unsigned long long seed; unsigned int id, step; const double *rp; int slot; };
+struct RngSrc { int mode; unsigned long long seed; unsigned int id, step; const double *rp; int slot; RefRng *rr; };
 // pos_old is only touched when the particle crosses a periodic face (a few per thousand per step) and, under Ermak, vel only when
 // it bounces off the ceiling: both are read / written on demand (pos_old_s points at the slot's three doubles, wrote_v reports the
 // bounce), which takes 72 of the 236 bytes per particle out of the streaming pass.
@@ -1339,11 +1339,60 @@ __device__ __forceinline__ bool atom_pbc_dev(const Geo &g, const Phys &ph, doubl
     acc.tr++;
     double ne;
     if (rs.mode == 1) ne = rs.rp[rs.slot];
+    else if (rs.mode == 2) ne = ref_ran(rs.rr);             // the reference's stream, drawn in list order by the sequential kernel
     else { Philox r; r.run(rs.seed, rs.id, rs.step, RS_PBC, 0u); ne = r.u01(0); }
     if (ne < ph.prob) { acc.de++; meta = (meta & ~MF_TYPE) | 3; depos = true; }
     q[0] = og[0]; q[1] = og[1]; q[2] = og[2];
   }
   return depos;
+}
+
+// One ref particle through ermak_a / cbrownian_hs + atom_pbc, its Gaussians already drawn (gs: r1, r2 per axis for Ermak, one
+// per axis for the Brownian step — the order the reference draws them in, dana.F90:1006-1015, 824-829).
+template <bool ERMAK>
+__device__ __forceinline__ void integrate_one(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ pos_old,
+                                              double *__restrict__ old_cg, double *__restrict__ ranv, DevScal *__restrict__ sc, const Geo &g, const Phys &ph,
+                                              double4 p, double v[3], const double a[3], const double gs[6], const RngSrc &rs, int s, BlockAcc &acc) {
+  long long m = meta_of(p);
+  double q[3] = {p.x, p.y, p.z}, og[3] = {p.x, p.y, p.z};
+  old_cg[3 * s] = og[0]; old_cg[3 * s + 1] = og[1]; old_cg[3 * s + 2] = og[2];
+  int zt = (int)(m & MF_TYPE);
+  if (ERMAK) {
+    double sm = ph.sqrt_mass[zt - 1];
+    double A = ph.skt / sm * ph.sdr, B = ph.skt / sm * ph.sdv;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double r1 = gs[2 * j], r2 = gs[2 * j + 1];
+      double ranr = A * r1;
+      q[j] = q[j] + ph.cc1 * v[j] + ph.cc2h * a[j] + ranr;
+      ranv[3 * s + j] = B * (ph.crv1 * r1 + ph.crv2 * r2);
+    }
+  } else {
+    double fac1 = (q[2] > ph.z_sei) ? ph.fac_sc : ph.fac_sei;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double posold = q[j];
+      q[j] = posold + gs[j] * fac1;
+      v[j] = (q[j] - posold) / ph.h;
+    }
+  }
+  double zmax = sc->zmax;
+  bool wrote_v = !ERMAK;                               // the Brownian step always rewrites vel
+  bool depos = atom_pbc_dev(g, ph, zmax, q, pos_old + 3 * (size_t)s, og, v, m, rs, acc, wrote_v);
+  if (!depos) {
+    if (!ERMAK) acc.mv = fmax(acc.mv, (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    m &= ~MF_SKIP;
+  }
+  {
+    double dx = q[0] - og[0], dy = q[1] - og[1], dz = q[2] - og[2];
+    dx = dx - g.box[0] * round(dx * g.one_box[0]); dy = dy - g.box[1] * round(dy * g.one_box[1]);
+    float df = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * 1.000001f;
+    m = with_disp(m, (unsigned int)__float_as_int(df));
+    acc.dmax = fmaxf(acc.dmax, df);
+  }
+  p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
+  st_rec(&posm[s], p);
+  if (wrote_v) { vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2]; }
 }
 
 template <bool ERMAK>
@@ -1364,11 +1413,7 @@ __global__ void __launch_bounds__(TPB, 4) k_integrate(double4 *__restrict__ posm
       for (int j = 0; j < 3; ++j) { v[j] = vel[3 * s + j]; a[j] = acel[3 * s + j]; }
     }
     const unsigned int id = (unsigned int)uid[s];
-    long long m = meta_of(p);
-    if (m & MF_REF) {
-      double q[3] = {p.x, p.y, p.z}, og[3] = {p.x, p.y, p.z};
-      old_cg[3 * s] = og[0]; old_cg[3 * s + 1] = og[1]; old_cg[3 * s + 2] = og[2];
-      int zt = (int)(m & MF_TYPE);
+    if (meta_of(p) & MF_REF) {
       double gs[6];
       if (ph.rng_mode == 1) {
 #pragma unroll
@@ -1379,46 +1424,55 @@ __global__ void __launch_bounds__(TPB, 4) k_integrate(double4 *__restrict__ posm
         r.run(ph.seed, id, step, RS_INTEG0, 0u); r.gauss4f(gs[0], gs[1], gs[2], gs[3]);
         if (ERMAK) { r.run(ph.seed, id, step, RS_INTEG1, 0u); r.gauss4f(gs[4], gs[5], sp0, sp1); }
       }
-      if (ERMAK) {
-        double sm = ph.sqrt_mass[zt - 1];
-        double A = ph.skt / sm * ph.sdr, B = ph.skt / sm * ph.sdv;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          double r1 = gs[2 * j], r2 = gs[2 * j + 1];
-          double ranr = A * r1;
-          q[j] = q[j] + ph.cc1 * v[j] + ph.cc2h * a[j] + ranr;
-          ranv[3 * s + j] = B * (ph.crv1 * r1 + ph.crv2 * r2);
-        }
-      } else {
-        double fac1 = (q[2] > ph.z_sei) ? ph.fac_sc : ph.fac_sei;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          double posold = q[j];
-          q[j] = posold + gs[j] * fac1;
-          v[j] = (q[j] - posold) / ph.h;
-        }
-      }
-      double zmax = sc->zmax;
-      RngSrc rs = {ph.rng_mode, ph.seed, id, step, rp_upbc, s};
-      bool wrote_v = !ERMAK;                               // the Brownian step always rewrites vel
-      bool depos = atom_pbc_dev(g, ph, zmax, q, pos_old + 3 * (size_t)s, og, v, m, rs, acc, wrote_v);
-      if (!depos) {
-        if (!ERMAK) acc.mv = fmax(acc.mv, (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
-        m &= ~MF_SKIP;
-      }
-      {
-        double dx = q[0] - og[0], dy = q[1] - og[1], dz = q[2] - og[2];
-        dx = dx - g.box[0] * round(dx * g.one_box[0]); dy = dy - g.box[1] * round(dy * g.one_box[1]);
-        float df = __double2float_ru(sqrt(dx * dx + dy * dy + dz * dz)) * 1.000001f;
-        m = with_disp(m, (unsigned int)__float_as_int(df));
-        acc.dmax = fmaxf(acc.dmax, df);
-      }
-      p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
-      st_rec(&posm[s], p);
-      if (wrote_v) { vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2]; }
+      RngSrc rs = {ph.rng_mode, ph.seed, id, step, rp_upbc, s, nullptr};
+      integrate_one<ERMAK>(posm, vel, pos_old, old_cg, ranv, sc, g, ph, p, v, a, gs, rs, s, acc);
     }
   }
   block_flush(acc, sc);
+}
+
+// DML_RNG_REFERENCE: the reference draws from ONE sequential stream while it walks hs%ref in list order (creation rank), and an
+// atom that reaches z <= 0 takes one more uniform in the middle of it (atom_pbc, dana.F90:1236-1240): whether it does depends on
+// the move it just made.  So one thread walks the ref atoms in creation-rank order (ord[rank] = slot, -1 = none), drawing and
+// integrating as it goes.  This mode exists to make the GPU-backed binary reproduce the reference's own test cases (tests/test.sh)
+// digit for digit; production runs use the counter-based generator.
+__global__ void k_ord_scatter(const double4 *__restrict__ posm, const int *__restrict__ uid, int *__restrict__ ord, int n, int nord) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  if (!(meta_of(ld_rec_nc(&posm[s])) & MF_REF)) return;
+  const int u = uid[s];
+  if (u >= 0 && u < nord) ord[u] = s;
+}
+template <bool ERMAK>
+__global__ void k_integrate_seq(double4 *__restrict__ posm, double *__restrict__ vel, const double *__restrict__ acel,
+                                double *__restrict__ pos_old, double *__restrict__ old_cg, double *__restrict__ ranv,
+                                const int *__restrict__ ord, int nord, DevScal *__restrict__ sc, Geo g, Phys ph) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  BlockAcc acc = {0, 0, 0.0, 0.0, 0.0f};
+  RefRng rr = sc->rr;
+  for (int u = 0; u < nord; ++u) {
+    const int s = ord[u];
+    if (s < 0) continue;
+    double4 p = ld_rec(&posm[s]);
+    double v[3] = {vel[3 * s], vel[3 * s + 1], vel[3 * s + 2]}, a[3] = {acel[3 * s], acel[3 * s + 1], acel[3 * s + 2]};
+    double gs[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = 0; i < (ERMAK ? 6 : 3); ++i) gs[i] = ref_gasdev(&rr);
+    RngSrc rs = {2, 0ull, 0u, 0u, nullptr, s, &rr};
+    integrate_one<ERMAK>(posm, vel, pos_old, old_cg, ranv, sc, g, ph, p, v, a, gs, rs, s, acc);
+  }
+  sc->rr = rr;
+  if (acc.tr) sc->try_ += acc.tr;
+  if (acc.de) sc->depo += acc.de;
+  if (acc.msd != 0.0) sc->msd_t += acc.msd;
+  if (acc.mv > 0.0) sc->max_vel = fmax(sc->max_vel, acc.mv);
+  if (acc.dmax > 0.0f) sc->step_disp_bits = max(sc->step_disp_bits, (unsigned int)__float_as_int(acc.dmax));
+}
+// overlap_moveback in this mode: with prob >= 1 the value of a deposition uniform never matters, only how many were drawn
+__global__ void k_rng_mark(DevScal *sc) { sc->rr_mark = sc->try_; }
+__global__ void k_rng_advance(DevScal *sc) {
+  RefRng rr = sc->rr;
+  for (long long i = sc->rr_mark; i < sc->try_; ++i) (void)ref_ran(&rr);
+  sc->rr = rr;
 }
 
 // ermak_b — dana.F90:1031-1052
@@ -1672,6 +1726,7 @@ __device__ __forceinline__ bool ov_one_pass(const double4 *__restrict__ posm, co
         acc.tr++;
         double ne;
         if (ph.rng_mode == 1) ne = ov_replay_draw(rp_uovl, a1, true, sc, ph.prob);
+        else if (ph.rng_mode == 2) ne = 0.0;                      // prob >= 1 in this mode: k_rng_advance consumes the stream afterwards
         else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
         if (ne < ph.prob) {
           acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
@@ -1857,6 +1912,7 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
             acc.tr++;
             double ne;
             if (ph.rng_mode == 1) ne = ov_replay_draw(rp_uovl, a1, lane == 0, sc, ph.prob);
+            else if (ph.rng_mode == 2) ne = 0.0;
             else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
             if (ne < ph.prob) {
               acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);

@@ -10,7 +10,7 @@ import numpy as np
 from . import build as _build
 
 F_REF, F_GCMC, F_SKIP, F_LIMBO = 1, 2, 4, 8
-RNG_PHILOX, RNG_REPLAY = 0, 1
+RNG_PHILOX, RNG_REPLAY, RNG_REFERENCE = 0, 1, 2
 CLS_FORCE, CLS_LIST, CLS_INTEG, CLS_OVERLAP, CLS_ALL, CLS_BIN, CLS_OTHER, CLS_GCMC = range(8)
 
 
@@ -53,8 +53,13 @@ SYMBOLS = [
     "dml_profile_get", "dml_profile_kernel", "dml_n_slots", "dml_set_strict_order", "dml_comm_unique_id", "dml_comm_init", "dml_slab_plan", "dml_slab_setup",
     "dml_slab_halo_exchange", "dml_slab_step", "dml_slab_info", "dml_launch_count", "dml_stream",
     "dml_salida_sums", "dml_density_profile", "dml_gr", "dml_membership_changes",
-    "dml_ensemble_step", "dml_set_ensemble_member", "dml_upload_positions", "dml_download_frame",
+    "dml_set_rng_state", "dml_get_rng_state", "dml_ensemble_step", "dml_set_ensemble_member", "dml_upload_positions", "dml_download_frame",
 ]
+
+class HostRng(C.Structure):
+    """dana's RNG state (include/dml_host.h)."""
+    _fields_ = [("idum", C.c_int32), ("ix", C.c_int32), ("iy", C.c_int32), ("stored", C.c_int32), ("g", C.c_double), ("calls", C.c_uint64)]
+
 
 _lib = None
 
@@ -112,6 +117,8 @@ def lib():
         L.dml_set_ensemble_member.argtypes = [vp, i32]
         L.dml_upload_positions.argtypes = [vp, i32, vp, vp]
         L.dml_download_frame.argtypes = [vp, i32, vp, vp]
+        L.dml_set_rng_state.argtypes = [vp, C.POINTER(HostRng)]
+        L.dml_get_rng_state.argtypes = [vp, C.POINTER(HostRng)]
         L.dml_launch_count.argtypes = [vp]
         L.dml_launch_count.restype = C.c_int64
         L.dml_stream.argtypes = [vp]
@@ -135,11 +142,6 @@ def _i32(a):
     if a is None:
         return None
     return np.ascontiguousarray(a, dtype=np.int32)
-
-
-class HostRng(C.Structure):
-    """dana's RNG state (include/dml_host.h)."""
-    _fields_ = [("idum", C.c_int32), ("ix", C.c_int32), ("iy", C.c_int32), ("stored", C.c_int32), ("g", C.c_double), ("calls", C.c_uint64)]
 
 
 def comm_unique_id():
@@ -361,6 +363,14 @@ class Ctx:
         pos, z = np.empty((n, 3)), np.empty(n, np.int32)
         self._chk(lib().dml_download_frame(self.h, n, _p(pos), _p(z)))
         return pos, z
+
+    def set_rng_state(self, r):
+        self._chk(lib().dml_set_rng_state(self.h, C.byref(r)))
+
+    def rng_state(self):
+        r = HostRng()
+        self._chk(lib().dml_get_rng_state(self.h, C.byref(r)))
+        return r
 
     def set_ensemble_member(self, on=True):
         self._chk(lib().dml_set_ensemble_member(self.h, 1 if on else 0))

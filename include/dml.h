@@ -33,6 +33,8 @@ typedef struct dml_ctx dml_ctx;
 
 #define DML_RNG_PHILOX 0  /* counter-based Philox4x32-10, keyed (seed; uid, step, stream) */
 #define DML_RNG_REPLAY 1  /* consume the numbers injected with dml_set_replay_*            */
+#define DML_RNG_REFERENCE 2 /* the reference's own ran / gasdev stream (src/dana.F90:1379-1428) drawn on the device in the reference's
+                             * order: one thread walks hs%ref; makes the reference's test cases reproducible digit for digit (needs prob = 1) */
 
 /* Filled by the host from the variables dana reads in entrada()/config_run() plus its parameters
  * (src/dana.F90:12-25,87-100,309-327,399-427). */
@@ -87,6 +89,10 @@ int dml_download(dml_ctx *ctx, int32_t n, double *pos, double *vel, double *acel
 int dml_set_scalars(dml_ctx *ctx, const dml_scalars *s);         /* z0,z1,zmax,rho,rho0,box after host-side changes */
 int dml_get_scalars(dml_ctx *ctx, dml_scalars *s);
 int dml_get_counters(dml_ctx *ctx, dml_counters *c);
+/* DML_RNG_REFERENCE: state of ran / gasdev (include/dml_host.h), e.g. as pos_inic left it (src/dana.F90:330-396) */
+struct dmlh_rng;
+int dml_set_rng_state(dml_ctx *ctx, const struct dmlh_rng *r);
+int dml_get_rng_state(dml_ctx *ctx, struct dmlh_rng *r);
 int dml_reset_try_depo(dml_ctx *ctx);                             /* salida(): try=0; depo=0 (src/dana.F90:1171-1174) */
 
 /* One entry per preserved call site of the loop body (src/dana.F90:173-265). */

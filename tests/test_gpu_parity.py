@@ -191,6 +191,25 @@ def test_dana_b200_driver_writes_reference_layout(tmp_path):
     assert "vecinos actualizados" in r.stdout
 
 
+@pytest.mark.parametrize("name", ["ermak", "brown", "gcmc"])
+def test_reference_test_cases_on_the_gpu_backed_binary(name, tmp_path):
+    """The reference's own regression test (tests/test.sh: run dana in the case directory, compare the last frame of Li.xyz textually
+    with ref.xyz) on dana_b200 --rng reference: the device draws the reference's ran / gasdev stream in the reference's order
+    (DML_RNG_REFERENCE), the host writes the frame in gfortran's list-directed layout.  No oracle involved: input files in, text out."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "din_mol_li_b200", "dana_b200")
+    for f in ("entrada.ini", "movedor.ini", "chunk.xyz"):
+        if os.path.exists(os.path.join(GOLD, name, f)):
+            shutil.copy(os.path.join(GOLD, name, f), tmp_path)
+    r = subprocess.run([exe, str(tmp_path), "--rng", "reference"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ref = open(os.path.join(GOLD, name, "ref.xyz")).read().split("\n")
+    out = open(os.path.join(tmp_path, "Li.xyz")).read().split("\n")
+    assert out[-len(ref):] == ref, "last frame of Li.xyz differs from the reference's ref.xyz"
+
+
 def _deposited(z):
     return int((z >= 2).sum())
 

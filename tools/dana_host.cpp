@@ -1,13 +1,15 @@
 // tools/dana_host.cpp — C++ stand-in for the reference's main program (src/dana.F90:1-305) driving libdml.so
 // through the same C ABI the Fortran shim binds (fortran/dml_cuda.F90 cannot be compiled in this image).
 //
-//   dana_b200 [case_dir] [--steps N] [--seed S] [--device D]
+//   dana_b200 [case_dir] [--steps N] [--seed S] [--device D] [--rng philox|reference]
 //
 // Reads entrada.ini / movedor.ini / chunk.xyz from case_dir (dana.F90:309-327,399-427,552-587), builds the initial
 // configuration with the reference's pos_inic rule and RNG (dmlh_pos_inic, stream-identical), runs the loop on the GPU
 // and writes pos_inic.xyz, Li.xyz, E.dat, T.dat, rho.dat, try.dat, depo.dat in the reference's list-directed layout
-// (dana.F90:1143-1183).  The hot path uses counter-based Philox noise, so trajectories are statistically — not
-// bitwise — equivalent to the Fortran binary; bit parity is what tests/ check in replay mode.
+// (dana.F90:1143-1183).  By default the hot path uses counter-based Philox noise, so trajectories are statistically — not
+// bitwise — equivalent to the Fortran binary.  With --rng reference the device draws the reference's own ran / gasdev stream
+// (src/dana.F90:1379-1428) in the reference's order, continuing from the state pos_inic left, and the last frame of Li.xyz is
+// the reference's ref.xyz digit for digit: tools/test_cases.sh is the reference's tests/test.sh run on this binary.
 #include "../include/dml.h"
 #include "../include/dml_host.h"
 #include <algorithm>
@@ -52,11 +54,12 @@ static std::string fort_real(double x) {
 
 int main(int argc, char **argv) {
   std::string dir = ".";
-  long steps_override = -1; long seed = 20240101; int device = 0;
+  long steps_override = -1; long seed = 20240101; int device = 0; bool rng_reference = false;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps_override = atol(argv[++i]);
     else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = atol(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--rng") && i + 1 < argc) rng_reference = !strcmp(argv[++i], "reference");
     else dir = argv[i];
   }
   // entrada() — dana.F90:309-327
@@ -105,9 +108,11 @@ int main(int argc, char **argv) {
   c.h = h; c.gama = 1.0; c.Tsist = 300.0; c.kB_ui = 8.617330350e-5 * (96.485 * 100.0);
   { const double ui_ev = 1.0e2 * 1.0e2 * 1.6605402e-27 * (1.0 / 1.60219e-19); c.kB_ui_gcmc = 8.617385e-05 * (1.0 / ui_ev); }
   c.dif_sc = dif_sc; c.dif_sei = dif_sei; c.z_sei = 80.0; c.prob = prob; c.z0 = z0; c.z1 = z1; c.zmax = zmax; c.tau = 0.1;
-  c.act = act; c.nadj = nadj; c.integrador = integrador; c.reservoir = reservoir; c.rng_mode = DML_RNG_PHILOX; c.seed = (uint64_t)seed;
+  c.act = act; c.nadj = nadj; c.integrador = integrador; c.reservoir = reservoir; c.rng_mode = rng_reference ? DML_RNG_REFERENCE : DML_RNG_PHILOX; c.seed = (uint64_t)seed;
+  c.strict_order = rng_reference ? 1 : 0;                   // digit-for-digit frames need the reference's summation order in fuerza
   dml_ctx *ctx = nullptr;
   CHECK(dml_create(&ctx, &c));
+  if (rng_reference) CHECK(dml_set_rng_state(ctx, &rng));      // the stream goes on where pos_inic stopped (one generator for the whole program)
 
   std::vector<int32_t> z(n, 1), flags(n, DML_F_REF | (reservoir == 3 ? DML_F_GCMC : 0));
   std::vector<double> og((size_t)n * 3, 1e8);
