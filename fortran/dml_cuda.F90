@@ -7,13 +7,14 @@
 ! How a maintainer wires it in (see INTEGRATION.md):
 !   * dana.F90 keeps its loop and its names; the bodies of fuerza / ermak_a / ermak_b / cbrownian_hs /
 !     overlap_moveback / gcmc_run / calc_rho / maxz / bloques and gems_neighbor::test_update call the wrappers below.
-!   * atom / group / igroup objects stay on the host; dml_sync_to_device / dml_sync_from_device pack them into the
-!     flat, hs-slot indexed arrays of include/dml.h whenever membership or salida() needs them.
+!   * atom / group / igroup objects stay on the host; fortran/dml_sync.F90 (pack_atoms / unpack_atoms /
+!     apply_membership_changes / shift_chunk_template) moves them to and from the flat, hs-slot indexed arrays of include/dml.h
+!     whenever membership or salida() needs them; fortran/Neighbor_gpu.F90 is the gems_neighbor module over this shim.
 module dml_cuda
   use, intrinsic :: iso_c_binding
   implicit none
   private
-  public :: dml_config, dml_ctx_t, dmlf_create, dmlf_check
+  public :: dml_config, dml_scalars, dml_counters, dmlh_rng, dml_ctx_t, dmlf_create, dmlf_check, gpu
 
   integer(c_int), parameter, public :: DML_F_REF = 1, DML_F_GCMC = 2, DML_F_SKIP = 4, DML_F_LIMBO = 8
 
@@ -34,9 +35,31 @@ module dml_cuda
     integer(c_int32_t) :: strict_order
   end type
 
+  ! mirrors struct dml_scalars / dml_counters of include/dml.h and dmlh_rng of include/dml_host.h
+  type, bind(C) :: dml_scalars
+    real(c_double)     :: box(3), z0, z1, zmax, rho, rho0, t
+    integer(c_int64_t) :: step
+  end type
+  type, bind(C) :: dml_counters
+    integer(c_int64_t) :: nupd_vlist, try_, depo, choques, choques2, choques3, list_entries
+    integer(c_int64_t) :: overlap_passes, gcmc_created, gcmc_destroyed, row_overflow
+    real(c_double)     :: max_vel, msd_t, msd_max
+    integer(c_int32_t) :: n_slots, nat_sys, nat_ref, nat_gcmc, ncells(3)
+    real(c_double)     :: cell(3)
+    integer(c_int32_t) :: tessellated, listed, rows_asym
+  end type
+  type, bind(C) :: dmlh_rng
+    integer(c_int32_t) :: idum, ix, iy, stored
+    real(c_double)     :: g
+    integer(c_int64_t) :: calls
+  end type
+
   type :: dml_ctx_t
     type(c_ptr) :: h = c_null_ptr
   end type
+
+  ! the one device context of a dana run (created by dmlf_create in the main program, used by gems_neighbor and dml_sync)
+  type(dml_ctx_t), save :: gpu
 
   interface
     integer(c_int) function dml_create(ctx, cfg) bind(C, name='dml_create')
@@ -121,6 +144,56 @@ module dml_cuda
       import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: max_changes
       integer(c_int32_t), intent(out) :: slot(*), kind(*), uid_now(*), z_now(*), n_changes
     end function
+    integer(c_int) function dml_set_scalars(ctx, s) bind(C, name='dml_set_scalars')
+      import; type(c_ptr), value :: ctx; type(dml_scalars), intent(in) :: s
+    end function
+    integer(c_int) function dml_get_scalars(ctx, s) bind(C, name='dml_get_scalars')
+      import; type(c_ptr), value :: ctx; type(dml_scalars), intent(out) :: s
+    end function
+    integer(c_int) function dml_get_counters(ctx, c) bind(C, name='dml_get_counters')
+      import; type(c_ptr), value :: ctx; type(dml_counters), intent(out) :: c
+    end function
+    integer(c_int) function dml_set_chunk_template(ctx, nchunk, cpos, cpos_old, dist, rhomedia) bind(C, name='dml_set_chunk_template')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: nchunk
+      real(c_double), intent(in) :: cpos(3,*), cpos_old(3,*); real(c_double), value :: dist, rhomedia
+    end function
+    ! rows(width,n): row i holds the hs indices MINUS ONE of the nn(i) neighbours of hs%a(i) (C order [n][width]); rc = 1: width too small
+    integer(c_int) function dml_get_neighbors(ctx, n, width, nn, rows) bind(C, name='dml_get_neighbors')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: n, width
+      integer(c_int32_t), intent(out) :: nn(*), rows(width,*)
+    end function
+    integer(c_int) function dml_upload_positions(ctx, n, pos, pos_old) bind(C, name='dml_upload_positions')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: n
+      real(c_double), intent(in) :: pos(3,*); type(c_ptr), value :: pos_old      ! c_null_ptr: pos_old stays resident
+    end function
+    integer(c_int) function dml_download_frame(ctx, n, pos, z) bind(C, name='dml_download_frame')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: n
+      real(c_double), intent(out) :: pos(3,*); integer(c_int32_t), intent(out) :: z(*)
+    end function
+    ! DML_RNG_REFERENCE (rng_mode = 2): hand the state of ran / gasdev over to the device (and take it back)
+    integer(c_int) function dml_set_rng_state(ctx, r) bind(C, name='dml_set_rng_state')
+      import; type(c_ptr), value :: ctx; type(dmlh_rng), intent(in) :: r
+    end function
+    integer(c_int) function dml_get_rng_state(ctx, r) bind(C, name='dml_get_rng_state')
+      import; type(c_ptr), value :: ctx; type(dmlh_rng), intent(out) :: r
+    end function
+    ! multi-GPU: z-slab decomposition of one box (one image / MPI rank per GPU; id128 = 128 bytes from dml_comm_unique_id on rank 0)
+    integer(c_int) function dml_comm_unique_id(id128) bind(C, name='dml_comm_unique_id')
+      import; character(kind=c_char), intent(out) :: id128(128)
+    end function
+    integer(c_int) function dml_comm_init(ctx, id128, rank, nranks) bind(C, name='dml_comm_init')
+      import; type(c_ptr), value :: ctx; character(kind=c_char), intent(in) :: id128(128); integer(c_int32_t), value :: rank, nranks
+    end function
+    integer(c_int) function dml_slab_plan(n, z, nranks, lo, hi, cuts) bind(C, name='dml_slab_plan')
+      import; integer(c_int32_t), value :: n, nranks; real(c_double), intent(in) :: z(*); real(c_double), value :: lo, hi
+      real(c_double), intent(out) :: cuts(*)
+    end function
+    integer(c_int) function dml_slab_setup(ctx, zlo, zhi) bind(C, name='dml_slab_setup')
+      import; type(c_ptr), value :: ctx; real(c_double), value :: zlo, zhi
+    end function
+    integer(c_int) function dml_slab_step(ctx, nsteps) bind(C, name='dml_slab_step')
+      import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: nsteps
+    end function
     integer(c_int) function dml_gr(ctx, rmax, nbins, type_mask, counts, n_selected) bind(C, name='dml_gr')
       import; type(c_ptr), value :: ctx; real(c_double), value :: rmax; integer(c_int32_t), value :: nbins, type_mask
       integer(c_int64_t), intent(out) :: counts(*); integer(c_int32_t), intent(out) :: n_selected
@@ -128,7 +201,10 @@ module dml_cuda
   end interface
   public :: dml_create, dml_destroy, dml_last_error, dml_upload, dml_download, dml_test_update, dml_fuerza, dml_ermak_a, &
             dml_ermak_b, dml_cbrownian_hs, dml_overlap_moveback, dml_msd_book, dml_promote, dml_gcmc_run, dml_calc_rho, &
-            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo, dml_salida_sums, dml_density_profile, dml_gr, dml_membership_changes
+            dml_maxz, dml_bloques, dml_step, dml_reset_try_depo, dml_salida_sums, dml_density_profile, dml_gr, dml_membership_changes, &
+            dml_set_scalars, dml_get_scalars, dml_get_counters, dml_set_chunk_template, dml_get_neighbors, dml_upload_positions, &
+            dml_download_frame, dml_set_rng_state, dml_get_rng_state, dml_comm_unique_id, dml_comm_init, dml_slab_plan, dml_slab_setup, &
+            dml_slab_step
 
 contains
 
