@@ -160,7 +160,9 @@ static void prof_collect(dml_ctx *ctx) {
   }
   ctx->evs.clear();
 }
-#define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx, cls); } while (0)
+// a launch that the driver refuses (too many resources, bad configuration) must not pass silently
+#define LAUNCH(cls, kern, grid, block, ...) do { prof_begin(ctx, cls); kern<<<(grid), (block), 0, ctx->st>>>(__VA_ARGS__); prof_end(ctx, cls); \
+  cudaError_t le_ = cudaPeekAtLastError(); if (le_ != cudaSuccess) { cudaGetLastError(); ctx->err = std::string("launch of " #kern ": ") + cudaGetErrorString(le_); return -1; } } while (0)
 
 #define LAUNCH_COOP(kid, kern, grid, argstruct) do { prof_begin(ctx, kid); void *a_[] = {(void *)&(argstruct)}; \
   cudaError_t e_ = cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(TPB), a_, 0, ctx->st); prof_end(ctx, kid); \
@@ -321,6 +323,7 @@ static int enq_materialize_rows(dml_ctx *ctx) {
   k_rows<<<std::min(nblk(n, RB), 148 * 2), RB, ROWS_SMEM, ctx->st>>>(ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_slot.p, ctx->sorted_cell.p, ctx->cell_start.p,
                                                   ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->sc, ctx->geo, nct, ctx->row_slack);
   prof_end(ctx, K_ROWS_FILL);
+  CKC(cudaPeekAtLastError());
   return 0;
 }
 
@@ -404,6 +407,12 @@ static int enq_integrate(dml_ctx *ctx, bool ermak) {
     else LAUNCH(K_INTEGRATE, (k_integrate_seq<false>), 1, 32, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p, ctx->ord.p, nord, ctx->sc, ctx->geo, ctx->ph);
     return 0;
   }
+  if (ermak)
+    LAUNCH(K_INTEGRATE, (k_integrate<true>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
+  else
+    LAUNCH(K_INTEGRATE, (k_integrate<false>), nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->pos_old.p, ctx->old_cg.p, ctx->ranv.p,
+           ctx->uid.p, ctx->rp_gauss.p, ctx->rp_upbc.p, ctx->sc, ctx->geo, ctx->ph, STEP_FROM_DEVICE, n);
   ctx->have_rp = false;
   return 0;
 }
