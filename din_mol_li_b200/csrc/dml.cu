@@ -51,7 +51,7 @@ struct dml_ctx {
   int64_t nupd = 0, step = 0, choques2 = 0, overlap_passes = 0;
   double t = 0.0;
   int64_t launches = 0;
-  bool profiling = false; int prof_only = -1; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
+  bool profiling = false, capturing = false; int prof_only = -1; std::vector<ProfEv> evs; std::vector<ProfEv> pool;
   double prof_ms[32] = {0}; int64_t prof_n[32] = {0};
   // particle state
   DBuf<float4> sorted_posf;                            // single-precision copy of the cell-sorted records (k_rows prefilter)
@@ -146,10 +146,14 @@ static void prof_begin(dml_ctx *ctx, int cls) {
   if (!ctx->pool.empty()) { ev = ctx->pool.back(); ctx->pool.pop_back(); }
   else { cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); }
   ev.cls = cls;
-  cudaEventRecord(ev.a, ctx->st);
+  // inside a stream capture a plain record is only a dependency marker: an external record node takes the timestamp at replay
+  if (ctx->capturing) cudaEventRecordWithFlags(ev.a, ctx->st, cudaEventRecordExternal); else cudaEventRecord(ev.a, ctx->st);
   ctx->evs.push_back(ev);
 }
-static void prof_end(dml_ctx *ctx, int cls) { if (ctx->profiling && !(ctx->prof_only >= 0 && ctx->prof_only != cls)) cudaEventRecord(ctx->evs.back().b, ctx->st); }
+static void prof_end(dml_ctx *ctx, int cls) {
+  if (!ctx->profiling || (ctx->prof_only >= 0 && ctx->prof_only != cls)) return;
+  if (ctx->capturing) cudaEventRecordWithFlags(ctx->evs.back().b, ctx->st, cudaEventRecordExternal); else cudaEventRecord(ctx->evs.back().b, ctx->st);
+}
 static void prof_collect(dml_ctx *ctx) {
   if (ctx->evs.empty()) return;
   cudaStreamSynchronize(ctx->st);
@@ -551,7 +555,7 @@ static int upload_d(dml_ctx *ctx, double *dst, const double *src, size_t cnt) {
 static int finish(dml_ctx *ctx) {
   TRY(pull_scal(ctx));
   if (ctx->sg_ran && !ctx->sg_evs.empty()) {              // kernels timed inside the captured step (the stream is idle here)
-    for (auto &ev : ctx->sg_evs) { float ms = 0; if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { ctx->prof_ms[ev.cls] += ms; ctx->prof_n[ev.cls]++; } }
+    for (auto &ev : ctx->sg_evs) { float ms = 0; if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { ctx->prof_ms[ev.cls] += ms; ctx->prof_n[ev.cls]++; } else cudaGetLastError(); }
   }
   ctx->sg_ran = false;
   ctx->n = ctx->hsc->n_slots;
@@ -666,7 +670,9 @@ static int launch_step_a(dml_ctx *ctx) {
     ctx->sg_evs.clear();
     cudaGraph_t g = nullptr;
     CKC(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
     const int rc = enq_step_a(ctx);
+    ctx->capturing = false;
     cudaError_t e = cudaStreamEndCapture(ctx->st, &g);
     ctx->sg_launches = ctx->launches - l0;
     ctx->step = step0; ctx->launches = l0;
@@ -794,6 +800,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(cudaMallocHost(&ctx->hsc, sizeof(DevScal)));
   memset(ctx->hsc, 0, sizeof(DevScal));
   ctx->hsc->z0 = cfg->z0; ctx->hsc->z1 = cfg->z1; ctx->hsc->zmax = cfg->zmax;
+  ctx->hsc->pist_P = 1.0;
   ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
   ctx->hsc->cols_tail0 = ctx->hsc->cols_used = cap * ROW_W;
   TRY(push_scal(ctx));

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   const int par = sc->tu_par;
   const bool tail = (A.fuse & 4) != 0;
   const double z0 = sc->z0, zl = A.use_z1 ? sc->z1 : sc->zmax;
+  const double pist_in = sc->pist_P, pist_c = 1.0 - 1.0 / pist_in;   // piston shift taken out of the recorded displacements (lay_note)
   double a1 = -1.0, a2 = -1.0;
   int c_rho = 0, c_dref = 0;
   if (gt == 0 && (A.fuse & 2)) {                                 // k_ov_apply's bookkeeping (dana.F90:939-941)
@@ -135,13 +136,14 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   if (gt == 0 && (A.fuse & 1)) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
   for (int s = gt; s < A.n; s += gsz) {
     if (A.fuse & 2) d_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, s);
-    double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s);
+    double rel2, zn;
+    double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s, z0, pist_c, rel2, zn);
     if (A.fuse & 1) {
       const long long m = meta_of(ld_rec(&A.posm[s]));
       A.parent[s] = s; A.comp_cnt[s] = 0; A.ov_head[s] = -1;
       A.ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
     }
-    if (rd >= 0.0) lay_note(s_lay, A.g, A.posm[s].z, rd);
+    if (rd >= 0.0) lay_note(s_lay, A.g, zn, rel2);
     top2_merge(a1, a2, rd, -1.0);
     if (tail) {                                                  // promotion loop + census of calc_rho (same pass as k_promote_rho)
       double4 p = ld_rec(&A.posm[s]);
@@ -192,11 +194,13 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   if (gt == 0) {
     sc->d1 = a1; sc->d2 = a2; sc->need_rebuild = need ? 1 : 0;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
+    sc->kappa_tu = need ? 0.0 : fabs(pist_c) * 1.01;
     if (!need) sc->lay_cur = lay_old ^ 1;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; sc->pist_P = 1.0; }
     if (tail && A.piston) {                                      // k_maxz's scalar part; the skip tables of this call are not read again inside dml_step
       sc->maxz_disp += fabs(lohi) * fmax(sc->zmax - z0, 0.0) * 1.01;
       sc->maxz_fac += fabs(lohi) * 1.01;
+      sc->pist_P = (need ? 1.0 : sc->pist_P) * (1.0 - lohi);
       sc->zmax = sc->zmax - lohi * (sc->zmax - z0);
     }
   }

@@ -204,6 +204,8 @@ struct DevScal {
   long long overlap_passes;
   unsigned int ticket3;             // last-block election of k_pbc_disp
   unsigned int ticket4;             // last-block election of k_integrate
+  double kappa_tu;                  // |1 - 1/pist_P| the displacement tables of the last test_update were recorded with (0 after a rebuild)
+  double pist_P;                    // product of (1 - lohi) of the maxz calls since the rows were built (1 without a piston): see lay_note
   RefRng rr; long long rr_mark;     // DML_RNG_REFERENCE: the reference's generator state; try_ when the running overlap_moveback started
   unsigned int istep;               // integrator calls so far: the step word of the Philox counters (kernels read it here so that a captured
                                     // CUDA graph of the loop body stays valid from step to step)

@@ -95,11 +95,14 @@ __global__ void __launch_bounds__(TPB) k_scan(int *__restrict__ in, int *__restr
 // K1  test_update (Neighbor.F90:668-713): do_pbc (Groups.F90:1440-1467) + the two largest squared displacements
 //     (inq_dispmax, Neighbor.F90:635-666) in one streaming pass; k_top2_final takes the rebuild decision on the device.
 // ================================================================================================
-__device__ __forceinline__ double d_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, const Geo &g, int s) {
+// rel2 (out): squared displacement with the piston's affine shift taken out (see lay_note); znow: the particle's height
+__device__ __forceinline__ double d_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, const Geo &g, int s,
+                                             double z0, double pist_c, double &rel2, double &znow) {
   double4 p = ld_rec(&posm[s]);
   long long m = meta_of(p);
+  rel2 = -1.0; znow = p.z;
   if (!(m & MF_TYPE)) return -1.0;
-  double po[3] = {pos_old[3 * s], pos_old[3 * s + 1], pos_old[3 * s + 2]};
+  double po[3] = {__ldcs(&pos_old[3 * s]), __ldcs(&pos_old[3 * s + 1]), __ldcs(&pos_old[3 * s + 2])};
   double q[3] = {p.x, p.y, p.z};
   bool ch = false;
 #pragma unroll
@@ -112,6 +115,8 @@ __device__ __forceinline__ double d_pbc_disp(double4 *__restrict__ posm, double 
     pos_old[3 * s] = po[0]; pos_old[3 * s + 1] = po[1]; pos_old[3 * s + 2] = po[2];
   }
   double vx = q[0] - po[0], vy = q[1] - po[1], vz = q[2] - po[2];
+  const double wz = vz - pist_c * fmax(q[2] - z0, 0.0);
+  rel2 = (vx * vx + vy * vy) + wz * wz;
   return (vx * vx + vy * vy) + vz * vz;
 }
 // block-wide top-2 of per-thread (a1,a2); result valid in thread 0
@@ -146,26 +151,16 @@ __device__ __forceinline__ int layer_of(const Geo &g, double z) {
   cz = cz < 0 ? 0 : (cz > g.nc[2] + 1 ? g.nc[2] + 1 : cz);
   return cz >> g.lay_shift;
 }
+// What the table records is NOT the displacement u = pos - pos_old itself but w = u - c(z), c(z) = (1 - 1/P) max(z - z0, 0) z^ being the
+// shift the piston (maxz: z -= lohi (z - z0), P = product of (1 - lohi) since the rows were built) gave a particle now at height z.
+// For a pair, u_i - u_j = (w_i - w_j) + (c(z_i) - c(z_j)) and |c(z_i) - c(z_j)| <= |1 - 1/P| |z_i - z_j| whatever c models, so
+// |change of the pair separation| <= |w_i| + |w_j| + kappa |z_i - z_j|: an identity, rigorous for any P.  The piston moves a particle
+// at the top of a 1 M box by ~1 A per step but a PAIR by ~0.01 A; with absolute displacements the skip bound of the upper layers
+// was used up two steps after every rebuild (pair force 31 us after a rebuild, 56 us on average).
 __device__ __forceinline__ void lay_note(unsigned int *s_lay, const Geo &g, double z, double rd) {
   if (rd < 0.0) return;
   float d = __double2float_ru(sqrt(rd)) * 1.000001f;
   atomicMax(&s_lay[layer_of(g, z)], (unsigned int)__float_as_int(d));
-}
-// Largest quantised build-time distance that still has to be examined by a particle at height z looking for partners
-// within rmax: D - S <= rmax with S = bound of |move of i| + |move of j| since the rows were built (see k_fuerza_sub).
-// Largest quantised build-time distance that still has to be examined by a particle at height z looking for partners
-// within rmax: D - S <= rmax with S = bound of |move of i| + |move of j| since the rows were built (see k_fuerza_sub).
-__device__ __forceinline__ int skip_qmax(const Geo &g, const DevScal *__restrict__ sc, const unsigned int *__restrict__ lay, double z, double rmax) {
-  const int l = layer_of(g, z);
-  const unsigned int *lt = lay + sc->lay_cur * LAY_MAX;
-  unsigned int mx = 0u;
-#pragma unroll
-  for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldg(&lt[q])); }
-  const double since = sc->maxz_fac * fmax(z + 2.0 * g.cell[2] * (1 << g.lay_shift) - sc->z0, 0.0) +
-                       (double)__int_as_float((int)sc->step_disp_bits);
-  double S = fmin(2.0 * (double)__int_as_float((int)mx), sc->dsum_tu) + 2.0 * since;
-  if (since > g.cell[2]) return 255;                  // particles may have changed layer: no skipping
-  return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
 }
 // The same bound tabulated per z-layer for overlap_moveback (table 1, rmax = rcut; table 0 holds the pair-force value).  The
 // single block that finishes test_update refreshes it (d_top2_final), so the overlap kernels that follow read one byte where
@@ -176,18 +171,24 @@ __device__ __forceinline__ int skip_qtab(const Geo &g, const unsigned int *__res
   const unsigned char *qt = reinterpret_cast<const unsigned char *>(lay + 2 * LAY_MAX) + which * LAY_MAX;
   return (int)__ldg(&qt[layer_of(g, z)]);
 }
+// Bound of the change of a pair separation since the rows were built: relative displacements recorded at the last test_update (mx, per
+// layer, piston shift taken out: lay_note) or the global top-2 sum if smaller, the piston's relative shift before (kappa) and after
+// (maxz_fac) that test_update over at most 2 list radii of height difference, and the integrator's move since (sdisp, each partner).
+__device__ __forceinline__ double pair_shift_bound(const Geo &g, double mx, double dsum, double kappa, double maxz_fac, double sdisp) {
+  const double R = 2.0 * sqrt(g.rc_list2);
+  return fmin(2.0 * mx + kappa * R, dsum) + maxz_fac * R + 2.0 * sdisp;
+}
 // One entry of the tables: the bound of layer l uses the top of the layer where the per-particle formula used z.
 __device__ __forceinline__ int qtab_entry(const unsigned int *lt, const Geo &g, int l, double thick, double maxz_fac, double z0, double zmax,
-                                          double dsum, double sdisp, double rmax) {
+                                          double dsum, double sdisp, double rmax, double kappa) {
   unsigned int mx = 0u;
 #pragma unroll
   for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldcg(&lt[q])); }
   double ztop = thick * (double)(l + 1);             // every particle of layer l sits below ...
   if (l == g.nlay - 1) ztop = fmax(ztop, zmax);      // ... except in the last one, which also takes what is above the box (up to the ceiling)
-  const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
-  const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
+  const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;     // absolute move of a particle of this layer since the tables were filled
   if (since > g.cell[2]) return 255;                 // particles may have changed layer: no skipping
-  return (int)fmin(255.0, ceil((rmax * 1.000001 + S) * g.bq_scale) + 1.0);
+  return (int)fmin(255.0, ceil((rmax * 1.000001 + pair_shift_bound(g, (double)__int_as_float((int)mx), dsum, kappa, maxz_fac, sdisp)) * g.bq_scale) + 1.0);
 }
 // Executed by one block.  sc is read around L1 (the block may hold a stale line of it from earlier in its kernel).
 __device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const DevScal *sc, const Geo &g, double rmax_f, double rmax_o) {
@@ -197,9 +198,10 @@ __device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const Dev
   const double thick = g.cell[2] * (double)(1 << g.lay_shift);
   const double maxz_fac = v->maxz_fac, z0 = v->z0, zmax = v->zmax, dsum = v->dsum_tu;
   const double sdisp = (double)__int_as_float((int)v->step_disp_bits);
+  const double kappa = v->kappa_tu;
   for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
-    qt[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_f);
-    qt[LAY_MAX + l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_o);
+    qt[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_f, kappa);
+    qt[LAY_MAX + l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_o, kappa);
   }
 }
 __global__ void k_qtab(unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, double rmax_f, double rmax_o) { d_qtab(lay, sc, g, rmax_f, rmax_o); }
@@ -226,8 +228,9 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
     int need = (!sc->listed) || (sqrt(a1) + sqrt(a2) > nb_dcut);     // Neighbor.F90:697-710
     sc->need_rebuild = need;
     sc->dsum_tu = need ? 0.0 : sqrt(a1) + sqrt(a2); sc->maxz_disp = 0.0; sc->maxz_fac = 0.0;
+    sc->kappa_tu = need ? 0.0 : fabs(1.0 - 1.0 / sc->pist_P) * 1.01;     // the factor k_pbc_disp took the piston shift out with
     s_need_sh = need;
-    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; }
+    if (need) { sc->nupd++; sc->listed = 1; sc->nlimbo = 0; sc->hole_lo = 0; sc->halo_flag = 0; sc->rev_valid = 0; sc->rows_pending = 1; sc->cols_used = sc->cols_tail0; sc->pist_P = 1.0; }
   }
   // z-layer tables: after a rebuild both are zero (displacements restart); otherwise the one just filled becomes current
   // and the previous one is cleared for the next test_update
@@ -253,10 +256,12 @@ __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, do
   __shared__ int s_last;
   for (int i = threadIdx.x; i < g.nlay; i += blockDim.x) s_lay[i] = 0u;
   __syncthreads();
+  const double z0p = sc->z0, pist_c = 1.0 - 1.0 / sc->pist_P;
   double a1 = -1.0, a2 = -1.0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-    double rd = d_pbc_disp(posm, pos_old, g, s);
-    if (rd >= 0.0) lay_note(s_lay, g, posm[s].z, rd);
+    double rel2, zn;
+    double rd = d_pbc_disp(posm, pos_old, g, s, z0p, pist_c, rel2, zn);
+    if (rd >= 0.0) lay_note(s_lay, g, zn, rel2);
     if (s < n_disp) top2_merge(a1, a2, rd, -1.0);        // slab mode: ghosts are measured by their owners
   }
   __syncthreads();
@@ -1246,7 +1251,8 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
       double ztop = thick * (double)(l + 1);
       if (l == g.nlay - 1) ztop = fmax(ztop, zmax);
       const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
-      const double S = fmin(2.0 * (double)__int_as_float((int)mx), dsum) + 2.0 * since;
+      const double kappa = __ldg(&sc->kappa_tu);
+      const double S = pair_shift_bound(g, (double)__int_as_float((int)mx), dsum, kappa, maxz_fac, sdisp);
       q8[l] = (unsigned char)((since > g.cell[2]) ? 255 : (int)fmin(255.0, ceil((ph.r0_max * 1.000001 + S) * g.bq_scale) + 1.0));
     }
   }
@@ -1257,13 +1263,16 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   const int qmax = (int)reinterpret_cast<const unsigned char *>(s_qt)[layer_of(g, p1.z)];
   const int asym = __ldg(&sc->rows_asym);                // 0 symmetric, 1 halo-only, 2 general
   const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
-  if (asym == 0 && rm.q5 > qmax) {
+  // asym == 1 (some particle sits in a halo cell above box(3): the usual state of a piston run): only the rows of those few
+  // particles are transposed, so a particle outside the halo that nobody's transposed row mentions is as good as symmetric
+  const bool plain = asym == 0 || (asym == 1 && halo_of[s] == 0 && rev_len[s] == 0);
+  if (plain && rm.q5 > qmax) {
     // every entry that has to be looked at is in the near list (row order)
     // (usually none or one of them is within the bound: no need to keep four partner records in flight)
     const int nrs[4] = {nr.x, nr.y, nr.z, nr.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if ((int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[nrs[k]]), 0, 0, false, a);
+      if ((int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) fuerza_pair(g, ph, p1, k3, ld_rec_nc(&posm[nrs[k]]), 0, asym, false, a);
   } else {
     const bool i_halo = asym == 1 && halo_of[s] != 0;
     fuerza_row(posm, cols, rev_start, rev_len, rev_cols, bq, rev_bq, g, ph, p1, k3, s, rm.start, rm.len, qmax, asym, i_halo, a);
@@ -1355,7 +1364,9 @@ __device__ __forceinline__ void integrate_one(double4 *__restrict__ posm, double
                                               double4 p, double v[3], const double a[3], const double gs[6], const RngSrc &rs, int s, BlockAcc &acc) {
   long long m = meta_of(p);
   double q[3] = {p.x, p.y, p.z}, og[3] = {p.x, p.y, p.z};
-  old_cg[3 * s] = og[0]; old_cg[3 * s + 1] = og[1]; old_cg[3 * s + 2] = og[2];
+  // written once per step and read by few: streaming stores keep these 48 bytes per particle from sitting dirty in the L2 in front
+  // of the pair force (which ran 66 us right behind this kernel and 31 us behind a clean L2)
+  __stcs(&old_cg[3 * s], og[0]); __stcs(&old_cg[3 * s + 1], og[1]); __stcs(&old_cg[3 * s + 2], og[2]);
   int zt = (int)(m & MF_TYPE);
   if (ERMAK) {
     double sm = ph.sqrt_mass[zt - 1];
@@ -1365,7 +1376,7 @@ __device__ __forceinline__ void integrate_one(double4 *__restrict__ posm, double
       double r1 = gs[2 * j], r2 = gs[2 * j + 1];
       double ranr = A * r1;
       q[j] = q[j] + ph.cc1 * v[j] + ph.cc2h * a[j] + ranr;
-      ranv[3 * s + j] = B * (ph.crv1 * r1 + ph.crv2 * r2);
+      __stcs(&ranv[3 * s + j], B * (ph.crv1 * r1 + ph.crv2 * r2));
     }
   } else {
     double fac1 = (q[2] > ph.z_sei) ? ph.fac_sc : ph.fac_sei;
@@ -1392,7 +1403,7 @@ __device__ __forceinline__ void integrate_one(double4 *__restrict__ posm, double
   }
   p.x = q[0]; p.y = q[1]; p.z = q[2]; p.w = meta_as_double(m);
   st_rec(&posm[s], p);
-  if (wrote_v) { vel[3 * s] = v[0]; vel[3 * s + 1] = v[1]; vel[3 * s + 2] = v[2]; }
+  if (wrote_v) { __stcs(&vel[3 * s], v[0]); __stcs(&vel[3 * s + 1], v[1]); __stcs(&vel[3 * s + 2], v[2]); }
 }
 
 template <bool ERMAK>
@@ -1410,7 +1421,7 @@ __global__ void __launch_bounds__(TPB, 4) k_integrate(double4 *__restrict__ posm
     double v[3] = {0.0, 0.0, 0.0}, a[3] = {0.0, 0.0, 0.0};
     if (ERMAK) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { v[j] = vel[3 * s + j]; a[j] = acel[3 * s + j]; }
+      for (int j = 0; j < 3; ++j) { v[j] = __ldcs(&vel[3 * s + j]); a[j] = __ldcs(&acel[3 * s + j]); }
     }
     const unsigned int id = (unsigned int)uid[s];
     if (meta_of(p) & MF_REF) {
@@ -1491,9 +1502,9 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
   const double fv[3] = {f4.x, f4.y, f4.z};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    double f = fv[k], a = acel[3 * s + k], v = vel[3 * s + k];
-    vel[3 * s + k] = ph.cc0 * v + ph.cc1mcc2 * a + ph.cc2 * f / mass + ranv[3 * s + k];
-    acel[3 * s + k] = f / mass;
+    double f = fv[k], a = __ldcs(&acel[3 * s + k]), v = __ldcs(&vel[3 * s + k]);
+    __stcs(&vel[3 * s + k], ph.cc0 * v + ph.cc1mcc2 * a + ph.cc2 * f / mass + __ldcs(&ranv[3 * s + k]));
+    __stcs(&acel[3 * s + k], f / mass);
   }
 }
 
@@ -2055,6 +2066,7 @@ __global__ void k_maxz(double4 *__restrict__ posm, DevScal *__restrict__ sc, dou
   if (s == 0) {
     sc->maxz_disp += fabs(lohi) * fmax(sc->zmax - z0, 0.0) * 1.01;
     sc->maxz_fac += fabs(lohi) * 1.01;   // |z shift| of any atom below the ceiling
+    sc->pist_P *= (1.0 - lohi);
     sc->zmax = sc->zmax - lohi * (sc->zmax - z0);
   }
 }
