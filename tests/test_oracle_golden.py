@@ -65,3 +65,20 @@ def test_chunk_fixture_is_pos_inic_rule():
     # the shipped chunk.xyz is the pos_inic rule at 100x100x50 up to its text precision
     ch = O.read_chunk(os.path.join(os.path.dirname(__file__), "golden", "brown", "chunk.xyz"))
     assert ch.shape == (301, 3)
+
+
+def test_logf_restatement_matches_libm(tmp_path):
+    """DML_RNG_REFERENCE draws gasdev on the device, whose single-precision logarithm must be the host libm's logf bit for bit
+    (src/dana.F90:1379-1404: rsq is real(sp)).  din_mol_li_b200/csrc/dml_device.cuh::ref_logf restates glibc's algorithm; the same
+    restatement in C (tests/ref_logf_check.c, same table and polynomial) is compared here with logf over EVERY float in (0, 1]."""
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_logf_check.c")
+    exe = os.path.join(tmp_path, "ref_logf_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-o", exe, src, "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "0 differ" in r.stdout, r.stdout
+    # the constants of the device function are the ones of the C file
+    dev = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "din_mol_li_b200", "csrc", "dml_device.cuh")).read()
+    for tok in ("0x1.661ec79f8f3bep+0", "-0x1.57bf7808caadep-2", "0x1.767dcf5534862p-1", "0x1.4043057b6ee09p-2", "-0x1.00ea348b88334p-2",
+                "0x1.5575b0be00b6ap-2", "-0x1.ffffef20a4123p-2", "0x1.62e42fefa39efp-1"):
+        assert tok in dev and tok in open(src).read()
