@@ -87,6 +87,7 @@ struct dml_ctx {
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
+  int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 4, 6, 8)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel
   int ov_guard_pass = 64;   // from this pass on, pairs that overlap at their previous positions are skipped in every mode
@@ -499,8 +500,10 @@ static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer
     return 0;
   }
   if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
-  LAUNCH(K_OV_DETECT, k_ov_detect, nblk(n), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, ctx->lay.p,
-         ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n);
+#define OVDET(L) LAUNCH(K_OV_DETECT, k_ov_detect<L>, nblk((long long)n * L), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, \
+                        ctx->lay.p, ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n)
+  if (ctx->ov_lanes >= 4) OVDET(4); else if (ctx->ov_lanes >= 2) OVDET(2); else OVDET(1);
+#undef OVDET
   const OvRp uovl = ov_replay(ctx);
   if (ctx->cfg.prob >= 1.0) {
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
@@ -745,6 +748,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
+  if (const char *e = getenv("DML_OV_LANES")) ctx->ov_lanes = atoi(e);
+  if (ctx->ov_lanes <= 0) ctx->ov_lanes = ctx->cfg.integrador ? 1 : 4;   // measured: Brownian 100 k 36 -> 33 us with 4; Ermak 1 M (near-list path) 53 -> 91 us
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 8) ctx->force_minb = v; }
   if (getenv("DML_FUSE_ERMAK_B")) ctx->fuse_ermak_b = true;
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   cg::grid_group grid = cg::this_grid();
   p_ov_init(A.posm, A.parent, A.ovst, A.comp_cnt, A.ov_head, A.sc, A.n);
   grid.sync();
-  p_ov_detect(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
+  p_ov_detect<1>(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.parent, A.ovst, A.sc, A.g, A.n);
   grid.sync();
   p_ov_link(A.parent, A.ovst, A.ov_head, A.ov_next, A.roots, A.sc, A.n);
   grid.sync();

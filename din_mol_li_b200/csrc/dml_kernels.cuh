@@ -1548,6 +1548,10 @@ __device__ __forceinline__ void uf_unite(int *parent, int a, int b) {
     if (old == a) return;
   }
 }
+// L lanes share one particle (L = 1, 2 or 4 adjacent threads): lane l looks at entries l, l+L, ... of the row (or at near entry
+// l, l+L, ...), so the dependent gathers of one row run side by side.  The conflict graph does not depend on the order the
+// edges are found in (uf_unite hooks the larger root under the smaller one).
+template <int L>
 __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
@@ -1555,7 +1559,8 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
                                                    DevScal *__restrict__ sc, Geo g, int n) {
   const int s_end = n;
   const double rcut = sqrt(g.rcut2);
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_end; s += gridDim.x * blockDim.x) {
+  const int lane = L > 1 ? (int)(threadIdx.x % L) : 0;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) / L; s < s_end; s += gridDim.x * blockDim.x / L) {
     // one round trip for everything addressed by the slot alone
     const double4 p1 = ld_rec_nc(&posm[s]);
     const int4 nr = rh_near(&rh[s]);
@@ -1594,7 +1599,10 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
     if (rm.q5 > qmax) {                                   // every entry that has to be looked at is in the near list of the head
       const int nrs[4] = {nr.x, nr.y, nr.z, nr.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if ((int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) look(nrs[k]);
+      for (int k = 0; k < 4; ++k) if ((L == 1 || (k % L) == lane) && (int)((rm.nbq >> (8 * k)) & 255u) <= qmax && nrs[k] >= 0) look(nrs[k]);
+    } else if (L > 1) {
+      for (int jj = lane; jj < len; jj += L)
+        if ((int)__ldg(&bq[b + jj]) <= qmax) look(__ldg(&cols[b + jj]));
     } else {
       for (int j0 = 0; j0 < len; j0 += 16) {
         unsigned int need = 0u;
@@ -1609,11 +1617,12 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
     if (inv) atomicOr(&ovst[s], OV_INVOLVED);
   }
 }
+template <int L>
 __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ posm, const double *__restrict__ old_cg,
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
+                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect<L>(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
