@@ -87,6 +87,8 @@ struct dml_ctx {
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
+  bool ov_unstaged = false; // DML_OV_UNSTAGED=1: k_ov_resolve replays from global memory (the form the cooperative kernel uses)
+  int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 4, 6, 8)
   bool fuse_ermak_b = false; // DML_FUSE_ERMAK_B=1: dml_step applies ermak_b inside the production pair-force kernel
@@ -507,9 +509,15 @@ static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer
   const OvRp uovl = ov_replay(ctx);
   if (ctx->cfg.prob >= 1.0) {
     LAUNCH(K_OV_LINK, k_ov_link, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->ov_head.p, ctx->ov_next.p, ctx->roots.p, ctx->sc, n);
-    LAUNCH(K_OV_PASS, k_ov_resolve, std::min(nblk(n, 4), 148 * 4), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
+    if (ctx->ov_unstaged) {
+      LAUNCH(K_OV_PASS, k_ov_resolve<false>, std::min(nblk(n, 4), 148 * ctx->ov_res_bpsm), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
            ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->ov_head.p, ctx->ov_next.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
            STEP_FROM_DEVICE, ctx->ov_guard_pass);
+    } else {
+      LAUNCH(K_OV_PASS, k_ov_resolve<true>, std::min(nblk(n, 4), 148 * ctx->ov_res_bpsm), 128, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p,
+           ctx->lay.p, ctx->ovst.p, ctx->roots.p, ctx->ov_head.p, ctx->ov_next.p, ctx->members.p, ctx->uid.p, uovl, ctx->sc, ctx->geo, ctx->ph,
+           STEP_FROM_DEVICE, ctx->ov_guard_pass);
+    }
   } else {
     LAUNCH(K_OV_COUNT, k_ov_count, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, n);
     LAUNCH(K_OV_ALLOC, k_ov_alloc, nblk(n), TPB, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->comp_off.p, ctx->roots.p, ctx->sc, n);
@@ -748,6 +756,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   ctx->row_slack = cfg->reservoir == 3 ? 8 : 0;
   if (const char *e = getenv("DML_COOP_MAX_N")) ctx->coop_max_n = ctx->coop_tu_max_n = atoi(e);
   if (const char *e = getenv("DML_COOP_TU_MAX_N")) ctx->coop_tu_max_n = atoi(e);
+  if (getenv("DML_OV_UNSTAGED")) ctx->ov_unstaged = true;
+  if (const char *e = getenv("DML_OV_RES_BPSM")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->ov_res_bpsm = v; }
   if (const char *e = getenv("DML_OV_LANES")) ctx->ov_lanes = atoi(e);
   if (ctx->ov_lanes <= 0) ctx->ov_lanes = ctx->cfg.integrador ? 1 : 4;   // measured: Brownian 100 k 36 -> 33 us with 4; Ermak 1 M (near-list path) 53 -> 91 us
   if (const char *e = getenv("DML_FORCE_MINB")) { int v = atoi(e); if (v >= 2 && v <= 8) ctx->force_minb = v; }

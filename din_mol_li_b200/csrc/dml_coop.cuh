@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(TPB) k_overlap_coop(OVArgs A) {
   grid.sync();
   p_ov_link(A.parent, A.ovst, A.ov_head, A.ov_next, A.roots, A.sc, A.n);
   grid.sync();
-  p_ov_resolve(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.ovst, A.roots, A.ov_head, A.ov_next, A.members, A.uid, A.rp_uovl,
-               A.sc, A.g, A.ph, A.step, A.guard_pass);
+  p_ov_resolve<false>(A.posm, A.old_cg, A.rh, A.cols, A.bq, A.lay, A.ovst, A.roots, A.ov_head, A.ov_next, A.members, A.uid, A.rp_uovl,
+               A.sc, A.g, A.ph, A.step, A.guard_pass, nullptr);
   grid.sync();
   p_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, A.sc, A.n);
 }

@@ -1816,12 +1816,29 @@ __global__ void k_ov_link(int *__restrict__ parent, const int *__restrict__ ovst
 // inside a visit the lanes take one row entry each.  That is exact because the entries of one row are independent given the
 // states at the start of the visit (they are distinct atoms, and an entry only changes its own state), except for the `exit`
 // at the first metal contact, which is applied with a ballot: entries behind it are ignored, entries before it act.
+//
+// STAGED (k_ov_resolve): the replay of a component is a chain of dependent loads — state of the member, its record, its row, the
+// state and record of every entry — repeated for every member at every recursion level; the kernel lasts as long as the longest
+// chain.  So a component of up to 32 members is first staged into shared memory with all loads of one kind issued side by side:
+// the members (both positions, state), then every row entry of every member at once (lanes over the concatenated rows), of which
+// only the entries that can be within rcut in ANY new/old combination are kept, in (member, row position) order.  The levels are
+// then replayed from shared memory.  Dropping the other entries is exact: the replay only ever tests those combinations.
+// Entries that are members read their state from the staged copy; metal partners never change; a mobile partner that is not a
+// member (not in ref: F atoms) keeps the global read/write of the unstaged form.
+constexpr int OVS_ENT = 64;                                   // staged entries per component; more -> unstaged replay
+struct OvStage {
+  double pn[32][3], po[32][3];                                // members: moved position, previous position
+  double ep[OVS_ENT][3];                                      // entries: partner's moved position
+  int st[32], slot[32], incl[32], rb[32], qm[32], eb[33];
+  int ea2[OVS_ENT], eloc[OVS_ENT], et2[OVS_ENT], em[OVS_ENT];
+};
+template <bool STAGED>
 __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const RowHead *__restrict__ rh,
                              const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                              const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
                              int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
-                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
+                             DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass, OvStage *stg_all) {
   if (step == STEP_FROM_DEVICE) step = sc->istep;
   const unsigned int FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -1854,6 +1871,159 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
     OvAcc acc = {0, 0, 0, 0};
     long long later = 0;
     int pass = 0;
+    bool staged = false;
+    if (STAGED && !big) {
+      OvStage &S = stg_all[threadIdx.x >> 5];
+      __syncwarp();
+      // ---- members, lane = rank in creation order ----
+      int rl = 0;
+      bool ghost = false;
+      if (sorted >= 0) {
+        const double4 rec = ld_rec_nc(&posm[sorted]);
+        const RowMeta rm = rh_meta(&rh[sorted]);
+        S.st[lane] = vst[sorted];
+        S.pn[lane][0] = rec.x; S.pn[lane][1] = rec.y; S.pn[lane][2] = rec.z;
+        S.po[lane][0] = old_cg[3 * sorted]; S.po[lane][1] = old_cg[3 * sorted + 1]; S.po[lane][2] = old_cg[3 * sorted + 2];
+        S.slot[lane] = sorted; S.rb[lane] = rm.start;
+        S.qm[lane] = skip_qtab(g, lay, rec.z, 1);
+        ghost = (meta_of(rec) & MF_GHOST) != 0;
+        rl = rm.len;
+      }
+      int incl = rl;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += t; }
+      S.incl[lane] = incl;
+      const int tot = __shfl_sync(FULL, incl, 31);
+      const bool any_ghost = __ballot_sync(FULL, ghost) != 0u;   // slab mode: a ghost member has no row here -> unstaged form
+      __syncwarp();
+      if (!any_ghost) {
+        // ---- every row entry of every member, lanes over the concatenated rows ----
+        int nent = 0;
+        for (int f0 = 0; f0 < tot; f0 += 32) {
+          const int f = f0 + lane;
+          bool rel = false;
+          int m = 0, a2 = -1, loc2 = -1, t2 = 0;
+          double p2[3] = {0.0, 0.0, 0.0};
+          if (f < tot) {
+            for (int i = 0; i < cnt; ++i) m += S.incl[i] <= f ? 1 : 0;
+            const int jj = f - (m ? S.incl[m - 1] : 0), rb = S.rb[m];
+            if ((int)__ldg(&bq[rb + jj]) <= S.qm[m]) {
+              a2 = __ldg(&cols[rb + jj]);
+              const int st2 = vst[a2];
+              t2 = (st2 >> OV_TSHIFT) & 3;
+              if (t2) {
+                const double4 r2 = ld_rec_nc(&posm[a2]);
+                p2[0] = r2.x; p2[1] = r2.y; p2[2] = r2.z;
+                for (int i = 0; i < cnt; ++i) if (S.slot[i] == a2) loc2 = i;
+                const double *n1 = S.pn[m], *o1 = S.po[m];
+                rel = !(dist2_idnint(g, n1[0], n1[1], n1[2], p2[0], p2[1], p2[2]) > g.rcut2) ||
+                      !(dist2_idnint(g, o1[0], o1[1], o1[2], p2[0], p2[1], p2[2]) > g.rcut2);
+                if (t2 != 2) {                                     // a partner that can be moved back: its previous position counts too
+                  double o2[3];
+                  if (loc2 >= 0) { o2[0] = S.po[loc2][0]; o2[1] = S.po[loc2][1]; o2[2] = S.po[loc2][2]; }
+                  else { o2[0] = old_cg[3 * a2]; o2[1] = old_cg[3 * a2 + 1]; o2[2] = old_cg[3 * a2 + 2]; loc2 = -2; }
+                  rel = rel || !(dist2_idnint(g, n1[0], n1[1], n1[2], o2[0], o2[1], o2[2]) > g.rcut2) ||
+                        !(dist2_idnint(g, o1[0], o1[1], o1[2], o2[0], o2[1], o2[2]) > g.rcut2);
+                }
+              }
+            }
+          }
+          const unsigned int mk = __ballot_sync(FULL, rel);
+          const int at = nent + __popc(mk & ((1u << lane) - 1u));
+          if (rel && at < OVS_ENT) {
+            S.ep[at][0] = p2[0]; S.ep[at][1] = p2[1]; S.ep[at][2] = p2[2];
+            S.ea2[at] = a2; S.eloc[at] = loc2; S.et2[at] = t2; S.em[at] = m;
+          }
+          nent += __popc(mk);
+        }
+        __syncwarp();
+        if (nent <= OVS_ENT) {
+          staged = true;
+          int eb = 0;
+          for (int k = 0; k < nent; ++k) eb += S.em[k] < lane ? 1 : 0;
+          S.eb[lane] = eb;
+          if (lane == 0) S.eb[32] = nent;
+          __syncwarp();
+          volatile int *sst = (volatile int *)S.st;
+          // ---- the recursion levels, from shared memory ----
+          for (;; ++pass) {
+            const int guard = (guard_pass > 0 && pass >= guard_pass) ? 1 : 0;
+            const long long ch0 = acc.ch;
+            bool again = false;
+            for (int i = 0; i < cnt; ++i) {
+              int st1 = sst[i];
+              if (st1 & OV_SKIP) continue;
+              if (!((st1 >> OV_TSHIFT) & 3)) continue;
+              st1 |= OV_SKIP;
+              const double *q1 = (st1 & OV_MOVED) ? S.po[i] : S.pn[i];
+              const double q1x = q1[0], q1y = q1[1], q1z = q1[2];
+              const bool at_old1 = q1x == S.po[i][0] && q1y == S.po[i][1] && q1z == S.po[i][2];
+              const int a1 = S.slot[i];
+              const int e0 = S.eb[i], e1 = i + 1 < 32 ? S.eb[i + 1] : nent;
+              bool stop = false;
+              for (int j0 = e0; j0 < e1 && !stop; j0 += 32) {
+                const int k = j0 + lane;
+                bool in = false;
+                int a2 = -1, st2 = 0, t2 = 0, loc2 = -1;
+                double q2[3] = {0.0, 0.0, 0.0};
+                bool at_old2 = false;
+                if (k < e1) {
+                  a2 = S.ea2[k]; loc2 = S.eloc[k];
+                  if (loc2 >= 0) {
+                    st2 = sst[loc2]; t2 = (st2 >> OV_TSHIFT) & 3;
+                    const double *q = (st2 & OV_MOVED) ? S.po[loc2] : S.pn[loc2];
+                    q2[0] = q[0]; q2[1] = q[1]; q2[2] = q[2];
+                    at_old2 = q2[0] == S.po[loc2][0] && q2[1] == S.po[loc2][1] && q2[2] == S.po[loc2][2];
+                  } else if (loc2 == -1) {
+                    t2 = S.et2[k]; q2[0] = S.ep[k][0]; q2[1] = S.ep[k][1]; q2[2] = S.ep[k][2];
+                  } else {
+                    st2 = vst[a2]; t2 = (st2 >> OV_TSHIFT) & 3;
+                    if (t2) {
+                      ov_pos(posm, old_cg, a2, st2, q2);
+                      at_old2 = q2[0] == old_cg[3 * a2] && q2[1] == old_cg[3 * a2 + 1] && q2[2] == old_cg[3 * a2 + 2];
+                    }
+                  }
+                  if (t2) in = !(dist2_idnint(g, q1x, q1y, q1z, q2[0], q2[1], q2[2]) > g.rcut2);
+                }
+                const unsigned int cgm = __ballot_sync(FULL, in && t2 == 2);
+                const int first = cgm ? __ffs(cgm) - 1 : 32;
+                const bool mob = in && t2 != 2 && lane < first;
+                const bool unsolv = mob && (ph.piston || guard) && at_old2 && at_old1;     // dana.F90:920-927
+                const bool mv = mob && !unsolv;
+                if (mv) {
+                  const int nst = (st2 | OV_MOVED | OV_ZERO) & ~OV_SKIP;
+                  if (loc2 >= 0) sst[loc2] = nst; else ovst[a2] = nst;
+                }
+                acc.ch3 += __popc(__ballot_sync(FULL, unsolv));
+                const int nm = __popc(__ballot_sync(FULL, mv));
+                acc.ch += nm;
+                if (nm) again = true;
+                if (cgm) {
+                  acc.tr++;
+                  double ne;
+                  if (ph.rng_mode == 1) ne = ov_replay_draw(rp_uovl, a1, lane == 0, sc, ph.prob);
+                  else if (ph.rng_mode == 2) ne = 0.0;
+                  else { Philox rr; rr.run(ph.seed, (unsigned int)uid[a1], step, RS_OVERLAP, (unsigned int)pass); ne = rr.u01(0); }
+                  if (ne < ph.prob) {
+                    acc.de++; st1 = (st1 & ~(3 << OV_TSHIFT)) | (3 << OV_TSHIFT);
+                    if (q1z > z0 && lane == 0) atomicCAS(&sc->err, 0, DML_E_SUPERO_Z0);
+                  } else { st1 |= OV_MOVED; st1 &= ~OV_SKIP; }
+                  stop = true;
+                }
+              }
+              __syncwarp();
+              if (lane == 0) sst[i] = st1;
+              __syncwarp();
+            }
+            if (pass >= 1) later += acc.ch - ch0;
+            if (!again) break;
+          }
+          if (sorted >= 0) ovst[sorted] = sst[lane];
+        }
+      }
+      __syncwarp();
+    }
+    if (!staged)
     for (;; ++pass) {
       const int guard = (guard_pass > 0 && pass >= guard_pass) ? 1 : 0;
       const long long ch0 = acc.ch;
@@ -1955,13 +2125,15 @@ __device__ __forceinline__ void p_ov_resolve(const double4 *__restrict__ posm, c
     }
   }
 }
+template <bool STAGED>
 __global__ void __launch_bounds__(128) k_ov_resolve(const double4 *__restrict__ posm, const double *__restrict__ old_cg, const RowHead *__restrict__ rh,
                              const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                              const unsigned int *__restrict__ lay, int *__restrict__ ovst,
                              const int *__restrict__ roots, const int *__restrict__ ov_head, const int *__restrict__ ov_next,
                              int *__restrict__ members, const int *__restrict__ uid, const OvRp rp_uovl,
                              DevScal *__restrict__ sc, Geo g, Phys ph, unsigned int step, int guard_pass) {
-  p_ov_resolve(posm, old_cg, rh, cols, bq, lay, ovst, roots, ov_head, ov_next, members, uid, rp_uovl, sc, g, ph, step, guard_pass);
+  __shared__ OvStage stg[STAGED ? 4 : 1];
+  p_ov_resolve<STAGED>(posm, old_cg, rh, cols, bq, lay, ovst, roots, ov_head, ov_next, members, uid, rp_uovl, sc, g, ph, step, guard_pass, stg);
 }
 // write the resolved state back: positions, zeroed vel/acel of moved-back atoms, skip flags and new F atoms
 __device__ __forceinline__ void d_ov_apply(double4 *__restrict__ posm, double *__restrict__ vel, double *__restrict__ acel,
