@@ -696,7 +696,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int 
 constexpr int RB = 256;          // sorted particles per block
 constexpr int WCAP = 384;        // staged candidates per stencil row
 constexpr size_t ROWS_OFF_HIT = (size_t)9 * WCAP * sizeof(float4);
-constexpr size_t ROWS_OFF_META = ROWS_OFF_HIT + (size_t)ROW_W * RB * sizeof(int);
+constexpr size_t ROWS_OFF_META = ROWS_OFF_HIT + (size_t)(ROW_W + 1) * RB * sizeof(int);   // + the spare row of the branch-free park
 constexpr size_t ROWS_OFF_QB = ROWS_OFF_META + (size_t)ROW_W * RB * sizeof(unsigned short);
 constexpr size_t ROWS_OFF_CNT = ROWS_OFF_QB + (size_t)ROW_W * RB;
 constexpr size_t ROWS_OFF_LONG = ROWS_OFF_CNT + (size_t)28 * RB;
@@ -802,13 +802,14 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
     // parked as one word (sorted index | run << 24 | x-neighbour << 28 | "inside the list radius for sure" << 30); everything a hit
     // needs beyond that (exact test, stencil position, rank, build-distance byte) is done afterwards with all lanes busy: inlined
     // here it ran in nearly every iteration for the two or three lanes that had a hit (20 M warp instructions, 4 of them useful).
-#define ROWS_CAND(U, Q, PX, PY, DXV, SEG) do {                                                                               \
+#define ROWS_CAND(OK, U, Q, PX, PY, DXV, SEG) do {                                                                           \
       const float vx_ = (Q).x - (PX), vy_ = (Q).y - (PY), vz_ = (Q).z - pzf;                                                 \
       const float d2_ = __fmaf_rn(vx_, vx_, __fmaf_rn(vy_, vy_, vz_ * vz_));                                                 \
-      if (d2_ <= rc2hi && ((SEG) != 4 || (U) != t)) {          /* the particle itself sits in the centre run */             \
-        if (npark < ROW_W) s_hit[npark][tid] = (U) | ((SEG) << 24) | ((DXV) << 28) | (d2_ < rc2lo ? (1 << 30) : 0);         \
-        ++npark;                                                                                                             \
-      }                                                                                                                      \
+      const bool h_ = (OK) && d2_ <= rc2hi && ((SEG) != 4 || (U) != t);   /* the particle itself sits in the centre run */    \
+      /* branch-free: a candidate that is not parked writes the spare row ROW_W (the branchy form spent a quarter of the     \
+         walk's instructions on BSSY / BSYNC / BRA) */                                                                        \
+      s_hit[h_ ? min(npark, ROW_W) : ROW_W][tid] = (U) | ((SEG) << 24) | ((DXV) << 28) | (d2_ < rc2lo ? (1 << 30) : 0);      \
+      npark += h_ ? 1 : 0;                                                                                                   \
     } while (0)
     // the bounds of the nine runs are requested together, before the wait for the staged windows (36 independent loads in flight
     // instead of nine dependent batches: with 5 A cells at skin 2 the cell table is 4.6 MB and every batch is an L2 round trip)
@@ -836,25 +837,22 @@ __global__ void __launch_bounds__(RB, 2) k_rows(const double4 *__restrict__ sort
         if (xw) { uw = __ldg(&cell_start[row + xw]); nw = __ldg(&cell_start[row + xw + 1]) - uw; }
         const int wlo = s_wlo[seg], whi = s_whi[seg];
         {
-          const float4 *cp = (u0 >= wlo && u0 + n <= whi) ? (s_win + seg * WCAP + (u0 - wlo)) : (sorted_posf + u0);
-          const int nmax = __reduce_max_sync(full, n);
-          for (int i = 0; i < nmax; i += 4) {              // four independent candidates per trip
+          const float4 *cp = n <= 0 ? s_win : ((u0 >= wlo && u0 + n <= whi) ? (s_win + seg * WCAP + (u0 - wlo)) : (sorted_posf + u0));
+          const int nmax = __reduce_max_sync(full, n), last = max(n - 1, 0);
+          for (int i = 0; i < nmax; i += 4) {              // four independent candidates per trip; lanes beyond their run re-read its last one
             float4 q[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) if (i + e < n) q[e] = cp[i + e];
+            for (int e = 0; e < 4; ++e) q[e] = cp[min(i + e, last)];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (i + e < n) { const int u = u0 + i + e; ROWS_CAND(u, q[e], pxf, pys, (u >= b1 ? 1 : 0) + (u >= b2 ? 1 : 0), seg); }
+            for (int e = 0; e < 4; ++e) { const int u = u0 + i + e; ROWS_CAND(i + e < n, u, q[e], pxf, pys, (u >= b1 ? 1 : 0) + (u >= b2 ? 1 : 0), seg); }
           }
         }
         if (anyw) {                                       // wrap cell of the particles at the periodic x edge
-          const float4 *cp = (uw >= wlo && uw + nw <= whi) ? (s_win + seg * WCAP + (uw - wlo)) : (sorted_posf + uw);
-          const int nmax = __reduce_max_sync(full, nw);
+          const float4 *cp = nw <= 0 ? s_win : ((uw >= wlo && uw + nw <= whi) ? (s_win + seg * WCAP + (uw - wlo)) : (sorted_posf + uw));
+          const int nmax = __reduce_max_sync(full, nw), last = max(nw - 1, 0);
           for (int i = 0; i < nmax; ++i) {
-            if (i < nw) {
-              const float4 q = cp[i];
-              ROWS_CAND(uw + i, q, pxw, pys, dxw + 1, seg);
-            }
+            const float4 q = cp[min(i, last)];
+            ROWS_CAND(i < nw, uw + i, q, pxw, pys, dxw + 1, seg);
           }
         }
       }
