@@ -44,4 +44,19 @@ ls.ctx.test_update()
 for i in range(steps):
     ls.step(check=False)
 ls.ctx.close()
+# round 2 paths: several members stepped from one host thread (dml_ensemble_step, one-block-per-SM cooperative grids), the frame
+# path of the host-buffer interface, the CUDA-graph replay of dml_step (any Philox ctx.step above), the block-staged row build
+# (bulk copies + mbarrier) and the staged overlap replay (every DML_NO_COOP=1 run above)
+d = O.read_case(os.path.join(GOLD, "ermak"))
+members = []
+for k in range(3):
+    c = P.ctx_from_oracle(O.Oracle(**d), rng_mode=dml.RNG_PHILOX, strict=0, seed=11 + k)
+    c.set_ensemble_member(True)
+    members.append(c)
+dml.ensemble_step(members, steps)
+pos, z = members[0].download_frame()
+members[0].upload_positions(pos)
+members[0].step(2)
+for c in members:
+    c.close()
 print("sanitize_run: done")
