@@ -84,9 +84,10 @@ struct dml_ctx {
   bool step_tail_done = false;       // enq_step_a folded the tail of the step into the second test_update
   bool sort_maybe_pending = false;   // a deferring test_update was enqueued since the last cell sort (k_sort_catchup is launched on demand)
   DBuf<double4> snap;       // positions of a rebuild whose cell sort was deferred
+  bool no_bi_fuse = false;  // DML_NO_BI_FUSE=1: the Brownian integrator stays a launch of its own inside dml_step
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
-  bool use_coop = true; int coop_grid_tu = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
+  bool use_coop = true; int coop_grid_tu = 0, coop_grid_tu_bi = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   bool ov_unstaged = false; // DML_OV_UNSTAGED=1: k_ov_resolve replays from global memory (the form the cooperative kernel uses)
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
@@ -348,6 +349,7 @@ static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force) {
   A.vel = ctx->vel.p; A.acel = ctx->acel.p; A.old_cg = ctx->old_cg.p;
   A.area = ctx->geo.box[0] * ctx->geo.box[1]; A.h_over_tau = ctx->cfg.h / ctx->cfg.tau; A.use_z1 = ctx->cfg.reservoir == 2 ? 1 : 0; A.piston = ctx->cfg.reservoir == 1 ? 1 : 0;
   A.defer = 0; A.snap = ctx->snap.p;
+  A.uid = ctx->uid.p; A.ranv = ctx->ranv.p; A.old_cg_w = ctx->old_cg.p; A.ph = ctx->ph;
 }
 // fuse: see TUArgs (bits 0-1 overlap_moveback's first / last pass, bit 2 the tail of the loop body); defer: leave the cell sort of a
 // rebuild to whoever needs the cells first
@@ -386,7 +388,8 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true,
     if (A.defer) { CKC(ctx->snap.ensure(ctx->cap, ctx->st)); A.snap = ctx->snap.p; ctx->sort_maybe_pending = true; }
     else ctx->sort_maybe_pending = false;                 // a sorting call catches up with (or supersedes) a deferred sort
     ctx->tu_fused = A.fuse;
-    LAUNCH_COOP(K_TU_COOP, k_test_update_coop, ctx->coop_grid_tu, A);
+    if (A.fuse & 8) LAUNCH_COOP(K_TU_COOP, k_test_update_coop<true>, ctx->coop_grid_tu_bi, A);
+    else LAUNCH_COOP(K_TU_COOP, k_test_update_coop<false>, ctx->coop_grid_tu, A);
     ctx->binned = true;
     return 0;
   }
@@ -631,9 +634,17 @@ static int enq_step_a(dml_ctx *ctx) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
     if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
       LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n, ctx->fnz.p);
-  } else TRY(enq_integrate(ctx, false));
+  }
+  // Brownian step with Philox noise: the integrator rides on the first pass of the test_update that follows it (one launch and one
+  // pass over the records less); DML_NO_BI_FUSE=1 keeps the launch of its own
+  tessellate(ctx);
+  const bool bi = !ctx->cfg.integrador && tu_can_fuse(ctx) && ctx->tessellated && ctx->ph.rng_mode == DML_RNG_PHILOX && !ctx->no_bi_fuse && ctx->coop_grid_tu_bi > 0;
+  if (!ctx->cfg.integrador) {
+    if (bi) { ctx->step++; LAUNCH(K_MISC, k_tick, 1, 1, ctx->sc); ctx->have_rp = false; }
+    else TRY(enq_integrate(ctx, false));
+  }
   const bool fz = tu_can_fuse(ctx) && ov_is_multi_launch(ctx);   // k_ov_init rides on the first test_update, k_ov_apply on the second
-  TRY(enq_test_update(ctx, fz ? 1 : 0, false));
+  TRY(enq_test_update(ctx, (fz ? 1 : 0) | (bi ? 8 : 0), false));
   TRY(enq_overlap(ctx, true, fz, fz));
   // the second test_update also carries the tail of the loop body (msd bookkeeping, promotion, calc_rho, maxz) when it runs as
   // one cooperative launch, and in Brownian mode leaves the cell sort of its rebuild to whoever needs it (nobody, usually: Q11)
@@ -765,6 +776,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (getenv("DML_ROWS_LEGACY")) ctx->rows_legacy = true;
   if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
+  if (getenv("DML_NO_BI_FUSE")) ctx->no_bi_fuse = true;
   if (getenv("DML_NO_GRAPH")) ctx->use_graph = false;
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
@@ -800,14 +812,17 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
+    int b1i = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop<false>, TPB, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1i, k_test_update_coop<true>, TPB, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, k_overlap_coop, TPB, 0);
     ctx->coop_grid_tu = nsm * std::min(b1, 4); ctx->coop_grid_ov = nsm * b2;   // a larger grid only makes the grid-wide barriers slower
+    ctx->coop_grid_tu_bi = nsm * std::min(b1i, 4);
     { int b3 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, k_rev_coop, TPB, 0); ctx->coop_grid_rev = getenv("DML_NO_REV_COOP") ? 0 : nsm * std::min(b3, 4); }
-    if (const char *e = getenv("DML_COOP_TU_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b1) ctx->coop_grid_tu = nsm * v; }   // blocks per SM of k_test_update_coop
+    if (const char *e = getenv("DML_COOP_TU_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b1) ctx->coop_grid_tu = nsm * v; if (v >= 1 && v <= b1i) ctx->coop_grid_tu_bi = nsm * v; }   // blocks per SM of k_test_update_coop
     if (const char *e = getenv("DML_COOP_OV_BPSM")) { int v = atoi(e); if (v >= 1 && v <= b2) ctx->coop_grid_ov = nsm * v; }
     ctx->use_coop = coop && b1 > 0 && b2 > 0 && !getenv("DML_NO_COOP");
-    int gmax = std::max(std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_ov), ctx->coop_grid_rev), 1);
+    int gmax = std::max(std::max(std::max(std::max(ctx->coop_grid_tu, ctx->coop_grid_tu_bi), ctx->coop_grid_ov), ctx->coop_grid_rev), 1);
     CKC(ctx->coop_sums.ensure((size_t)gmax + 8, ctx->st));
     CKC(ctx->part.ensure((size_t)2 * std::max(gmax, nblk(cap)) + 8, ctx->st));
   }
@@ -1077,8 +1092,11 @@ int dml_ensemble_step(dml_ctx **ctxs, int32_t nctx, int32_t nsteps) {
 int dml_set_ensemble_member(dml_ctx *ctx, int32_t on) { ENTER(ctx);
   int dev = 0, nsm = 0;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  int b1 = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop, TPB, 0);
+  int b1 = 0, b1i = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_test_update_coop<false>, TPB, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1i, k_test_update_coop<true>, TPB, 0);
   ctx->coop_grid_tu = nsm * (on ? 1 : std::min(b1, 4));
+  ctx->coop_grid_tu_bi = nsm * (on ? 1 : std::min(b1i, 4));
   return 0;
 }
 

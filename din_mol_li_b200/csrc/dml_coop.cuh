@@ -82,6 +82,9 @@ struct TUArgs {
   // defer = 1: a rebuild snapshots the positions (snap) and leaves the cell sort to whoever needs the cells first (sc->sort_pending):
   // the list rebuilt by the second test_update of a Brownian step is superseded by the next step's rebuild before anything reads it
   int defer; double4 *snap;
+  // fuse bit 3 (k_test_update_coop<true>, Brownian integrator, Philox noise): cbrownian_hs + atom_pbc (dana.F90:798-846,1187-1250) of
+  // slot s run in front of do_pbc of slot s in the same pass: the call site in front of the first test_update of a step
+  const int *uid; double *ranv, *old_cg_w; Phys ph;
 };
 
 // cgroup_sort (Cells.F90:267-302) by the whole grid: bin -> scan -> scatter -> order inside every cell; three grid-wide barriers.
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(TPB) k_sort_catchup(TUArgs A) {
 }
 
 // test_update (Neighbor.F90:668-713) in one launch
+template <bool BI>
 __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
   cg::grid_group grid = cg::this_grid();
   const int gsz = gridDim.x * blockDim.x, gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,7 +138,21 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
     sc->overlap_passes += sc->any_active > 0 ? sc->any_active : 1;
   }
   if (gt == 0 && (A.fuse & 1)) { sc->again = 0; sc->n_roots = 0; sc->member_cursor = 0; sc->ch_later = 0; sc->any_active = 0; }
+  BlockAcc iacc = {0, 0, 0.0, 0.0, 0.0f};
+  const unsigned int istep = BI ? sc->istep : 0u;
   for (int s = gt; s < A.n; s += gsz) {
+    if (BI) {                                                    // the Brownian step of this slot (same code as k_integrate<false>)
+      const double4 p = ld_rec(&A.posm[s]);
+      if (meta_of(p) & MF_REF) {
+        const unsigned int id = (unsigned int)A.uid[s];
+        double gs[6], v[3] = {0.0, 0.0, 0.0};
+        const double a[3] = {0.0, 0.0, 0.0};
+        Philox r;
+        r.run(A.ph.seed, id, istep, RS_INTEG0, 0u); r.gauss4f(gs[0], gs[1], gs[2], gs[3]);
+        RngSrc rs = {0, A.ph.seed, id, istep, nullptr, s, nullptr};
+        integrate_one<false>(A.posm, A.vel, A.pos_old, A.old_cg_w, A.ranv, sc, A.g, A.ph, p, v, a, gs, rs, s, iacc);
+      }
+    }
     if (A.fuse & 2) d_ov_apply(A.posm, A.vel, A.acel, A.old_cg, A.ovst, s);
     double rel2, zn;
     double rd = d_pbc_disp(A.posm, A.pos_old, A.g, s, z0, pist_c, rel2, zn);
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
       if ((m & MF_TYPE) && p.z > z0 && p.z < zl) c_rho++;
     }
   }
+  if (BI) block_flush(iacc, sc);                                 // counters and the largest move of the step (read by d_qtab behind the barrier)
   __syncthreads();
   for (int i = threadIdx.x; i < A.g.nlay; i += blockDim.x) if (s_lay[i]) atomicMax(&A.lay[(lay_old ^ 1) * LAY_MAX + i], s_lay[i]);
   block_top2(a1, a2);

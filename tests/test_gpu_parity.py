@@ -423,6 +423,30 @@ def test_step_with_folded_overlap_passes_bit_identical(name, nsteps, monkeypatch
     assert out[0][1:] == out[1][1:] and out[0][1] > 0
 
 
+@pytest.mark.parametrize("env", ["DML_NO_BI_FUSE=1", "DML_NO_GRAPH=1", "DML_NO_COOP=1", "DML_COOP_MAX_N=100,DML_NO_BI_FUSE=1"])
+def test_brownian_step_variants_bit_identical(env, monkeypatch):
+    """Inside dml_step the Brownian integrator (cbrownian_hs + atom_pbc) rides on the first pass of the test_update behind it
+    (k_test_update_coop<true>).  The Philox trajectory of tests/brown (chunk reservoir, depositions, move-backs) must be bit-identical
+    with the integrator as a launch of its own, without the step graph, and with every phase as its own launch."""
+    d, o = case("brown")
+    out = []
+    for variant in ("", env):
+        for kv in [x for x in variant.split(",") if x]:
+            k, v = kv.split("=")
+            monkeypatch.setenv(k, v)
+        ctx = P.ctx_from_oracle(o, rng_mode=dml.RNG_PHILOX, strict=0, seed=77)
+        ch = P.ChunkTemplate(d["chunk_xyz"], o.scalars().zmax, o.params.dist + 3.2)
+        ctx.set_chunk_template(ch.pos, ch.pos_old, ch.dist, P.RHOMEDIA)
+        ctx.step(150)
+        c = ctx.counters()
+        out.append((ctx.download(c.n_slots), c.choques, c.depo, c.try_, c.nupd_vlist, c.max_vel, c.msd_t))
+        ctx.close()
+    for k in ("pos", "vel", "pos_old", "old_cg", "z", "flags"):
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    assert out[0][1:6] == out[1][1:6] and out[0][1] > 0
+    assert abs(out[0][6] - out[1][6]) <= 1e-12 * abs(out[0][6])      # msd_t: a sum of per-block partials added atomically (order not fixed)
+
+
 @pytest.mark.parametrize("integrador,nsteps", [(1, 300), (0, 120)])
 def test_box_without_cell_lists_uses_verlet_rows(integrador, nsteps):
     """A box with fewer than 4 cells on every axis is not tessellated (Cells.F90:231): the reference builds its rows with the
