@@ -68,7 +68,7 @@ struct dml_ctx {
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
   DBuf<int> send_lo, send_hi, slab_counts, pack_uid_lo, pack_uid_hi; DBuf<double4> pack_lo, pack_hi;
   double zlo = 0.0, zhi = 0.0; int slab_holes = 0; bool slab_ready = false;     // slab bounds, holes in the owned region
-  DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri, cnt_own, cnt_all;
+  DBuf<int> mig_list_lo, mig_list_hi, mig_rc, mig_holes, mig_si_lo, mig_si_hi, mig_ri;
   DBuf<double> mig_sd_lo, mig_sd_hi, mig_rd, top2_own, top2_all;
   int nsend_lo = 0, nsend_hi = 0, nrecv_lo = 0, nrecv_hi = 0, ghost_lo_first = 0, ghost_hi_first = 0;
   bool rows_legacy = false; // DML_ROWS_LEGACY=1: 27-cell ordered walk of one thread for every row (the staged walk needs >= 3 cells per axis)
@@ -89,6 +89,7 @@ struct dml_ctx {
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_tu_bi = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   bool ov_unstaged = false; // DML_OV_UNSTAGED=1: k_ov_resolve replays from global memory (the form the cooperative kernel uses)
+  bool rows_eager = false;  // inside dml_slab_step: the consumers' guarded row-build launches are left out
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
   int force_minb = 4;       // resident blocks per SM the production pair-force kernel is compiled for (DML_FORCE_MINB: 4, 6, 8)
@@ -126,7 +127,7 @@ struct dml_ctx {
 static int gcmc_run_impl(dml_ctx *ctx);
 static int enq_build_rev(dml_ctx *ctx);
 static int enq_sort_cells(dml_ctx *ctx, int force);
-static int enq_materialize_rows(dml_ctx *ctx);
+static int enq_materialize_rows(dml_ctx *ctx, bool force = false);
 static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force);
 static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
@@ -314,8 +315,9 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
 // ngroup_cells (Neighbor.F90:465-548) from the cell-sorted snapshot of the last rebuild; no-op unless rows are pending.
 // Rows are always built on demand (the first consumer after a rebuild): in Brownian mode the list rebuilt by the second
 // test_update of a step is superseded by the next step's rebuild before anything reads it.
-static int enq_materialize_rows(dml_ctx *ctx) {
+static int enq_materialize_rows(dml_ctx *ctx, bool force) {
   int n = ctx->n, nct = ctx->nct;
+  if (ctx->rows_eager && !force) return 0;                // dml_slab_step builds the rows at the rebuild itself: nothing can be pending here
   if (ctx->sort_maybe_pending && ctx->tessellated) {      // the cell sort a deferring test_update left behind (no-op unless pending)
     TUArgs A;
     fill_tu_args(ctx, A, 0);
@@ -854,7 +856,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->send_lo.release(); ctx->send_hi.release(); ctx->slab_counts.release(); ctx->pack_uid_lo.release(); ctx->pack_uid_hi.release();
   ctx->pack_lo.release(); ctx->pack_hi.release();
   ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
-  ctx->mig_ri.release(); ctx->cnt_own.release(); ctx->cnt_all.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
+  ctx->mig_ri.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
   ctx->top2_own.release(); ctx->top2_all.release();
   ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
@@ -1265,8 +1267,11 @@ int dml_slab_plan(int32_t n, const double *z, int32_t nranks, double lo, double 
 static int slab_exchange(dml_ctx *ctx, bool with_uid, bool measure = false) {
   NcclApi *N = nccl_api();
   const bool has_lo = ctx->rank > 0, has_hi = ctx->rank < ctx->nranks - 1;
-  if (has_lo && ctx->nsend_lo) LAUNCH(K_PACK, k_slab_pack, nblk(ctx->nsend_lo), TPB, ctx->posm.p, ctx->uid.p, ctx->send_lo.p, ctx->nsend_lo, ctx->pack_lo.p, with_uid ? ctx->pack_uid_lo.p : nullptr);
-  if (has_hi && ctx->nsend_hi) LAUNCH(K_PACK, k_slab_pack, nblk(ctx->nsend_hi), TPB, ctx->posm.p, ctx->uid.p, ctx->send_hi.p, ctx->nsend_hi, ctx->pack_hi.p, with_uid ? ctx->pack_uid_hi.p : nullptr);
+  {
+    const int nlo = has_lo ? ctx->nsend_lo : 0, nhi = has_hi ? ctx->nsend_hi : 0;
+    if (nlo + nhi) LAUNCH(K_PACK, k_slab_pack2, nblk(nlo + nhi), TPB, ctx->posm.p, ctx->uid.p, ctx->send_lo.p, nlo, ctx->pack_lo.p, with_uid ? ctx->pack_uid_lo.p : nullptr,
+                          ctx->send_hi.p, nhi, ctx->pack_hi.p, with_uid ? ctx->pack_uid_hi.p : nullptr);
+  }
   NCK(N->GroupStart());
   if (has_hi) {
     if (ctx->nsend_hi) NCK(N->Send(ctx->pack_hi.p, (size_t)ctx->nsend_hi * 4, ncclDouble, ctx->rank + 1, ctx->comm, ctx->st));
@@ -1379,7 +1384,7 @@ static int slab_migrate(dml_ctx *ctx) {
   return 0;
 }
 // test_update (Neighbor.F90:668-713) on the decomposed box: global decision, migration + ghost re-selection + rows at a rebuild
-static int slab_test_update(dml_ctx *ctx) {
+static int slab_test_update(dml_ctx *ctx, bool with_rho = false) {
   NcclApi *N = nccl_api();
   tessellate(ctx);
   if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction");
@@ -1390,11 +1395,19 @@ static int slab_test_update(dml_ctx *ctx) {
     CKC(cudaMemsetAsync(ctx->cell_cur.p, 0, ctx->cell_cur.cap * sizeof(int), ctx->st));
   }
   const int nb = std::min(nblk(n), 148 * 6);
-  CKC(ctx->part.ensure((size_t)2 * nb, ctx->st)); CKC(ctx->top2_own.ensure(2, ctx->st)); CKC(ctx->top2_all.ensure((size_t)2 * ctx->nranks, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 0, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
-  LAUNCH(K_TOP2, k_top2_local, 1, 256, ctx->part.p, nb, ctx->top2_own.p);
-  NCK(N->AllGather(ctx->top2_own.p, ctx->top2_all.p, 2, ncclDouble, ctx->comm, ctx->st));
-  LAUNCH(K_TOP2, k_top2_final, 1, 256, ctx->top2_all.p, ctx->nranks, ctx->sc, ctx->lay.p, ctx->geo, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
+  const size_t per = sizeof(SlabTU) / sizeof(double);
+  CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
+  if (!ctx->top2_own.p) { CKC(ctx->top2_own.ensure(per, ctx->st)); CKC(cudaMemsetAsync(ctx->top2_own.p, 0, sizeof(SlabTU), ctx->st)); }
+  CKC(ctx->top2_all.ensure(per * ctx->nranks, ctx->st));
+  SlabTU *own = reinterpret_cast<SlabTU *>(ctx->top2_own.p), *all = reinterpret_cast<SlabTU *>(ctx->top2_all.p);
+  // second test_update of a step: F -> CG promotion and the census of calc_rho ride on the same all-gather (they come in front
+  // of the rebuild decision like in the fused tail of the single-GPU step)
+  if (with_rho) LAUNCH(K_PROMOTE, k_slab_promote_count, std::min(nblk(ctx->n_owned), 148 * 8), TPB, ctx->posm.p, ctx->sc, own->cnt, ctx->n_owned);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 2, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut,
+         ctx->top2_own.p);
+  NCK(N->AllGather(own, all, sizeof(SlabTU), ncclChar, ctx->comm, ctx->st));
+  LAUNCH(K_TOP2, k_slab_tu_final, 1, 256, all, ctx->nranks, own, ctx->sc, ctx->lay.p, ctx->geo, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut, with_rho ? 1 : 0,
+         ctx->geo.box[0] * ctx->geo.box[1]);
   TRY(pull_scal(ctx));
   if (ctx->hsc->need_rebuild) {
     TRY(slab_migrate(ctx));
@@ -1403,25 +1416,17 @@ static int slab_test_update(dml_ctx *ctx) {
     ctx->hsc->n_slots = ctx->n; ctx->hsc->b_amax = ctx->n;
     TRY(push_scal(ctx));
     TRY(enq_sort_cells(ctx, 0));
-    TRY(enq_materialize_rows(ctx));
+    TRY(enq_materialize_rows(ctx, true));
     }
   ctx->binned = true;
-  return 0;
-}
-// promotion + calc_rho with the global census
-static int slab_promote_rho(dml_ctx *ctx) {
-  NcclApi *N = nccl_api();
-  if (!ctx->cnt_own.p) { CKC(ctx->cnt_own.ensure(4, ctx->st)); CKC(cudaMemsetAsync(ctx->cnt_own.p, 0, 4 * sizeof(int), ctx->st)); }
-  CKC(ctx->cnt_all.ensure((size_t)4 * ctx->nranks, ctx->st));
-  LAUNCH(K_PROMOTE, k_slab_promote_count, std::min(nblk(ctx->n_owned), 148 * 8), TPB, ctx->posm.p, ctx->sc, ctx->cnt_own.p, ctx->n_owned);
-  NCK(N->AllGather(ctx->cnt_own.p, ctx->cnt_all.p, 4, ncclInt, ctx->comm, ctx->st));
-  LAUNCH(K_PROMOTE, k_slab_rho_final, 1, 1, ctx->cnt_all.p, ctx->nranks, ctx->cnt_own.p, ctx->sc, ctx->geo.box[0] * ctx->geo.box[1]);
   return 0;
 }
 // nsteps iterations of dana's loop body (dana.F90:173-265; Ermak integrator + piston) on the decomposed box
 int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
   if (!ctx->comm || !ctx->slab_ready) FAIL("dml_slab_step: call dml_comm_init and dml_slab_setup first");
   if (!ctx->cfg.integrador || ctx->cfg.reservoir != 1) FAIL("dml_slab_step: the decomposed box runs the Ermak integrator with the piston reservoir");
+  ctx->rows_eager = true;
+  struct Eager { dml_ctx *c; ~Eager() { c->rows_eager = false; } } eager_guard{ctx};
   for (int i = 0; i < nsteps; ++i) {
     const int ng = ctx->n - ctx->n_owned;
     if (ng) LAUNCH(K_PACK, k_slab_ghost_save, nblk(ng), TPB, ctx->posm.p, ctx->old_cg.p, ctx->n_owned, ng);
@@ -1433,8 +1438,7 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
     TRY(slab_test_update(ctx));
     TRY(enq_overlap(ctx, true));
     TRY(slab_exchange(ctx, false, true));
-    TRY(slab_test_update(ctx));
-    TRY(slab_promote_rho(ctx));
+    TRY(slab_test_update(ctx, true));
     TRY(enq_maxz(ctx));
     ctx->t = ctx->t + ctx->cfg.h;
   }

@@ -208,10 +208,10 @@ __global__ void k_qtab(unsigned int *__restrict__ lay, const DevScal *__restrict
 // Final step of test_update, run by ONE block: merges the per-block top-2 partials, takes the rebuild decision
 // (Neighbor.F90:697-710) and rotates the z-layer tables.
 __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, const Geo &g,
-                                             double nb_dcut, double rmax_f, double rmax_o) {
+                                             double nb_dcut, double rmax_f, double rmax_o, int stride = 2) {
   const int nlay = g.nlay;
   double a1 = 1e-16, a2 = 1e-16;     // Neighbor.F90:643-644
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, __ldcg(&part[2 * i]), __ldcg(&part[2 * i + 1]));
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, __ldcg(&part[stride * i]), __ldcg(&part[stride * i + 1]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
@@ -246,11 +246,13 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
   __syncthreads();
   d_qtab(lay, sc, g, rmax_f, rmax_o);                  // the skip tables the next consumers (overlap_moveback, pair force) will read
 }
-// finalize != 0: the last block to finish runs d_top2_final itself (single-GPU path, one launch less per test_update);
-// finalize == 0: the partials are left in part[] for the caller (slab mode merges them across ranks first).
+// finalize == 1: the last block to finish runs d_top2_final itself (single-GPU path, one launch less per test_update);
+// finalize == 0: the partials are left in part[] for the caller;
+// finalize == 2 (slab mode): the last block reduces the partials to this rank's two largest (own_out[0..1]), which are then merged
+// across the ranks.
 __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *part,
                                                   unsigned int *__restrict__ lay, DevScal *__restrict__ sc, Geo g, int n, int n_disp,
-                                                  int finalize, double nb_dcut, double rmax_f, double rmax_o) {
+                                                  int finalize, double nb_dcut, double rmax_f, double rmax_o, double *__restrict__ own_out = nullptr) {
   // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
   __shared__ unsigned int s_lay[LAY_MAX];
   __shared__ int s_last;
@@ -276,6 +278,13 @@ __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, do
   if (!s_last) return;
   if (threadIdx.x == 0) sc->ticket3 = 0u;
   __threadfence();
+  if (finalize == 2) {
+    double b1 = -1.0, b2 = -1.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) top2_merge(b1, b2, __ldcg(&part[2 * i]), __ldcg(&part[2 * i + 1]));
+    block_top2(b1, b2);
+    if (threadIdx.x == 0) { own_out[0] = b1; own_out[1] = b2; }
+    return;
+  }
   d_top2_final(part, (int)gridDim.x, sc, lay, g, nb_dcut, rmax_f, rmax_o);
 }
 __global__ void k_top2_final(const double *part, int nb, DevScal *__restrict__ sc, unsigned int *__restrict__ lay, Geo g,

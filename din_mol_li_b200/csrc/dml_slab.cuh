@@ -69,6 +69,21 @@ __global__ void k_slab_pack(const double4 *__restrict__ posm, const int *__restr
   st_rec(&out_p[i], ld_rec_nc(&posm[s]));
   if (out_uid) out_uid[i] = uid[s];
 }
+// both faces in one launch
+__global__ void k_slab_pack2(const double4 *__restrict__ posm, const int *__restrict__ uid, const int *__restrict__ list_lo, int cnt_lo,
+                             double4 *__restrict__ out_lo, int *__restrict__ uid_lo, const int *__restrict__ list_hi, int cnt_hi,
+                             double4 *__restrict__ out_hi, int *__restrict__ uid_hi) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt_lo) {
+    const int s = list_lo[i];
+    st_rec(&out_lo[i], ld_rec_nc(&posm[s]));
+    if (uid_lo) uid_lo[i] = uid[s];
+  } else if (i < cnt_lo + cnt_hi) {
+    const int k = i - cnt_lo, s = list_hi[k];
+    st_rec(&out_hi[k], ld_rec_nc(&posm[s]));
+    if (uid_hi) uid_hi[k] = uid[s];
+  }
+}
 // received records become ghosts: keep position, element and skip flag, drop the owner's membership flags.  With old_cg
 // (refresh inside a step) the move of the ghost since the step started is measured: it goes into the record (prefilter of
 // k_ov_detect) and into step_disp_bits, because the gather-skip bound must cover the ghosts' moves as well as the local ones.
@@ -168,15 +183,8 @@ __global__ void k_slab_ghost_save(const double4 *__restrict__ posm, double *__re
   const double4 p = ld_rec_nc(&posm[s]);
   old_cg[3 * s] = p.x; old_cg[3 * s + 1] = p.y; old_cg[3 * s + 2] = p.z;
 }
-// own two largest squared displacements out of the per-block partials (one block)
-__global__ void k_top2_local(const double *__restrict__ part, int nb, double *__restrict__ out) {
-  double a1 = -1.0, a2 = -1.0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) top2_merge(a1, a2, part[2 * i], part[2 * i + 1]);
-  block_top2(a1, a2);
-  if (threadIdx.x == 0) { out[0] = a1; out[1] = a2; }
-}
 // F -> CG promotion (dana.F90:228-236) and the census of calc_rho (521-549) over the OWNED particles; the counts of all
-// ranks are gathered and k_slab_rho_final turns them into the same rho everywhere
+// ranks are gathered (with the displacements of the test_update in front of it) and k_slab_tu_final turns them into the same rho everywhere
 __global__ void __launch_bounds__(TPB) k_slab_promote_count(double4 *__restrict__ posm, DevScal *__restrict__ sc, int *__restrict__ out, int n_owned) {
   const double z0 = sc->z0, zl = sc->zmax;
   int c = 0, dref = 0, nref = 0;
@@ -194,15 +202,25 @@ __global__ void __launch_bounds__(TPB) k_slab_promote_count(double4 *__restrict_
   c = __reduce_add_sync(0xffffffffu, c); dref = __reduce_add_sync(0xffffffffu, dref); nref = __reduce_add_sync(0xffffffffu, nref);
   if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(&out[0], c); if (dref) atomicAdd(&out[1], dref); if (nref) atomicAdd(&out[2], nref); }
 }
-__global__ void k_slab_rho_final(const int *__restrict__ gathered, int nranks, int *__restrict__ own, DevScal *__restrict__ sc, double area) {
-  long long c = 0, dref = 0, nref = 0;
-  for (int r = 0; r < nranks; ++r) { c += gathered[4 * r]; dref += gathered[4 * r + 1]; nref += gathered[4 * r + 2]; }
-  sc->msd_t = sc->msd_t / (double)(nref + dref);          // dana.F90:201-202 (before the promotion loop; local sum, global count)
-  sc->msd_max = fmax(sc->msd_max, sc->msd_t);
-  sc->nat_ref -= own[1];
-  sc->rho = (double)c / (area * (sc->zmax - sc->z0));
-  sc->step_disp_bits = 0u;
-  own[0] = own[1] = own[2] = own[3] = 0;
+// What one rank contributes to the merged all-gather of a test_update of the decomposed box: its two largest squared displacements
+// and (second test_update of a step) the census of k_slab_promote_count.
+struct SlabTU { double a1, a2; int cnt[4]; };
+// test_update's decision from the gathered contributions (d_top2_final) and, with_rho, calc_rho + the msd bookkeeping from the
+// gathered census
+__global__ void k_slab_tu_final(const SlabTU *__restrict__ all, int nranks, SlabTU *__restrict__ own, DevScal *__restrict__ sc,
+                                unsigned int *__restrict__ lay, Geo g, double nb_dcut, double rmax_f, double rmax_o, int with_rho, double area) {
+  d_top2_final(reinterpret_cast<const double *>(all), nranks, sc, lay, g, nb_dcut, rmax_f, rmax_o, (int)(sizeof(SlabTU) / sizeof(double)));
+  __syncthreads();
+  if (with_rho && threadIdx.x == 0) {
+    long long c = 0, dref = 0, nref = 0;
+    for (int r = 0; r < nranks; ++r) { c += all[r].cnt[0]; dref += all[r].cnt[1]; nref += all[r].cnt[2]; }
+    sc->msd_t = sc->msd_t / (double)(nref + dref);          // dana.F90:201-202 (before the promotion loop; local sum, global count)
+    sc->msd_max = fmax(sc->msd_max, sc->msd_t);
+    sc->nat_ref -= own->cnt[1];
+    sc->rho = (double)c / (area * (sc->zmax - sc->z0));
+    sc->step_disp_bits = 0u;
+    own->cnt[0] = own->cnt[1] = own->cnt[2] = own->cnt[3] = 0;
+  }
 }
 
 } // namespace dml
