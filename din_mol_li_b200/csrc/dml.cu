@@ -14,6 +14,7 @@ namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, in
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <functional>
 
 using namespace dml;
 
@@ -89,6 +90,10 @@ struct dml_ctx {
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
   bool use_coop = true; int coop_grid_tu = 0, coop_grid_tu_bi = 0, coop_grid_ov = 0, coop_grid_rev = 0; DBuf<int> coop_sums;   // persistent cooperative kernels (dml_coop.cuh)
   bool ov_unstaged = false; // DML_OV_UNSTAGED=1: k_ov_resolve replays from global memory (the form the cooperative kernel uses)
+  // decomposed step: the two host read-backs of a step cut it into two segments, each captured as a CUDA graph (NCCL calls included)
+  // and replayed until a rebuild changes the slab (slot counts, ghost lists): see slab_segment
+  struct SlabGraph { cudaGraphExec_t exec = nullptr; bool warm = false; int64_t launches = 0, steps = 0; } sgA, sgB;
+  bool slab_graph_on = true; Geo slab_geo; int slab_since = 0, slab_last_interval = 1 << 20;   // steps since the last rebuild, length of the interval before it
   bool rows_eager = false;  // inside dml_slab_step: the consumers' guarded row-build launches are left out
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
@@ -131,6 +136,9 @@ static int enq_materialize_rows(dml_ctx *ctx, bool force = false);
 static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force);
 static int finish(dml_ctx *ctx);
 static int pull_scal(dml_ctx *ctx);
+static void slab_graphs_drop(dml_ctx *ctx) {
+  for (auto *G : {&ctx->sgA, &ctx->sgB}) { if (G->exec) cudaGraphExecDestroy(G->exec); G->exec = nullptr; G->warm = false; }
+}
 
 enum { CLS_FORCE = 0, CLS_LIST = 1, CLS_INTEG = 2, CLS_OVERLAP = 3, CLS_ALL = 4, CLS_BIN = 5, CLS_OTHER = 6, CLS_GCMC = 7 };
 // one id per kernel so bench.py can time each of them with CUDA events on the ctx stream
@@ -585,6 +593,7 @@ static int finish(dml_ctx *ctx) {
     ctx->hsc->cols_cap = (int)std::min<size_t>(ctx->cols.cap, 0x7fffffff);
     ctx->hsc->rev_valid = 0;
     ctx->sg_n = -1;                                         // the captured step holds the old pointers
+    slab_graphs_drop(ctx);
     TRY(push_scal(ctx));
     CKC(cudaStreamSynchronize(ctx->st));
   }
@@ -779,6 +788,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
   if (getenv("DML_NO_BI_FUSE")) ctx->no_bi_fuse = true;
+  if (getenv("DML_NO_SLAB_GRAPH") || getenv("DML_NO_GRAPH")) ctx->slab_graph_on = false;
   if (getenv("DML_NO_GRAPH")) ctx->use_graph = false;
   size_t c3 = (size_t)cap * 3;
   CKC(ctx->posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posm.ensure(cap, ctx->st)); CKC(ctx->sorted_posf.ensure(cap, ctx->st));
@@ -845,6 +855,7 @@ void dml_destroy(dml_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaStreamSynchronize(ctx->st);
   if (ctx->step_graph) cudaGraphExecDestroy(ctx->step_graph);
+  slab_graphs_drop(ctx);
   prof_collect(ctx);
   for (auto &ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   ctx->posm.release(); ctx->sorted_posm.release(); ctx->sorted_posf.release(); ctx->vel.release(); ctx->acel.release(); ctx->fe.release();
@@ -1384,7 +1395,8 @@ static int slab_migrate(dml_ctx *ctx) {
   return 0;
 }
 // test_update (Neighbor.F90:668-713) on the decomposed box: global decision, migration + ghost re-selection + rows at a rebuild
-static int slab_test_update(dml_ctx *ctx, bool with_rho = false) {
+// test_update of the decomposed box, device part: displacements, merged all-gather, decision (and calc_rho with_rho)
+static int slab_tu_enqueue(dml_ctx *ctx, bool with_rho) {
   NcclApi *N = nccl_api();
   tessellate(ctx);
   if (!ctx->tessellated) FAIL("box smaller than 4 cells in every direction");
@@ -1408,8 +1420,14 @@ static int slab_test_update(dml_ctx *ctx, bool with_rho = false) {
   NCK(N->AllGather(own, all, sizeof(SlabTU), ncclChar, ctx->comm, ctx->st));
   LAUNCH(K_TOP2, k_slab_tu_final, 1, 256, all, ctx->nranks, own, ctx->sc, ctx->lay.p, ctx->geo, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut, with_rho ? 1 : 0,
          ctx->geo.box[0] * ctx->geo.box[1]);
+  return 0;
+}
+// host part: read the decision back; at a rebuild migrate, re-select the ghosts, sort the cells and build the rows
+static int slab_tu_decide(dml_ctx *ctx) {
   TRY(pull_scal(ctx));
   if (ctx->hsc->need_rebuild) {
+    slab_graphs_drop(ctx);                                // slot counts and ghost lists change: the captured segments are void
+    ctx->slab_last_interval = ctx->slab_since; ctx->slab_since = 0;
     TRY(slab_migrate(ctx));
     TRY(slab_refresh_ghosts(ctx));
     TRY(pull_scal(ctx));
@@ -1417,8 +1435,35 @@ static int slab_test_update(dml_ctx *ctx, bool with_rho = false) {
     TRY(push_scal(ctx));
     TRY(enq_sort_cells(ctx, 0));
     TRY(enq_materialize_rows(ctx, true));
-    }
+  }
   ctx->binned = true;
+  return 0;
+}
+// One segment of the decomposed step (everything between two host read-backs).  The first pass after the slab changed runs as
+// plain launches (buffers grow, NCCL sets up its connections), the second is captured into a graph, later ones replay it: the
+// segment's ~10 launches and its NCCL operations then cost one graph launch on the host and no launch gaps on the device.
+static int slab_segment(dml_ctx *ctx, dml_ctx::SlabGraph &G, const std::function<int()> &enq) {
+  if (!ctx->slab_graph_on || ctx->profiling) return enq();
+  if (memcmp(&ctx->slab_geo, &ctx->geo, sizeof(Geo)) != 0) { slab_graphs_drop(ctx); ctx->slab_geo = ctx->geo; }
+  if (!G.exec) {
+    // capture + instantiation cost about ten replays' worth of savings: only when the list is expected to live that long
+    const bool pays = ctx->slab_since >= (ctx->slab_last_interval >= 10 ? 1 : 10);
+    if (!G.warm || !pays) { G.warm = true; return enq(); }
+    const int64_t l0 = ctx->launches, s0 = ctx->step;
+    cudaGraph_t g = nullptr;
+    CKC(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    const int rc = enq();
+    ctx->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(ctx->st, &g);
+    G.launches = ctx->launches - l0; G.steps = ctx->step - s0;
+    ctx->launches = l0; ctx->step = s0;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e == cudaSuccess && g) { e = cudaGraphInstantiate(&G.exec, g, 0); cudaGraphDestroy(g); }
+    if (e != cudaSuccess || !G.exec) { cudaGetLastError(); G.exec = nullptr; ctx->slab_graph_on = false; return enq(); }   // not capturable here: plain launches from now on
+  }
+  ctx->launches += G.launches; ctx->step += G.steps;
+  CKC(cudaGraphLaunch(G.exec, ctx->st));
   return 0;
 }
 // nsteps iterations of dana's loop body (dana.F90:173-265; Ermak integrator + piston) on the decomposed box
@@ -1428,18 +1473,27 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
   ctx->rows_eager = true;
   struct Eager { dml_ctx *c; ~Eager() { c->rows_eager = false; } } eager_guard{ctx};
   for (int i = 0; i < nsteps; ++i) {
-    const int ng = ctx->n - ctx->n_owned;
-    if (ng) LAUNCH(K_PACK, k_slab_ghost_save, nblk(ng), TPB, ctx->posm.p, ctx->old_cg.p, ctx->n_owned, ng);
-    TRY(enq_integrate(ctx, true));
-    TRY(slab_exchange(ctx, false, true));                 // ghosts at their new positions; their moves enter the skip bound
-    TRY(enq_fuerza(ctx, true));
-    if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
-      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
-    TRY(slab_test_update(ctx));
-    TRY(enq_overlap(ctx, true));
-    TRY(slab_exchange(ctx, false, true));
-    TRY(slab_test_update(ctx, true));
+    // segment A: integrator, ghost refresh, pair force, ermak_b, first test_update up to the gathered decision
+    TRY(slab_segment(ctx, ctx->sgA, [&]() -> int {
+      const int ng = ctx->n - ctx->n_owned;
+      if (ng) LAUNCH(K_PACK, k_slab_ghost_save, nblk(ng), TPB, ctx->posm.p, ctx->old_cg.p, ctx->n_owned, ng);
+      TRY(enq_integrate(ctx, true));
+      TRY(slab_exchange(ctx, false, true));               // ghosts at their new positions; their moves enter the skip bound
+      TRY(enq_fuerza(ctx, true));
+      if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
+        LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
+      return slab_tu_enqueue(ctx, false);
+    }));
+    TRY(slab_tu_decide(ctx));                             // host read-back; migration and list rebuild when due
+    // segment B: overlap_moveback, ghost refresh, second test_update (with promotion and the census of calc_rho)
+    TRY(slab_segment(ctx, ctx->sgB, [&]() -> int {
+      TRY(enq_overlap(ctx, true));
+      TRY(slab_exchange(ctx, false, true));
+      return slab_tu_enqueue(ctx, true);
+    }));
+    TRY(slab_tu_decide(ctx));
     TRY(enq_maxz(ctx));
+    ctx->slab_since++;
     ctx->t = ctx->t + ctx->cfg.h;
   }
   return finish(ctx);
