@@ -15,6 +15,7 @@ namespace dml { __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, in
 #include <vector>
 #include <algorithm>
 #include <functional>
+#include <chrono>
 
 using namespace dml;
 
@@ -93,7 +94,7 @@ struct dml_ctx {
   // decomposed step: the two host read-backs of a step cut it into two segments, each captured as a CUDA graph (NCCL calls included)
   // and replayed until a rebuild changes the slab (slot counts, ghost lists): see slab_segment
   struct SlabGraph { cudaGraphExec_t exec = nullptr; bool warm = false; int64_t launches = 0, steps = 0; } sgA, sgB;
-  bool slab_graph_on = true; Geo slab_geo; int slab_since = 0, slab_last_interval = 1 << 20;   // steps since the last rebuild, length of the interval before it
+  bool slab_graph_on = true; Geo slab_geo; int slab_since = 0, slab_last_interval = 0;   // steps since the last rebuild, length of the interval before it
   bool rows_eager = false;  // inside dml_slab_step: the consumers' guarded row-build launches are left out
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
@@ -1446,11 +1447,13 @@ static int slab_segment(dml_ctx *ctx, dml_ctx::SlabGraph &G, const std::function
   if (!ctx->slab_graph_on || ctx->profiling) return enq();
   if (memcmp(&ctx->slab_geo, &ctx->geo, sizeof(Geo)) != 0) { slab_graphs_drop(ctx); ctx->slab_geo = ctx->geo; }
   if (!G.exec) {
-    // capture + instantiation cost about ten replays' worth of savings: only when the list is expected to live that long
-    const bool pays = ctx->slab_since >= (ctx->slab_last_interval >= 10 ? 1 : 10);
+    // capturing the two segments costs ~1 ms (measured: 0.4-0.7 ms each, the NCCL calls dominate) and a replayed step saves ~25 us:
+    // only when the list is expected to live for more than ~40 steps (at 1 M particles and h = 1e-2 it lives 5-28: plain launches)
+    const bool pays = ctx->slab_since >= (ctx->slab_last_interval >= 80 ? 1 : 40);
     if (!G.warm || !pays) { G.warm = true; return enq(); }
     const int64_t l0 = ctx->launches, s0 = ctx->step;
     cudaGraph_t g = nullptr;
+    const auto t_cap0 = std::chrono::steady_clock::now();
     CKC(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
     const int rc = enq();
@@ -1461,6 +1464,9 @@ static int slab_segment(dml_ctx *ctx, dml_ctx::SlabGraph &G, const std::function
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e == cudaSuccess && g) { e = cudaGraphInstantiate(&G.exec, g, 0); cudaGraphDestroy(g); }
     if (e != cudaSuccess || !G.exec) { cudaGetLastError(); G.exec = nullptr; ctx->slab_graph_on = false; return enq(); }   // not capturable here: plain launches from now on
+    if (getenv("DML_SLAB_GRAPH_DEBUG"))
+      fprintf(stderr, "[dml] rank %d: slab segment captured in %.1f us (%lld launches)\n", ctx->rank,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_cap0).count(), (long long)G.launches);
   }
   ctx->launches += G.launches; ctx->step += G.steps;
   CKC(cudaGraphLaunch(G.exec, ctx->st));
