@@ -64,7 +64,7 @@ struct dml_ctx {
   DBuf<int> b2slot;          // boxes without cell lists (ngroup_verlet): slot of every hs%b index
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
-  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, fnz; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, fnz, dq; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -95,6 +95,7 @@ struct dml_ctx {
   // and replayed until a rebuild changes the slab (slot counts, ghost lists): see slab_segment
   struct SlabGraph { cudaGraphExec_t exec = nullptr; bool warm = false; int64_t launches = 0, steps = 0; } sgA, sgB;
   bool slab_graph_on = true; Geo slab_geo; int slab_since = 0, slab_last_interval = 0;   // steps since the last rebuild, length of the interval before it
+  bool use_dq = false;      // per-particle refinement of the gather-skip bound (dq_byte); DML_NO_DQ=1: layer bound only
   bool rows_eager = false;  // inside dml_slab_step: the consumers' guarded row-build launches are left out
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
   int ov_lanes = 0;         // threads per particle of the overlap detection (DML_OV_LANES: 1, 2, 4; 0 = by integrator)
@@ -315,7 +316,7 @@ static int enq_sort_cells(dml_ctx *ctx, int force) {
   LAUNCH(K_BIN, k_bin, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->cell_of.p, ctx->cell_cnt.p, ctx->rh.p, ctx->halo_of.p, ctx->sc, ctx->geo, n, force);
   TRY(scan_excl(ctx, ctx->cell_cnt.p, ctx->cell_start.p, nct, ctx->cell_start.p + nct, true, 0, force));
   LAUNCH(K_SCATTER, k_scatter, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->pos_old.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p,
-         ctx->sorted_raw.p, ctx->sc, n, force);
+         ctx->sorted_raw.p, ctx->sc, n, force, ctx->use_dq ? ctx->dq.p : nullptr);
   LAUNCH(K_CELL_ORDER, k_cell_order, std::min(nblk(n), 148 * 8), TPB, ctx->posm.p, ctx->slot_b.p, ctx->cell_of.p, ctx->cell_start.p, ctx->cell_cur.p, ctx->sorted_raw.p,
          ctx->sorted_slot.p, ctx->sorted_posm.p, ctx->sorted_posf.p, ctx->sorted_cell.p, ctx->sc, nct, force);
   return 0;
@@ -361,6 +362,7 @@ static void fill_tu_args(dml_ctx *ctx, TUArgs &A, int force) {
   A.area = ctx->geo.box[0] * ctx->geo.box[1]; A.h_over_tau = ctx->cfg.h / ctx->cfg.tau; A.use_z1 = ctx->cfg.reservoir == 2 ? 1 : 0; A.piston = ctx->cfg.reservoir == 1 ? 1 : 0;
   A.defer = 0; A.snap = ctx->snap.p;
   A.uid = ctx->uid.p; A.ranv = ctx->ranv.p; A.old_cg_w = ctx->old_cg.p; A.ph = ctx->ph;
+  A.dq = ctx->use_dq ? ctx->dq.p : nullptr;
 }
 // fuse: see TUArgs (bits 0-1 overlap_moveback's first / last pass, bit 2 the tail of the loop body); defer: leave the cell sort of a
 // rebuild to whoever needs the cells first
@@ -406,7 +408,8 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true,
   }
   int nb = std::min(nblk(n), 148 * 6);
   CKC(ctx->part.ensure((size_t)2 * nb, ctx->st));
-  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut);
+  LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, n, 1, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut,
+         (double *)nullptr, ctx->use_dq ? ctx->dq.p : nullptr);
   TRY(enq_sort_cells(ctx, force));
   ctx->binned = true;
   return 0;
@@ -474,7 +477,7 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   }
 #define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p)
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p, ctx->use_dq ? (const unsigned char *)ctx->dq.p : (const unsigned char *)nullptr)
   if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 6) FSUB(true, 6); else FSUB(true, 4); }
   else if (ctx->force_minb >= 8) FSUB(false, 8);
   else if (ctx->force_minb >= 6) FSUB(false, 6);
@@ -517,7 +520,7 @@ static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer
   }
   if (!init_done) LAUNCH(K_OV_INIT, k_ov_init, nblk(n), TPB, ctx->posm.p, ctx->parent.p, ctx->ovst.p, ctx->comp_cnt.p, ctx->ov_head.p, ctx->sc, n);
 #define OVDET(L) LAUNCH(K_OV_DETECT, k_ov_detect<L>, nblk((long long)n * L), TPB, ctx->posm.p, ctx->old_cg.p, ctx->rh.p, ctx->cols.p, ctx->bq.p, \
-                        ctx->lay.p, ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n)
+                        ctx->lay.p, ctx->parent.p, ctx->ovst.p, ctx->sc, ctx->geo, n, ctx->use_dq ? (const unsigned char *)ctx->dq.p : (const unsigned char *)nullptr)
   if (ctx->ov_lanes >= 4) OVDET(4); else if (ctx->ov_lanes >= 2) OVDET(2); else OVDET(1);
 #undef OVDET
   const OvRp uovl = ov_replay(ctx);
@@ -805,6 +808,8 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->sorted_cell.ensure(cap, ctx->st));
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
   CKC(ctx->fnz.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->fnz.p, 0, cap, ctx->st));
+  CKC(ctx->dq.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->dq.p, 0xff, cap, ctx->st));
+  ctx->use_dq = cfg->reservoir != 3 && !getenv("DML_NO_DQ");   // (gcmc reuses slots and appends rows between rebuilds: the layer bound alone)
   CKC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM));
   CKC(ctx->lay.ensure(3 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0xff, 3 * LAY_MAX * sizeof(unsigned int), ctx->st));   // 2 displacement tables + the skip tables (k_qtab)
   CKC(cudaMemsetAsync(ctx->lay.p, 0, 2 * LAY_MAX * sizeof(unsigned int), ctx->st));
@@ -870,7 +875,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
   ctx->mig_ri.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
   ctx->top2_own.release(); ctx->top2_all.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->sorted_cell.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->dq.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -1123,7 +1128,7 @@ int dml_upload_positions(dml_ctx *ctx, int32_t n, const double *pos, const doubl
   CKC(ctx->stage_d.ensure(n3, ctx->st));
   CKC(cudaMemcpyAsync(ctx->stage_d.p, pos, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
   if (pos_old) CKC(cudaMemcpyAsync(ctx->pos_old.p, pos_old, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-  LAUNCH(K_PACK, k_repos, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, n);
+  LAUNCH(K_PACK, k_repos, nblk(n), TPB, ctx->posm.p, ctx->stage_d.p, n, ctx->sc);
   return 0;                                               // stream-ordered: the next call on this ctx sees the new positions
 }
 int dml_download_frame(dml_ctx *ctx, int32_t n, double *pos, int32_t *z) { ENTER(ctx);
@@ -1417,7 +1422,7 @@ static int slab_tu_enqueue(dml_ctx *ctx, bool with_rho) {
   // of the rebuild decision like in the fused tail of the single-GPU step)
   if (with_rho) LAUNCH(K_PROMOTE, k_slab_promote_count, std::min(nblk(ctx->n_owned), 148 * 8), TPB, ctx->posm.p, ctx->sc, own->cnt, ctx->n_owned);
   LAUNCH(K_PBC_BIN, k_pbc_disp, nb, TPB, ctx->posm.p, ctx->pos_old.p, ctx->part.p, ctx->lay.p, ctx->sc, ctx->geo, n, ctx->n_owned, 2, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut,
-         ctx->top2_own.p);
+         ctx->top2_own.p, ctx->use_dq ? ctx->dq.p : nullptr);
   NCK(N->AllGather(own, all, sizeof(SlabTU), ncclChar, ctx->comm, ctx->st));
   LAUNCH(K_TOP2, k_slab_tu_final, 1, 256, all, ctx->nranks, own, ctx->sc, ctx->lay.p, ctx->geo, ctx->cfg.nb_dcut, ctx->ph.r0_max, ctx->cfg.rcut, with_rho ? 1 : 0,
          ctx->geo.box[0] * ctx->geo.box[1]);

@@ -85,6 +85,7 @@ struct TUArgs {
   // fuse bit 3 (k_test_update_coop<true>, Brownian integrator, Philox noise): cbrownian_hs + atom_pbc (dana.F90:798-846,1187-1250) of
   // slot s run in front of do_pbc of slot s in the same pass: the call site in front of the first test_update of a step
   const int *uid; double *ranv, *old_cg_w; Phys ph;
+  unsigned char *dq;                                          // own displacement since the build, one byte per slot (dq_byte), or nullptr
 };
 
 // cgroup_sort (Cells.F90:267-302) by the whole grid: bin -> scan -> scatter -> order inside every cell; three grid-wide barriers.
@@ -96,7 +97,7 @@ __device__ __forceinline__ void coop_sort_cells(cg::grid_group &grid, const TUAr
   grid.sync();
   coop_scan<true>(grid, A.cell_cnt, A.cell_start, A.nct, A.sums, A.cell_start + A.nct);
   grid.sync();
-  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, src, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, snapshot, s);
+  for (int s = gt; s < A.n; s += gsz) d_scatter(A.posm, A.pos_old, src, A.cell_of, A.cell_start, A.cell_cur, A.sorted_raw, snapshot, s, A.dq);
   grid.sync();
   if (gt == 0 && rebuild) { sc->rows_asym = sc->halo_flag ? 1 : 0; sc->sort_pending = 0; }
   const int nsorted = A.cell_start[A.nct];
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
       A.ovst[s] = ((m & MF_SKIP) ? OV_SKIP : 0) | ((int)(m & MF_TYPE) << OV_TSHIFT);
     }
     if (rd >= 0.0) lay_note(s_lay, A.g, zn, rel2);
+    if (A.dq) A.dq[s] = dq_byte(A.g, rel2);
     top2_merge(a1, a2, rd, -1.0);
     if (tail) {                                                  // promotion loop + census of calc_rho (same pass as k_promote_rho)
       double4 p = ld_rec(&A.posm[s]);
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(TPB) k_test_update_coop(TUArgs A) {
       const long long m = meta_of(p);
       if (m & MF_TYPE) { A.pos_old[3 * s] = p.x; A.pos_old[3 * s + 1] = p.y; A.pos_old[3 * s + 2] = p.z; }
       else if (m & MF_LIMBO) { p.w = meta_as_double(0); st_rec(&A.posm[s], p); }
+      if (A.dq) A.dq[s] = 0;
       st_rec(&A.snap[s], p);
     }
     if (gt == 0) sc->sort_pending = 1;

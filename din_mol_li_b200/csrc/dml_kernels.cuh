@@ -178,6 +178,34 @@ __device__ __forceinline__ double pair_shift_bound(const Geo &g, double mx, doub
   const double R = 2.0 * sqrt(g.rc_list2);
   return fmin(2.0 * mx + kappa * R, dsum) + maxz_fac * R + 2.0 * sdisp;
 }
+// Per-particle refinement: a pair moved at most (own displacement) + (largest displacement of the partner's layers), where the
+// layer formula charges the layer maximum twice.  The own displacement (relative, like the layer table's) is kept as one byte per
+// slot in units of the build-distance bytes, rounded up (dq, written by every test_update, zero after a rebuild); the second set of
+// tables holds the bound without the own share: qmax_i = min(layer entry, base entry + dq_i).  The layer maximum of a few ten
+// thousand particles is ~4 sigma of the displacement distribution, the typical particle sits at ~1.6 sigma.
+__device__ __forceinline__ unsigned char dq_byte(const Geo &g, double rel2) {
+  if (rel2 < 0.0) return 0;
+  return (unsigned char)fmin(255.0, ceil(sqrt(rel2) * 1.000001 * g.bq_scale) + 1.0);
+}
+__device__ __forceinline__ int qtab_base_entry(const unsigned int *lt, const Geo &g, int l, double thick, double maxz_fac, double z0, double zmax,
+                                               double sdisp, double rmax, double kappa) {
+  unsigned int mx = 0u;
+#pragma unroll
+  for (int d = -2; d <= 2; ++d) { int q = l + d; if (q >= 0 && q < g.nlay) mx = max(mx, __ldcg(&lt[q])); }
+  double ztop = thick * (double)(l + 1);
+  if (l == g.nlay - 1) ztop = fmax(ztop, zmax);
+  const double since = maxz_fac * fmax(ztop + 2.0 * thick - z0, 0.0) + sdisp;
+  if (since > g.cell[2]) return 255;
+  const double R = 2.0 * sqrt(g.rc_list2);
+  return (int)fmin(255.0, ceil((rmax * 1.000001 + (double)__int_as_float((int)mx) + kappa * R + maxz_fac * R + 2.0 * sdisp) * g.bq_scale) + 1.0);
+}
+__device__ __forceinline__ int skip_qmax(const Geo &g, const unsigned int *__restrict__ lay, double z, int which, const unsigned char *__restrict__ dq, int s) {
+  const unsigned char *qt = reinterpret_cast<const unsigned char *>(lay + 2 * LAY_MAX);
+  const int l = layer_of(g, z);
+  const int cap = (int)__ldg(&qt[which * LAY_MAX + l]);
+  if (!dq) return cap;
+  return min(cap, min(255, (int)__ldg(&qt[(2 + which) * LAY_MAX + l]) + (int)__ldg(&dq[s])));
+}
 // One entry of the tables: the bound of layer l uses the top of the layer where the per-particle formula used z.
 __device__ __forceinline__ int qtab_entry(const unsigned int *lt, const Geo &g, int l, double thick, double maxz_fac, double z0, double zmax,
                                           double dsum, double sdisp, double rmax, double kappa) {
@@ -202,6 +230,8 @@ __device__ __forceinline__ void d_qtab(unsigned int *__restrict__ lay, const Dev
   for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
     qt[l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_f, kappa);
     qt[LAY_MAX + l] = (unsigned char)qtab_entry(lt, g, l, thick, maxz_fac, z0, zmax, dsum, sdisp, rmax_o, kappa);
+    qt[2 * LAY_MAX + l] = (unsigned char)qtab_base_entry(lt, g, l, thick, maxz_fac, z0, zmax, sdisp, rmax_f, kappa);
+    qt[3 * LAY_MAX + l] = (unsigned char)qtab_base_entry(lt, g, l, thick, maxz_fac, z0, zmax, sdisp, rmax_o, kappa);
   }
 }
 __global__ void k_qtab(unsigned int *__restrict__ lay, const DevScal *__restrict__ sc, Geo g, double rmax_f, double rmax_o) { d_qtab(lay, sc, g, rmax_f, rmax_o); }
@@ -252,7 +282,8 @@ __device__ __forceinline__ void d_top2_final(const double *part, int nb, DevScal
 // across the ranks.
 __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, double *__restrict__ pos_old, double *part,
                                                   unsigned int *__restrict__ lay, DevScal *__restrict__ sc, Geo g, int n, int n_disp,
-                                                  int finalize, double nb_dcut, double rmax_f, double rmax_o, double *__restrict__ own_out = nullptr) {
+                                                  int finalize, double nb_dcut, double rmax_f, double rmax_o, double *__restrict__ own_out = nullptr,
+                                                  unsigned char *__restrict__ dq = nullptr) {
   // persistent grid (a few blocks per SM, grid-stride): one flush of the per-block layer table per block
   __shared__ unsigned int s_lay[LAY_MAX];
   __shared__ int s_last;
@@ -264,6 +295,7 @@ __global__ void __launch_bounds__(TPB) k_pbc_disp(double4 *__restrict__ posm, do
     double rel2, zn;
     double rd = d_pbc_disp(posm, pos_old, g, s, z0p, pist_c, rel2, zn);
     if (rd >= 0.0) lay_note(s_lay, g, zn, rel2);
+    if (dq) dq[s] = dq_byte(g, rel2);
     if (s < n_disp) top2_merge(a1, a2, rd, -1.0);        // slab mode: ghosts are measured by their owners
   }
   __syncthreads();
@@ -331,9 +363,10 @@ __global__ void __launch_bounds__(TPB) k_bin(const double4 *__restrict__ posm, i
 // src: where the binned positions came from (the records, or the snapshot of a deferred rebuild: dml_coop.cuh)
 __device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const double4 *src, const int *__restrict__ cell_of,
                                           const int *__restrict__ cell_start, int *__restrict__ cell_cur, int *__restrict__ sorted_slot,
-                                          bool snapshot, int s) {
+                                          bool snapshot, int s, unsigned char *__restrict__ dq = nullptr) {
   double4 p = ld_rec(&src[s]);
   long long m = meta_of(p);
+  if (snapshot && dq) dq[s] = 0;                          // pos_old = pos: nobody has moved since this build
   if (m & MF_TYPE) {
     int lin = cell_of[s];
     if (lin >= 0) { int idx = cell_start[lin] + atomicAdd(&cell_cur[lin], 1); sorted_slot[idx] = s; }
@@ -342,11 +375,12 @@ __device__ __forceinline__ void d_scatter(double4 *__restrict__ posm, double *__
 }
 __global__ void __launch_bounds__(TPB) k_scatter(double4 *__restrict__ posm, double *__restrict__ pos_old, const int *__restrict__ cell_of,
                                                  const int *__restrict__ cell_start, int *__restrict__ cell_cur,
-                                                 int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force) {
+                                                 int *__restrict__ sorted_slot, const DevScal *__restrict__ sc, int n, int force,
+                                                 unsigned char *__restrict__ dq = nullptr) {
   REBUILD_GUARD(sc, force);
   const bool snapshot = ((volatile const DevScal *)sc)->need_rebuild != 0;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
-    d_scatter(posm, pos_old, posm, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s);
+    d_scatter(posm, pos_old, posm, cell_of, cell_start, cell_cur, sorted_slot, snapshot, s, dq);
 }
 // One thread per binned particle (raw = the scatter's output, in-cell order arbitrary): its place in the cell is the number of
 // cell mates with a larger b index (chains are visited in descending b index, Cells.F90:267-302), found with independent loads;
@@ -1232,8 +1266,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
     const int *__restrict__ rev_cols, const unsigned char *__restrict__ bq, const unsigned char *__restrict__ rev_bq,
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
     const DevScal *__restrict__ sc, double4 *__restrict__ fe, const __grid_constant__ Geo g, const __grid_constant__ Phys ph, int n,
-    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, unsigned char *__restrict__ fnz) {
-  __shared__ unsigned int s_qt[LAY_MAX / 4];
+    double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, unsigned char *__restrict__ fnz,
+    const unsigned char *__restrict__ dq) {
+  __shared__ unsigned int s_qt[LAY_MAX / 4], s_qb[LAY_MAX / 4];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = s < n;
   // everything addressed by the slot alone is requested together
@@ -1242,12 +1277,14 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   RowMeta rm; rm.nbq = 0xffffffffu; rm.start = 0; rm.len = 0; rm.cap = 0; rm.q5 = 255;
   if (in) rm = rh_meta(&rh[s]);
   const int was_nz = in ? (int)fnz[s] : 0;
+  const int dqi = (in && dq) ? (int)__ldg(&dq[s]) : 255;  // own displacement since the build (see dq_byte); 255: refinement off
   {
     // skip bound per z-layer for the largest cut-off of the pair table, from the displacement table of the last test_update and what
     // the integrator / maxz moved since (same formula as d_qtab; every block tabulates it for itself while its records travel)
     // (both displacement tables are requested before lay_cur is known: one round trip, in parallel with the record's)
-    unsigned char *q8 = reinterpret_cast<unsigned char *>(s_qt);
+    unsigned char *q8 = reinterpret_cast<unsigned char *>(s_qt), *qb8 = reinterpret_cast<unsigned char *>(s_qb);
     const double thick = g.cell[2] * (double)(1 << g.lay_shift);
+    const double Rl = 2.0 * sqrt(g.rc_list2);
     for (int l = threadIdx.x; l < g.nlay; l += blockDim.x) {
       unsigned int m0 = 0u, m1_ = 0u;
 #pragma unroll
@@ -1261,13 +1298,17 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
       const double kappa = __ldg(&sc->kappa_tu);
       const double S = pair_shift_bound(g, (double)__int_as_float((int)mx), dsum, kappa, maxz_fac, sdisp);
       q8[l] = (unsigned char)((since > g.cell[2]) ? 255 : (int)fmin(255.0, ceil((ph.r0_max * 1.000001 + S) * g.bq_scale) + 1.0));
+      // the same without the particle's own share (qtab_base_entry): qmax = min(q8, qb8 + dq)
+      const double Sb = (double)__int_as_float((int)mx) + kappa * Rl + maxz_fac * Rl + 2.0 * sdisp;
+      qb8[l] = (unsigned char)((since > g.cell[2]) ? 255 : (int)fmin(255.0, ceil((ph.r0_max * 1.000001 + Sb) * g.bq_scale) + 1.0));
     }
   }
   __syncthreads();
   const long long m1 = meta_of(p1);
   if (!in || !(m1 & MF_REF)) return;
   FAcc a = {0.0, 0.0, 0.0, 0.0};
-  const int qmax = (int)reinterpret_cast<const unsigned char *>(s_qt)[layer_of(g, p1.z)];
+  const int lyr = layer_of(g, p1.z);
+  const int qmax = min((int)reinterpret_cast<const unsigned char *>(s_qt)[lyr], min(255, (int)reinterpret_cast<const unsigned char *>(s_qb)[lyr] + dqi));
   const int asym = __ldg(&sc->rows_asym);                // 0 symmetric, 1 halo-only, 2 general
   const int k3 = ((int)(m1 & MF_TYPE) - 1) * 3;
   // asym == 1 (some particle sits in a halo cell above box(3): the usual state of a piston run): only the rows of those few
@@ -1563,7 +1604,7 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) {
+                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ dq = nullptr) {
   const int s_end = n;
   const double rcut = sqrt(g.rcut2);
   const int lane = L > 1 ? (int)(threadIdx.x % L) : 0;
@@ -1575,7 +1616,7 @@ __device__ __forceinline__ void p_ov_detect(const double4 *__restrict__ posm, co
     const long long m1 = meta_of(p1);
     if (!(m1 & MF_REF)) continue;
     const float d1 = disp_of(m1);
-    const int qmax = skip_qtab(g, lay, p1.z, 1);          // same build-distance skip as the pair force (covers new and old positions)
+    const int qmax = skip_qmax(g, lay, p1.z, 1, dq, s);   // same build-distance skip as the pair force (covers new and old positions)
     const int b = rm.start, len = rm.len;
     bool inv = false, have_o1 = false;
     double o1[3] = {0.0, 0.0, 0.0};
@@ -1629,7 +1670,9 @@ __global__ void __launch_bounds__(TPB) k_ov_detect(const double4 *__restrict__ p
                                                    const RowHead *__restrict__ rh,
                                                    const int *__restrict__ cols, const unsigned char *__restrict__ bq,
                                                    const unsigned int *__restrict__ lay, int *__restrict__ parent, int *__restrict__ ovst,
-                                                   DevScal *__restrict__ sc, Geo g, int n) { p_ov_detect<L>(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n); }
+                                                   DevScal *__restrict__ sc, Geo g, int n, const unsigned char *__restrict__ dq) {
+  p_ov_detect<L>(posm, old_cg, rh, cols, bq, lay, parent, ovst, sc, g, n, dq);
+}
 __device__ __forceinline__ void p_ov_count(int *__restrict__ parent, const int *__restrict__ ovst, int *__restrict__ comp_cnt, int n) {
 
   const int s_end = n;
@@ -2274,8 +2317,10 @@ __global__ void k_pack(double4 *__restrict__ posm, const double *__restrict__ po
   st_rec(&posm[s], p);
 }
 // new coordinates for the same atoms (dml_upload_positions): element, membership and flags stay; the displacement bound is unknown
-__global__ void k_repos(double4 *__restrict__ posm, const double *__restrict__ pos, int n) {
+__global__ void k_repos(double4 *__restrict__ posm, const double *__restrict__ pos, int n, DevScal *__restrict__ sc) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
+  // the caller may have moved anything anywhere: no gather skipping until the next test_update has measured the displacements
+  if (s == 0) atomicMax(&sc->step_disp_bits, 0x7f800000u);
   if (s >= n) return;
   double4 p = ld_rec(&posm[s]);
   const long long m = meta_of(p);
