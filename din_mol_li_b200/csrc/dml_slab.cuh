@@ -61,14 +61,6 @@ __global__ void k_slab_select(const double4 *__restrict__ posm, int *__restrict_
   if (has_lo && p.z < zlo + w) send_lo[atomicAdd(&counts[0], 1)] = s;
   if (has_hi && p.z >= zhi - w) send_hi[atomicAdd(&counts[1], 1)] = s;
 }
-__global__ void k_slab_pack(const double4 *__restrict__ posm, const int *__restrict__ uid, const int *__restrict__ list, int cnt,
-                            double4 *__restrict__ out_p, int *__restrict__ out_uid) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cnt) return;
-  int s = list[i];
-  st_rec(&out_p[i], ld_rec_nc(&posm[s]));
-  if (out_uid) out_uid[i] = uid[s];
-}
 // both faces in one launch
 __global__ void k_slab_pack2(const double4 *__restrict__ posm, const int *__restrict__ uid, const int *__restrict__ list_lo, int cnt_lo,
                              double4 *__restrict__ out_lo, int *__restrict__ uid_lo, const int *__restrict__ list_hi, int cnt_hi,
