@@ -64,7 +64,7 @@ struct dml_ctx {
   DBuf<int> b2slot;          // boxes without cell lists (ngroup_verlet): slot of every hs%b index
   DBuf<int> cell_of, cell_cnt, cell_start, cell_cur, sorted_slot, sorted_raw, sorted_cell, chain_pos;   // sorted_raw: scatter output (in-cell order arbitrary)
   // rows
-  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, fnz, dq; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
+  DBuf<RowHead> rh; DBuf<int> cols; DBuf<unsigned char> bq, rev_bq, halo_of, fnz, dq, kb; DBuf<unsigned int> lay;   // bq: quantised build-time distance per entry
   DBuf<int> rev_start, rev_len, rev_cur, rev_cols; bool rows_asym = false; bool rev_valid = false;
   // slab decomposition (dml_slab.cuh)
   ncclComm_t comm = nullptr; int rank = 0, nranks = 1, n_owned = 0;
@@ -86,6 +86,7 @@ struct dml_ctx {
   bool step_tail_done = false;       // enq_step_a folded the tail of the step into the second test_update
   bool sort_maybe_pending = false;   // a deferring test_update was enqueued since the last cell sort (k_sort_catchup is launched on demand)
   DBuf<double4> snap;       // positions of a rebuild whose cell sort was deferred
+  bool no_flat_b = false;   // DML_NO_FLAT_B=1: ermak_b always reads the records (k_ermak_b)
   bool no_bi_fuse = false;  // DML_NO_BI_FUSE=1: the Brownian integrator stays a launch of its own inside dml_step
   bool no_tu_fuse = false;  // DML_NO_TU_FUSE=1: keep k_ov_init / k_ov_apply as launches of their own inside dml_step
   int l2_slots = 0; long long l2_max_persist = -1, l2_max_window = 0; bool no_l2_persist = false;   // slots covered by the persisting-L2 window (l2_window)
@@ -95,6 +96,7 @@ struct dml_ctx {
   // and replayed until a rebuild changes the slab (slot counts, ghost lists): see slab_segment
   struct SlabGraph { cudaGraphExec_t exec = nullptr; bool warm = false; int64_t launches = 0, steps = 0; } sgA, sgB;
   bool slab_graph_on = true; Geo slab_geo; int slab_since = 0, slab_last_interval = 0;   // steps since the last rebuild, length of the interval before it
+  bool kb_valid = false;    // kb[] (element / ref byte per slot) was written by the pair-force call that has just been enqueued
   bool use_dq = false;      // per-particle refinement of the gather-skip bound (dq_byte); DML_NO_DQ=1: layer bound only
   bool rows_eager = false;  // inside dml_slab_step: the consumers' guarded row-build launches are left out
   int ov_res_bpsm = 8;      // blocks of 4 warps per SM of k_ov_resolve (one warp per conflict component; DML_OV_RES_BPSM)
@@ -416,6 +418,7 @@ static int enq_test_update(dml_ctx *ctx, int fuse = 0, bool cells_wanted = true,
 }
 
 static int enq_integrate(dml_ctx *ctx, bool ermak) {
+  ctx->kb_valid = false;
   int n = ctx->n;
   ctx->step++;
   if (ctx->ph.rng_mode == DML_RNG_REPLAY && !ctx->have_rp) FAIL("replay mode: call dml_set_replay_integrator before the integrator");
@@ -465,6 +468,16 @@ static int enq_qtab(dml_ctx *ctx) {
   LAUNCH(K_MISC, k_qtab, 1, 256, ctx->lay.p, ctx->sc, ctx->geo, ctx->ph.r0_max, ctx->cfg.rcut);
   return 0;
 }
+// ermak_b (dana.F90:1031-1052): right behind a pair-force call the flat form (k_ermak_b_flat), else the form that reads the records
+static int enq_ermak_b(dml_ctx *ctx) {
+  const int n = ctx->n;
+  if (ctx->kb_valid && !ctx->no_flat_b)
+    LAUNCH(K_ERMAK_B, k_ermak_b_flat, nblk(3 * n), TPB, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, 3 * n, ctx->fnz.p, ctx->kb.p);
+  else
+    LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n, ctx->fnz.p);
+  ctx->kb_valid = false;
+  return 0;
+}
 // fused = called from the step sequence: the production kernel may also apply ermak_b (k_fuerza_sub<true, ..>)
 static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   int n = ctx->n;
@@ -472,17 +485,19 @@ static int enq_fuerza(dml_ctx *ctx, bool fused = false) {
   TRY(enq_build_rev(ctx));                              // guarded on the device: no-ops unless rows are asymmetric and the transposed rows stale
   if (ctx->cfg.strict_order) {
     LAUNCH(K_FUERZA, (k_fuerza<true>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p,
-           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->fnz.p);
+           ctx->rev_len.p, ctx->rev_cols.p, ctx->sc, ctx->uid.p, ctx->fe.p, ctx->geo, ctx->ph, n, ctx->fnz.p, ctx->kb.p);
+    ctx->kb_valid = true;
     return 0;
   }
 #define FSUB(F, B) LAUNCH(K_FUERZA, (k_fuerza_sub<F, B>), nblk(n), TPB, ctx->posm.p, ctx->rh.p, ctx->cols.p, ctx->rev_start.p, \
                        ctx->rev_len.p, ctx->rev_cols.p, ctx->bq.p, ctx->rev_bq.p, ctx->halo_of.p, ctx->lay.p, ctx->sc, ctx->fe.p, ctx->geo, ctx->ph, n, \
-                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p, ctx->use_dq ? (const unsigned char *)ctx->dq.p : (const unsigned char *)nullptr)
+                       ctx->vel.p, ctx->acel.p, ctx->ranv.p, ctx->fnz.p, ctx->use_dq ? (const unsigned char *)ctx->dq.p : (const unsigned char *)nullptr, ctx->kb.p)
   if (fused && ctx->fuse_ermak_b) { if (ctx->force_minb >= 6) FSUB(true, 6); else FSUB(true, 4); }
   else if (ctx->force_minb >= 8) FSUB(false, 8);
   else if (ctx->force_minb >= 6) FSUB(false, 6);
   else FSUB(false, 4);
 #undef FSUB
+  ctx->kb_valid = true;
   return 0;
 }
 
@@ -504,6 +519,7 @@ static int enq_overlap(dml_ctx *ctx, bool fused = false, bool init_done = false,
   return 0;
 }
 static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer_apply) {
+  ctx->kb_valid = false;
   int n = ctx->n;
   TRY(enq_materialize_rows(ctx));
   if (!fused) TRY(enq_qtab(ctx));
@@ -562,6 +578,7 @@ static int enq_overlap_impl(dml_ctx *ctx, bool fused, bool init_done, bool defer
 }
 
 static int enq_promote(dml_ctx *ctx) {
+  ctx->kb_valid = false;
   if (ctx->cfg.reservoir == 3) LAUNCH(K_PROMOTE, k_gcmc_tomb, nblk(ctx->n), TPB, ctx->posm.p, ctx->gorder.p, ctx->gpos.p, ctx->sc, ctx->n);
   LAUNCH(K_PROMOTE, k_promote, nblk(ctx->n), TPB, ctx->posm.p, ctx->sc, ctx->n);
   return 0;
@@ -606,6 +623,7 @@ static int finish(dml_ctx *ctx) {
 
 // bloques — dana.F90:716-773 (host side: needs rho, appends the template block, changes the box)
 static int do_bloques(dml_ctx *ctx, int nchunk, const double *cpos, const double *cpos_old, double dist, double rhomedia, int *fired) {
+  ctx->kb_valid = false;
   TRY(pull_scal(ctx));
   double drho = ctx->hsc->rho - rhomedia;
   if (fired) *fired = 0;
@@ -648,7 +666,7 @@ static int enq_step_a(dml_ctx *ctx) {
   if (ctx->cfg.integrador) {
     TRY(enq_integrate(ctx, true)); TRY(enq_fuerza(ctx, true));
     if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
-      LAUNCH(K_ERMAK_B, k_ermak_b, nblk(n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, n, ctx->fnz.p);
+      TRY(enq_ermak_b(ctx));
   }
   // Brownian step with Philox noise: the integrator rides on the first pass of the test_update that follows it (one launch and one
   // pass over the records less); DML_NO_BI_FUSE=1 keeps the launch of its own
@@ -792,6 +810,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   if (getenv("DML_NO_L2_PERSIST")) ctx->no_l2_persist = true;
   if (getenv("DML_NO_TU_FUSE")) ctx->no_tu_fuse = true;
   if (getenv("DML_NO_BI_FUSE")) ctx->no_bi_fuse = true;
+  if (getenv("DML_NO_FLAT_B")) ctx->no_flat_b = true;
   if (getenv("DML_NO_SLAB_GRAPH") || getenv("DML_NO_GRAPH")) ctx->slab_graph_on = false;
   if (getenv("DML_NO_GRAPH")) ctx->use_graph = false;
   size_t c3 = (size_t)cap * 3;
@@ -809,6 +828,7 @@ int dml_create(dml_ctx **out, const dml_config *cfg) {
   CKC(ctx->halo_of.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->halo_of.p, 0, cap, ctx->st));
   CKC(ctx->fnz.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->fnz.p, 0, cap, ctx->st));
   CKC(ctx->dq.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->dq.p, 0xff, cap, ctx->st));
+  CKC(ctx->kb.ensure(cap, ctx->st)); CKC(cudaMemsetAsync(ctx->kb.p, 0, cap, ctx->st));
   ctx->use_dq = cfg->reservoir != 3 && !getenv("DML_NO_DQ");   // (gcmc reuses slots and appends rows between rebuilds: the layer bound alone)
   CKC(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ROWS_SMEM));
   CKC(ctx->lay.ensure(3 * LAY_MAX, ctx->st)); CKC(cudaMemsetAsync(ctx->lay.p, 0xff, 3 * LAY_MAX * sizeof(unsigned int), ctx->st));   // 2 displacement tables + the skip tables (k_qtab)
@@ -875,7 +895,7 @@ void dml_destroy(dml_ctx *ctx) {
   ctx->mig_list_lo.release(); ctx->mig_list_hi.release(); ctx->mig_rc.release(); ctx->mig_holes.release(); ctx->mig_si_lo.release(); ctx->mig_si_hi.release();
   ctx->mig_ri.release(); ctx->mig_sd_lo.release(); ctx->mig_sd_hi.release(); ctx->mig_rd.release();
   ctx->top2_own.release(); ctx->top2_all.release();
-  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->dq.release(); ctx->sorted_cell.release(); ctx->lay.release();
+  ctx->bq.release(); ctx->rev_bq.release(); ctx->halo_of.release(); ctx->fnz.release(); ctx->dq.release(); ctx->kb.release(); ctx->sorted_cell.release(); ctx->lay.release();
   ctx->rev_start.release(); ctx->rev_len.release(); ctx->rev_cur.release(); ctx->rev_cols.release(); ctx->rev_cnt.release();
   ctx->coop_sums.release(); ctx->scan_state.release(); if (ctx->scan_tickets) cudaFree(ctx->scan_tickets);
   ctx->gorder.release(); ctx->gpos.release(); ctx->gcc.release(); ctx->gpend.release(); ctx->b_occ.release();
@@ -901,6 +921,7 @@ static int member_snapshot(dml_ctx *ctx) {
 int dml_upload(dml_ctx *ctx, int32_t n, const double *pos, const double *vel, const double *acel, const double *pos_old,
                const double *old_cg, const int32_t *z, const int32_t *flags, const int32_t *uid, const int32_t *slot_b) { ENTER(ctx);
   TRY(ensure_particles(ctx, n));
+  ctx->kb_valid = false;
   if (!pos || !z || !flags) FAIL("dml_upload: pos, z and flags are required");
   size_t n3 = (size_t)n * 3;
   CKC(ctx->stage_d.ensure(n3, ctx->st)); CKC(ctx->stage_i.ensure((size_t)n * 2, ctx->st));
@@ -1052,7 +1073,7 @@ int dml_fuerza(dml_ctx *ctx) { ENTER(ctx);
 }
 int dml_ermak_a(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, true)); return finish(ctx); }
 int dml_ermak_b(dml_ctx *ctx) { ENTER(ctx);
-  LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
+  TRY(enq_ermak_b(ctx));
   return finish(ctx);
 }
 int dml_cbrownian_hs(dml_ctx *ctx) { ENTER(ctx); TRY(enq_integrate(ctx, false)); return finish(ctx); }
@@ -1492,7 +1513,7 @@ int dml_slab_step(dml_ctx *ctx, int32_t nsteps) { ENTER(ctx);
       TRY(slab_exchange(ctx, false, true));               // ghosts at their new positions; their moves enter the skip bound
       TRY(enq_fuerza(ctx, true));
       if (ctx->cfg.strict_order || !ctx->fuse_ermak_b)
-        LAUNCH(K_ERMAK_B, k_ermak_b, nblk(ctx->n), TPB, ctx->posm.p, ctx->vel.p, ctx->acel.p, ctx->fe.p, ctx->ranv.p, ctx->ph, ctx->n, ctx->fnz.p);
+        TRY(enq_ermak_b(ctx));
       return slab_tu_enqueue(ctx, false);
     }));
     TRY(slab_tu_decide(ctx));                             // host read-back; migration and list rebuild when due

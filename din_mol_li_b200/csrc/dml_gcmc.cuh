@@ -410,6 +410,7 @@ __global__ void k_gcmc_tomb(const double4 *__restrict__ posm, int *__restrict__ 
 } // namespace dml
 
 static int gcmc_run_impl(dml_ctx *ctx) {
+  ctx->kb_valid = false;
   using namespace dml;
   if (ctx->cfg.reservoir != 3) return 0;
   if (!ctx->binned || !ctx->tessellated) FAIL("gcmc_run: call test_update first");

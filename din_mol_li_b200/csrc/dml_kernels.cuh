@@ -1068,11 +1068,12 @@ __global__ void __launch_bounds__(TPB) k_fuerza(const double4 *__restrict__ posm
                                                 const int *__restrict__ rev_start, const int *__restrict__ rev_len,
                                                 const int *__restrict__ rev_cols, const DevScal *__restrict__ sc,
                                                 const int *__restrict__ uid, double4 *__restrict__ fe,
-                                                Geo g, Phys ph, int n, unsigned char *__restrict__ fnz) {
+                                                Geo g, Phys ph, int n, unsigned char *__restrict__ fnz, unsigned char *__restrict__ kb) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   double4 p1 = ld_rec_nc(&posm[s]);
   long long m1 = meta_of(p1);
+  kb[s] = (m1 & MF_REF) ? (unsigned char)(m1 & MF_TYPE) : (unsigned char)0;   // what ermak_b needs of the record (k_ermak_b_flat)
   if (!(m1 & MF_REF)) return;
   int k = (int)(m1 & MF_TYPE);
   const int asym = sc->rows_asym;
@@ -1267,7 +1268,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
     const unsigned char *__restrict__ halo_of, const unsigned int *__restrict__ lay,
     const DevScal *__restrict__ sc, double4 *__restrict__ fe, const __grid_constant__ Geo g, const __grid_constant__ Phys ph, int n,
     double *__restrict__ vel, double *__restrict__ acel, const double *__restrict__ ranv, unsigned char *__restrict__ fnz,
-    const unsigned char *__restrict__ dq) {
+    const unsigned char *__restrict__ dq, unsigned char *__restrict__ kb) {
   __shared__ unsigned int s_qt[LAY_MAX / 4], s_qb[LAY_MAX / 4];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = s < n;
@@ -1305,6 +1306,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_fuerza_sub(
   }
   __syncthreads();
   const long long m1 = meta_of(p1);
+  if (in) kb[s] = (m1 & MF_REF) ? (unsigned char)(m1 & MF_TYPE) : (unsigned char)0;   // what ermak_b needs of the record (k_ermak_b_flat)
   if (!in || !(m1 & MF_REF)) return;
   FAcc a = {0.0, 0.0, 0.0, 0.0};
   const int lyr = layer_of(g, p1.z);
@@ -1554,6 +1556,25 @@ __global__ void __launch_bounds__(TPB) k_ermak_b(const double4 *__restrict__ pos
     __stcs(&vel[3 * s + k], ph.cc0 * v + ph.cc1mcc2 * a + ph.cc2 * f / mass + __ldcs(&ranv[3 * s + k]));
     __stcs(&acel[3 * s + k], f / mass);
   }
+}
+
+// ermak_b right behind a pair-force call, one thread per COMPONENT: the update is elementwise over vel / acel / ranv ([n][3]
+// doubles read as flat arrays: 8 contiguous bytes per thread instead of three 24-byte-strided requests per array), the force
+// component comes from fe only where fnz says it is non-zero, and element + ref membership come from the byte the pair-force kernel
+// left per slot (kb) instead of the 32-byte record.  Same arithmetic as k_ermak_b.
+__global__ void __launch_bounds__(TPB) k_ermak_b_flat(double *__restrict__ vel, double *__restrict__ acel, const double4 *__restrict__ fe,
+                                                      const double *__restrict__ ranv, Phys ph, int n3, const unsigned char *__restrict__ fnz,
+                                                      const unsigned char *__restrict__ kb) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n3) return;
+  const int s = e / 3, k = e - 3 * s;
+  const int zt = (int)__ldg(&kb[s]);
+  if (zt == 0 || zt == 2) return;
+  const double mass = ph.mass[zt - 1];
+  const double f = __ldg(&fnz[s]) ? reinterpret_cast<const double *>(&fe[s])[k] : 0.0;
+  const double a = __ldcs(&acel[e]), v = __ldcs(&vel[e]);
+  __stcs(&vel[e], ph.cc0 * v + ph.cc1mcc2 * a + ph.cc2 * f / mass + __ldcs(&ranv[e]));
+  __stcs(&acel[e], f / mass);
 }
 
 // ================================================================================================

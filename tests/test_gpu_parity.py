@@ -333,7 +333,7 @@ def test_fused_ermak_b_is_bit_identical(monkeypatch):
     assert np.abs(out[0]["vel"]).sum() > 0
 
 
-@pytest.mark.parametrize("env", ["DML_NO_DQ=1", "DML_NO_GRAPH=1", "DML_FORCE_MINB=6", "DML_FORCE_MINB=8", "DML_ROWS_LEGACY=1", "DML_NO_COOP=1", "DML_NO_COOP=1,DML_OV_LANES=4", "DML_NO_COOP=1,DML_OV_UNSTAGED=1",
+@pytest.mark.parametrize("env", ["DML_NO_FLAT_B=1", "DML_NO_DQ=1", "DML_NO_GRAPH=1", "DML_FORCE_MINB=6", "DML_FORCE_MINB=8", "DML_ROWS_LEGACY=1", "DML_NO_COOP=1", "DML_NO_COOP=1,DML_OV_LANES=4", "DML_NO_COOP=1,DML_OV_UNSTAGED=1",
                                  "DML_NO_COOP=1,DML_OV_LANES=2"])
 def test_kernel_launch_variants_bit_identical(env, monkeypatch):
     """Regression test, device against device (the oracle comparisons are the lock-step tests): other register budgets of the
