@@ -40,3 +40,19 @@ def test_sass_has_256bit_record_loads():
     import subprocess
     out = subprocess.run(["cuobjdump", "-sass", B.LIB], capture_output=True, text=True).stdout
     assert "LDG.E.256" in out or "LDG.E.ENL2.256" in out or ".256" in out
+
+
+def test_every_runtime_switch_is_documented():
+    """INTEGRATION.md §5 lists the environment switches dml_create reads: every getenv("DML_*") of the library is in the table and
+    the table names no switch that the code does not read."""
+    import glob
+    import re
+    code = "".join(open(f).read() for f in glob.glob(os.path.join(ROOT, "din_mol_li_b200", "csrc", "*.cu*")))
+    read = set(re.findall(r'getenv\("(DML_[A-Z0-9_]+)"\)', code))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    sec = doc[doc.index("## 5. Run-time switches"):]
+    table = set(re.findall(r"`(DML_[A-Z0-9_]+)", sec))
+    gone = set(re.findall(r"`(DML_[A-Z0-9_/]+)", sec[:sec.index("| variable | effect |")]))        # the paragraph about removed switches
+    gone = {g for x in gone for g in ([x] if "/" not in x else [])} | {"DML_FORCE_WQ", "DML_ROWS_LANES", "DML_EAGER_ROWS"}
+    assert read <= table, "undocumented: %s" % sorted(read - table)
+    assert (table - gone) <= read, "documented but not read by the code: %s" % sorted(table - gone - read)
