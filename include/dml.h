@@ -126,7 +126,9 @@ int dml_step(dml_ctx *ctx, int32_t nsteps);
 int dml_ensemble_step(dml_ctx **ctxs, int32_t nctx, int32_t nsteps);
 int dml_set_ensemble_member(dml_ctx *ctx, int32_t on);
 /* Frame path of a host that only follows the coordinates (what salida() reads, src/dana.F90:1151-1157): new positions of the same
- * atoms in (membership, velocities, lists stay resident; n must equal the current slot count; the copy is stream-ordered),
+ * atoms in (membership, velocities, lists stay resident; n must equal the current slot count; the copy is stream-ordered; the
+ * library no longer knows how far anything moved, so the pair force and overlap_moveback look at every list entry until the next
+ * test_update has measured the displacements, and that test_update rebuilds the list if they exceed the skin),
  * positions + element out (synchronous). */
 int dml_upload_positions(dml_ctx *ctx, int32_t n, const double *pos, const double *pos_old);
 int dml_download_frame(dml_ctx *ctx, int32_t n, double *pos, int32_t *z);
